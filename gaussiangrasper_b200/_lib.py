@@ -1,0 +1,131 @@
+"""ctypes binding of libgg_b200.so (the C ABI declared in include/gg_b200.h).
+
+There is no CPU fallback: if the shared library is missing and cannot be built, or a call
+fails, this module raises.  PyTorch is used only to own device memory and name the stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import torch
+
+from . import build as _build
+
+_lock = threading.Lock()
+_lib = None
+
+_i, _ll, _f, _p, _sz = C.c_int, C.c_longlong, C.c_float, C.c_void_p, C.c_size_t
+
+_SIGNATURES = {
+    "gg_version": (C.c_int, []),
+    "gg_last_error_string": (C.c_char_p, []),
+    "gg_launch_count": (C.c_ulonglong, []),
+    "gg_check_device": (C.c_int, []),
+    "gg_project_fwd": (C.c_int, [_i, _p, _p, _f, _p, _p, _p, _f, _f, _f, _f, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _p, _p]),
+    "gg_project_bwd": (C.c_int, [_i, _p, _p, _f, _p, _p, _p, _f, _f, _f, _f, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "gg_project_fwd_views": (C.c_int, [_i, _i, _p, _p, _f, _p, _p, _p, _p, _f, _f, _f, _f, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _p, _p]),
+    "gg_project_bwd_views": (C.c_int, [_i, _i, _p, _p, _f, _p, _p, _p, _p, _f, _f, _f, _f, _i, _i, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p]),
+    "gg_sh_fwd": (C.c_int, [_i, _i, _i, _p, _p, _p, _p]),
+    "gg_sh_bwd": (C.c_int, [_i, _i, _i, _p, _p, _p, _p]),
+    "gg_cumsum_workspace_bytes": (C.c_size_t, [_ll]),
+    "gg_cumsum": (C.c_int, [_ll, _p, _p, _p, _p, _sz, _p]),
+    "gg_map_to_intersects": (C.c_int, [_i, _i, _p, _p, _p, _p, _i, _i, _p, _p, _p]),
+    "gg_sort_workspace_bytes": (C.c_size_t, [_ll]),
+    "gg_sort_pairs": (C.c_int, [_ll, _i, _p, _p, _p, _p, _p, _sz, _p]),
+    "gg_tile_ranges": (C.c_int, [_ll, _p, _ll, _p, _p]),
+    "gg_blend_max_channels": (C.c_int, []),
+    "gg_pack_geo": (C.c_int, [_ll, _i, _p, _p, _p, _i, _p, _p]),
+    "gg_blend_fwd": (C.c_int, [_i, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "gg_blend_bwd": (C.c_int, [_i, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "gg_unpack_vgeo": (C.c_int, [_ll, _i, _p, _p, _p, _p, _i, _p]),
+}
+
+# optional symbols of later translation units (bound when present)
+_OPTIONAL = {}
+
+
+class GGError(RuntimeError):
+    pass
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load():
+    """Load (building in-tree first if needed) libgg_b200.so; raises if that is impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if _build.needs_build():
+            try:
+                _build.build()
+            except Exception as e:  # no nvcc on this box and no prebuilt library
+                if not os.path.exists(_build.LIB):
+                    raise ImportError(
+                        "gaussiangrasper_b200: libgg_b200.so is missing and could not be built "
+                        f"({e}); there is no CPU fallback") from e
+        lib = C.CDLL(_build.LIB)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the library does not export the header's symbol
+            fn.restype = res
+            fn.argtypes = args
+        for name, (res, args) in _OPTIONAL.items():
+            if hasattr(lib, name):
+                fn = getattr(lib, name)
+                fn.restype = res
+                fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def exported_symbols():
+    return list(_SIGNATURES)
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().gg_last_error_string().decode("utf-8", "replace")
+        raise GGError(f"{what or 'gg_b200'} failed (code {rc}): {msg}")
+
+
+def launch_count() -> int:
+    return int(load().gg_launch_count())
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda(*tensors) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise GGError("gaussiangrasper_b200 runs on CUDA tensors only (no CPU fallback); got a "
+                          f"{t.device} tensor")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise GGError(f"tensors on different devices: {dev} vs {t.device}")
+    return dev
+
+
+def f32c(t: torch.Tensor) -> torch.Tensor:
+    """float32, contiguous view/copy of t."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()

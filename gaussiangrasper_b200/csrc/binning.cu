@@ -1,0 +1,433 @@
+// Tile binning: prefix sum of intersection counts, 64-bit tile|depth key emission, in-house
+// onesweep LSD radix sort (64-bit keys, 32-bit payload) and per-tile ranges.
+//
+// Replaces gsplat 0.1.0 utils.compute_cumulative_intersects / bin_and_sort_gaussians
+// (torch.cumsum + map_gaussian_to_intersects + torch.sort + gather + get_tile_bin_edges), which
+// the reference re-runs inside every RasterizeGaussians / NDRasterizeGaussians.forward
+// (nerfstudio/models/gaussian_splatting.py:735,747,759,773).  All outputs are integers and are
+// bit-exact against the CPU oracle; ties in the sort are broken by ascending Gaussian id because
+// emission is id-ordered and every pass of the LSD sort is stable.
+//
+// Compiled with -fmad=false (tile_box() must reproduce the projection kernel's tile bbox).
+#include "gg_common.cuh"
+#include "gg_math.cuh"
+#include "gg_b200.h"
+
+#include <atomic>
+
+namespace gg {
+
+// ---------------------------------------------------------------------------------------------
+// Inclusive int32 prefix sum: reduce -> spine -> downsweep.  4096 items per block.
+// ---------------------------------------------------------------------------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanIpt = 16;
+constexpr int kScanTile = kScanThreads * kScanIpt;
+
+__device__ __forceinline__ int warp_incl_scan(int v) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// exclusive scan of one int per thread across a 256-thread block; returns exclusive prefix and
+// (through total) the block total.  sm must hold 8 ints.
+__device__ __forceinline__ int block_excl_scan_256(int v, int* sm, int& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int incl = warp_incl_scan(v);
+    if (lane == 31) sm[warp] = incl;
+    __syncthreads();
+    int woff = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        const int t = sm[w];
+        if (w < warp) woff += t;
+        tot += t;
+    }
+    total = tot;
+    __syncthreads();
+    return woff + incl - v;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_reduce_kernel(long long n, const int32_t* __restrict__ in, int32_t* __restrict__ block_sums) {
+    __shared__ int sm[8];
+    const long long base = (long long)blockIdx.x * kScanTile + (long long)threadIdx.x * kScanIpt;
+    int s = 0;
+    if (base + kScanIpt <= n) {
+        const int4* p = reinterpret_cast<const int4*>(in + base);
+#pragma unroll
+        for (int k = 0; k < kScanIpt / 4; ++k) { const int4 v = __ldg(p + k); s += v.x + v.y + v.z + v.w; }
+    } else {
+        for (int k = 0; k < kScanIpt; ++k) if (base + k < n) s += __ldg(in + base + k);
+    }
+    int total;
+    block_excl_scan_256(s, sm, total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+// single block: exclusive scan of block_sums in place, grand total to *total_out (and *total_out2)
+__global__ void __launch_bounds__(kScanThreads)
+scan_spine_kernel(int nb, int32_t* __restrict__ block_sums, int32_t* __restrict__ total_out) {
+    __shared__ int sm[8];
+    int carry = 0;
+    for (int base = 0; base < nb; base += kScanThreads) {
+        const int i = base + threadIdx.x;
+        const int v = i < nb ? block_sums[i] : 0;
+        int total;
+        const int ex = block_excl_scan_256(v, sm, total);
+        if (i < nb) block_sums[i] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0 && total_out) *total_out = carry;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_down_kernel(long long n, const int32_t* __restrict__ in, const int32_t* __restrict__ block_offsets,
+                 int32_t* __restrict__ out) {
+    __shared__ int sm[8];
+    const long long base = (long long)blockIdx.x * kScanTile + (long long)threadIdx.x * kScanIpt;
+    int v[kScanIpt];
+    const bool full = base + kScanIpt <= n;
+    if (full) {
+        const int4* p = reinterpret_cast<const int4*>(in + base);
+#pragma unroll
+        for (int k = 0; k < kScanIpt / 4; ++k) {
+            const int4 t = __ldg(p + k);
+            v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < kScanIpt; ++k) v[k] = (base + k < n) ? __ldg(in + base + k) : 0;
+    }
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanIpt; ++k) { s += v[k]; v[k] = s; }
+    int total;
+    const int ex = block_excl_scan_256(s, sm, total) + block_offsets[blockIdx.x];
+    if (full) {
+        int4* p = reinterpret_cast<int4*>(out + base);
+#pragma unroll
+        for (int k = 0; k < kScanIpt / 4; ++k)
+            p[k] = make_int4(v[4 * k] + ex, v[4 * k + 1] + ex, v[4 * k + 2] + ex, v[4 * k + 3] + ex);
+    } else {
+#pragma unroll
+        for (int k = 0; k < kScanIpt; ++k) if (base + k < n) out[base + k] = v[k] + ex;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Key emission.  One thread per (view, Gaussian); entry k of Gaussian g goes to cum[g-1] + k with
+// tiles visited row-major inside the bbox.  key = (view * T + tile) << 32 | depth bits.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+emit_keys_kernel(int n, int n_views, const float* __restrict__ xys, const float* __restrict__ depths,
+                 const int32_t* __restrict__ radii, const int32_t* __restrict__ cum, int tiles_x, int tiles_y,
+                 int64_t* __restrict__ keys, int32_t* __restrict__ ids) {
+    const long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= (long long)n * n_views) return;
+    const int r = radii[gi];
+    if (r <= 0) return;
+    const int view = (int)(gi / n);
+    const int g = (int)(gi - (long long)view * n);
+    const float2 c = __ldg(reinterpret_cast<const float2*>(xys) + gi);
+    const TileBox tb = tile_box(c.x, c.y, (float)r, tiles_x, tiles_y);
+    long long cur = gi == 0 ? 0 : cum[gi - 1];
+    const uint64_t dbits = (uint64_t)__float_as_uint(depths[gi]);
+    const long long tile0 = (long long)view * tiles_x * tiles_y;
+    for (int ty = tb.y0; ty < tb.y1; ++ty)
+        for (int tx = tb.x0; tx < tb.x1; ++tx) {
+            const uint64_t tile = (uint64_t)(tile0 + (long long)ty * tiles_x + tx);
+            keys[cur] = (int64_t)((tile << 32) | dbits);
+            ids[cur] = g;
+            ++cur;
+        }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Onesweep LSD radix sort, 8-bit digits, 256 threads x 16 keys per tile.
+//   1 upfront kernel  : digit histograms of every pass
+//   1 tiny kernel     : exclusive scan of each 256-bin histogram
+//   P pass kernels    : rank (warp match), decoupled look-back across tiles, shared-memory
+//                       reorder, coalesced scatter
+// Tile status words are 64 bit: [generation:32 | flag:2 | count:30]; a per-process generation
+// counter makes stale words from earlier passes/calls invisible, so the status array is zeroed
+// only once, by whoever allocates the workspace.
+// ---------------------------------------------------------------------------------------------
+constexpr int kRsThreads = 256;
+constexpr int kRsIpt = 16;
+constexpr int kRsTile = kRsThreads * kRsIpt;  // 4096
+constexpr int kRadix = 256;
+constexpr int kMaxPasses = 8;
+constexpr uint32_t kFlagAgg = 1u << 30;
+constexpr uint32_t kFlagIncl = 1u << 31;
+constexpr uint32_t kValueMask = (1u << 30) - 1;
+
+__global__ void __launch_bounds__(256)
+radix_hist_kernel(const uint64_t* __restrict__ keys, long long m, int passes, uint32_t* __restrict__ ghist) {
+    __shared__ uint32_t sh[kMaxPasses * kRadix];
+    for (int i = threadIdx.x; i < passes * kRadix; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long rounds = (m + stride - 1) / stride;
+    for (long long r = 0; r < rounds; ++r) {
+        const long long i = r * stride + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        const bool valid = i < m;
+        const uint64_t k = valid ? __ldg(keys + i) : 0;
+        for (int p = 0; p < passes; ++p) {
+            const uint32_t d = valid ? (uint32_t)(k >> (8 * p)) & 255u : 256u + lane;
+            const uint32_t mask = __match_any_sync(0xffffffffu, d);
+            if (valid && lane == __ffs(mask) - 1) atomicAdd(&sh[p * kRadix + d], (uint32_t)__popc(mask));
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < passes * kRadix; i += blockDim.x) {
+        const uint32_t v = sh[i];
+        if (v) atomicAdd(&ghist[i], v);
+    }
+}
+
+__global__ void __launch_bounds__(256) radix_scan_hist_kernel(uint32_t* __restrict__ ghist) {
+    __shared__ int sm[8];
+    uint32_t* h = ghist + blockIdx.x * kRadix;
+    int total;
+    const int v = (int)h[threadIdx.x];
+    h[threadIdx.x] = (uint32_t)block_excl_scan_256(v, sm, total);
+}
+
+__global__ void __launch_bounds__(kRsThreads)
+radix_pass_kernel(const uint64_t* __restrict__ kin, const uint32_t* __restrict__ vin, uint64_t* __restrict__ kout,
+                  uint32_t* __restrict__ vout, long long m, int shift, const uint32_t* __restrict__ ghist_excl,
+                  volatile uint64_t* tile_state, uint32_t* ticket, uint32_t generation) {
+    // everything lives in dynamic shared memory (59.5 KB > the 48 KB static limit)
+    extern __shared__ __align__(16) unsigned char dyn[];
+    uint64_t* keys_sm = reinterpret_cast<uint64_t*>(dyn);
+    uint32_t* vals_sm = reinterpret_cast<uint32_t*>(dyn + sizeof(uint64_t) * kRsTile);
+    uint32_t(*warp_hist)[kRadix] = reinterpret_cast<uint32_t(*)[kRadix]>(vals_sm + kRsTile);
+    uint32_t* local_start = reinterpret_cast<uint32_t*>(warp_hist + kRsThreads / 32);
+    uint32_t* global_base = local_start + kRadix;
+    int* scan_sm = reinterpret_cast<int*>(global_base + kRadix);
+    uint32_t& s_tile = *reinterpret_cast<uint32_t*>(scan_sm + 8);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+#pragma unroll
+    for (int w = 0; w < kRsThreads / 32; ++w) warp_hist[w][tid] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const long long base = (long long)tile * kRsTile;
+    const long long wbase = base + (long long)warp * (32 * kRsIpt);
+
+    uint64_t key[kRsIpt];
+#pragma unroll
+    for (int j = 0; j < kRsIpt; ++j) {
+        const long long idx = wbase + j * 32 + lane;
+        key[j] = idx < m ? __ldg(kin + idx) : ~0ull;
+    }
+    // stable rank inside the warp: items are ordered (j, lane)
+    uint32_t rank[kRsIpt];
+#pragma unroll
+    for (int j = 0; j < kRsIpt; ++j) {
+        const uint32_t d = (uint32_t)(key[j] >> shift) & 255u;
+        const uint32_t mask = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(mask) - 1;
+        uint32_t prev = 0;
+        if (lane == leader) {
+            prev = warp_hist[warp][d];
+            warp_hist[warp][d] = prev + (uint32_t)__popc(mask);
+        }
+        prev = __shfl_sync(0xffffffffu, prev, leader);
+        rank[j] = prev + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+        __syncwarp();
+    }
+    __syncthreads();
+    // thread tid owns digit tid: warp-exclusive offsets, tile count, look-back
+    uint32_t count = 0;
+#pragma unroll
+    for (int w = 0; w < kRsThreads / 32; ++w) {
+        const uint32_t t = warp_hist[w][tid];
+        warp_hist[w][tid] = count;
+        count += t;
+    }
+    const uint64_t gen = (uint64_t)generation << 32;
+    volatile uint64_t* my_state = tile_state + (size_t)tile * kRadix + tid;
+    uint32_t excl = 0;
+    if (tile == 0) {
+        *my_state = gen | kFlagIncl | count;
+    } else {
+        *my_state = gen | kFlagAgg | count;
+        long long prev = (long long)tile - 1;
+        while (true) {
+            uint64_t s;
+            do {
+                s = tile_state[(size_t)prev * kRadix + tid];
+            } while ((s >> 32) != generation || ((uint32_t)s & (kFlagAgg | kFlagIncl)) == 0);
+            excl += (uint32_t)s & kValueMask;
+            if ((uint32_t)s & kFlagIncl) break;
+            --prev;
+        }
+        *my_state = gen | kFlagIncl | ((excl + count) & kValueMask);
+    }
+    int total;
+    const uint32_t lstart = (uint32_t)block_excl_scan_256((int)count, scan_sm, total);
+    local_start[tid] = lstart;
+    global_base[tid] = ghist_excl[tid] + excl - lstart;
+    __syncthreads();
+    // reorder through shared memory so that the scatter writes runs of consecutive addresses
+#pragma unroll
+    for (int j = 0; j < kRsIpt; ++j) {
+        const uint32_t d = (uint32_t)(key[j] >> shift) & 255u;
+        const uint32_t pos = local_start[d] + warp_hist[warp][d] + rank[j];
+        const long long idx = wbase + j * 32 + lane;
+        keys_sm[pos] = key[j];
+        vals_sm[pos] = idx < m ? __ldg(vin + idx) : 0u;
+    }
+    __syncthreads();
+    const long long remain = m - base;
+    const int valid = remain < kRsTile ? (int)remain : kRsTile;
+#pragma unroll
+    for (int k = 0; k < kRsIpt; ++k) {
+        const int pos = k * kRsThreads + tid;
+        if (pos < valid) {
+            const uint64_t kk = keys_sm[pos];
+            const uint32_t d = (uint32_t)(kk >> shift) & 255u;
+            const uint32_t gpos = global_base[d] + (uint32_t)pos;
+            kout[gpos] = kk;
+            vout[gpos] = vals_sm[pos];
+        }
+    }
+}
+
+// tile_ranges[t] = (first, last+1) of the run of sorted keys whose high word is t; must be
+// zero-initialised (empty tiles stay (0,0)).
+__global__ void __launch_bounds__(256)
+tile_ranges_kernel(long long m, const int64_t* __restrict__ keys_sorted, int32_t* __restrict__ tile_ranges) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int32_t t = (int32_t)(keys_sorted[i] >> 32);
+    if (i == 0 || (int32_t)(keys_sorted[i - 1] >> 32) != t) tile_ranges[2 * (size_t)t] = (int32_t)i;
+    if (i == m - 1 || (int32_t)(keys_sorted[i + 1] >> 32) != t) tile_ranges[2 * (size_t)t + 1] = (int32_t)(i + 1);
+}
+
+static std::atomic<uint32_t> g_generation{1};
+
+struct SortLayout {
+    size_t off_hist, off_ticket, off_state, off_keys, off_vals, total;
+    long long tiles;
+};
+
+static SortLayout sort_layout(long long m) {
+    SortLayout L;
+    L.tiles = (m + kRsTile - 1) / kRsTile;
+    if (L.tiles < 1) L.tiles = 1;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~(size_t)255; return r; };
+    L.off_hist = take(sizeof(uint32_t) * kMaxPasses * kRadix);
+    L.off_ticket = take(sizeof(uint32_t) * kMaxPasses);
+    L.off_state = take(sizeof(uint64_t) * (size_t)L.tiles * kRadix);
+    L.off_keys = take(sizeof(uint64_t) * (size_t)(m > 0 ? m : 1));
+    L.off_vals = take(sizeof(uint32_t) * (size_t)(m > 0 ? m : 1));
+    L.total = o;
+    return L;
+}
+
+}  // namespace gg
+
+using namespace gg;
+
+extern "C" size_t gg_cumsum_workspace_bytes(long long n) {
+    return sizeof(int32_t) * (size_t)(div_up(n > 0 ? n : 1, kScanTile) + 1);
+}
+
+extern "C" int gg_cumsum(long long n, const int32_t* in, int32_t* out, int32_t* total_dev, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+    GG_REQUIRE(n >= 1 && n < (1ll << 40), "gg_cumsum: need n >= 1");
+    GG_REQUIRE(in && out && workspace, "gg_cumsum: null pointer");
+    GG_REQUIRE(workspace_bytes >= gg_cumsum_workspace_bytes(n), "gg_cumsum: workspace too small");
+    GG_REQUIRE(((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0, "gg_cumsum: arrays must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nb = div_up(n, kScanTile);
+    int32_t* sums = reinterpret_cast<int32_t*>(workspace);
+    scan_reduce_kernel<<<nb, kScanThreads, 0, st>>>(n, in, sums);
+    scan_spine_kernel<<<1, kScanThreads, 0, st>>>(nb, sums, total_dev);
+    scan_down_kernel<<<nb, kScanThreads, 0, st>>>(n, in, sums, out);
+    count_launch(3);
+    return check_launch("gg_cumsum");
+}
+
+extern "C" int gg_map_to_intersects(int n, int n_views, const float* xys, const float* depths, const int32_t* radii,
+                                    const int32_t* cum_tiles_hit, int tiles_x, int tiles_y, int64_t* keys,
+                                    int32_t* ids, void* stream) {
+    GG_REQUIRE(n >= 1 && n_views >= 1, "gg_map_to_intersects: need n >= 1");
+    GG_REQUIRE(xys && depths && radii && cum_tiles_hit && keys && ids, "gg_map_to_intersects: null pointer");
+    GG_REQUIRE((long long)n_views * tiles_x * tiles_y < (1ll << 31), "gg_map_to_intersects: too many tiles");
+    const long long total = (long long)n * n_views;
+    emit_keys_kernel<<<div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(n, n_views, xys, depths, radii,
+                                                                           cum_tiles_hit, tiles_x, tiles_y, keys, ids);
+    count_launch();
+    return check_launch("emit_keys_kernel");
+}
+
+extern "C" size_t gg_sort_workspace_bytes(long long m) { return sort_layout(m).total; }
+
+extern "C" int gg_sort_pairs(long long m, int key_bits, const int64_t* keys_in, const int32_t* vals_in,
+                             int64_t* keys_out, int32_t* vals_out, void* workspace, size_t workspace_bytes,
+                             void* stream) {
+    GG_REQUIRE(m >= 0 && m < (1ll << 30), "gg_sort_pairs: need 0 <= m < 2^30");
+    GG_REQUIRE(key_bits >= 1 && key_bits <= 64, "gg_sort_pairs: key_bits out of range");
+    if (m == 0) return GG_OK;
+    GG_REQUIRE(keys_in && vals_in && keys_out && vals_out && workspace, "gg_sort_pairs: null pointer");
+    const SortLayout L = sort_layout(m);
+    GG_REQUIRE(workspace_bytes >= L.total, "gg_sort_pairs: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
+    uint32_t* ghist = reinterpret_cast<uint32_t*>(ws + L.off_hist);
+    uint32_t* tickets = reinterpret_cast<uint32_t*>(ws + L.off_ticket);
+    uint64_t* state = reinterpret_cast<uint64_t*>(ws + L.off_state);
+    uint64_t* kalt = reinterpret_cast<uint64_t*>(ws + L.off_keys);
+    uint32_t* valt = reinterpret_cast<uint32_t*>(ws + L.off_vals);
+    const int passes = (key_bits + 7) / 8;
+
+    const size_t dyn = (sizeof(uint64_t) + sizeof(uint32_t)) * kRsTile +
+                       sizeof(uint32_t) * ((kRsThreads / 32) * kRadix + 2 * kRadix) + sizeof(int) * 8 + 16;
+    GG_CUDA(cudaFuncSetAttribute(radix_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    // histograms + tickets are contiguous at the start of the workspace
+    GG_CUDA(cudaMemsetAsync(ws, 0, L.off_state, st));
+    int hist_blocks = div_up(m, 256 * 8);
+    if (hist_blocks > 148 * 8) hist_blocks = 148 * 8;
+    radix_hist_kernel<<<hist_blocks, 256, 0, st>>>(reinterpret_cast<const uint64_t*>(keys_in), m, passes, ghist);
+    radix_scan_hist_kernel<<<passes, 256, 0, st>>>(ghist);
+    const uint64_t* kin = reinterpret_cast<const uint64_t*>(keys_in);
+    const uint32_t* vin = reinterpret_cast<const uint32_t*>(vals_in);
+    for (int p = 0; p < passes; ++p) {
+        // the last pass must land in keys_out: passes-1-p even -> out, odd -> alt
+        const bool to_out = ((passes - 1 - p) & 1) == 0;
+        uint64_t* ko = to_out ? reinterpret_cast<uint64_t*>(keys_out) : kalt;
+        uint32_t* vo = to_out ? reinterpret_cast<uint32_t*>(vals_out) : valt;
+        const uint32_t gen = g_generation.fetch_add(1);
+        radix_pass_kernel<<<(unsigned)L.tiles, kRsThreads, dyn, st>>>(kin, vin, ko, vo, m, 8 * p, ghist + p * kRadix,
+                                                                      state, tickets + p, gen == 0 ? 1u : gen);
+        kin = ko;
+        vin = vo;
+    }
+    count_launch(2 + passes);
+    return check_launch("gg_sort_pairs");
+}
+
+extern "C" int gg_tile_ranges(long long m, const int64_t* keys_sorted, long long num_tiles, int32_t* tile_ranges,
+                              void* stream) {
+    GG_REQUIRE(m >= 0 && num_tiles >= 1, "gg_tile_ranges: bad sizes");
+    GG_REQUIRE(tile_ranges && (m == 0 || keys_sorted), "gg_tile_ranges: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    GG_CUDA(cudaMemsetAsync(tile_ranges, 0, sizeof(int32_t) * 2 * (size_t)num_tiles, st));
+    if (m > 0) {
+        tile_ranges_kernel<<<div_up(m, 256), 256, 0, st>>>(m, keys_sorted, tile_ranges);
+        count_launch();
+    }
+    return check_launch("tile_ranges_kernel");
+}

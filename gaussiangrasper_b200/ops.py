@@ -1,0 +1,296 @@
+"""Thin tensor-level wrappers over the C ABI (no autograd here).
+
+Every function takes CUDA tensors, allocates its outputs with torch on the same device and
+enqueues the kernels on torch's current stream.  Mirrors, one to one, the gsplat.cuda bindings
+that gsplat 0.1.0's Python layer calls (see include/gg_b200.h for the mapping).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import check, f32c, ptr, require_cuda, stream_ptr
+
+TILE = 16
+
+
+def tile_bounds_for(img_height: int, img_width: int) -> Tuple[int, int, int]:
+    return ((img_width + TILE - 1) // TILE, (img_height + TILE - 1) // TILE, 1)
+
+
+# ------------------------------------------------------------------------------------------
+# per-device workspace for the binning stage
+# ------------------------------------------------------------------------------------------
+class _Workspace:
+    def __init__(self, device):
+        self.device = device
+        self.scan = None
+        self.sort = None
+        self.keys = None
+        self.ids = None
+        self.keys_sorted = None
+        self.total = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def scan_ws(self, n):
+        need = int(_lib.load().gg_cumsum_workspace_bytes(n))
+        if self.scan is None or self.scan.numel() < need:
+            self.scan = torch.empty(int(need * 1.5) + 256, dtype=torch.uint8, device=self.device)
+        return self.scan
+
+    def sort_ws(self, m):
+        need = int(_lib.load().gg_sort_workspace_bytes(m))
+        if self.sort is None or self.sort.numel() < need:
+            # zero-filled once: the library owns the look-back status words afterwards
+            self.sort = torch.zeros(int(need * 1.5) + 256, dtype=torch.uint8, device=self.device)
+        return self.sort
+
+    def key_buffers(self, m):
+        if self.keys is None or self.keys.numel() < m:
+            cap = int(m * 1.5) + 1024
+            self.keys = torch.empty(cap, dtype=torch.int64, device=self.device)
+            self.ids = torch.empty(cap, dtype=torch.int32, device=self.device)
+            self.keys_sorted = torch.empty(cap, dtype=torch.int64, device=self.device)
+        return self.keys, self.ids, self.keys_sorted
+
+
+_workspaces = {}
+
+
+def workspace(device) -> _Workspace:
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    ws = _workspaces.get(key)
+    if ws is None:
+        ws = _workspaces[key] = _Workspace(device)
+    return ws
+
+
+# ------------------------------------------------------------------------------------------
+# projection / SH
+# ------------------------------------------------------------------------------------------
+def project_fwd(means3d, scales, glob_scale, quats, viewmat, fullmat, fx, fy, cx, cy, img_height, img_width,
+                tile_bounds, clip_thresh=0.01):
+    dev = require_cuda(means3d, scales, quats, viewmat, fullmat)
+    means3d, scales, quats = f32c(means3d), f32c(scales), f32c(quats)
+    vm = f32c(viewmat).reshape(-1)
+    fm = f32c(fullmat).reshape(-1)
+    if vm.numel() < 12 or fm.numel() != 16:
+        raise ValueError("viewmat must have at least 3x4 and fullmat 4x4 entries")
+    n = means3d.shape[0]
+    cov3d = torch.empty((n, 6), dtype=torch.float32, device=dev)
+    xys = torch.empty((n, 2), dtype=torch.float32, device=dev)
+    depths = torch.empty((n,), dtype=torch.float32, device=dev)
+    radii = torch.empty((n,), dtype=torch.int32, device=dev)
+    conics = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    nth = torch.empty((n,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.load().gg_project_fwd(
+            n, ptr(means3d), ptr(scales), float(glob_scale), ptr(quats), ptr(vm), ptr(fm), float(fx), float(fy),
+            float(cx), float(cy), int(img_height), int(img_width), int(tile_bounds[0]), int(tile_bounds[1]),
+            float(clip_thresh), ptr(cov3d), ptr(xys), ptr(depths), ptr(radii), ptr(conics), ptr(nth),
+            stream_ptr(dev)), "gg_project_fwd")
+    return xys, depths, radii, conics, nth, cov3d
+
+
+def project_bwd(means3d, scales, glob_scale, quats, viewmat, fullmat, fx, fy, cx, cy, img_height, img_width, radii,
+                conics, v_xys, v_depths, v_conics):
+    dev = require_cuda(means3d, scales, quats, viewmat, fullmat, radii, conics, v_xys, v_conics)
+    means3d, scales, quats = f32c(means3d), f32c(scales), f32c(quats)
+    vm, fm = f32c(viewmat).reshape(-1), f32c(fullmat).reshape(-1)
+    conics, v_xys, v_conics = f32c(conics), f32c(v_xys), f32c(v_conics)
+    v_depths = f32c(v_depths) if v_depths is not None else None
+    n = means3d.shape[0]
+    v_means = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    v_scales = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    v_quats = torch.empty((n, 4), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.load().gg_project_bwd(
+            n, ptr(means3d), ptr(scales), float(glob_scale), ptr(quats), ptr(vm), ptr(fm), float(fx), float(fy),
+            float(cx), float(cy), int(img_height), int(img_width), ptr(radii), ptr(conics), ptr(v_xys),
+            ptr(v_depths), ptr(v_conics), ptr(v_means), ptr(v_scales), ptr(v_quats), stream_ptr(dev)),
+            "gg_project_bwd")
+    return v_means, v_scales, v_quats
+
+
+def sh_degree_from_bases(num_bases: int) -> int:
+    table = {1: 0, 4: 1, 9: 2, 16: 3, 25: 4}
+    if num_bases not in table:
+        raise ValueError(f"coeffs has {num_bases} SH bases; expected 1, 4, 9, 16 or 25")
+    return table[num_bases]
+
+
+def sh_fwd(degrees_to_use, viewdirs, coeffs):
+    dev = require_cuda(viewdirs, coeffs)
+    viewdirs, coeffs = f32c(viewdirs), f32c(coeffs)
+    n = coeffs.shape[0]
+    degree = sh_degree_from_bases(coeffs.shape[-2])
+    colors = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.load().gg_sh_fwd(n, degree, int(degrees_to_use), ptr(viewdirs), ptr(coeffs), ptr(colors),
+                                    stream_ptr(dev)), "gg_sh_fwd")
+    return colors
+
+
+def sh_bwd(degree, degrees_to_use, viewdirs, v_colors):
+    dev = require_cuda(viewdirs, v_colors)
+    viewdirs, v_colors = f32c(viewdirs), f32c(v_colors)
+    n = viewdirs.shape[0]
+    nb = (degree + 1) ** 2
+    v_coeffs = torch.empty((n, nb, 3), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.load().gg_sh_bwd(n, int(degree), int(degrees_to_use), ptr(viewdirs), ptr(v_colors), ptr(v_coeffs),
+                                    stream_ptr(dev)), "gg_sh_bwd")
+    return v_coeffs
+
+
+# ------------------------------------------------------------------------------------------
+# binning
+# ------------------------------------------------------------------------------------------
+def cumsum_i32(x: torch.Tensor, total_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    dev = require_cuda(x)
+    x = x.contiguous()
+    assert x.dtype == torch.int32
+    out = torch.empty_like(x)
+    ws = workspace(dev).scan_ws(x.numel())
+    with torch.cuda.device(dev):
+        check(_lib.load().gg_cumsum(x.numel(), ptr(x), ptr(out), ptr(total_out), ptr(ws), ws.numel(),
+                                    stream_ptr(dev)), "gg_cumsum")
+    return out
+
+
+def key_bits_for(num_tiles_total: int) -> int:
+    return 32 + max(1, (max(num_tiles_total, 1) - 1).bit_length())
+
+
+def map_to_intersects(n, n_views, xys, depths, radii, cum, tile_bounds, keys, ids):
+    dev = xys.device
+    with torch.cuda.device(dev):
+        check(_lib.load().gg_map_to_intersects(int(n), int(n_views), ptr(xys), ptr(depths), ptr(radii), ptr(cum),
+                                               int(tile_bounds[0]), int(tile_bounds[1]), ptr(keys), ptr(ids),
+                                               stream_ptr(dev)), "gg_map_to_intersects")
+
+
+def sort_pairs(m, key_bits, keys_in, ids_in, keys_out, ids_out):
+    dev = keys_in.device
+    ws = workspace(dev).sort_ws(m)
+    with torch.cuda.device(dev):
+        check(_lib.load().gg_sort_pairs(int(m), int(key_bits), ptr(keys_in), ptr(ids_in), ptr(keys_out), ptr(ids_out),
+                                        ptr(ws), ws.numel(), stream_ptr(dev)), "gg_sort_pairs")
+
+
+def tile_ranges(m, keys_sorted, num_tiles):
+    dev = keys_sorted.device
+    ranges = torch.empty((num_tiles, 2), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.load().gg_tile_ranges(int(m), ptr(keys_sorted), int(num_tiles), ptr(ranges), stream_ptr(dev)),
+              "gg_tile_ranges")
+    return ranges
+
+
+@dataclass
+class Binning:
+    """Sorted intersection list of one batch of views (what the blend kernels consume)."""
+    n: int
+    n_views: int
+    num_intersects: int
+    ids_sorted: torch.Tensor    # [M] int32
+    tile_ranges: torch.Tensor   # [V*T, 2] int32
+    tile_bounds: Tuple[int, int, int]
+
+
+def bin_views(n, n_views, xys, depths, radii, num_tiles_hit, tile_bounds) -> Binning:
+    """cumsum -> (one host read of M) -> key emission -> radix sort -> tile ranges."""
+    dev = require_cuda(xys, depths, radii, num_tiles_hit)
+    ws = workspace(dev)
+    xys, depths = f32c(xys), f32c(depths)
+    radii, num_tiles_hit = radii.contiguous(), num_tiles_hit.contiguous()
+    cum = cumsum_i32(num_tiles_hit.reshape(-1), ws.total)
+    m = int(ws.total.item())
+    if m < 0:
+        raise _lib.GGError("number of tile intersections overflows int32")
+    num_tiles = int(tile_bounds[0]) * int(tile_bounds[1]) * n_views
+    ids_sorted = torch.empty((max(m, 1),), dtype=torch.int32, device=dev)
+    if m > 0:
+        keys, ids, keys_sorted = ws.key_buffers(m)
+        map_to_intersects(n, n_views, xys, depths, radii, cum, tile_bounds, keys, ids)
+        sort_pairs(m, key_bits_for(num_tiles), keys, ids, keys_sorted, ids_sorted)
+        ranges = tile_ranges(m, keys_sorted, num_tiles)
+    else:
+        ranges = torch.zeros((num_tiles, 2), dtype=torch.int32, device=dev)
+    return Binning(n, n_views, m, ids_sorted[:m] if m > 0 else ids_sorted[:0], ranges, tuple(tile_bounds))
+
+
+# ------------------------------------------------------------------------------------------
+# blending
+# ------------------------------------------------------------------------------------------
+def pack_geo(n, n_views, xys, conics, opacity, opac_per_view=False):
+    dev = require_cuda(xys, conics, opacity)
+    xys, conics, opacity = f32c(xys), f32c(conics), f32c(opacity).reshape(-1)
+    geo = torch.empty((n * n_views, 8), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.load().gg_pack_geo(int(n), int(n_views), ptr(xys), ptr(conics), ptr(opacity),
+                                      1 if opac_per_view else 0, ptr(geo), stream_ptr(dev)), "gg_pack_geo")
+    return geo
+
+
+def max_channels() -> int:
+    return int(_lib.load().gg_blend_max_channels())
+
+
+def blend_fwd(binning: Binning, geo, colors, background, img_height, img_width, colors_per_view=False,
+              pair_counter: Optional[torch.Tensor] = None):
+    """colors [rows, C] (C arbitrary; split into launches of <= 64 channels).  Returns
+    (out [V,H,W,C], final_T [V,H,W], final_idx [V,H,W])."""
+    dev = require_cuda(geo, colors, background)
+    colors, background = f32c(colors), f32c(background)
+    V, n, C = binning.n_views, binning.n, colors.shape[1]
+    out = torch.empty((V, img_height, img_width, C), dtype=torch.float32, device=dev)
+    final_T = torch.empty((V, img_height, img_width), dtype=torch.float32, device=dev)
+    final_idx = torch.empty((V, img_height, img_width), dtype=torch.int32, device=dev)
+    tb = binning.tile_bounds
+    step = max_channels()
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        for c0 in range(0, C, step):
+            c1 = min(C, c0 + step)
+            check(lib.gg_blend_fwd(
+                V, n, c1 - c0, C, 1 if colors_per_view else 0, C, int(img_height), int(img_width), tb[0], tb[1],
+                ptr(binning.ids_sorted), ptr(binning.tile_ranges), ptr(geo), colors.data_ptr() + 4 * c0,
+                background.data_ptr() + 4 * c0, out.data_ptr() + 4 * c0, ptr(final_T), ptr(final_idx),
+                ptr(pair_counter) if c0 == 0 else None, stream_ptr(dev)), "gg_blend_fwd")
+    return out, final_T, final_idx
+
+
+def blend_bwd(binning: Binning, geo, colors, background, final_T, final_idx, v_out, img_height, img_width,
+              colors_per_view=False):
+    """Returns (v_geo [V*n, 8], v_colors like colors)."""
+    dev = require_cuda(geo, colors, background, v_out)
+    colors, background, v_out = f32c(colors), f32c(background), f32c(v_out)
+    V, n, C = binning.n_views, binning.n, colors.shape[1]
+    v_geo = torch.zeros((V * n, 8), dtype=torch.float32, device=dev)
+    v_colors = torch.zeros_like(colors)
+    tb = binning.tile_bounds
+    step = max_channels()
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        for c0 in range(0, C, step):
+            c1 = min(C, c0 + step)
+            check(lib.gg_blend_bwd(
+                V, n, c1 - c0, C, 1 if colors_per_view else 0, C, int(img_height), int(img_width), tb[0], tb[1],
+                ptr(binning.ids_sorted), ptr(binning.tile_ranges), ptr(geo), colors.data_ptr() + 4 * c0,
+                background.data_ptr() + 4 * c0, ptr(final_T), ptr(final_idx), v_out.data_ptr() + 4 * c0, ptr(v_geo),
+                v_colors.data_ptr() + 4 * c0, stream_ptr(dev)), "gg_blend_bwd")
+    return v_geo, v_colors
+
+
+def unpack_vgeo(n, n_views, v_geo):
+    dev = v_geo.device
+    v_xys = torch.empty((n_views * n, 2), dtype=torch.float32, device=dev)
+    v_conics = torch.empty((n_views * n, 3), dtype=torch.float32, device=dev)
+    v_opac = torch.empty((n,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.load().gg_unpack_vgeo(int(n), int(n_views), ptr(v_geo), ptr(v_xys), ptr(v_conics), ptr(v_opac), 0,
+                                         stream_ptr(dev)), "gg_unpack_vgeo")
+    return v_xys, v_conics, v_opac

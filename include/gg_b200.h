@@ -1,0 +1,122 @@
+/*
+ * gg_b200.h -- C ABI of the B200-native Gaussian-splatting rasterizer (libgg_b200.so).
+ *
+ * Drop-in boundary for the one hot path of leejaehot/GaussianGrasper: the gsplat==0.1.0
+ * operators its nerfstudio Gaussian model calls (reference requirements.txt:78;
+ * nerfstudio/models/gaussian_splatting.py:46-50 imports, :699-784 calls).  gsplat's own FFI is a
+ * torch C++ extension (gsplat.cuda: project_gaussians_forward, compute_sh_forward,
+ * map_gaussian_to_intersects, get_tile_bin_edges, rasterize_forward, nd_rasterize_forward and
+ * their backward twins); each entry point below names the binding it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless stated; fp32 / int32 / int64 as typed;
+ *     row-major, contiguous; no torch types cross this boundary;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing
+ *     synchronises the device;
+ *   - return 0 on success, <0 for an argument error, >0 for a cudaError_t; the message is
+ *     available from gg_last_error_string() (thread-local); the library never throws or aborts;
+ *   - tiles are 16x16 pixels (gaussian_splatting.py:677-682); pixel (row i, col j) is sampled at
+ *     (x=j, y=i); quaternions are (w,x,y,z).
+ */
+#ifndef GG_B200_H
+#define GG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library state ---------------------------------------------------------------------- */
+int gg_version(void);
+const char* gg_last_error_string(void);
+/* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
+unsigned long long gg_launch_count(void);
+/* 0 iff the current CUDA device is compute capability 10.x */
+int gg_check_device(void);
+
+/* ---- projection: replaces gsplat.cuda.project_gaussians_forward / _backward ---------------
+ * (ProjectGaussians.apply, gaussian_splatting.py:699-713).  viewmat: 12 floats (rows 0..2 of
+ * the 4x4 world->camera matrix), fullmat: 16 floats (projmat @ viewmat).  Outputs are written
+ * for every Gaussian; culled Gaussians get zeros. */
+int gg_project_fwd(int n, const float* means, const float* scales, float glob_scale, const float* quats,
+                   const float* viewmat, const float* fullmat, float fx, float fy, float cx, float cy, int img_h,
+                   int img_w, int tiles_x, int tiles_y, float clip_thresh, float* cov3d /*[n,6]*/,
+                   float* xys /*[n,2]*/, float* depths /*[n]*/, int32_t* radii /*[n]*/, float* conics /*[n,3]*/,
+                   int32_t* num_tiles_hit /*[n]*/, void* stream);
+int gg_project_bwd(int n, const float* means, const float* scales, float glob_scale, const float* quats,
+                   const float* viewmat, const float* fullmat, float fx, float fy, float cx, float cy, int img_h,
+                   int img_w, const int32_t* radii, const float* conics, const float* v_xys,
+                   const float* v_depths /*nullable*/, const float* v_conics, float* v_means /*[n,3]*/,
+                   float* v_scales /*[n,3]*/, float* v_quats /*[n,4]*/, void* stream);
+/* multi-view variants: viewmats [V,12], fullmats [V,16], intrins [V,4]=(fx,fy,cx,cy) or NULL to
+ * use the scalar arguments for every view; per-view outputs at [view*n + i].  The backward sums
+ * the contributions of all V views (accumulate != 0 adds to the existing v_* contents). */
+int gg_project_fwd_views(int n, int n_views, const float* means, const float* scales, float glob_scale,
+                         const float* quats, const float* viewmats, const float* fullmats, const float* intrins,
+                         float fx, float fy, float cx, float cy, int img_h, int img_w, int tiles_x, int tiles_y,
+                         float clip_thresh, float* cov3d, float* xys, float* depths, int32_t* radii, float* conics,
+                         int32_t* num_tiles_hit, void* stream);
+int gg_project_bwd_views(int n, int n_views, const float* means, const float* scales, float glob_scale,
+                         const float* quats, const float* viewmats, const float* fullmats, const float* intrins,
+                         float fx, float fy, float cx, float cy, int img_h, int img_w, const int32_t* radii,
+                         const float* conics, const float* v_xys, const float* v_depths, const float* v_conics,
+                         int accumulate, float* v_means, float* v_scales, float* v_quats, void* stream);
+
+/* ---- spherical harmonics: replaces gsplat.cuda.compute_sh_forward / _backward --------------
+ * (SphericalHarmonics.apply, gaussian_splatting.py:730).  coeffs [n, (degree+1)^2, 3]. */
+int gg_sh_fwd(int n, int degree, int degrees_to_use, const float* dirs /*[n,3]*/, const float* coeffs,
+              float* colors /*[n,3]*/, void* stream);
+int gg_sh_bwd(int n, int degree, int degrees_to_use, const float* dirs, const float* v_colors /*[n,3]*/,
+              float* v_coeffs, void* stream);
+
+/* ---- binning: replaces gsplat.utils.compute_cumulative_intersects / bin_and_sort_gaussians --
+ * (torch.cumsum + gsplat.cuda.map_gaussian_to_intersects + torch.sort + gather +
+ * gsplat.cuda.get_tile_bin_edges, run inside every rasterize forward). */
+size_t gg_cumsum_workspace_bytes(long long n);
+/* inclusive int32 prefix sum; *total_dev (nullable) receives the grand total */
+int gg_cumsum(long long n, const int32_t* in, int32_t* out, int32_t* total_dev, void* workspace,
+              size_t workspace_bytes, void* stream);
+/* key = ((view*tiles + tile) << 32) | float_bits(depth); id = Gaussian index inside its view */
+int gg_map_to_intersects(int n, int n_views, const float* xys, const float* depths, const int32_t* radii,
+                         const int32_t* cum_tiles_hit, int tiles_x, int tiles_y, int64_t* keys, int32_t* ids,
+                         void* stream);
+size_t gg_sort_workspace_bytes(long long m);
+/* stable LSD radix sort of (key, value) pairs on the low `key_bits` bits.  The workspace must be
+ * zero-filled once when it is allocated and is then owned by the library between calls (it
+ * carries the look-back status words); one workspace per concurrent stream. */
+int gg_sort_pairs(long long m, int key_bits, const int64_t* keys_in, const int32_t* vals_in, int64_t* keys_out,
+                  int32_t* vals_out, void* workspace, size_t workspace_bytes, void* stream);
+/* tile_ranges [num_tiles,2] = (start,end) of each tile's run in the sorted keys, (0,0) if empty */
+int gg_tile_ranges(long long m, const int64_t* keys_sorted, long long num_tiles, int32_t* tile_ranges,
+                   void* stream);
+
+/* ---- blending: replaces gsplat.cuda.rasterize_forward / nd_rasterize_forward and backward ---
+ * (RasterizeGaussians / NDRasterizeGaussians, gaussian_splatting.py:735,747,759,773).
+ * geo is the packed per-Gaussian record {x, y, A/2, B, C/2, opacity, tau, 0} built by gg_pack_geo.
+ * colors rows are color_stride floats apart; `channels` <= gg_blend_max_channels() per launch
+ * (split wider feature maps into channel ranges by offsetting colors/out/bg).  colors_per_view:
+ * 0 = one [n, stride] table shared by all views, 1 = [V*n, stride]. */
+int gg_blend_max_channels(void);
+int gg_pack_geo(long long n, int n_views, const float* xys, const float* conics, const float* opac,
+                int opac_per_view, float* geo /*[V*n,8]*/, void* stream);
+int gg_blend_fwd(int n_views, long long n, int channels, int color_stride, int colors_per_view, int out_stride,
+                 int img_h, int img_w, int tiles_x, int tiles_y, const int32_t* ids_sorted,
+                 const int32_t* tile_ranges, const float* geo, const float* colors, const float* bg,
+                 float* out /*[V,H,W,out_stride]*/, float* final_T /*[V,H,W]*/, int32_t* final_idx /*[V,H,W]*/,
+                 unsigned long long* pair_counter /*nullable*/, void* stream);
+/* v_geo [V*n,8] and v_colors (indexed like colors) are accumulated into: zero them first */
+int gg_blend_bwd(int n_views, long long n, int channels, int color_stride, int colors_per_view, int out_stride,
+                 int img_h, int img_w, int tiles_x, int tiles_y, const int32_t* ids_sorted,
+                 const int32_t* tile_ranges, const float* geo, const float* colors, const float* bg,
+                 const float* final_T, const int32_t* final_idx, const float* v_out, float* v_geo,
+                 float* v_colors, void* stream);
+/* v_geo -> v_xys [V*n,2], v_conics [V*n,3], v_opac [n] (summed over views; nullable) */
+int gg_unpack_vgeo(long long n, int n_views, const float* v_geo, float* v_xys, float* v_conics, float* v_opac,
+                   int accumulate_opac, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GG_B200_H */

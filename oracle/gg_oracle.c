@@ -1,0 +1,436 @@
+/*
+ * gg_oracle.c -- CPU restatement of the gsplat 0.1.0 rasterization path that
+ * GaussianGrasper drives from nerfstudio/models/gaussian_splatting.py:699-784.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the product path (gaussiangrasper_b200/,
+ * gsplat/) may import, link or execute this file.  Only tests/, bench.py's
+ * cpu_baseline / --impl reference legs and __graft_entry__.smoke() use it, and
+ * only as the checker.
+ *
+ * PARITY UNPINNED: the arithmetic of this path lives in the third-party wheel
+ * gsplat==0.1.0 (reference requirements.txt:78), which is neither vendored under
+ * /root/reference nor installable here, and the reference's tests hold no golden
+ * vector for it.  This file restates gsplat 0.1.0's
+ * published algorithm and is anchored on the
+ * reference's call sites:
+ *   ProjectGaussians.apply      gaussian_splatting.py:699-713
+ *   SphericalHarmonics.apply    gaussian_splatting.py:730
+ *   RasterizeGaussians.apply    gaussian_splatting.py:735,759,773
+ *   NDRasterizeGaussians.apply  gaussian_splatting.py:747
+ *
+ * Floating point discipline: every fp32 expression below is written with an
+ * explicit left-to-right operation order and must be compiled with
+ * -ffp-contract=off (no FMA contraction) so that the integer outputs (radii,
+ * num_tiles_hit, sort keys, tile ranges) are reproducible bit for bit.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define GG_TILE 16
+
+static inline int f2i_sat(float x) {
+    /* float -> int32 truncation toward zero, saturating, NaN -> 0 */
+    if (x != x) return 0;
+    if (x >= 2147483648.0f) return INT32_MAX;
+    if (x <= -2147483648.0f) return INT32_MIN;
+    return (int)x;
+}
+static inline int imin(int a, int b) { return a < b ? a : b; }
+static inline int imax(int a, int b) { return a > b ? a : b; }
+
+/* A6: tile bounding box of a disc (centre, radius) in 16x16 tiles. */
+static void tile_bbox(float cx, float cy, float radius, int tiles_x, int tiles_y,
+                      int *minx, int *miny, int *maxx, int *maxy) {
+    float tcx = cx / (float)GG_TILE, tcy = cy / (float)GG_TILE;
+    float tr = radius / (float)GG_TILE;
+    *minx = imin(imax(0, f2i_sat(tcx - tr)), tiles_x);
+    *maxx = imin(imax(0, f2i_sat(tcx + tr + 1.0f)), tiles_x);
+    *miny = imin(imax(0, f2i_sat(tcy - tr)), tiles_y);
+    *maxy = imin(imax(0, f2i_sat(tcy + tr + 1.0f)), tiles_y);
+}
+
+/* ------------------------------------------------------------------------- */
+/* A1..A6: EWA projection (ProjectGaussians.forward, gaussian_splatting.py:699) */
+/* ------------------------------------------------------------------------- */
+void gg_oracle_project_fwd(int n, const float *means, const float *scales, float glob_scale,
+                           const float *quats, const float *vm /*>=12, row-major 3x4*/,
+                           const float *fm /*16*/, float fx, float fy, float cx, float cy,
+                           int img_h, int img_w, int tiles_x, int tiles_y, float clip,
+                           float *cov3d, float *xys, float *depths, int32_t *radii,
+                           float *conics, int32_t *num_tiles_hit) {
+    memset(cov3d, 0, sizeof(float) * 6 * (size_t)n);
+    memset(xys, 0, sizeof(float) * 2 * (size_t)n);
+    memset(depths, 0, sizeof(float) * (size_t)n);
+    memset(radii, 0, sizeof(int32_t) * (size_t)n);
+    memset(conics, 0, sizeof(float) * 3 * (size_t)n);
+    memset(num_tiles_hit, 0, sizeof(int32_t) * (size_t)n);
+    const float tan_fovx = 0.5f * (float)img_w / fx;
+    const float tan_fovy = 0.5f * (float)img_h / fy;
+    const float limx = 1.3f * tan_fovx, limy = 1.3f * tan_fovy;
+    for (int i = 0; i < n; ++i) {
+        const float px = means[3 * i], py = means[3 * i + 1], pz = means[3 * i + 2];
+        /* A1 near-plane clip */
+        float tx = vm[0] * px + vm[1] * py + vm[2] * pz + vm[3];
+        float ty = vm[4] * px + vm[5] * py + vm[6] * pz + vm[7];
+        const float tz = vm[8] * px + vm[9] * py + vm[10] * pz + vm[11];
+        if (tz <= clip) continue;
+        /* A2 cov3d = (R S)(R S)^T */
+        const float qw = quats[4 * i], qx = quats[4 * i + 1], qy = quats[4 * i + 2], qz = quats[4 * i + 3];
+        const float inv = 1.0f / sqrtf(qw * qw + qx * qx + qy * qy + qz * qz);
+        const float w = qw * inv, x = qx * inv, y = qy * inv, z = qz * inv;
+        const float R00 = 1.0f - 2.0f * (y * y + z * z), R01 = 2.0f * (x * y - w * z), R02 = 2.0f * (x * z + w * y);
+        const float R10 = 2.0f * (x * y + w * z), R11 = 1.0f - 2.0f * (x * x + z * z), R12 = 2.0f * (y * z - w * x);
+        const float R20 = 2.0f * (x * z - w * y), R21 = 2.0f * (y * z + w * x), R22 = 1.0f - 2.0f * (x * x + y * y);
+        const float sx = glob_scale * scales[3 * i], sy = glob_scale * scales[3 * i + 1], sz = glob_scale * scales[3 * i + 2];
+        const float M00 = R00 * sx, M01 = R01 * sy, M02 = R02 * sz;
+        const float M10 = R10 * sx, M11 = R11 * sy, M12 = R12 * sz;
+        const float M20 = R20 * sx, M21 = R21 * sy, M22 = R22 * sz;
+        const float V00 = M00 * M00 + M01 * M01 + M02 * M02;
+        const float V01 = M00 * M10 + M01 * M11 + M02 * M12;
+        const float V02 = M00 * M20 + M01 * M21 + M02 * M22;
+        const float V11 = M10 * M10 + M11 * M11 + M12 * M12;
+        const float V12 = M10 * M20 + M11 * M21 + M12 * M22;
+        const float V22 = M20 * M20 + M21 * M21 + M22 * M22;
+        float *cv = cov3d + 6 * (size_t)i;
+        cv[0] = V00; cv[1] = V01; cv[2] = V02; cv[3] = V11; cv[4] = V12; cv[5] = V22;
+        /* A3 EWA: cov2d = (J W) V (J W)^T + 0.3 I */
+        tx = tz * fminf(limx, fmaxf(-limx, tx / tz));
+        ty = tz * fminf(limy, fmaxf(-limy, ty / tz));
+        const float rz = 1.0f / tz, rz2 = rz * rz;
+        const float J00 = fx * rz, J02 = -fx * tx * rz2;
+        const float J11 = fy * rz, J12 = -fy * ty * rz2;
+        const float T00 = J00 * vm[0] + J02 * vm[8], T01 = J00 * vm[1] + J02 * vm[9], T02 = J00 * vm[2] + J02 * vm[10];
+        const float T10 = J11 * vm[4] + J12 * vm[8], T11 = J11 * vm[5] + J12 * vm[9], T12 = J11 * vm[6] + J12 * vm[10];
+        const float U00 = T00 * V00 + T01 * V01 + T02 * V02;
+        const float U01 = T00 * V01 + T01 * V11 + T02 * V12;
+        const float U02 = T00 * V02 + T01 * V12 + T02 * V22;
+        const float U10 = T10 * V00 + T11 * V01 + T12 * V02;
+        const float U11 = T10 * V01 + T11 * V11 + T12 * V12;
+        const float U12 = T10 * V02 + T11 * V12 + T12 * V22;
+        const float a = (U00 * T00 + U01 * T01 + U02 * T02) + 0.3f;
+        const float b = U00 * T10 + U01 * T11 + U02 * T12;
+        const float c = (U10 * T10 + U11 * T11 + U12 * T12) + 0.3f;
+        /* A4 conic and radius */
+        const float det = a * c - b * b;
+        if (det == 0.0f) continue;
+        const float inv_det = 1.0f / det;
+        const float mid = 0.5f * (a + c);
+        const float sq = sqrtf(fmaxf(0.1f, mid * mid - det));
+        const float v1 = mid + sq, v2 = mid - sq;
+        const float radius = ceilf(3.0f * sqrtf(fmaxf(v1, v2)));
+        /* A5 pixel centre through the full projection matrix */
+        const float hx = fm[0] * px + fm[1] * py + fm[2] * pz + fm[3];
+        const float hy = fm[4] * px + fm[5] * py + fm[6] * pz + fm[7];
+        const float hw = fm[12] * px + fm[13] * py + fm[14] * pz + fm[15];
+        const float rw = 1.0f / (hw + 1e-6f);
+        const float ux = 0.5f * (float)img_w * (hx * rw) + cx - 0.5f;
+        const float uy = 0.5f * (float)img_h * (hy * rw) + cy - 0.5f;
+        /* A6 tile bbox */
+        int minx, miny, maxx, maxy;
+        tile_bbox(ux, uy, radius, tiles_x, tiles_y, &minx, &miny, &maxx, &maxy);
+        const int area = (maxx - minx) * (maxy - miny);
+        if (area <= 0) continue;
+        num_tiles_hit[i] = area;
+        depths[i] = tz;
+        radii[i] = f2i_sat(radius);
+        xys[2 * i] = ux; xys[2 * i + 1] = uy;
+        conics[3 * i] = c * inv_det; conics[3 * i + 1] = -b * inv_det; conics[3 * i + 2] = a * inv_det;
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* A10: spherical harmonics -> colour (SphericalHarmonics.forward, :730)       */
+/* ------------------------------------------------------------------------- */
+static const float SH_C0 = 0.28209479177387814f;
+static const float SH_C1 = 0.4886025119029199f;
+static const float SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                               -1.0925484305920792f, 0.5462742152960396f};
+static const float SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f, 0.3731763325901154f,
+                               -0.4570457994644658f, 1.445305721320277f, -0.5900435899266435f};
+static const float SH_C4[9] = {2.5033429417967046f, -1.7701307697799304f, 0.9461746957575601f,
+                               -0.6690465435572892f, 0.10578554691520431f, -0.6690465435572892f,
+                               0.47308734787878004f, -1.7701307697799304f, 0.6258357354491761f};
+
+int gg_oracle_num_sh_bases(int degree) {
+    if (degree == 0) return 1;
+    if (degree == 1) return 4;
+    if (degree == 2) return 9;
+    if (degree == 3) return 16;
+    return 25;
+}
+
+/* basis values Y_b(d) for b < (deg+1)^2, direction normalised here */
+static void sh_basis(int deg, float dx, float dy, float dz, float *Y) {
+    Y[0] = SH_C0;
+    if (deg < 1) return;
+    const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);
+    const float x = dx / nrm, y = dy / nrm, z = dz / nrm;
+    Y[1] = SH_C1 * (-y); Y[2] = SH_C1 * z; Y[3] = SH_C1 * (-x);
+    if (deg < 2) return;
+    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+    Y[4] = SH_C2[0] * xy; Y[5] = SH_C2[1] * yz; Y[6] = SH_C2[2] * (2.0f * zz - xx - yy);
+    Y[7] = SH_C2[3] * xz; Y[8] = SH_C2[4] * (xx - yy);
+    if (deg < 3) return;
+    Y[9] = SH_C3[0] * y * (3.0f * xx - yy);
+    Y[10] = SH_C3[1] * xy * z;
+    Y[11] = SH_C3[2] * y * (4.0f * zz - xx - yy);
+    Y[12] = SH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy);
+    Y[13] = SH_C3[4] * x * (4.0f * zz - xx - yy);
+    Y[14] = SH_C3[5] * z * (xx - yy);
+    Y[15] = SH_C3[6] * x * (xx - 3.0f * yy);
+    if (deg < 4) return;
+    Y[16] = SH_C4[0] * xy * (xx - yy);
+    Y[17] = SH_C4[1] * yz * (3.0f * xx - yy);
+    Y[18] = SH_C4[2] * xy * (7.0f * zz - 1.0f);
+    Y[19] = SH_C4[3] * yz * (7.0f * zz - 3.0f);
+    Y[20] = SH_C4[4] * (zz * (35.0f * zz - 30.0f) + 3.0f);
+    Y[21] = SH_C4[5] * xz * (7.0f * zz - 3.0f);
+    Y[22] = SH_C4[6] * (xx - yy) * (7.0f * zz - 1.0f);
+    Y[23] = SH_C4[7] * xz * (xx - 3.0f * yy);
+    Y[24] = SH_C4[8] * (xx * (xx - 3.0f * yy) - yy * (3.0f * xx - yy));
+}
+
+void gg_oracle_sh_fwd(int n, int degree, int degrees_to_use, const float *dirs, const float *coeffs,
+                      float *colors) {
+    const int nb = gg_oracle_num_sh_bases(degree);
+    const int nuse = gg_oracle_num_sh_bases(degrees_to_use);
+    for (int i = 0; i < n; ++i) {
+        float Y[25];
+        sh_basis(degrees_to_use, dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2], Y);
+        const float *cf = coeffs + (size_t)i * nb * 3;
+        for (int c = 0; c < 3; ++c) {
+            float acc = 0.0f;
+            for (int b = 0; b < nuse; ++b) acc = acc + Y[b] * cf[3 * b + c];
+            colors[3 * i + c] = acc;
+        }
+    }
+}
+
+void gg_oracle_sh_bwd(int n, int degree, int degrees_to_use, const float *dirs, const float *v_colors,
+                      float *v_coeffs) {
+    const int nb = gg_oracle_num_sh_bases(degree);
+    const int nuse = gg_oracle_num_sh_bases(degrees_to_use);
+    memset(v_coeffs, 0, sizeof(float) * (size_t)n * nb * 3);
+    for (int i = 0; i < n; ++i) {
+        float Y[25];
+        sh_basis(degrees_to_use, dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2], Y);
+        float *vc = v_coeffs + (size_t)i * nb * 3;
+        for (int b = 0; b < nuse; ++b)
+            for (int c = 0; c < 3; ++c) vc[3 * b + c] = Y[b] * v_colors[3 * i + c];
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* A7/A8: binning (compute_cumulative_intersects + bin_and_sort_gaussians)     */
+/* ------------------------------------------------------------------------- */
+void gg_oracle_cumsum(int n, const int32_t *num_tiles_hit, int32_t *cum) {
+    int32_t acc = 0;
+    for (int i = 0; i < n; ++i) { acc += num_tiles_hit[i]; cum[i] = acc; }
+}
+
+/* keys/ids must hold cum[n-1] entries */
+void gg_oracle_map_to_intersects(int n, const float *xys, const float *depths, const int32_t *radii,
+                                 const int32_t *cum, int tiles_x, int tiles_y, int64_t *keys,
+                                 int32_t *ids) {
+    for (int i = 0; i < n; ++i) {
+        if (radii[i] <= 0) continue;
+        int minx, miny, maxx, maxy;
+        tile_bbox(xys[2 * i], xys[2 * i + 1], (float)radii[i], tiles_x, tiles_y, &minx, &miny, &maxx, &maxy);
+        int64_t cur = (i == 0) ? 0 : cum[i - 1];
+        int32_t dbits;
+        memcpy(&dbits, &depths[i], 4);
+        for (int ty = miny; ty < maxy; ++ty)
+            for (int tx = minx; tx < maxx; ++tx) {
+                const int64_t tile = (int64_t)ty * tiles_x + tx;
+                keys[cur] = (tile << 32) | (int64_t)(uint32_t)dbits;
+                ids[cur] = i;
+                ++cur;
+            }
+    }
+}
+
+typedef struct { int64_t key; int32_t id; } kv_t;
+static int kv_cmp(const void *a, const void *b) {
+    const kv_t *x = (const kv_t *)a, *y = (const kv_t *)b;
+    if (x->key != y->key) return x->key < y->key ? -1 : 1;
+    return (x->id > y->id) - (x->id < y->id); /* tie rule: ascending gaussian id */
+}
+
+void gg_oracle_sort(int64_t m, const int64_t *keys, const int32_t *ids, int64_t *keys_sorted,
+                    int32_t *ids_sorted) {
+    kv_t *kv = (kv_t *)malloc(sizeof(kv_t) * (size_t)(m > 0 ? m : 1));
+    for (int64_t i = 0; i < m; ++i) { kv[i].key = keys[i]; kv[i].id = ids[i]; }
+    qsort(kv, (size_t)m, sizeof(kv_t), kv_cmp);
+    for (int64_t i = 0; i < m; ++i) { keys_sorted[i] = kv[i].key; ids_sorted[i] = kv[i].id; }
+    free(kv);
+}
+
+/* tile_ranges: [num_tiles, 2] int32, (start, end), (0,0) for empty tiles */
+void gg_oracle_tile_ranges(int64_t m, const int64_t *keys_sorted, int num_tiles, int32_t *tile_ranges) {
+    memset(tile_ranges, 0, sizeof(int32_t) * 2 * (size_t)num_tiles);
+    for (int64_t i = 0; i < m; ++i) {
+        const int32_t t = (int32_t)(keys_sorted[i] >> 32);
+        if (i == 0 || (int32_t)(keys_sorted[i - 1] >> 32) != t) tile_ranges[2 * t] = (int32_t)i;
+        if (i == m - 1 || (int32_t)(keys_sorted[i + 1] >> 32) != t) tile_ranges[2 * t + 1] = (int32_t)(i + 1);
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* A9: forward alpha compositing (rasterize_forward / nd_rasterize_forward)    */
+/*                                                                             */
+/* final_idx[p] = one past the index (in the sorted list) of the last entry    */
+/* that contributed to pixel p, or the tile's range start if none did.         */
+/* fragile[p] (optional) is set when any visited pair lies within `eps`        */
+/* (relative) of a branch threshold, so that a 1-ulp difference in exp() could */
+/* flip it; parity tests compare those pixels at a looser bound.               */
+/* Returns the number of pixel-Gaussian pairs visited (K of SURVEY 8d).        */
+/* ------------------------------------------------------------------------- */
+int64_t gg_oracle_blend_fwd(int channels, int img_h, int img_w, int tiles_x, int tiles_y,
+                            const int32_t *ids_sorted, const int32_t *tile_ranges, const float *xys,
+                            const float *conics, const float *opac, const float *colors,
+                            const float *bg, float *out, float *final_T, int32_t *final_idx,
+                            uint8_t *fragile, float eps) {
+    int64_t pairs = 0;
+    (void)tiles_y;
+#pragma omp parallel for schedule(dynamic, 4) reduction(+ : pairs)
+    for (int py = 0; py < img_h; ++py) {
+        for (int pxi = 0; pxi < img_w; ++pxi) {
+            const int tile = (py / GG_TILE) * tiles_x + (pxi / GG_TILE);
+            const int start = tile_ranges[2 * tile], end = tile_ranges[2 * tile + 1];
+            const size_t pix = (size_t)py * img_w + pxi;
+            float *o = out + pix * channels;
+            for (int c = 0; c < channels; ++c) o[c] = 0.0f;
+            float T = 1.0f;
+            int last = start;
+            uint8_t frag = 0;
+            const float fx = (float)pxi, fy = (float)py;
+            for (int k = start; k < end; ++k) {
+                ++pairs;
+                const int g = ids_sorted[k];
+                const float dx = xys[2 * g] - fx, dy = xys[2 * g + 1] - fy;
+                const float A = conics[3 * g], B = conics[3 * g + 1], C = conics[3 * g + 2];
+                const float sigma = 0.5f * (A * dx * dx + C * dy * dy) + B * dx * dy;
+                if (fabsf(sigma) <= 1e-6f) frag = 1;
+                if (sigma < 0.0f) continue;
+                const float araw = opac[g] * expf(-sigma);
+                const float alpha = fminf(0.999f, araw);
+                if (fabsf(alpha - (1.0f / 255.0f)) <= eps * (1.0f / 255.0f)) frag = 1;
+                if (alpha < 1.0f / 255.0f) continue;
+                const float next_T = T * (1.0f - alpha);
+                if (fabsf(next_T - 1e-4f) <= eps * 1e-4f) frag = 1;
+                if (next_T <= 1e-4f) break;
+                const float vis = alpha * T;
+                const float *col = colors + (size_t)g * channels;
+                for (int c = 0; c < channels; ++c) o[c] = o[c] + vis * col[c];
+                T = next_T;
+                last = k + 1;
+            }
+            for (int c = 0; c < channels; ++c) o[c] = o[c] + T * bg[c];
+            final_T[pix] = T;
+            final_idx[pix] = last;
+            if (fragile) fragile[pix] = frag;
+        }
+    }
+    return pairs;
+}
+
+/* ------------------------------------------------------------------------- */
+/* A11: backward of the blend, analytic, accumulated in double.                */
+/* Convention: exact derivative of A9; alpha clamped at      */
+/* 0.999 passes no gradient to sigma/opacity.                                  */
+/* v_xy[N,2], v_conic[N,3], v_colors[N,C], v_opac[N] are doubles.              */
+/* ------------------------------------------------------------------------- */
+void gg_oracle_blend_bwd(int n, int channels, int img_h, int img_w, int tiles_x,
+                         const int32_t *ids_sorted, const int32_t *tile_ranges, const float *xys,
+                         const float *conics, const float *opac, const float *colors,
+                         const float *bg, const float *v_out, double *v_xy, double *v_conic,
+                         double *v_colors, double *v_opac) {
+    memset(v_xy, 0, sizeof(double) * 2 * (size_t)n);
+    memset(v_conic, 0, sizeof(double) * 3 * (size_t)n);
+    memset(v_colors, 0, sizeof(double) * (size_t)channels * (size_t)n);
+    memset(v_opac, 0, sizeof(double) * (size_t)n);
+    double *S = (double *)malloc(sizeof(double) * (size_t)channels);
+    for (int py = 0; py < img_h; ++py) {
+        for (int pxi = 0; pxi < img_w; ++pxi) {
+            const int tile = (py / GG_TILE) * tiles_x + (pxi / GG_TILE);
+            const int start = tile_ranges[2 * tile], end = tile_ranges[2 * tile + 1];
+            const size_t pix = (size_t)py * img_w + pxi;
+            const float *vo = v_out + pix * channels;
+            const float fx = (float)pxi, fy = (float)py;
+            /* forward replay in fp32 to find the contributing set exactly as A9 does */
+            float T = 1.0f;
+            int last = start;
+            for (int k = start; k < end; ++k) {
+                const int g = ids_sorted[k];
+                const float dx = xys[2 * g] - fx, dy = xys[2 * g + 1] - fy;
+                const float A = conics[3 * g], B = conics[3 * g + 1], C = conics[3 * g + 2];
+                const float sigma = 0.5f * (A * dx * dx + C * dy * dy) + B * dx * dy;
+                if (sigma < 0.0f) continue;
+                const float alpha = fminf(0.999f, opac[g] * expf(-sigma));
+                if (alpha < 1.0f / 255.0f) continue;
+                const float next_T = T * (1.0f - alpha);
+                if (next_T <= 1e-4f) break;
+                T = next_T;
+                last = k + 1;
+            }
+            /* back-to-front, double precision */
+            double Tfin = 1.0;
+            /* recompute T_final in double over the contributing set */
+            for (int k = start; k < last; ++k) {
+                const int g = ids_sorted[k];
+                const float dx = xys[2 * g] - fx, dy = xys[2 * g + 1] - fy;
+                const float A = conics[3 * g], B = conics[3 * g + 1], C = conics[3 * g + 2];
+                const float sigma = 0.5f * (A * dx * dx + C * dy * dy) + B * dx * dy;
+                if (sigma < 0.0f) continue;
+                const float alpha_f = fminf(0.999f, opac[g] * expf(-sigma));
+                if (alpha_f < 1.0f / 255.0f) continue;
+                const double ddx = (double)xys[2 * g] - fx, ddy = (double)xys[2 * g + 1] - fy;
+                const double sg = 0.5 * ((double)A * ddx * ddx + (double)C * ddy * ddy) + (double)B * ddx * ddy;
+                double al = (double)opac[g] * exp(-sg);
+                if (al > 0.999) al = 0.999;
+                Tfin *= (1.0 - al);
+            }
+            double bgdot = 0.0;
+            for (int c = 0; c < channels; ++c) { S[c] = 0.0; bgdot += (double)bg[c] * vo[c]; }
+            double Tcur = Tfin; /* transmittance after entry k */
+            for (int k = last - 1; k >= start; --k) {
+                const int g = ids_sorted[k];
+                const float dxf = xys[2 * g] - fx, dyf = xys[2 * g + 1] - fy;
+                const float A = conics[3 * g], B = conics[3 * g + 1], C = conics[3 * g + 2];
+                const float sigma_f = 0.5f * (A * dxf * dxf + C * dyf * dyf) + B * dxf * dyf;
+                if (sigma_f < 0.0f) continue;
+                const float alpha_f = fminf(0.999f, opac[g] * expf(-sigma_f));
+                if (alpha_f < 1.0f / 255.0f) continue;
+                const double dx = (double)xys[2 * g] - fx, dy = (double)xys[2 * g + 1] - fy;
+                const double sg = 0.5 * ((double)A * dx * dx + (double)C * dy * dy) + (double)B * dx * dy;
+                const double vis = exp(-sg);
+                double al = (double)opac[g] * vis;
+                const int clamped = al > 0.999;
+                if (clamped) al = 0.999;
+                const double ra = 1.0 / (1.0 - al);
+                const double Tb = Tcur * ra; /* transmittance before entry k */
+                const double fac = al * Tb;
+                const float *col = colors + (size_t)g * channels;
+                double v_alpha = 0.0;
+                for (int c = 0; c < channels; ++c) {
+                    v_colors[(size_t)g * channels + c] += fac * vo[c];
+                    v_alpha += ((double)col[c] * Tb - S[c] * ra) * vo[c];
+                    S[c] += (double)col[c] * fac;
+                }
+                v_alpha += -Tfin * ra * bgdot;
+                Tcur = Tb;
+                if (clamped) continue;
+                const double v_sigma = -al * v_alpha; /* d alpha / d sigma = -o e^-s */
+                v_opac[g] += vis * v_alpha;
+                v_conic[3 * g] += 0.5 * v_sigma * dx * dx;
+                v_conic[3 * g + 1] += v_sigma * dx * dy;
+                v_conic[3 * g + 2] += 0.5 * v_sigma * dy * dy;
+                v_xy[2 * g] += v_sigma * ((double)A * dx + (double)B * dy);
+                v_xy[2 * g + 1] += v_sigma * ((double)B * dx + (double)C * dy);
+            }
+        }
+    }
+    free(S);
+}
