@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""bench.py -- Mpixels/s of the Gaussian-splatting hot path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (CUDA, sm_100a)
+  python bench.py --impl reference --steps K --warmup W    the reference's PyTorch-CPU maths
+
+A step is one render of the configured views -- SH + projection + binning + one blend of
+RGB(3)+depth(1)+normal(3)+feature(D) -- forward AND backward to the leaf gradients (means,
+log-scales, quats, opacity logits, SH coefficients, features), plus, at N>1, the NCCL all-reduce
+of those gradients.  N=1 runs BASELINE.json configs[1]: 500k Gaussians, one 640x480 view, D=16.
+At N>1 every rank renders its own view of the same (replicated) scene: weak scaling by view.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "Mpixels/s rendered (RGB+depth+16-ch feature, fwd+bwd)"
+UNIT = "Mpixels/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d.get("hbm_gbs", 6650.0)), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's CPU maths (oracle/torch_oracle.py is the port of gsplat's _torch_impl)
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_step(sc, cam, D, tiles, threads):
+    """One fwd+bwd of the reference maths on the host: full SH + projection + binning for all
+    Gaussians (timed), blend fwd+bwd on the sampled tiles (timed); returns (t_geom, t_blend)."""
+    from oracle import torch_oracle as to
+    torch.set_num_threads(threads)
+    P = {k: v.clone().requires_grad_(True) for k, v in sc.items()}
+    t0 = time.perf_counter()
+    scales = torch.exp(P["log_scales"])
+    q = P["quats"] / P["quats"].norm(dim=-1, keepdim=True)
+    xys, depths, radii, conics, nth, _ = to.project_gaussians(P["means"], scales, 1.0, q, cam.viewmat, cam.fullmat,
+                                                              cam.fx, cam.fy, cam.cx, cam.cy, cam.H, cam.W,
+                                                              cam.tile_bounds)
+    dirs = P["means"].detach() - cam.position
+    rgbs = torch.clamp(to.spherical_harmonics(4, dirs, P["sh_coeffs"]) + 0.5, 0.0, 1.0)
+    op = torch.sigmoid(P["opacity_logit"]).reshape(-1)
+    R = to.quat_to_rotmat(P["quats"])
+    idx = P["log_scales"].min(dim=-1)[1][..., None, None].expand(-1, 3, -1)
+    normals = R.gather(2, idx).squeeze(dim=2)
+    cols = torch.cat([rgbs, depths[:, None], normals, P["features"]], dim=1)
+    _, _, ids_s, ranges = to.bin_and_sort(xys, depths, radii, nth, cam.tile_bounds)
+    t1 = time.perf_counter()
+    bg = torch.zeros(cols.shape[1]); bg[3] = 10.0
+    g = torch.Generator().manual_seed(0)
+    v_out = torch.randn((cam.H, cam.W, cols.shape[1]), generator=g)
+    out, v_xys, v_con, v_op, v_col = to.rasterize_grads(xys.detach(), conics.detach(), op.detach(), cols.detach(),
+                                                        ids_s, ranges, cam.H, cam.W, bg, v_out, tiles=tiles)
+    t2 = time.perf_counter()
+    torch.autograd.backward([xys, conics, op, cols], [v_xys, v_con, v_op, v_col])
+    t3 = time.perf_counter()
+    return (t1 - t0) + (t3 - t2), (t2 - t1)
+
+
+def sample_tiles(cam, count):
+    tx, ty = cam.tile_bounds[0], cam.tile_bounds[1]
+    total = tx * ty
+    stride = max(1, total // count)
+    return list(range(stride // 2, total, stride))[:count], total
+
+
+def run_reference(args):
+    from gaussiangrasper_b200 import scenes
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = scenes.CONFIGS[1]
+    threads = os.cpu_count() or 1
+    sc = scenes.random_scene(cfg["n"], feature_dim=cfg["D"], seed=1235)
+    cam = scenes.orbit_cameras(1, cfg["W"], cfg["H"])[0]
+    tiles, total_tiles = sample_tiles(cam, 12)
+    times = []
+    for s in range(args.warmup + args.steps):
+        tg, tb = cpu_reference_step(sc, cam, cfg["D"], tiles, threads)
+        if s >= args.warmup:
+            times.append(tg + tb * total_tiles / len(tiles))
+    t = sum(times) / len(times)
+    mpix = cfg["W"] * cfg["H"] / 1e6
+    val = mpix / t
+    sample = (f"each step: SH+projection+binning of all {cfg['n']} Gaussians fwd+bwd (timed in full) + blend "
+              f"fwd+bwd of {len(tiles)} of {total_tiles} tiles, blend time scaled by {total_tiles}/{len(tiles)}")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg["name"], "gaussians": cfg["n"], "image": [cfg["W"], cfg["H"]], "views": 1,
+                       "channels": 7 + cfg["D"]},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+
+    from gaussiangrasper_b200 import _lib, scenes
+    from gaussiangrasper_b200.render import ViewBatch, render_views
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py (our arm) needs a CUDA device; there is no CPU fallback"
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.check(_lib.load().gg_check_device(), "gg_check_device")
+
+    cfg = scenes.CONFIGS[args.config]
+    n, W, H, D = cfg["n"], cfg["W"], cfg["H"], cfg["D"]
+    V = args.views if args.views else (1 if args.config == 1 else cfg["views"])
+    C = 7 + D
+    CP = (C + 3) // 4 * 4
+    sc = scenes.random_scene(n, feature_dim=D, seed=1234 + args.config)
+    names = ("means", "log_scales", "quats", "opacity_logit", "sh_coeffs", "features")
+    P = {k: sc[k].to(dev).requires_grad_(cfg["backward"]) for k in names}
+    total_views = V * world
+    cams = scenes.orbit_cameras(V, W, H, first=rank * V, total=max(total_views, 8))
+    views = ViewBatch.from_cameras(cams, dev)
+    g = torch.Generator().manual_seed(100 + rank)
+    v_img = torch.randn((V, H, W, CP), generator=g).to(dev)
+    flat_grads = None
+
+    def step():
+        for p in P.values():
+            p.grad = None
+        out = render_views(P["means"], P["log_scales"], P["quats"], P["opacity_logit"], P["sh_coeffs"],
+                           P["features"], views)
+        if cfg["backward"]:
+            out["image"].backward(v_img)
+            if world > 1:
+                flat = torch.cat([P[k].grad.reshape(-1) for k in names])
+                dist.all_reduce(flat)
+                return flat
+        return out["image"]
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+
+    # --- timed region: exactly K steps, device-timed, max over ranks -------------------------
+    sampler = ClockSampler(local) if rank == 0 else None
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    if sampler:
+        sampler.start()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with _lib.profile() as prof:
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        per_call = prof.ms()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    ms = e0.elapsed_time(e1)
+    t_ms = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t_ms.item()) / args.steps
+    mpix_per_step = total_views * W * H / 1e6
+    value = mpix_per_step / (ms_per_step * 1e-3)
+
+    # --- e2e: host buffers in, host results out, every step ---------------------------------
+    target_host = torch.randn((V, H, W, CP), generator=g).pin_memory()
+    rgb_host = torch.empty((V, H, W, 3)).pin_memory()
+    loss_host = torch.empty((1,)).pin_memory()
+
+    def e2e_step():
+        for p in P.values():
+            p.grad = None
+        vb = ViewBatch.from_cameras(cams, dev)                      # H2D: cameras (pinned)
+        target = target_host.to(dev, non_blocking=True)             # H2D: supervision images (pinned)
+        out = render_views(P["means"], P["log_scales"], P["quats"], P["opacity_logit"], P["sh_coeffs"],
+                           P["features"], vb)
+        loss = ((out["image"] - target) ** 2).mean()
+        if cfg["backward"]:
+            loss.backward()
+            if world > 1:
+                flat = torch.cat([P[k].grad.reshape(-1) for k in names])
+                dist.all_reduce(flat)
+        rgb_host.copy_(out["rgb"].detach(), non_blocking=True)      # D2H: rendered rgb
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)  # D2H: loss
+        torch.cuda.synchronize()
+        return float(loss_host[0])
+
+    for _ in range(2):
+        e2e_step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    t_e2e = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_val = mpix_per_step * args.steps / float(t_e2e.item())
+    h2d = target_host.numel() * 4 + V * 35 * 4
+    d2h = rgb_host.numel() * 4 + 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # --- roofline of the dominant kernel ------------------------------------------------------
+    hbm_peak, peak_src = load_peaks()
+    avg = {k: sum(v) / len(v) for k, v in per_call.items() if v}
+    share = {k: sum(v) / args.steps for k, v in per_call.items()}
+    stats = torch.zeros(1, dtype=torch.int64, device=dev)
+    with torch.no_grad():
+        o = render_views(*(P[k].detach() for k in names), views, stats=stats)
+    torch.cuda.synchronize()
+    pairs = int(stats.item())
+    binning_m = None
+    # measured FP32 FMA roof (same process, same clocks)
+    lib = _lib.load()
+    probe = torch.zeros(1, device=dev)
+    fl = ctypes.c_double(0.0)
+    for _ in range(2):
+        lib.gg_bench_fma(148 * 8, 20000, probe.data_ptr(), ctypes.byref(fl), torch.cuda.current_stream().cuda_stream)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    lib.gg_bench_fma(148 * 8, 20000, probe.data_ptr(), ctypes.byref(fl), torch.cuda.current_stream().cuda_stream)
+    b.record()
+    torch.cuda.synchronize()
+    fma_tflops = fl.value / (a.elapsed_time(b) * 1e-3) / 1e12
+    dom = max(avg, key=lambda k: share[k]) if avg else None
+    flops_fwd = pairs * (12 + 2 * C)
+    flops_bwd = pairs * (30 + 8 * C)
+    roof = None
+    if dom in ("gg_blend_bwd", "gg_blend_fwd"):
+        fl_k = flops_bwd if dom == "gg_blend_bwd" else flops_fwd
+        ach = fl_k / (avg[dom] * 1e-3) / 1e12
+        roof = {"kernel": dom, "bound": "fp32", "achieved": ach, "peak": fma_tflops, "unit": "TFLOP/s",
+                "frac": ach / fma_tflops, "traffic": None, "peak_source": "FMA probe kernel timed in this run",
+                "algorithmic_flops": fl_k, "pairs": pairs, "avg_launch_ms": avg[dom]}
+    elif dom is not None:
+        roof = {"kernel": dom, "bound": "hbm", "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None,
+                "traffic": None, "peak_source": peak_src, "avg_launch_ms": avg[dom]}
+    # HBM-bound stages against the measured copy bandwidth
+    nuse = 25
+    bytes_model = {
+        "gg_sh_fwd": n * (12 + 12 * nuse + 12) * V, "gg_sh_bwd": n * (12 + 12 + 12 * nuse) * V,
+        "gg_project_fwd_views": n * V * 96, "gg_project_bwd_views": n * V * 180,
+    }
+    hbm_stages = {}
+    for k, bts in bytes_model.items():
+        if k in avg:
+            per_launch = bts / (len(per_call[k]) / args.steps)
+            gbs = per_launch / (avg[k] * 1e-3) / 1e9
+            hbm_stages[k] = {"GB/s": gbs, "frac": gbs / hbm_peak, "avg_launch_ms": avg[k]}
+
+    # --- CPU baseline (rank 0, N=1 only): the reference maths on the host cores ---------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        sc_cpu = {k: sc[k] for k in names}
+        cam0 = cams[0]
+        tiles, total_tiles = sample_tiles(cam0, 8)
+        tg, tb = cpu_reference_step(sc_cpu, cam0, D, tiles, threads)
+        t_full = tg + tb * total_tiles / len(tiles)
+        cpu = {"value": (W * H / 1e6) / t_full, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": (f"torch-CPU port of the reference maths, 1 step: SH+projection+binning fwd+bwd of all {n} "
+                          f"Gaussians ({tg:.2f} s) + blend fwd+bwd of {len(tiles)}/{total_tiles} tiles ({tb:.2f} s, "
+                          f"scaled to the frame)")}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg["name"], "gaussians": n, "image": [W, H], "views_per_gpu": V,
+                   "channels": C, "backward": cfg["backward"], "parallelism": f"view-sharded x{world}",
+                   "l2": "inputs larger than L2 (parameters+gradients 2x%.0f MB per step)" % (n * (86 + D) * 4 / 1e6)},
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": roof,
+        "hbm_stages": hbm_stages,
+        "stage_ms_per_step": share,
+        "fma_probe_tflops": fma_tflops,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=1, help="index into BASELINE.json configs (default 1)")
+    ap.add_argument("--views", type=int, default=0, help="views per GPU per step (default: config's)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

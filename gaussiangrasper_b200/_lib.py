@@ -23,6 +23,7 @@ _SIGNATURES = {
     "gg_last_error_string": (C.c_char_p, []),
     "gg_launch_count": (C.c_ulonglong, []),
     "gg_check_device": (C.c_int, []),
+    "gg_bench_fma": (C.c_int, [_i, _i, _p, _p, _p]),
     "gg_project_fwd": (C.c_int, [_i, _p, _p, _f, _p, _p, _p, _f, _f, _f, _f, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _p, _p]),
     "gg_project_bwd": (C.c_int, [_i, _p, _p, _f, _p, _p, _p, _f, _f, _f, _f, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "gg_project_fwd_views": (C.c_int, [_i, _i, _p, _p, _f, _p, _p, _p, _p, _f, _f, _f, _f, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _p, _p]),
@@ -92,6 +93,45 @@ def check(rc: int, what: str = "") -> None:
     if rc != 0:
         msg = load().gg_last_error_string().decode("utf-8", "replace")
         raise GGError(f"{what or 'gg_b200'} failed (code {rc}): {msg}")
+
+
+# optional per-call CUDA-event timing (bench.py: "measured live inside the timed region")
+_profile = None
+
+
+class profile:
+    """with _lib.profile() as prof: ...  ->  prof.ms() = {entry point: [ms per call]}"""
+
+    def __enter__(self):
+        global _profile
+        self.records = {}
+        _profile = self.records
+        return self
+
+    def __exit__(self, *exc):
+        global _profile
+        _profile = None
+        return False
+
+    def ms(self):
+        torch.cuda.synchronize()
+        return {k: [a.elapsed_time(b) for a, b in v] for k, v in self.records.items()}
+
+
+def call(name: str, *args) -> None:
+    """Invoke a C-ABI entry point on torch's current stream and raise on a non-zero status."""
+    fn = getattr(load(), name)
+    if _profile is None:
+        rc = fn(*args)
+    else:
+        a = torch.cuda.Event(enable_timing=True)
+        b = torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = fn(*args)
+        b.record()
+        _profile.setdefault(name, []).append((a, b))
+    if rc != 0:
+        check(rc, name)
 
 
 def launch_count() -> int:

@@ -46,3 +46,33 @@ extern "C" int gg_check_device(void) {
     }
     return GG_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// FP32 FMA throughput probe used by bench.py as the practical roof of the blend kernels
+// ("measure an FMA micro-benchmark and use it as the practical roof").
+// Each thread runs 8 independent FMA chains; flops = grid * block * iters * 8 * 2.
+// ---------------------------------------------------------------------------------------------
+namespace gg {
+__global__ void __launch_bounds__(256) fma_probe_kernel(int iters, float* out) {
+    float a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = 1.0f + 0.001f * (float)(threadIdx.x + k);
+    const float m = 0.9999f, c = 1e-4f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = fmaf(a[k], m, c);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += a[k];
+    if (s == 123.456f) out[0] = s;  // never true; keeps the chains alive
+}
+}  // namespace gg
+
+extern "C" int gg_bench_fma(int blocks, int iters, float* out, double* flops, void* stream) {
+    GG_REQUIRE(blocks > 0 && iters > 0 && out, "gg_bench_fma: bad arguments");
+    gg::fma_probe_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, out);
+    gg::count_launch();
+    if (flops) *flops = (double)blocks * 256.0 * (double)iters * 16.0;
+    return gg::check_launch("fma_probe_kernel");
+}

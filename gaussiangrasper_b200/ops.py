@@ -86,11 +86,11 @@ def project_fwd(means3d, scales, glob_scale, quats, viewmat, fullmat, fx, fy, cx
     conics = torch.empty((n, 3), dtype=torch.float32, device=dev)
     nth = torch.empty((n,), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
-        check(_lib.load().gg_project_fwd(
+        _lib.call("gg_project_fwd", 
             n, ptr(means3d), ptr(scales), float(glob_scale), ptr(quats), ptr(vm), ptr(fm), float(fx), float(fy),
             float(cx), float(cy), int(img_height), int(img_width), int(tile_bounds[0]), int(tile_bounds[1]),
             float(clip_thresh), ptr(cov3d), ptr(xys), ptr(depths), ptr(radii), ptr(conics), ptr(nth),
-            stream_ptr(dev)), "gg_project_fwd")
+            stream_ptr(dev))
     return xys, depths, radii, conics, nth, cov3d
 
 
@@ -106,11 +106,10 @@ def project_bwd(means3d, scales, glob_scale, quats, viewmat, fullmat, fx, fy, cx
     v_scales = torch.empty((n, 3), dtype=torch.float32, device=dev)
     v_quats = torch.empty((n, 4), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        check(_lib.load().gg_project_bwd(
+        _lib.call("gg_project_bwd", 
             n, ptr(means3d), ptr(scales), float(glob_scale), ptr(quats), ptr(vm), ptr(fm), float(fx), float(fy),
             float(cx), float(cy), int(img_height), int(img_width), ptr(radii), ptr(conics), ptr(v_xys),
-            ptr(v_depths), ptr(v_conics), ptr(v_means), ptr(v_scales), ptr(v_quats), stream_ptr(dev)),
-            "gg_project_bwd")
+            ptr(v_depths), ptr(v_conics), ptr(v_means), ptr(v_scales), ptr(v_quats), stream_ptr(dev))
     return v_means, v_scales, v_quats
 
 
@@ -128,8 +127,8 @@ def sh_fwd(degrees_to_use, viewdirs, coeffs):
     degree = sh_degree_from_bases(coeffs.shape[-2])
     colors = torch.empty((n, 3), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        check(_lib.load().gg_sh_fwd(n, degree, int(degrees_to_use), ptr(viewdirs), ptr(coeffs), ptr(colors),
-                                    stream_ptr(dev)), "gg_sh_fwd")
+        _lib.call("gg_sh_fwd", n, degree, int(degrees_to_use), ptr(viewdirs), ptr(coeffs), ptr(colors),
+                                    stream_ptr(dev))
     return colors
 
 
@@ -140,8 +139,8 @@ def sh_bwd(degree, degrees_to_use, viewdirs, v_colors):
     nb = (degree + 1) ** 2
     v_coeffs = torch.empty((n, nb, 3), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        check(_lib.load().gg_sh_bwd(n, int(degree), int(degrees_to_use), ptr(viewdirs), ptr(v_colors), ptr(v_coeffs),
-                                    stream_ptr(dev)), "gg_sh_bwd")
+        _lib.call("gg_sh_bwd", n, int(degree), int(degrees_to_use), ptr(viewdirs), ptr(v_colors), ptr(v_coeffs),
+                                    stream_ptr(dev))
     return v_coeffs
 
 
@@ -155,8 +154,8 @@ def cumsum_i32(x: torch.Tensor, total_out: Optional[torch.Tensor] = None) -> tor
     out = torch.empty_like(x)
     ws = workspace(dev).scan_ws(x.numel())
     with torch.cuda.device(dev):
-        check(_lib.load().gg_cumsum(x.numel(), ptr(x), ptr(out), ptr(total_out), ptr(ws), ws.numel(),
-                                    stream_ptr(dev)), "gg_cumsum")
+        _lib.call("gg_cumsum", x.numel(), ptr(x), ptr(out), ptr(total_out), ptr(ws), ws.numel(),
+                                    stream_ptr(dev))
     return out
 
 
@@ -167,25 +166,24 @@ def key_bits_for(num_tiles_total: int) -> int:
 def map_to_intersects(n, n_views, xys, depths, radii, cum, tile_bounds, keys, ids):
     dev = xys.device
     with torch.cuda.device(dev):
-        check(_lib.load().gg_map_to_intersects(int(n), int(n_views), ptr(xys), ptr(depths), ptr(radii), ptr(cum),
+        _lib.call("gg_map_to_intersects", int(n), int(n_views), ptr(xys), ptr(depths), ptr(radii), ptr(cum),
                                                int(tile_bounds[0]), int(tile_bounds[1]), ptr(keys), ptr(ids),
-                                               stream_ptr(dev)), "gg_map_to_intersects")
+                                               stream_ptr(dev))
 
 
 def sort_pairs(m, key_bits, keys_in, ids_in, keys_out, ids_out):
     dev = keys_in.device
     ws = workspace(dev).sort_ws(m)
     with torch.cuda.device(dev):
-        check(_lib.load().gg_sort_pairs(int(m), int(key_bits), ptr(keys_in), ptr(ids_in), ptr(keys_out), ptr(ids_out),
-                                        ptr(ws), ws.numel(), stream_ptr(dev)), "gg_sort_pairs")
+        _lib.call("gg_sort_pairs", int(m), int(key_bits), ptr(keys_in), ptr(ids_in), ptr(keys_out), ptr(ids_out),
+                                        ptr(ws), ws.numel(), stream_ptr(dev))
 
 
 def tile_ranges(m, keys_sorted, num_tiles):
     dev = keys_sorted.device
     ranges = torch.empty((num_tiles, 2), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
-        check(_lib.load().gg_tile_ranges(int(m), ptr(keys_sorted), int(num_tiles), ptr(ranges), stream_ptr(dev)),
-              "gg_tile_ranges")
+        _lib.call("gg_tile_ranges", int(m), ptr(keys_sorted), int(num_tiles), ptr(ranges), stream_ptr(dev))
     return ranges
 
 
@@ -230,8 +228,8 @@ def pack_geo(n, n_views, xys, conics, opacity, opac_per_view=False):
     xys, conics, opacity = f32c(xys), f32c(conics), f32c(opacity).reshape(-1)
     geo = torch.empty((n * n_views, 8), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        check(_lib.load().gg_pack_geo(int(n), int(n_views), ptr(xys), ptr(conics), ptr(opacity),
-                                      1 if opac_per_view else 0, ptr(geo), stream_ptr(dev)), "gg_pack_geo")
+        _lib.call("gg_pack_geo", int(n), int(n_views), ptr(xys), ptr(conics), ptr(opacity),
+                                      1 if opac_per_view else 0, ptr(geo), stream_ptr(dev))
     return geo
 
 
@@ -255,11 +253,11 @@ def blend_fwd(binning: Binning, geo, colors, background, img_height, img_width, 
     with torch.cuda.device(dev):
         for c0 in range(0, C, step):
             c1 = min(C, c0 + step)
-            check(lib.gg_blend_fwd(
+            _lib.call("gg_blend_fwd", 
                 V, n, c1 - c0, C, 1 if colors_per_view else 0, C, int(img_height), int(img_width), tb[0], tb[1],
                 ptr(binning.ids_sorted), ptr(binning.tile_ranges), ptr(geo), colors.data_ptr() + 4 * c0,
                 background.data_ptr() + 4 * c0, out.data_ptr() + 4 * c0, ptr(final_T), ptr(final_idx),
-                ptr(pair_counter) if c0 == 0 else None, stream_ptr(dev)), "gg_blend_fwd")
+                ptr(pair_counter) if c0 == 0 else None, stream_ptr(dev))
     return out, final_T, final_idx
 
 
@@ -277,11 +275,11 @@ def blend_bwd(binning: Binning, geo, colors, background, final_T, final_idx, v_o
     with torch.cuda.device(dev):
         for c0 in range(0, C, step):
             c1 = min(C, c0 + step)
-            check(lib.gg_blend_bwd(
+            _lib.call("gg_blend_bwd", 
                 V, n, c1 - c0, C, 1 if colors_per_view else 0, C, int(img_height), int(img_width), tb[0], tb[1],
                 ptr(binning.ids_sorted), ptr(binning.tile_ranges), ptr(geo), colors.data_ptr() + 4 * c0,
                 background.data_ptr() + 4 * c0, ptr(final_T), ptr(final_idx), v_out.data_ptr() + 4 * c0, ptr(v_geo),
-                v_colors.data_ptr() + 4 * c0, stream_ptr(dev)), "gg_blend_bwd")
+                v_colors.data_ptr() + 4 * c0, stream_ptr(dev))
     return v_geo, v_colors
 
 
@@ -291,6 +289,6 @@ def unpack_vgeo(n, n_views, v_geo):
     v_conics = torch.empty((n_views * n, 3), dtype=torch.float32, device=dev)
     v_opac = torch.empty((n,), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        check(_lib.load().gg_unpack_vgeo(int(n), int(n_views), ptr(v_geo), ptr(v_xys), ptr(v_conics), ptr(v_opac), 0,
-                                         stream_ptr(dev)), "gg_unpack_vgeo")
+        _lib.call("gg_unpack_vgeo", int(n), int(n_views), ptr(v_geo), ptr(v_xys), ptr(v_conics), ptr(v_opac), 0,
+                                         stream_ptr(dev))
     return v_xys, v_conics, v_opac

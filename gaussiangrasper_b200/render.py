@@ -1,0 +1,167 @@
+"""Fused multi-view entry point: one projection, ONE binning and ONE blend pass per batch of
+views for everything GaussianGrasper renders per view -- RGB (SH), depth, normal and the D-channel
+latent language feature -- instead of the reference's 1 projection + 4 rasterizations with 4
+identical binning passes (nerfstudio/models/gaussian_splatting.py:699-784).
+
+Channel layout of the blended image: [rgb(3) | depth(1) | normal(3) | feature(D)], padded to a
+multiple of 4 floats per Gaussian row so that rows are gathered with 16-byte cp.async.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence
+
+import torch
+from torch.autograd import Function
+
+from . import _lib, ops
+from ._torch_impl import quat_to_rotmat
+from .sh import SphericalHarmonics
+
+
+@dataclass
+class ViewBatch:
+    """Cameras of one batch of views, already on the device (same image size for all)."""
+    viewmats: torch.Tensor   # [V, 12] rows 0..2 of world->camera
+    fullmats: torch.Tensor   # [V, 16] projmat @ viewmat
+    intrins: torch.Tensor    # [V, 4]  fx, fy, cx, cy
+    positions: torch.Tensor  # [V, 3]  camera centres (for SH view directions)
+    H: int
+    W: int
+
+    @property
+    def n_views(self) -> int:
+        return self.viewmats.shape[0]
+
+    @staticmethod
+    def from_cameras(cams: Sequence, device) -> "ViewBatch":
+        vm = torch.stack([c.viewmat[:3].reshape(-1) for c in cams]).float()
+        fm = torch.stack([c.fullmat.reshape(-1) for c in cams]).float()
+        intr = torch.tensor([[c.fx, c.fy, c.cx, c.cy] for c in cams], dtype=torch.float32)
+        pos = torch.stack([c.position for c in cams]).float()
+        packed = torch.cat([vm, fm, intr, pos], dim=1)  # one H2D copy for the whole batch
+        packed = packed.pin_memory().to(device, non_blocking=True) if device.type == "cuda" else packed
+        return ViewBatch(packed[:, :12].contiguous(), packed[:, 12:28].contiguous(), packed[:, 28:32].contiguous(),
+                         packed[:, 32:35].contiguous(), cams[0].H, cams[0].W)
+
+
+class _ProjectViews(Function):
+    @staticmethod
+    def forward(ctx, means, scales, quats, viewmats, fullmats, intrins, H, W, clip_thresh):
+        dev = _lib.require_cuda(means, scales, quats, viewmats, fullmats, intrins)
+        means, scales, quats = ops.f32c(means), ops.f32c(scales), ops.f32c(quats)
+        n, V = means.shape[0], viewmats.shape[0]
+        tb = ops.tile_bounds_for(H, W)
+        cov3d = torch.empty((V, n, 6), dtype=torch.float32, device=dev)
+        xys = torch.empty((V, n, 2), dtype=torch.float32, device=dev)
+        depths = torch.empty((V, n), dtype=torch.float32, device=dev)
+        radii = torch.empty((V, n), dtype=torch.int32, device=dev)
+        conics = torch.empty((V, n, 3), dtype=torch.float32, device=dev)
+        nth = torch.empty((V, n), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.call("gg_project_fwd_views", 
+                n, V, ops.ptr(means), ops.ptr(scales), 1.0, ops.ptr(quats), ops.ptr(viewmats), ops.ptr(fullmats),
+                ops.ptr(intrins), 0.0, 0.0, 0.0, 0.0, int(H), int(W), tb[0], tb[1], float(clip_thresh),
+                ops.ptr(cov3d), ops.ptr(xys), ops.ptr(depths), ops.ptr(radii), ops.ptr(conics), ops.ptr(nth),
+                ops.stream_ptr(dev))
+        ctx.size = (int(H), int(W))
+        ctx.save_for_backward(means, scales, quats, viewmats, fullmats, intrins, radii, conics)
+        ctx.mark_non_differentiable(radii, nth)
+        return xys, depths, radii, conics, nth
+
+    @staticmethod
+    def backward(ctx, v_xys, v_depths, v_radii, v_conics, v_nth):
+        means, scales, quats, viewmats, fullmats, intrins, radii, conics = ctx.saved_tensors
+        dev = means.device
+        n, V = means.shape[0], viewmats.shape[0]
+        H, W = ctx.size
+        v_xys = ops.f32c(v_xys) if v_xys is not None else torch.zeros((V, n, 2), device=dev)
+        v_conics = ops.f32c(v_conics) if v_conics is not None else torch.zeros((V, n, 3), device=dev)
+        v_depths = ops.f32c(v_depths) if v_depths is not None else None
+        v_means = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        v_scales = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        v_quats = torch.empty((n, 4), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.call("gg_project_bwd_views", 
+                n, V, ops.ptr(means), ops.ptr(scales), 1.0, ops.ptr(quats), ops.ptr(viewmats), ops.ptr(fullmats),
+                ops.ptr(intrins), 0.0, 0.0, 0.0, 0.0, H, W, ops.ptr(radii), ops.ptr(conics), ops.ptr(v_xys),
+                ops.ptr(v_depths), ops.ptr(v_conics), 0, ops.ptr(v_means), ops.ptr(v_scales), ops.ptr(v_quats),
+                ops.stream_ptr(dev))
+        return v_means, v_scales, v_quats, None, None, None, None, None, None
+
+
+class _BlendViews(Function):
+    @staticmethod
+    def forward(ctx, xys, depths, radii, conics, nth, colors, opacity, background, H, W, stats):
+        V, n = xys.shape[0], xys.shape[1]
+        tb = ops.tile_bounds_for(H, W)
+        binning = ops.bin_views(n, V, xys.detach().reshape(V * n, 2), depths.detach().reshape(-1),
+                                radii.reshape(-1), nth.reshape(-1), tb)
+        geo = ops.pack_geo(n, V, xys.detach().reshape(V * n, 2), conics.detach().reshape(V * n, 3), opacity.detach())
+        colors_c = ops.f32c(colors.detach()).reshape(V * n, -1)
+        background = ops.f32c(background.detach())
+        out, final_T, final_idx = ops.blend_fwd(binning, geo, colors_c, background, H, W, colors_per_view=True,
+                                                pair_counter=stats)
+        ctx.binning = binning
+        ctx.size = (int(H), int(W))
+        ctx.opacity_shape = tuple(opacity.shape)
+        ctx.save_for_backward(geo, colors_c, background, final_T, final_idx)
+        ctx.mark_non_differentiable(final_T)
+        return out, final_T
+
+    @staticmethod
+    def backward(ctx, v_out, _v_T):
+        geo, colors_c, background, final_T, final_idx = ctx.saved_tensors
+        b = ctx.binning
+        H, W = ctx.size
+        v_geo, v_colors = ops.blend_bwd(b, geo, colors_c, background, final_T, final_idx, v_out, H, W,
+                                        colors_per_view=True)
+        v_xys, v_conics, v_opac = ops.unpack_vgeo(b.n, b.n_views, v_geo)
+        V, n = b.n_views, b.n
+        return (v_xys.reshape(V, n, 2), None, None, v_conics.reshape(V, n, 3), None, v_colors.reshape(V, n, -1),
+                v_opac.reshape(ctx.opacity_shape), None, None, None, None)
+
+
+def smallest_axis_normals(quats: torch.Tensor, log_scales: torch.Tensor) -> torch.Tensor:
+    """gaussian_splatting.py:605-619: column of R(quat) along the smallest scale."""
+    R = quat_to_rotmat(quats)
+    idx = log_scales.min(dim=-1)[1][..., None, None].expand(-1, 3, -1)
+    return R.gather(2, idx).squeeze(dim=2)
+
+
+def render_views(means, log_scales, quats, opacity_logit, sh_coeffs, features, views: ViewBatch,
+                 degrees_to_use: int = 4, depth_background: float = 10.0, clip_thresh: float = 0.01,
+                 stats: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+    """Render rgb [V,H,W,3], depth [V,H,W,1], normal [V,H,W,3], feature [V,H,W,D] for V views.
+
+    Inputs are the model's raw parameters (gaussian_splatting.py:270-292): log-scales, un-normalised
+    wxyz quaternions, opacity logits, SH coefficients [N,(deg+1)^2,3], features [N,D].
+    Backgrounds follow the model: 0 for rgb/normal/feature, 10 for depth.
+    `xys` (per-view pixel centres, [V,N,2]) is returned as a non-leaf so callers can retain its
+    gradient for densification (gaussian_splatting.py:725,377).
+    """
+    dev = means.device
+    V, H, W = views.n_views, views.H, views.W
+    n, D = means.shape[0], features.shape[1]
+    scales = torch.exp(log_scales)
+    qn = quats / quats.norm(dim=-1, keepdim=True)
+    opacity = torch.sigmoid(opacity_logit)
+    xys, depths, radii, conics, nth = _ProjectViews.apply(means, scales, qn, views.viewmats, views.fullmats,
+                                                          views.intrins, H, W, clip_thresh)
+    normals = smallest_axis_normals(quats, log_scales)
+    rgbs = []
+    md = means.detach()
+    for v in range(V):
+        dirs = md - views.positions[v]
+        rgbs.append(torch.clamp(SphericalHarmonics.apply(degrees_to_use, dirs, sh_coeffs) + 0.5, 0.0, 1.0))
+    C = 7 + D
+    CP = (C + 3) // 4 * 4
+    parts = [torch.stack(rgbs, 0), depths[..., None], normals[None].expand(V, -1, -1), features[None].expand(V, -1, -1)]
+    if CP > C:
+        parts.append(torch.zeros((V, n, CP - C), dtype=torch.float32, device=dev))
+    colors = torch.cat(parts, dim=-1)
+    bg = torch.zeros(CP, dtype=torch.float32, device=dev)
+    bg[3] = depth_background
+    out, final_T = _BlendViews.apply(xys, depths, radii, conics, nth, colors, opacity, bg, H, W, stats)
+    return dict(rgb=out[..., 0:3], depth=out[..., 3:4], normal=out[..., 4:7], feature=out[..., 7:7 + D],
+                image=out, alpha=1.0 - final_T, xys=xys, radii=radii, num_tiles_hit=nth)

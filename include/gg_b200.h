@@ -36,6 +36,10 @@ unsigned long long gg_launch_count(void);
 /* 0 iff the current CUDA device is compute capability 10.x */
 int gg_check_device(void);
 
+/* FP32 FMA throughput probe (bench.py's practical roof for the blend kernels): launches
+ * `blocks` x 256 threads x `iters` x 8 FMAs; *flops (host pointer, nullable) receives the count. */
+int gg_bench_fma(int blocks, int iters, float* out, double* flops, void* stream);
+
 /* ---- projection: replaces gsplat.cuda.project_gaussians_forward / _backward ---------------
  * (ProjectGaussians.apply, gaussian_splatting.py:699-713).  viewmat: 12 floats (rows 0..2 of
  * the 4x4 world->camera matrix), fullmat: 16 floats (projmat @ viewmat).  Outputs are written
