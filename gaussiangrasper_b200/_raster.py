@@ -56,14 +56,15 @@ def rasterize_forward(ctx, xys, depths, radii, conics, num_tiles_hit, colors, op
     geo = ops.pack_geo(n, 1, xys.detach(), conics.detach(), opacity.detach())
     colors_c = ops.f32c(colors.detach())
     background = ops.f32c(background.detach())
-    out, final_T, final_idx = ops.blend_fwd(binning, geo, colors_c, background, img_height, img_width)
+    out, final_T, final_idx = ops.blend_fwd(binning, geo, colors_c, background, img_height, img_width,
+                                            single_image=True)
     ctx.binning = binning
     ctx.img_size = (int(img_height), int(img_width))
     ctx.opacity_shape = tuple(opacity.shape)
     # only inputs and the transmittance / last-contributor maps are saved (never the image: the
     # model writes into it in place before backward, gaussian_splatting.py:884)
     ctx.save_for_backward(geo, colors_c, background, final_T, final_idx)
-    return out[0]
+    return out
 
 
 def rasterize_backward(ctx, v_out):

@@ -238,13 +238,16 @@ def max_channels() -> int:
 
 
 def blend_fwd(binning: Binning, geo, colors, background, img_height, img_width, colors_per_view=False,
-              pair_counter: Optional[torch.Tensor] = None):
+              pair_counter: Optional[torch.Tensor] = None, single_image: bool = False):
     """colors [rows, C] (C arbitrary; split into launches of <= 64 channels).  Returns
     (out [V,H,W,C], final_T [V,H,W], final_idx [V,H,W])."""
     dev = require_cuda(geo, colors, background)
     colors, background = f32c(colors), f32c(background)
     V, n, C = binning.n_views, binning.n, colors.shape[1]
-    out = torch.empty((V, img_height, img_width, C), dtype=torch.float32, device=dev)
+    # single_image: the drop-in rasterizers return [H,W,C]; it must not be a view of a batched
+    # tensor because the model writes into it in place (gaussian_splatting.py:884)
+    shape = (img_height, img_width, C) if single_image else (V, img_height, img_width, C)
+    out = torch.empty(shape, dtype=torch.float32, device=dev)
     final_T = torch.empty((V, img_height, img_width), dtype=torch.float32, device=dev)
     final_idx = torch.empty((V, img_height, img_width), dtype=torch.int32, device=dev)
     tb = binning.tile_bounds
