@@ -33,6 +33,7 @@ _SIGNATURES = {
     "gg_cumsum_workspace_bytes": (C.c_size_t, [_ll]),
     "gg_cumsum": (C.c_int, [_ll, _p, _p, _p, _p, _sz, _p]),
     "gg_map_to_intersects": (C.c_int, [_i, _i, _p, _p, _p, _p, _i, _i, _p, _p, _p]),
+    "gg_map_to_intersects_geo": (C.c_int, [_i, _i, _p, _p, _p, _p, _i, _i, _p, _p, _p]),
     "gg_sort_workspace_bytes": (C.c_size_t, [_ll]),
     "gg_sort_pairs": (C.c_int, [_ll, _i, _p, _p, _p, _p, _p, _sz, _p]),
     "gg_tile_ranges": (C.c_int, [_ll, _p, _ll, _p, _p]),
@@ -41,6 +42,8 @@ _SIGNATURES = {
     "gg_blend_fwd": (C.c_int, [_i, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "gg_blend_bwd": (C.c_int, [_i, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "gg_unpack_vgeo": (C.c_int, [_ll, _i, _p, _p, _p, _p, _i, _p]),
+    "gg_prepare_views": (C.c_int, [_i] * 6 + [_p] * 10 + [_i] * 4 + [_f] + [_p] * 8),
+    "gg_prepare_views_bwd": (C.c_int, [_i] * 6 + [_p] * 9 + [_i] * 2 + [_p] * 12),
 }
 
 # optional symbols of later translation units (bound when present)

@@ -125,7 +125,7 @@ scan_down_kernel(long long n, const int32_t* __restrict__ in, const int32_t* __r
 // tiles visited row-major inside the bbox.  key = (view * T + tile) << 32 | depth bits.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-emit_keys_kernel(int n, int n_views, const float* __restrict__ xys, const float* __restrict__ depths,
+emit_keys_kernel(int n, int n_views, const float* __restrict__ xys, int xy_stride, const float* __restrict__ depths,
                  const int32_t* __restrict__ radii, const int32_t* __restrict__ cum, int tiles_x, int tiles_y,
                  int64_t* __restrict__ keys, int32_t* __restrict__ ids) {
     const long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -134,7 +134,7 @@ emit_keys_kernel(int n, int n_views, const float* __restrict__ xys, const float*
     if (r <= 0) return;
     const int view = (int)(gi / n);
     const int g = (int)(gi - (long long)view * n);
-    const float2 c = __ldg(reinterpret_cast<const float2*>(xys) + gi);
+    const float2 c = __ldg(reinterpret_cast<const float2*>(xys + gi * xy_stride));
     const TileBox tb = tile_box(c.x, c.y, (float)r, tiles_x, tiles_y);
     long long cur = gi == 0 ? 0 : cum[gi - 1];
     const uint64_t dbits = (uint64_t)__float_as_uint(depths[gi]);
@@ -360,17 +360,31 @@ extern "C" int gg_cumsum(long long n, const int32_t* in, int32_t* out, int32_t* 
     return check_launch("gg_cumsum");
 }
 
-extern "C" int gg_map_to_intersects(int n, int n_views, const float* xys, const float* depths, const int32_t* radii,
-                                    const int32_t* cum_tiles_hit, int tiles_x, int tiles_y, int64_t* keys,
-                                    int32_t* ids, void* stream) {
+static int map_to_intersects(int n, int n_views, const float* xys, int xy_stride, const float* depths,
+                             const int32_t* radii, const int32_t* cum_tiles_hit, int tiles_x, int tiles_y,
+                             int64_t* keys, int32_t* ids, void* stream) {
     GG_REQUIRE(n >= 1 && n_views >= 1, "gg_map_to_intersects: need n >= 1");
     GG_REQUIRE(xys && depths && radii && cum_tiles_hit && keys && ids, "gg_map_to_intersects: null pointer");
+    GG_REQUIRE(((uintptr_t)xys & 7) == 0, "gg_map_to_intersects: xys misaligned");
     GG_REQUIRE((long long)n_views * tiles_x * tiles_y < (1ll << 31), "gg_map_to_intersects: too many tiles");
     const long long total = (long long)n * n_views;
-    emit_keys_kernel<<<div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(n, n_views, xys, depths, radii,
+    emit_keys_kernel<<<div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(n, n_views, xys, xy_stride, depths, radii,
                                                                            cum_tiles_hit, tiles_x, tiles_y, keys, ids);
     count_launch();
     return check_launch("emit_keys_kernel");
+}
+
+extern "C" int gg_map_to_intersects(int n, int n_views, const float* xys, const float* depths, const int32_t* radii,
+                                    const int32_t* cum_tiles_hit, int tiles_x, int tiles_y, int64_t* keys,
+                                    int32_t* ids, void* stream) {
+    return map_to_intersects(n, n_views, xys, 2, depths, radii, cum_tiles_hit, tiles_x, tiles_y, keys, ids, stream);
+}
+
+// same, reading the pixel centres from the packed geo records ([V*n, 8], x and y first)
+extern "C" int gg_map_to_intersects_geo(int n, int n_views, const float* geo, const float* depths,
+                                        const int32_t* radii, const int32_t* cum_tiles_hit, int tiles_x, int tiles_y,
+                                        int64_t* keys, int32_t* ids, void* stream) {
+    return map_to_intersects(n, n_views, geo, 8, depths, radii, cum_tiles_hit, tiles_x, tiles_y, keys, ids, stream);
 }
 
 extern "C" size_t gg_sort_workspace_bytes(long long m) { return sort_layout(m).total; }

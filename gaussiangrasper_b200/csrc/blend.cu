@@ -24,7 +24,7 @@ constexpr int kBlendThreads = 256;
 constexpr float kAlphaMin = 1.0f / 255.0f;
 constexpr float kAlphaMax = 0.999f;
 constexpr float kTStop = 1e-4f;
-constexpr float kTauMargin = 1e-3f;
+constexpr float kTauMargin = GG_TAU_MARGIN;
 
 struct BlendArgs {
     int channels;        // real channel count handled by this launch (<= CP)

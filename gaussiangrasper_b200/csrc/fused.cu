@@ -1,0 +1,348 @@
+// Fused per-(view, Gaussian) preparation for the multi-view entry point (render_views):
+//   activation (exp / normalise / sigmoid) + EWA projection + SH->RGB (+0.5, clamp) + smallest-axis
+//   normal + feature copy, written straight into the packed records the blend kernels gather:
+//       geo [V*N, 8]   = {x, y, A/2, B, C/2, opacity, tau, 0}
+//       chan[V*N, CP]  = {r, g, b, depth, nx, ny, nz, feature[0..D), 0-pad}
+// and its exact backward (sum over views) to the raw model parameters.  This replaces, in one
+// launch each way, the reference's ProjectGaussians + SphericalHarmonics + ~10 ATen elementwise
+// kernels per view (nerfstudio/models/gaussian_splatting.py:699-731, :605-619, :742-780).
+//
+// Compiled with -fmad=false: radii / num_tiles_hit / depth bits must equal what the stand-alone
+// projection kernel (and the CPU oracle) produce from the same activated inputs.
+#include "gg_common.cuh"
+#include "gg_math.cuh"
+#include "gg_b200.h"
+
+namespace gg {
+
+constexpr int kPrepWarps = 4;
+constexpr int kPrepThreads = kPrepWarps * 32;
+
+struct PrepArgs {
+    int n, n_views, feat_dim, cp, nb, deg_use;
+    int img_h, img_w, tiles_x, tiles_y;
+    float clip;
+    const float* means;          // [N,3]
+    const float* log_scales;     // [N,3]
+    const float* quats;          // [N,4] raw
+    const float* opacity_logit;  // [N]
+    const float* sh;             // [N,nb,3]
+    const float* features;       // [N,D]
+    const float* viewmats;       // [V,12]
+    const float* fullmats;       // [V,16]
+    const float* intrins;        // [V,4]
+    const float* positions;      // [V,3]
+};
+
+__device__ __forceinline__ Camera load_camera_regs(const PrepArgs& a, int view) {
+    Camera cam;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) cam.vm[k] = __ldg(a.viewmats + (size_t)view * 12 + k);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) cam.fm[k] = __ldg(a.fullmats + (size_t)view * 16 + k);
+    cam.fx = __ldg(a.intrins + 4 * view);
+    cam.fy = __ldg(a.intrins + 4 * view + 1);
+    cam.cx = __ldg(a.intrins + 4 * view + 2);
+    cam.cy = __ldg(a.intrins + 4 * view + 3);
+    return cam;
+}
+
+struct Activated {
+    float p[3], ls[3], s[3], q_raw[4], qh[4], inv_qnorm, logit, opacity;
+    int kmin;
+};
+
+__device__ __forceinline__ Activated load_activated(const PrepArgs& a, long long i) {
+    Activated g;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        g.p[k] = __ldg(a.means + 3 * i + k);
+        g.ls[k] = __ldg(a.log_scales + 3 * i + k);
+        g.s[k] = expf(g.ls[k]);
+    }
+    const float4 q = __ldg(reinterpret_cast<const float4*>(a.quats) + i);
+    g.q_raw[0] = q.x; g.q_raw[1] = q.y; g.q_raw[2] = q.z; g.q_raw[3] = q.w;
+    const float qn = sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+    g.inv_qnorm = 1.0f / qn;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) g.qh[k] = g.q_raw[k] / qn;
+    g.logit = __ldg(a.opacity_logit + i);
+    g.opacity = 1.0f / (1.0f + expf(-g.logit));
+    // argmin of the scales, first minimum on ties (torch.min)
+    g.kmin = 0;
+    if (g.ls[1] < g.ls[g.kmin]) g.kmin = 1;
+    if (g.ls[2] < g.ls[g.kmin]) g.kmin = 2;
+    return g;
+}
+
+__global__ void __launch_bounds__(kPrepThreads)
+prepare_views_kernel(const PrepArgs a, float* __restrict__ geo, float* __restrict__ chan,
+                     float* __restrict__ depths, int32_t* __restrict__ radii, int32_t* __restrict__ num_tiles_hit,
+                     float* __restrict__ scales_out, float* __restrict__ quats_out, int slab_row) {
+    extern __shared__ __align__(16) float sm[];
+    const int view = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* slab = sm + (size_t)warp * 32 * slab_row;
+    const long long first = ((long long)blockIdx.x * kPrepWarps + warp) * 32;
+    if (first >= a.n) return;  // whole warp; no block-level barrier is used in this kernel
+    const long long i = first + lane;
+    const bool active = i < a.n;
+    const int rows_here = (int)min((long long)32, a.n - first);
+    const long long vrow = (long long)view * a.n + i;
+    const Camera cam = load_camera_regs(a, view);
+
+    Activated g;
+    ProjOut o;
+    o.tiles = 0;
+    if (active) {
+        g = load_activated(a, i);
+        o = project_one(g.p, g.s, 1.0f, g.qh, cam, a.img_h, a.img_w, a.tiles_x, a.tiles_y, a.clip);
+        depths[vrow] = o.depth;
+        radii[vrow] = o.radius;
+        num_tiles_hit[vrow] = o.tiles;
+        const bool vis = o.tiles > 0;
+        const float tau = (vis && g.opacity * 255.0f > 1.0f) ? __logf(g.opacity * 255.0f) + GG_TAU_MARGIN : -1.0f;
+        float4* gd = reinterpret_cast<float4*>(geo) + 2 * vrow;
+        gd[0] = make_float4(o.ux, o.uy, 0.5f * o.conic[0], o.conic[1]);
+        gd[1] = make_float4(0.5f * o.conic[2], vis ? g.opacity : 0.0f, tau, 0.0f);
+        if (view == 0 && scales_out) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) scales_out[3 * i + k] = g.s[k];
+        }
+        if (view == 0 && quats_out)
+            reinterpret_cast<float4*>(quats_out)[i] = make_float4(g.qh[0], g.qh[1], g.qh[2], g.qh[3]);
+    }
+    const bool vis = active && o.tiles > 0;
+    if (!__any_sync(0xffffffffu, vis)) return;  // nothing of this warp reaches a tile list
+
+    // ---- SH coefficients of the warp's 32 Gaussians: one contiguous span, 16-byte loads ----
+    const int row = a.nb * 3;
+    {
+        const float* gspan = a.sh + first * row;
+        const int span = rows_here * row;
+        const int nvec = span >> 2;
+        const float4* g4 = reinterpret_cast<const float4*>(gspan);
+        float4* s4 = reinterpret_cast<float4*>(slab);
+        for (int k = lane; k < nvec; k += 32) s4[k] = __ldg(g4 + k);
+        for (int k = (nvec << 2) + lane; k < span; k += 32) slab[k] = __ldg(gspan + k);
+    }
+    __syncwarp();
+    float rgb[3] = {0.f, 0.f, 0.f}, nrm[3] = {0.f, 0.f, 0.f};
+    if (vis) {
+        float Y[25];
+        sh_basis(a.deg_use, g.p[0] - __ldg(a.positions + 3 * view), g.p[1] - __ldg(a.positions + 3 * view + 1),
+                 g.p[2] - __ldg(a.positions + 3 * view + 2), Y);
+        const int nuse = sh_num_bases(a.deg_use);
+        const float* cf = slab + lane * row;
+        for (int b = 0; b < nuse; ++b) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) rgb[c] = rgb[c] + Y[b] * cf[3 * b + c];
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) rgb[c] = fminf(1.0f, fmaxf(0.0f, rgb[c] + 0.5f));
+        const Rot3 R = quat_to_rot(g.qh[0], g.qh[1], g.qh[2], g.qh[3]);
+        nrm[0] = R.m[g.kmin]; nrm[1] = R.m[3 + g.kmin]; nrm[2] = R.m[6 + g.kmin];
+    }
+    __syncwarp();
+    // ---- assemble the channel rows in shared memory, store them as one coalesced span ----
+    {
+        float* r = slab + lane * a.cp;
+        if (vis) {
+            r[0] = rgb[0]; r[1] = rgb[1]; r[2] = rgb[2]; r[3] = o.depth;
+            r[4] = nrm[0]; r[5] = nrm[1]; r[6] = nrm[2];
+            for (int d = 0; d < a.feat_dim; ++d) r[7 + d] = __ldg(a.features + i * a.feat_dim + d);
+            for (int d = 7 + a.feat_dim; d < a.cp; ++d) r[d] = 0.0f;
+        } else {
+            for (int d = 0; d < a.cp; ++d) r[d] = 0.0f;
+        }
+    }
+    __syncwarp();
+    {
+        float* gspan = chan + ((long long)view * a.n + first) * a.cp;
+        const int nvec = (rows_here * a.cp) >> 2;  // cp is a multiple of 4
+        float4* g4 = reinterpret_cast<float4*>(gspan);
+        const float4* s4 = reinterpret_cast<const float4*>(slab);
+        for (int k = lane; k < nvec; k += 32) g4[k] = s4[k];
+    }
+}
+
+// Sum over views of the vector-Jacobian product of prepare_views_kernel.
+//   v_geo [V*N, 8] : v_x, v_y, v_A, v_B, v_C (w.r.t. the conic, not its halves), v_opacity
+//   v_chan[V*N, CP]: v_rgb(3), v_depth, v_normal(3), v_feature(D)
+__global__ void __launch_bounds__(kPrepThreads)
+prepare_views_bwd_kernel(const PrepArgs a, const float* __restrict__ geo, const float* __restrict__ chan,
+                         const int32_t* __restrict__ radii, const float* __restrict__ v_geo,
+                         const float* __restrict__ v_chan, float* __restrict__ v_means,
+                         float* __restrict__ v_log_scales, float* __restrict__ v_quats,
+                         float* __restrict__ v_opacity_logit, float* __restrict__ v_sh,
+                         float* __restrict__ v_features) {
+    extern __shared__ __align__(16) float sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = a.nb * 3;
+    const int D = a.feat_dim;
+    float* slab = sm + (size_t)warp * 32 * (row + D);  // [32][row] SH grads, then [32][D] feature grads
+    float* fslab = slab + 32 * row;
+    const long long first = ((long long)blockIdx.x * kPrepWarps + warp) * 32;
+    if (first >= a.n) return;
+    const long long i = first + lane;
+    const bool active = i < a.n;
+    const int rows_here = (int)min((long long)32, a.n - first);
+    for (int k = lane; k < 32 * (row + D); k += 32) slab[k] = 0.0f;
+    __syncwarp();
+
+    Activated g;
+    if (active) g = load_activated(a, i);
+    float gm[3] = {0.f, 0.f, 0.f}, gs[3] = {0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f}, go = 0.0f;
+    const int nuse = sh_num_bases(a.deg_use);
+    for (int view = 0; view < a.n_views; ++view) {
+        const long long vrow = (long long)view * a.n + i;
+        if (!(active && radii[vrow] > 0)) continue;
+        const Camera cam = load_camera_regs(a, view);
+        const float4 ga = __ldg(reinterpret_cast<const float4*>(geo) + 2 * vrow);
+        const float4 gb = __ldg(reinterpret_cast<const float4*>(geo) + 2 * vrow + 1);
+        const float4 va = __ldg(reinterpret_cast<const float4*>(v_geo) + 2 * vrow);
+        const float4 vb = __ldg(reinterpret_cast<const float4*>(v_geo) + 2 * vrow + 1);
+        const float* vc = v_chan + vrow * a.cp;
+        const float4 c0 = __ldg(reinterpret_cast<const float4*>(vc));
+        const float4 c1 = __ldg(reinterpret_cast<const float4*>(vc) + 1);
+        const float conic[3] = {2.0f * ga.z, ga.w, 2.0f * gb.x};
+        const float v_xy[2] = {va.x, va.y};
+        const float v_conic[3] = {va.z, va.w, vb.x};
+        go += vb.y;
+        // normal channel: column kmin of R(qh)
+        float vR[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) vR[k] = 0.0f;
+        vR[g.kmin] = c1.x; vR[3 + g.kmin] = c1.y; vR[6 + g.kmin] = c1.z;
+        const ProjGrad pg = project_bwd_one(g.p, g.s, 1.0f, g.qh, cam, a.img_h, a.img_w, conic, v_xy, c0.w, v_conic, vR);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { gm[k] += pg.v_mean[k]; gs[k] += pg.v_scale[k]; }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) gq[k] += pg.v_quat[k];
+        // SH: rgb = clamp(sh + 0.5, 0, 1); the clamp passes gradient strictly inside (0,1)
+        const float* cr = chan + vrow * a.cp;
+        float vrgb[3] = {c0.x, c0.y, c0.z};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float v = __ldg(cr + c);
+            if (!(v > 0.0f && v < 1.0f)) vrgb[c] = 0.0f;
+        }
+        float Y[25];
+        sh_basis(a.deg_use, g.p[0] - __ldg(a.positions + 3 * view), g.p[1] - __ldg(a.positions + 3 * view + 1),
+                 g.p[2] - __ldg(a.positions + 3 * view + 2), Y);
+        float* sr = slab + lane * row;
+        for (int b = 0; b < nuse; ++b) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) sr[3 * b + c] += Y[b] * vrgb[c];
+        }
+        float* fr = fslab + lane * D;
+        for (int d = 0; d < D; ++d) fr[d] += __ldg(vc + 7 + d);
+    }
+    if (active) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            v_means[3 * i + k] = gm[k];
+            v_log_scales[3 * i + k] = gs[k] * g.s[k];
+        }
+        // qh = q / |q|
+        const float dotq = g.qh[0] * gq[0] + g.qh[1] * gq[1] + g.qh[2] * gq[2] + g.qh[3] * gq[3];
+        reinterpret_cast<float4*>(v_quats)[i] =
+            make_float4((gq[0] - g.qh[0] * dotq) * g.inv_qnorm, (gq[1] - g.qh[1] * dotq) * g.inv_qnorm,
+                        (gq[2] - g.qh[2] * dotq) * g.inv_qnorm, (gq[3] - g.qh[3] * dotq) * g.inv_qnorm);
+        v_opacity_logit[i] = go * g.opacity * (1.0f - g.opacity);
+    }
+    __syncwarp();
+    {
+        float* gspan = v_sh + first * row;
+        const int span = rows_here * row;
+        const int nvec = span >> 2;
+        float4* g4 = reinterpret_cast<float4*>(gspan);
+        const float4* s4 = reinterpret_cast<const float4*>(slab);
+        for (int k = lane; k < nvec; k += 32) g4[k] = s4[k];
+        for (int k = (nvec << 2) + lane; k < span; k += 32) gspan[k] = slab[k];
+    }
+    if (D > 0) {
+        float* gspan = v_features + first * D;
+        const int span = rows_here * D;
+        for (int k = lane; k < span; k += 32) gspan[k] = fslab[k];
+    }
+}
+
+static int fill_args(PrepArgs& a, int n, int n_views, int feat_dim, int cp, int degree, int degrees_to_use,
+                     const float* means, const float* log_scales, const float* quats, const float* opacity_logit,
+                     const float* sh, const float* features, const float* viewmats, const float* fullmats,
+                     const float* intrins, const float* positions, int img_h, int img_w, int tiles_x, int tiles_y,
+                     float clip) {
+    GG_REQUIRE(n >= 1 && n_views >= 1, "gg_prepare_views: need n >= 1 and n_views >= 1");
+    GG_REQUIRE(feat_dim >= 0 && feat_dim <= 64, "gg_prepare_views: feature dim must be in [0, 64]");
+    GG_REQUIRE(cp % 4 == 0 && cp >= 7 + feat_dim && cp <= 72, "gg_prepare_views: cp must be a multiple of 4, >= 7 + D");
+    GG_REQUIRE(degree >= 0 && degree <= 4 && degrees_to_use >= 0 && degrees_to_use <= degree,
+               "gg_prepare_views: need 0 <= degrees_to_use <= degree <= 4");
+    GG_REQUIRE(means && log_scales && quats && opacity_logit && sh && (features || feat_dim == 0) && viewmats &&
+                   fullmats && intrins && positions,
+               "gg_prepare_views: null input pointer");
+    GG_REQUIRE(((uintptr_t)quats & 15) == 0 && ((uintptr_t)sh & 15) == 0, "gg_prepare_views: quats/sh misaligned");
+    GG_REQUIRE(img_h > 0 && img_w > 0 && tiles_x > 0 && tiles_y > 0, "gg_prepare_views: bad image / tile bounds");
+    a.n = n; a.n_views = n_views; a.feat_dim = feat_dim; a.cp = cp; a.nb = sh_num_bases(degree);
+    a.deg_use = degrees_to_use; a.img_h = img_h; a.img_w = img_w; a.tiles_x = tiles_x; a.tiles_y = tiles_y;
+    a.clip = clip; a.means = means; a.log_scales = log_scales; a.quats = quats; a.opacity_logit = opacity_logit;
+    a.sh = sh; a.features = features; a.viewmats = viewmats; a.fullmats = fullmats; a.intrins = intrins;
+    a.positions = positions;
+    return GG_OK;
+}
+
+}  // namespace gg
+
+using namespace gg;
+
+extern "C" int gg_prepare_views(int n, int n_views, int feat_dim, int cp, int degree, int degrees_to_use,
+                                const float* means, const float* log_scales, const float* quats,
+                                const float* opacity_logit, const float* sh_coeffs, const float* features,
+                                const float* viewmats, const float* fullmats, const float* intrins,
+                                const float* positions, int img_h, int img_w, int tiles_x, int tiles_y,
+                                float clip_thresh, float* geo, float* chan, float* depths, int32_t* radii,
+                                int32_t* num_tiles_hit, float* scales_out, float* quats_out, void* stream) {
+    PrepArgs a;
+    const int rc = fill_args(a, n, n_views, feat_dim, cp, degree, degrees_to_use, means, log_scales, quats,
+                             opacity_logit, sh_coeffs, features, viewmats, fullmats, intrins, positions, img_h, img_w,
+                             tiles_x, tiles_y, clip_thresh);
+    if (rc != GG_OK) return rc;
+    GG_REQUIRE(geo && chan && depths && radii && num_tiles_hit, "gg_prepare_views: null output pointer");
+    GG_REQUIRE(((uintptr_t)geo & 15) == 0 && ((uintptr_t)chan & 15) == 0, "gg_prepare_views: geo/chan misaligned");
+    const int slab_row = a.nb * 3 > cp ? a.nb * 3 : cp;
+    const size_t smem = sizeof(float) * kPrepWarps * 32 * (size_t)slab_row;
+    GG_CUDA(cudaFuncSetAttribute(prepare_views_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(div_up(n, kPrepThreads), n_views);
+    prepare_views_kernel<<<grid, kPrepThreads, smem, (cudaStream_t)stream>>>(a, geo, chan, depths, radii,
+                                                                             num_tiles_hit, scales_out, quats_out,
+                                                                             slab_row);
+    count_launch();
+    return check_launch("prepare_views_kernel");
+}
+
+extern "C" int gg_prepare_views_bwd(int n, int n_views, int feat_dim, int cp, int degree, int degrees_to_use,
+                                    const float* means, const float* log_scales, const float* quats,
+                                    const float* opacity_logit, const float* features, const float* viewmats,
+                                    const float* fullmats, const float* intrins, const float* positions, int img_h,
+                                    int img_w, const float* geo, const float* chan, const int32_t* radii,
+                                    const float* v_geo, const float* v_chan, float* v_means, float* v_log_scales,
+                                    float* v_quats, float* v_opacity_logit, float* v_sh_coeffs, float* v_features,
+                                    void* stream) {
+    PrepArgs a;
+    // the SH table itself is not read by the backward; pass v_sh_coeffs for the alignment check
+    const int rc = fill_args(a, n, n_views, feat_dim, cp, degree, degrees_to_use, means, log_scales, quats,
+                             opacity_logit, v_sh_coeffs, features, viewmats, fullmats, intrins, positions, img_h,
+                             img_w, 1, 1, 0.0f);
+    if (rc != GG_OK) return rc;
+    GG_REQUIRE(geo && chan && radii && v_geo && v_chan, "gg_prepare_views_bwd: null input pointer");
+    GG_REQUIRE(v_means && v_log_scales && v_quats && v_opacity_logit && v_sh_coeffs && (v_features || feat_dim == 0),
+               "gg_prepare_views_bwd: null output pointer");
+    GG_REQUIRE(((uintptr_t)v_quats & 15) == 0 && ((uintptr_t)v_geo & 15) == 0 && ((uintptr_t)v_chan & 15) == 0,
+               "gg_prepare_views_bwd: misaligned");
+    const size_t smem = sizeof(float) * kPrepWarps * 32 * (size_t)(a.nb * 3 + feat_dim);
+    GG_CUDA(cudaFuncSetAttribute(prepare_views_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    prepare_views_bwd_kernel<<<div_up(n, kPrepThreads), kPrepThreads, smem, (cudaStream_t)stream>>>(
+        a, geo, chan, radii, v_geo, v_chan, v_means, v_log_scales, v_quats, v_opacity_logit, v_sh_coeffs, v_features);
+    count_launch();
+    return check_launch("prepare_views_bwd_kernel");
+}

@@ -4,6 +4,8 @@
 #include <stdint.h>
 
 #define GG_TILE 16
+// slack added to tau = ln(255*opacity): pairs with sigma > tau are skipped before the exp
+#define GG_TAU_MARGIN 1e-3f
 #define GG_OK 0
 #define GG_ERR_ARG (-1)
 #define GG_ERR_CHANNELS (-2)

@@ -174,11 +174,11 @@ struct ProjGrad {
 };
 
 // A11 (projection part): exact vector-Jacobian product of project_one for a Gaussian that was
-// not culled.  v_conic is the gradient w.r.t. the stored (A, B, C) triple, B being the single
+// not culled.  v_R_extra (optional, 9 floats) is added to the gradient of the rotation matrix.  v_conic is the gradient w.r.t. the stored (A, B, C) triple, B being the single
 // off-diagonal entry.
 GG_HD ProjGrad project_bwd_one(const float p[3], const float s[3], float glob, const float q[4], const Camera& cam,
                                int img_h, int img_w, const float conic[3], const float v_xy[2], float v_depth,
-                               const float v_conic[3]) {
+                               const float v_conic[3], const float* v_R_extra = nullptr) {
     ProjGrad g;
     const float* vm = cam.vm;
     const float* fm = cam.fm;
@@ -253,6 +253,10 @@ GG_HD ProjGrad project_bwd_one(const float p[3], const float s[3], float glob, c
         g.v_scale[c] = glob * (R.m[c] * vM[c] + R.m[3 + c] * vM[3 + c] + R.m[6 + c] * vM[6 + c]);
 #pragma unroll
         for (int r = 0; r < 3; ++r) vR[3 * r + c] = vM[3 * r + c] * sc[c];
+    }
+    if (v_R_extra) {  // gradient that reaches R directly (the normal channel reads a column of R)
+#pragma unroll
+        for (int k = 0; k < 9; ++k) vR[k] += v_R_extra[k];
     }
     // ---- R -> unit quaternion -> raw quaternion ----
     const float w = q[0] * inv_qn, x = q[1] * inv_qn, y = q[2] * inv_qn, z = q[3] * inv_qn;

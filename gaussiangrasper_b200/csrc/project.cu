@@ -227,9 +227,8 @@ sh_kernel(int n, int nb, int deg_use, const float* __restrict__ dirs, const floa
             float v[3] = {__ldg(in + 3 * i), __ldg(in + 3 * i + 1), __ldg(in + 3 * i + 2)};
             float* cf = slab + lane * row;
             for (int b = 0; b < nb; ++b) {
-                const float yb = b < nuse ? Y[b] : 0.0f;
 #pragma unroll
-                for (int c = 0; c < 3; ++c) cf[3 * b + c] = yb * v[c];
+                for (int c = 0; c < 3; ++c) cf[3 * b + c] = b < nuse ? Y[b] * v[c] : 0.0f;  // unused bands: +0
             }
         }
         __syncwarp();

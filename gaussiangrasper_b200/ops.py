@@ -163,10 +163,10 @@ def key_bits_for(num_tiles_total: int) -> int:
     return 32 + max(1, (max(num_tiles_total, 1) - 1).bit_length())
 
 
-def map_to_intersects(n, n_views, xys, depths, radii, cum, tile_bounds, keys, ids):
+def map_to_intersects(n, n_views, xys, depths, radii, cum, tile_bounds, keys, ids, xy_from_geo=False):
     dev = xys.device
     with torch.cuda.device(dev):
-        _lib.call("gg_map_to_intersects", int(n), int(n_views), ptr(xys), ptr(depths), ptr(radii), ptr(cum),
+        _lib.call("gg_map_to_intersects_geo" if xy_from_geo else "gg_map_to_intersects", int(n), int(n_views), ptr(xys), ptr(depths), ptr(radii), ptr(cum),
                                                int(tile_bounds[0]), int(tile_bounds[1]), ptr(keys), ptr(ids),
                                                stream_ptr(dev))
 
@@ -198,8 +198,9 @@ class Binning:
     tile_bounds: Tuple[int, int, int]
 
 
-def bin_views(n, n_views, xys, depths, radii, num_tiles_hit, tile_bounds) -> Binning:
-    """cumsum -> (one host read of M) -> key emission -> radix sort -> tile ranges."""
+def bin_views(n, n_views, xys, depths, radii, num_tiles_hit, tile_bounds, xy_from_geo=False) -> Binning:
+    """cumsum -> (one host read of M) -> key emission -> radix sort -> tile ranges.
+    xy_from_geo: `xys` is the packed [V*n, 8] geo table (pixel centres in columns 0..1)."""
     dev = require_cuda(xys, depths, radii, num_tiles_hit)
     ws = workspace(dev)
     xys, depths = f32c(xys), f32c(depths)
@@ -212,7 +213,7 @@ def bin_views(n, n_views, xys, depths, radii, num_tiles_hit, tile_bounds) -> Bin
     ids_sorted = torch.empty((max(m, 1),), dtype=torch.int32, device=dev)
     if m > 0:
         keys, ids, keys_sorted = ws.key_buffers(m)
-        map_to_intersects(n, n_views, xys, depths, radii, cum, tile_bounds, keys, ids)
+        map_to_intersects(n, n_views, xys, depths, radii, cum, tile_bounds, keys, ids, xy_from_geo)
         sort_pairs(m, key_bits_for(num_tiles), keys, ids, keys_sorted, ids_sorted)
         ranges = tile_ranges(m, keys_sorted, num_tiles)
     else:

@@ -90,36 +90,75 @@ class _ProjectViews(Function):
         return v_means, v_scales, v_quats, None, None, None, None, None, None
 
 
-class _BlendViews(Function):
+class _RenderViews(Function):
+    """prepare (activations + projection + SH + packing) -> bin -> blend, and the exact backward,
+    as three + two kernel groups with no torch glue in between."""
+
     @staticmethod
-    def forward(ctx, xys, depths, radii, conics, nth, colors, opacity, background, H, W, stats):
-        V, n = xys.shape[0], xys.shape[1]
+    def forward(ctx, means, log_scales, quats, opacity_logit, sh_coeffs, features, views, degrees_to_use,
+                depth_background, clip_thresh, stats, holder):
+        dev = _lib.require_cuda(means, log_scales, quats, opacity_logit, sh_coeffs, features)
+        means, log_scales, quats = ops.f32c(means), ops.f32c(log_scales), ops.f32c(quats)
+        opacity_logit, sh_coeffs, features = ops.f32c(opacity_logit), ops.f32c(sh_coeffs), ops.f32c(features)
+        n, D = means.shape[0], features.shape[1]
+        V, H, W = views.n_views, views.H, views.W
+        degree = ops.sh_degree_from_bases(sh_coeffs.shape[-2])
+        C = 7 + D
+        CP = (C + 3) // 4 * 4
         tb = ops.tile_bounds_for(H, W)
-        binning = ops.bin_views(n, V, xys.detach().reshape(V * n, 2), depths.detach().reshape(-1),
-                                radii.reshape(-1), nth.reshape(-1), tb)
-        geo = ops.pack_geo(n, V, xys.detach().reshape(V * n, 2), conics.detach().reshape(V * n, 3), opacity.detach())
-        colors_c = ops.f32c(colors.detach()).reshape(V * n, -1)
-        background = ops.f32c(background.detach())
-        out, final_T, final_idx = ops.blend_fwd(binning, geo, colors_c, background, H, W, colors_per_view=True,
+        geo = torch.empty((V * n, 8), dtype=torch.float32, device=dev)
+        chan = torch.empty((V * n, CP), dtype=torch.float32, device=dev)
+        depths = torch.empty((V * n,), dtype=torch.float32, device=dev)
+        radii = torch.empty((V * n,), dtype=torch.int32, device=dev)
+        nth = torch.empty((V * n,), dtype=torch.int32, device=dev)
+        dbg = holder.get("debug_activations") if holder is not None else None
+        s_out = torch.empty((n, 3), dtype=torch.float32, device=dev) if dbg else None
+        q_out = torch.empty((n, 4), dtype=torch.float32, device=dev) if dbg else None
+        with torch.cuda.device(dev):
+            _lib.call("gg_prepare_views", n, V, D, CP, degree, int(degrees_to_use), ops.ptr(means), ops.ptr(log_scales),
+                      ops.ptr(quats), ops.ptr(opacity_logit), ops.ptr(sh_coeffs), ops.ptr(features),
+                      ops.ptr(views.viewmats), ops.ptr(views.fullmats), ops.ptr(views.intrins),
+                      ops.ptr(views.positions), H, W, tb[0], tb[1], float(clip_thresh), ops.ptr(geo), ops.ptr(chan),
+                      ops.ptr(depths), ops.ptr(radii), ops.ptr(nth), ops.ptr(s_out), ops.ptr(q_out),
+                      ops.stream_ptr(dev))
+        binning = ops.bin_views(n, V, geo, depths, radii, nth, tb, xy_from_geo=True)
+        bg = torch.zeros(CP, dtype=torch.float32, device=dev)
+        bg[3] = depth_background
+        out, final_T, final_idx = ops.blend_fwd(binning, geo, chan, bg, H, W, colors_per_view=True,
                                                 pair_counter=stats)
-        ctx.binning = binning
-        ctx.size = (int(H), int(W))
-        ctx.opacity_shape = tuple(opacity.shape)
-        ctx.save_for_backward(geo, colors_c, background, final_T, final_idx)
+        ctx.binning, ctx.views, ctx.dims = binning, views, (n, V, D, CP, degree, int(degrees_to_use), H, W)
+        ctx.holder = holder
+        ctx.save_for_backward(means, log_scales, quats, opacity_logit, features, geo, chan, radii, bg, final_T,
+                              final_idx)
+        if holder is not None:
+            holder.update(geo=geo, radii=radii.view(V, n), num_tiles_hit=nth.view(V, n), depths=depths.view(V, n),
+                          binning=binning, scales=s_out, quats=q_out)
         ctx.mark_non_differentiable(final_T)
         return out, final_T
 
     @staticmethod
     def backward(ctx, v_out, _v_T):
-        geo, colors_c, background, final_T, final_idx = ctx.saved_tensors
-        b = ctx.binning
-        H, W = ctx.size
-        v_geo, v_colors = ops.blend_bwd(b, geo, colors_c, background, final_T, final_idx, v_out, H, W,
-                                        colors_per_view=True)
-        v_xys, v_conics, v_opac = ops.unpack_vgeo(b.n, b.n_views, v_geo)
-        V, n = b.n_views, b.n
-        return (v_xys.reshape(V, n, 2), None, None, v_conics.reshape(V, n, 3), None, v_colors.reshape(V, n, -1),
-                v_opac.reshape(ctx.opacity_shape), None, None, None, None)
+        means, log_scales, quats, opacity_logit, features, geo, chan, radii, bg, final_T, final_idx = ctx.saved_tensors
+        n, V, D, CP, degree, deg_use, H, W = ctx.dims
+        views, dev = ctx.views, means.device
+        v_geo, v_chan = ops.blend_bwd(ctx.binning, geo, chan, bg, final_T, final_idx, v_out, H, W,
+                                      colors_per_view=True)
+        nb = (degree + 1) ** 2
+        v_means = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        v_ls = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        v_q = torch.empty((n, 4), dtype=torch.float32, device=dev)
+        v_op = torch.empty((n,), dtype=torch.float32, device=dev)
+        v_sh = torch.empty((n, nb, 3), dtype=torch.float32, device=dev)
+        v_f = torch.empty((n, D), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.call("gg_prepare_views_bwd", n, V, D, CP, degree, deg_use, ops.ptr(means), ops.ptr(log_scales),
+                      ops.ptr(quats), ops.ptr(opacity_logit), ops.ptr(features), ops.ptr(views.viewmats),
+                      ops.ptr(views.fullmats), ops.ptr(views.intrins), ops.ptr(views.positions), H, W, ops.ptr(geo),
+                      ops.ptr(chan), ops.ptr(radii), ops.ptr(v_geo), ops.ptr(v_chan), ops.ptr(v_means), ops.ptr(v_ls),
+                      ops.ptr(v_q), ops.ptr(v_op), ops.ptr(v_sh), ops.ptr(v_f), ops.stream_ptr(dev))
+        if ctx.holder is not None:
+            ctx.holder["v_geo"] = v_geo  # [V*n, 8]: columns 0..1 are d loss / d xys (densification statistic)
+        return (v_means, v_ls, v_q, v_op.reshape(opacity_logit.shape), v_sh, v_f, None, None, None, None, None, None)
 
 
 def smallest_axis_normals(quats: torch.Tensor, log_scales: torch.Tensor) -> torch.Tensor:
@@ -131,37 +170,19 @@ def smallest_axis_normals(quats: torch.Tensor, log_scales: torch.Tensor) -> torc
 
 def render_views(means, log_scales, quats, opacity_logit, sh_coeffs, features, views: ViewBatch,
                  degrees_to_use: int = 4, depth_background: float = 10.0, clip_thresh: float = 0.01,
-                 stats: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+                 stats: Optional[torch.Tensor] = None, holder: Optional[dict] = None) -> Dict[str, torch.Tensor]:
     """Render rgb [V,H,W,3], depth [V,H,W,1], normal [V,H,W,3], feature [V,H,W,D] for V views.
 
     Inputs are the model's raw parameters (gaussian_splatting.py:270-292): log-scales, un-normalised
-    wxyz quaternions, opacity logits, SH coefficients [N,(deg+1)^2,3], features [N,D].
-    Backgrounds follow the model: 0 for rgb/normal/feature, 10 for depth.
-    `xys` (per-view pixel centres, [V,N,2]) is returned as a non-leaf so callers can retain its
-    gradient for densification (gaussian_splatting.py:725,377).
+    wxyz quaternions, opacity logits, SH coefficients [N,(deg+1)^2,3], features [N,D] (D <= 64).
+    Backgrounds follow the model: 0 for rgb/normal/feature, `depth_background` (10) for depth.
+    `holder` (a dict, optional) receives the per-view projection by-products -- packed geo records
+    (pixel centres in columns 0..1), radii, num_tiles_hit, depths, the binning -- and, after
+    backward, `v_geo` whose first two columns are d loss / d xys, the statistic the model's
+    densification reads from `xys.grad` (gaussian_splatting.py:725,377).
     """
-    dev = means.device
-    V, H, W = views.n_views, views.H, views.W
-    n, D = means.shape[0], features.shape[1]
-    scales = torch.exp(log_scales)
-    qn = quats / quats.norm(dim=-1, keepdim=True)
-    opacity = torch.sigmoid(opacity_logit)
-    xys, depths, radii, conics, nth = _ProjectViews.apply(means, scales, qn, views.viewmats, views.fullmats,
-                                                          views.intrins, H, W, clip_thresh)
-    normals = smallest_axis_normals(quats, log_scales)
-    rgbs = []
-    md = means.detach()
-    for v in range(V):
-        dirs = md - views.positions[v]
-        rgbs.append(torch.clamp(SphericalHarmonics.apply(degrees_to_use, dirs, sh_coeffs) + 0.5, 0.0, 1.0))
-    C = 7 + D
-    CP = (C + 3) // 4 * 4
-    parts = [torch.stack(rgbs, 0), depths[..., None], normals[None].expand(V, -1, -1), features[None].expand(V, -1, -1)]
-    if CP > C:
-        parts.append(torch.zeros((V, n, CP - C), dtype=torch.float32, device=dev))
-    colors = torch.cat(parts, dim=-1)
-    bg = torch.zeros(CP, dtype=torch.float32, device=dev)
-    bg[3] = depth_background
-    out, final_T = _BlendViews.apply(xys, depths, radii, conics, nth, colors, opacity, bg, H, W, stats)
+    out, final_T = _RenderViews.apply(means, log_scales, quats, opacity_logit, sh_coeffs, features, views,
+                                      int(degrees_to_use), float(depth_background), float(clip_thresh), stats, holder)
+    D = features.shape[1]
     return dict(rgb=out[..., 0:3], depth=out[..., 3:4], normal=out[..., 4:7], feature=out[..., 7:7 + D],
-                image=out, alpha=1.0 - final_T, xys=xys, radii=radii, num_tiles_hit=nth)
+                image=out, alpha=1.0 - final_T)

@@ -86,6 +86,10 @@ int gg_cumsum(long long n, const int32_t* in, int32_t* out, int32_t* total_dev, 
 int gg_map_to_intersects(int n, int n_views, const float* xys, const float* depths, const int32_t* radii,
                          const int32_t* cum_tiles_hit, int tiles_x, int tiles_y, int64_t* keys, int32_t* ids,
                          void* stream);
+/* same, with the pixel centres read from packed geo records ([V*n,8], x and y first) */
+int gg_map_to_intersects_geo(int n, int n_views, const float* geo, const float* depths, const int32_t* radii,
+                             const int32_t* cum_tiles_hit, int tiles_x, int tiles_y, int64_t* keys, int32_t* ids,
+                             void* stream);
 size_t gg_sort_workspace_bytes(long long m);
 /* stable LSD radix sort of (key, value) pairs on the low `key_bits` bits.  The workspace must be
  * zero-filled once when it is allocated and is then owned by the library between calls (it
@@ -119,6 +123,29 @@ int gg_blend_bwd(int n_views, long long n, int channels, int color_stride, int c
 /* v_geo -> v_xys [V*n,2], v_conics [V*n,3], v_opac [n] (summed over views; nullable) */
 int gg_unpack_vgeo(long long n, int n_views, const float* v_geo, float* v_xys, float* v_conics, float* v_opac,
                    int accumulate_opac, void* stream);
+
+/* ---- fused multi-view preparation (no upstream twin: it fuses what the reference model does in
+ * ~12 separate launches per view, gaussian_splatting.py:699-731, :605-619, :742-780) ------------
+ * Raw model parameters in: log-scales, un-normalised wxyz quats, opacity logits, SH coefficients
+ * [n,(degree+1)^2,3], features [n,D].  Out, per (view, Gaussian): the packed geo record, the
+ * channel row chan[V*n, cp] = {r,g,b (SH+0.5 clamped), depth, normal(3), feature(D), 0-pad},
+ * depths, radii, num_tiles_hit.  cp is a multiple of 4, >= 7 + D.  scales_out [n,3] / quats_out
+ * [n,4] (nullable) receive the activated inputs of the projection (used by the parity tests). */
+int gg_prepare_views(int n, int n_views, int feat_dim, int cp, int degree, int degrees_to_use, const float* means,
+                     const float* log_scales, const float* quats, const float* opacity_logit,
+                     const float* sh_coeffs, const float* features, const float* viewmats, const float* fullmats,
+                     const float* intrins, const float* positions, int img_h, int img_w, int tiles_x, int tiles_y,
+                     float clip_thresh, float* geo, float* chan, float* depths, int32_t* radii,
+                     int32_t* num_tiles_hit, float* scales_out, float* quats_out, void* stream);
+/* exact backward, summed over the views: v_geo [V*n,8] = {v_x, v_y, v_A, v_B, v_C, v_opacity,.,.}
+ * and v_chan [V*n,cp] in; gradients of the raw parameters out (overwritten). */
+int gg_prepare_views_bwd(int n, int n_views, int feat_dim, int cp, int degree, int degrees_to_use,
+                         const float* means, const float* log_scales, const float* quats,
+                         const float* opacity_logit, const float* features, const float* viewmats,
+                         const float* fullmats, const float* intrins, const float* positions, int img_h, int img_w,
+                         const float* geo, const float* chan, const int32_t* radii, const float* v_geo,
+                         const float* v_chan, float* v_means, float* v_log_scales, float* v_quats,
+                         float* v_opacity_logit, float* v_sh_coeffs, float* v_features, void* stream);
 
 #ifdef __cplusplus
 }

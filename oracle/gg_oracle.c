@@ -434,3 +434,50 @@ void gg_oracle_blend_bwd(int n, int channels, int img_h, int img_w, int tiles_x,
     }
     free(S);
 }
+
+/* ------------------------------------------------------------------------- */
+/* Workload statistics for DESIGN.md / bench roofline accounting (not parity). */
+/* stats[0] = pairs visited, stats[1] = pairs that pass the alpha test         */
+/* (contributors), stats[2] = sum over (tile, entry) of warps (16x2 pixel      */
+/* strips) with at least one contributor, stats[3] = entries summed over tiles */
+/* ------------------------------------------------------------------------- */
+void gg_oracle_blend_stats(int img_h, int img_w, int tiles_x, int tiles_y, const int32_t *ids_sorted,
+                           const int32_t *tile_ranges, const float *xys, const float *conics,
+                           const float *opac, int64_t *stats) {
+    int64_t visited = 0, hits = 0, warp_hits = 0, entries = 0;
+    for (int ty = 0; ty < tiles_y; ++ty)
+        for (int tx = 0; tx < tiles_x; ++tx) {
+            const int tile = ty * tiles_x + tx;
+            const int start = tile_ranges[2 * tile], end = tile_ranges[2 * tile + 1];
+            entries += end - start;
+            float T[256];
+            unsigned char done[256];
+            for (int p = 0; p < 256; ++p) {
+                T[p] = 1.0f;
+                const int px = tx * 16 + (p & 15), py = ty * 16 + (p >> 4);
+                done[p] = !(px < img_w && py < img_h);
+            }
+            for (int k = start; k < end; ++k) {
+                const int g = ids_sorted[k];
+                unsigned char warp_hit[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                for (int p = 0; p < 256; ++p) {
+                    if (done[p]) continue;
+                    ++visited;
+                    const float dx = xys[2 * g] - (float)(tx * 16 + (p & 15));
+                    const float dy = xys[2 * g + 1] - (float)(ty * 16 + (p >> 4));
+                    const float sigma = 0.5f * (conics[3 * g] * dx * dx + conics[3 * g + 2] * dy * dy) +
+                                        conics[3 * g + 1] * dx * dy;
+                    if (sigma < 0.0f) continue;
+                    const float alpha = fminf(0.999f, opac[g] * expf(-sigma));
+                    if (alpha < 1.0f / 255.0f) continue;
+                    const float nT = T[p] * (1.0f - alpha);
+                    if (nT <= 1e-4f) { done[p] = 1; continue; }
+                    T[p] = nT;
+                    ++hits;
+                    warp_hit[p >> 5] = 1;
+                }
+                for (int w = 0; w < 8; ++w) warp_hits += warp_hit[w];
+            }
+        }
+    stats[0] = visited; stats[1] = hits; stats[2] = warp_hits; stats[3] = entries;
+}

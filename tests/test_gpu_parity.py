@@ -396,6 +396,68 @@ def test_model_render_end_to_end_gradients(dev):
     grad_close(outs["xys"].grad.cpu().numpy(), ref_grad["xys"].numpy(), "xys.grad", rtol=2e-3)
 
 
+def test_render_views_fused_multi_view(dev):
+    """Fused entry point (prepare -> bin once -> one 7+D channel blend, V views per launch): integer
+    outputs bit-exact against the C oracle fed with the kernel's own activated inputs, images and
+    gradients against fp64 autograd of the oracle summed over the views."""
+    from gaussiangrasper_b200.render import ViewBatch, render_views
+    n, W, H, D, V = 3000, 80, 64, 6, 3
+    sc = scenes.random_scene(n, feature_dim=D, seed=78)
+    sc["log_scales"] = sc["log_scales"] + 0.8
+    cams = scenes.orbit_cameras(V, W, H, total=7)
+    g = torch.Generator().manual_seed(1)
+    v = [dict(rgb=torch.randn((H, W, 3), generator=g), feature=torch.randn((H, W, D), generator=g),
+              depth=torch.randn((H, W, 1), generator=g) * 0.1, normal=torch.randn((H, W, 3), generator=g))
+         for _ in range(V)]
+    P = {k: sc[k].to(dev).clone().requires_grad_(True) for k in
+         ("means", "log_scales", "quats", "opacity_logit", "sh_coeffs", "features")}
+    holder = {"debug_activations": True}
+    out = render_views(P["means"], P["log_scales"], P["quats"], P["opacity_logit"], P["sh_coeffs"], P["features"],
+                       ViewBatch.from_cameras(cams, dev), holder=holder)
+    loss = 0
+    for k in ("rgb", "feature", "depth", "normal"):
+        loss = loss + (out[k] * torch.stack([vv[k] for vv in v]).to(dev)).sum()
+    loss.backward()
+    # activations: 2 ulp of torch's
+    s_k, q_k = holder["scales"].cpu(), holder["quats"].cpu()
+    assert torch.allclose(s_k, sc["log_scales"].exp(), rtol=3e-7, atol=0)
+    assert torch.allclose(q_k, sc["quats"] / sc["quats"].norm(dim=-1, keepdim=True), rtol=0, atol=2e-7)
+    geo = holder["geo"].view(V, n, 8).cpu().numpy()
+    ref_grads = None
+    for i, cam in enumerate(cams):
+        # bit-exact integers / sort for this view given the kernel's activated inputs
+        ref = c_oracle.project_fwd(sc["means"].numpy(), s_k.numpy(), 1.0, q_k.numpy(), cam.viewmat[:3].numpy(),
+                                   cam.fullmat.numpy(), cam.fx, cam.fy, cam.cx, cam.cy, H, W, cam.tile_bounds)
+        assert np.array_equal(holder["radii"][i].cpu().numpy(), ref[2])
+        assert np.array_equal(holder["num_tiles_hit"][i].cpu().numpy(), ref[4])
+        assert holder["depths"][i].cpu().numpy().tobytes() == ref[1].tobytes()
+        assert geo[i, :, :2].tobytes() == ref[0].tobytes()
+        ref_out, grads = oracle_model(sc, cam, v[i])
+        for k in ("rgb", "feature", "depth", "normal"):
+            err = (out[k][i].detach().cpu().double() - ref_out[k].detach()).abs()
+            assert float(torch.quantile(err.flatten(), 0.999)) < 2e-4 * max(1.0, float(ref_out[k].detach().abs().max())), k
+        vxy = holder["v_geo"].view(V, n, 8)[i, :, :2].cpu().numpy()
+        grad_close(vxy, grads.pop("xys").numpy(), f"xys.grad view {i}", rtol=2e-3)
+        ref_grads = grads if ref_grads is None else {k: ref_grads[k] + grads[k] for k in grads}
+    # sorted ids / tile ranges of the whole batch, bit-exact (keys carry view*T + tile)
+    b = holder["binning"]
+    T = cams[0].tile_bounds[0] * cams[0].tile_bounds[1]
+    off = 0
+    for i, cam in enumerate(cams):
+        ref = c_oracle.project_fwd(sc["means"].numpy(), s_k.numpy(), 1.0, q_k.numpy(), cam.viewmat[:3].numpy(),
+                                   cam.fullmat.numpy(), cam.fx, cam.fy, cam.cx, cam.cy, H, W, cam.tile_bounds)
+        _, _, _, _, ids_s, ranges = c_oracle.bin_and_sort(ref[0], ref[1], ref[2], ref[4], cam.tile_bounds)
+        m = len(ids_s)
+        assert np.array_equal(b.ids_sorted[off:off + m].cpu().numpy(), ids_s)
+        got_r = b.tile_ranges[i * T:(i + 1) * T].cpu().numpy()
+        nonempty = ranges[:, 1] > ranges[:, 0]
+        assert np.array_equal(got_r[nonempty], ranges[nonempty] + off) and not got_r[~nonempty].any()
+        off += m
+    assert off == b.num_intersects
+    for k in ("means", "log_scales", "quats", "opacity_logit", "sh_coeffs", "features"):
+        grad_close(P[k].grad.cpu().numpy(), ref_grads[k].numpy(), k, rtol=2e-3)
+
+
 def test_config1_full_size_forward_and_backward(dev):
     """BASELINE config 1 geometry (500k Gaussians, 640x480) at full size against the C oracle:
     RGB+depth+normal+16-ch feature = 23 channels, forward and blend backward."""
