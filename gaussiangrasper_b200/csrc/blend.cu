@@ -68,6 +68,14 @@ __device__ __forceinline__ float eval_sigma(float dx, float dy, float hA, float 
     return __fmaf_rn(dx, u, __fmul_rn(__fmul_rn(hC, dy), dy));
 }
 
+// Thread -> pixel inside the 16x16 tile: every warp owns a compact 8x4 block (2 x 4 blocks per
+// tile), which a Gaussian's footprint either misses entirely or covers with many lanes.
+__device__ __forceinline__ void tile_pixel(int& tx, int& ty) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    tx = (lane & 7) | ((warp & 1) << 3);
+    ty = (lane >> 3) | ((warp >> 1) << 2);
+}
+
 // Stage entries [first, first+cnt) of the sorted list into shared memory.
 template <int CP, int BATCH, bool kVec>
 __device__ __forceinline__ void stage_batch(const BlendArgs& a, long long geo_base, long long color_base, int first,
@@ -104,7 +112,8 @@ blend_fwd_kernel(const BlendArgs a) {
     const int view = blockIdx.y;
     const int tile = blockIdx.x;
     const int tile_y = tile / a.tiles_x, tile_x = tile - tile_y * a.tiles_x;
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    int tx, ty;
+    tile_pixel(tx, ty);
     const int px = tile_x * GG_TILE + tx, py = tile_y * GG_TILE + ty;
     const bool inside = px < a.img_w && py < a.img_h;
     const float fpx = (float)px, fpy = (float)py;
@@ -252,7 +261,8 @@ blend_bwd_kernel(const BlendArgs a) {
     const int view = blockIdx.y;
     const int tile = blockIdx.x;
     const int tile_y = tile / a.tiles_x, tile_x = tile - tile_y * a.tiles_x;
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    int tx, ty;
+    tile_pixel(tx, ty);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int px = tile_x * GG_TILE + tx, py = tile_y * GG_TILE + ty;
     const bool inside = px < a.img_w && py < a.img_h;
@@ -265,11 +275,11 @@ blend_bwd_kernel(const BlendArgs a) {
     // padding lanes of the staged colour rows are read by the gradient sums: keep them finite
     for (int k = threadIdx.x; k < 2 * BATCH * CP; k += kBlendThreads) col_sm[k] = 0.0f;
 
-    float vo[CP], S[CP];
+    float vo[CP];
     float T_final = 1.0f, bgdot = 0.0f;
     int last = range.x;
 #pragma unroll
-    for (int c = 0; c < CP; ++c) { vo[c] = 0.0f; S[c] = 0.0f; }
+    for (int c = 0; c < CP; ++c) vo[c] = 0.0f;
     if (inside) {
         T_final = a.final_T[pix];
         last = a.final_idx[pix];
@@ -279,6 +289,9 @@ blend_bwd_kernel(const BlendArgs a) {
             if (c < a.channels) { vo[c] = __ldg(v + c); bgdot = fmaf(__ldg(a.bg + c), vo[c], bgdot); }
     }
     float T = T_final;
+    // R = T_final * <bg, v_out> + sum over the entries behind the current one of fac * <colour, v_out>:
+    // the only state the alpha gradient needs from "behind" (replaces C running colour sums)
+    float R = T_final * bgdot;
     // tile-wide last contributing index
     int wmax = last;
 #pragma unroll
@@ -316,13 +329,11 @@ blend_bwd_kernel(const BlendArgs a) {
             const float4 ga = g4[2 * e], gb = g4[2 * e + 1];
             const float dx = ga.x - fpx, dy = ga.y - fpy;
             const float sigma = eval_sigma(dx, dy, ga.z, ga.w, gb.x);
-            bool valid = (first + e < last) && !(sigma < 0.0f || sigma > gb.z);
-            float vis = 0.0f, alpha = 0.0f;
-            if (valid) {
-                vis = __expf(-sigma);
-                alpha = fminf(kAlphaMax, gb.y * vis);
-                valid = alpha >= kAlphaMin;
-            }
+            // branch-free replay of the forward test (same arithmetic as blend_fwd_kernel)
+            const float vis = __expf(-sigma);
+            const float araw = gb.y * vis;
+            const float alpha = fminf(kAlphaMax, araw);
+            const bool valid = (first + e < last) && !(sigma < 0.0f || sigma > gb.z) && (alpha >= kAlphaMin);
             if (!__any_sync(0xffffffffu, valid)) continue;
             constexpr int NV0 = (CP + 6 <= 32) ? next_pow2(CP + 6) : 32;  // first tree: 6 geo + channels
             constexpr int C0 = (CP + 6 <= 32) ? CP : 26;                  // channels carried by tree 0
@@ -334,21 +345,18 @@ blend_bwd_kernel(const BlendArgs a) {
                 const float ra = 1.0f / (1.0f - alpha);
                 T *= ra;  // transmittance in front of this entry
                 fac = alpha * T;
-                float v_alpha = 0.0f;
+                float dot = 0.0f;
 #pragma unroll
                 for (int q = 0; q < CP / 4; ++q) {
                     const float4 cc = c4[e * (CP / 4) + q];
-                    const float col[4] = {cc.x, cc.y, cc.z, cc.w};
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int c = 4 * q + k;
-                        v_alpha = fmaf(fmaf(col[k], T, -S[c] * ra), vo[c], v_alpha);
-                        S[c] = fmaf(col[k], fac, S[c]);
-                    }
+                    dot = fmaf(cc.x, vo[4 * q], dot);
+                    dot = fmaf(cc.y, vo[4 * q + 1], dot);
+                    dot = fmaf(cc.z, vo[4 * q + 2], dot);
+                    dot = fmaf(cc.w, vo[4 * q + 3], dot);
                 }
-                v_alpha = fmaf(-T_final * ra, bgdot, v_alpha);
-                const bool clamped = gb.y * vis > kAlphaMax;
-                if (!clamped) {
+                const float v_alpha = fmaf(dot, T, -R * ra);
+                R = fmaf(fac, dot, R);
+                if (araw <= kAlphaMax) {  // a clamped alpha passes no gradient to sigma / opacity
                     const float v_sigma = -alpha * v_alpha;
                     // conic as stored by the caller is (A, B, C); geo holds (A/2, B, C/2)
                     r[0] = v_sigma * fmaf(2.0f * ga.z, dx, ga.w * dy);
