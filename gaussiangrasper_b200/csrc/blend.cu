@@ -4,7 +4,7 @@
 // nerfstudio/models/gaussian_splatting.py:735,747,759,773).
 //
 // Data layout: the per-Gaussian 2D geometry is consumed as packed 32-byte records
-//   geo[g] = { x, y, A/2, B, C/2, opacity, tau, 0 }      (one DRAM sector per gather)
+//   geo[g] = { x, y, A/2, B, C/2, opacity, tau, rcut2 }  (one DRAM sector per gather)
 // where (A,B,C) is the conic and tau = ln(255*opacity) + margin is the largest sigma for which
 // alpha = opacity*exp(-sigma) can still reach 1/255 (pairs beyond it are skipped before the
 // exp; pairs inside the margin still take the exact alpha test, so results are unchanged).
@@ -16,6 +16,7 @@
 // 32x5) after which lane l owns component l and issues a single red.global.add -- one atomic
 // per warp per component instead of one per pixel.
 #include "gg_common.cuh"
+#include "gg_geo.cuh"
 #include "gg_b200.h"
 
 namespace gg {
@@ -24,7 +25,7 @@ constexpr int kBlendThreads = 256;
 constexpr float kAlphaMin = 1.0f / 255.0f;
 constexpr float kAlphaMax = 0.999f;
 constexpr float kTStop = 1e-4f;
-constexpr float kTauMargin = GG_TAU_MARGIN;
+
 
 struct BlendArgs {
     int channels;        // real channel count handled by this launch (<= CP)
@@ -103,6 +104,28 @@ __device__ __forceinline__ void stage_batch(const BlendArgs& a, long long geo_ba
     }
 }
 
+// Conservative per-warp culling of a staged batch: lane l tests entries l, l+32, ... against the
+// warp's 8x4 pixel rectangle using geo[7] = rcut2, a bound on the squared distance at which the
+// Gaussian can still reach alpha >= 1/255 (sigma >= lambda_min(Q)/2 * d^2).  Entries that fail
+// would be skipped by the per-pixel test anyway, so results are unchanged; only their cost goes.
+template <int BATCH>
+__device__ __forceinline__ void cull_batch(const float* __restrict__ geo_buf, int cnt, float rx0, float ry0,
+                                           float rx1, float ry1, unsigned (&mask)[BATCH / 32]) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < BATCH / 32; ++k) {
+        const int e = k * 32 + lane;
+        bool pass = false;
+        if (e < cnt) {
+            const float gx = geo_buf[e * 8], gy = geo_buf[e * 8 + 1], rc = geo_buf[e * 8 + 7];
+            const float ddx = fmaxf(fmaxf(rx0 - gx, gx - rx1), 0.0f);
+            const float ddy = fmaxf(fmaxf(ry0 - gy, gy - ry1), 0.0f);
+            pass = ddx * ddx + ddy * ddy <= rc;
+        }
+        mask[k] = __ballot_sync(0xffffffffu, pass);
+    }
+}
+
 template <int CP, int BATCH, bool kVec>
 __global__ void __launch_bounds__(kBlendThreads)
 blend_fwd_kernel(const BlendArgs a) {
@@ -114,9 +137,12 @@ blend_fwd_kernel(const BlendArgs a) {
     const int tile_y = tile / a.tiles_x, tile_x = tile - tile_y * a.tiles_x;
     int tx, ty;
     tile_pixel(tx, ty);
+    const int warp = threadIdx.x >> 5;
     const int px = tile_x * GG_TILE + tx, py = tile_y * GG_TILE + ty;
     const bool inside = px < a.img_w && py < a.img_h;
     const float fpx = (float)px, fpy = (float)py;
+    const float rx0 = (float)(tile_x * GG_TILE + ((warp & 1) << 3)), ry0 = (float)(tile_y * GG_TILE + ((warp >> 1) << 2));
+    const float rx1 = rx0 + 7.0f, ry1 = ry0 + 3.0f;
     const int2 range = __ldg(reinterpret_cast<const int2*>(a.tile_ranges) + (long long)view * a.tiles_x * a.tiles_y + tile);
     const long long geo_base = (long long)view * a.geo_view_stride;
     const long long color_base = (long long)view * a.color_view_stride;
@@ -126,8 +152,9 @@ blend_fwd_kernel(const BlendArgs a) {
     for (int c = 0; c < CP; ++c) acc[c] = 0.0f;
     float T = 1.0f;
     int last = range.x;
+    int stop = range.y;  // one past the last entry this pixel looked at
     bool done = !inside;
-    long long n_vis = 0;
+    bool warp_done = __all_sync(0xffffffffu, done);
 
     const int total = range.y - range.x;
     const int nb = (total + BATCH - 1) / BATCH;
@@ -149,34 +176,43 @@ blend_fwd_kernel(const BlendArgs a) {
         __syncthreads();
         const int first = range.x + b * BATCH;
         const int cnt = min(BATCH, range.y - first);
-        if (!done) {
-            const float4* g4 = reinterpret_cast<const float4*>(geo_sm + buf * BATCH * 8);
+        if (!warp_done) {
+            const float* gbuf = geo_sm + buf * BATCH * 8;
+            const float4* g4 = reinterpret_cast<const float4*>(gbuf);
             const float4* c4 = reinterpret_cast<const float4*>(col_sm + buf * BATCH * CP);
-            int e_end = cnt;
-            for (int e = 0; e < cnt; ++e) {
-                const float4 ga = g4[2 * e], gb = g4[2 * e + 1];
-                const float dx = ga.x - fpx, dy = ga.y - fpy;
-                const float sigma = eval_sigma(dx, dy, ga.z, ga.w, gb.x);
-                if (sigma < 0.0f || sigma > gb.z) continue;
-                const float alpha = fminf(kAlphaMax, gb.y * __expf(-sigma));
-                if (alpha < kAlphaMin) continue;
-                const float next_T = T * (1.0f - alpha);
-                if (next_T <= kTStop) { done = true; e_end = e + 1; break; }
-                const float vis = alpha * T;
+            unsigned mask[BATCH / 32];
+            cull_batch<BATCH>(gbuf, cnt, rx0, ry0, rx1, ry1, mask);
 #pragma unroll
-                for (int q = 0; q < CP / 4; ++q) {
-                    const float4 cc = c4[e * (CP / 4) + q];
-                    acc[4 * q] = fmaf(vis, cc.x, acc[4 * q]);
-                    acc[4 * q + 1] = fmaf(vis, cc.y, acc[4 * q + 1]);
-                    acc[4 * q + 2] = fmaf(vis, cc.z, acc[4 * q + 2]);
-                    acc[4 * q + 3] = fmaf(vis, cc.w, acc[4 * q + 3]);
+            for (int k = 0; k < BATCH / 32; ++k) {
+                unsigned m = mask[k];
+                while (m) {
+                    const int e = k * 32 + __ffs(m) - 1;
+                    m &= m - 1;
+                    if (done) continue;
+                    const float4 ga = g4[2 * e], gb = g4[2 * e + 1];
+                    const float dx = ga.x - fpx, dy = ga.y - fpy;
+                    const float sigma = eval_sigma(dx, dy, ga.z, ga.w, gb.x);
+                    if (sigma < 0.0f || sigma > gb.z) continue;
+                    const float alpha = fminf(kAlphaMax, gb.y * __expf(-sigma));
+                    if (alpha < kAlphaMin) continue;
+                    const float next_T = T * (1.0f - alpha);
+                    if (next_T <= kTStop) { done = true; stop = first + e + 1; continue; }
+                    const float vis = alpha * T;
+#pragma unroll
+                    for (int q = 0; q < CP / 4; ++q) {
+                        const float4 cc = c4[e * (CP / 4) + q];
+                        acc[4 * q] = fmaf(vis, cc.x, acc[4 * q]);
+                        acc[4 * q + 1] = fmaf(vis, cc.y, acc[4 * q + 1]);
+                        acc[4 * q + 2] = fmaf(vis, cc.z, acc[4 * q + 2]);
+                        acc[4 * q + 3] = fmaf(vis, cc.w, acc[4 * q + 3]);
+                    }
+                    T = next_T;
+                    last = first + e + 1;
                 }
-                T = next_T;
-                last = first + e + 1;
+                if (__all_sync(0xffffffffu, done)) { warp_done = true; break; }
             }
-            n_vis += e_end;
         }
-        if (__syncthreads_count(done) == kBlendThreads) break;
+        if (__syncthreads_count(warp_done) == kBlendThreads) break;
     }
     cp_async_wait<0>();
     if (inside) {
@@ -189,6 +225,8 @@ blend_fwd_kernel(const BlendArgs a) {
         a.final_idx[pix] = last;
     }
     if (a.pair_counter) {
+        // K of SURVEY 8d: entries between the tile's start and the last one this pixel looked at
+        long long n_vis = inside ? (long long)(stop - range.x) : 0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) n_vis += __shfl_xor_sync(0xffffffffu, n_vis, o);
         if ((threadIdx.x & 31) == 0 && n_vis) atomicAdd(a.pair_counter, (unsigned long long)n_vis);
@@ -196,67 +234,34 @@ blend_fwd_kernel(const BlendArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Transposed warp reduction: v holds NV (power of two <= 32) per-lane partials; on return v[0]
-// is the warp total of component (lane >> log2(32/NV)).
+// Backward.  Per warp (8x4 pixels), back to front over the culled entries of the tile:
+//   phase A (lane = pixel): replay alpha, T; the alpha gradient needs from "behind" only the scalar
+//     R = T_final*<bg,v> + sum_behind fac*<colour,v>; each entry with a contributor stores two
+//     scalars per pixel in a warp-private shared-memory matrix: fac = alpha*T_front and
+//     w = e^{-sigma} * dL/dalpha (0 when alpha is clamped);
+//   phase B (lane = entry, every 32 stored entries): lane e walks the 32 pixels and accumulates
+//     v_colour[c] = sum_p fac[p]*v_out[p][c] (v_out rows broadcast from shared memory) and the six
+//     moments sum_p w*{1,dx,dy,dx^2,dxdy,dy^2} from which v_xy, v_conic, v_opacity follow; then one
+//     red.global.add per component.
+// No cross-lane shuffle reduction and no per-pixel atomics: the transposition through shared
+// memory turns the per-Gaussian reduction into register accumulation at full lane occupancy.
 // ---------------------------------------------------------------------------------------------
-template <int N, int OFF>
-struct TreeReduce {
-    template <int NV>
-    static __device__ __forceinline__ void run(float (&v)[NV], int lane) {
-        if constexpr (N > 1) {
-            constexpr int H = N / 2;
-            const bool up = (lane & OFF) != 0;
-#pragma unroll
-            for (int i = 0; i < H; ++i) {
-                const float send = up ? v[i] : v[i + H];
-                const float keep = up ? v[i + H] : v[i];
-                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
-            }
-            if constexpr (OFF > 1) TreeReduce<H, OFF / 2>::run(v, lane);
-        } else {
-            v[0] += __shfl_xor_sync(0xffffffffu, v[0], OFF);
-            if constexpr (OFF > 1) TreeReduce<1, OFF / 2>::run(v, lane);
-        }
-    }
-};
+constexpr int kHitRow = 33;                                  // padded row: conflict-free both ways
+constexpr int kWarpScratch = 2 * 32 * kHitRow + 32;          // facm, wm, hit ids (floats)
 
-__host__ __device__ constexpr int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
-
-// Reduce NREAL (<=32) values across the warp and add component k to dst(k) with one red per
-// component.  `addr(k)` returns the destination of component k (nullptr to skip).
-template <int NREAL, typename AddrFn>
-__device__ __forceinline__ void reduce_and_add(float (&v)[next_pow2(NREAL)], int lane, AddrFn addr) {
-    constexpr int NV = next_pow2(NREAL);
-    constexpr int REP = 32 / NV;  // lanes holding the same component
-    TreeReduce<NV, 16>::run(v, lane);
-    const int comp = lane / REP;
-    if ((lane % REP) == 0 && comp < NREAL) {
-        float* p = addr(comp);
-        if (p && v[0] != 0.0f) atomicAdd(p, v[0]);
-    }
-}
-
-// channels [START, CP) of the colour gradient, 32 per tree
-template <int START, int CP>
-__device__ __forceinline__ void reduce_rest(const float (&vo)[CP], float fac, int lane, float* vc, int nch) {
-    if constexpr (START < CP) {
-        constexpr int CNT = (CP - START) >= 32 ? 32 : (CP - START);
-        constexpr int NV = next_pow2(CNT);
-        float r2[NV];
-#pragma unroll
-        for (int k = 0; k < NV; ++k) r2[k] = (k < CNT) ? fac * vo[k < CNT ? START + k : START] : 0.0f;
-        reduce_and_add<CNT>(r2, lane, [&](int k) -> float* { return START + k < nch ? vc + START + k : nullptr; });
-        reduce_rest<START + CNT, CP>(vo, fac, lane, vc, nch);
-    }
+template <int CP, int BATCH>
+constexpr size_t blend_bwd_smem() {
+    return sizeof(float) * (2 * BATCH * (8 + CP) + 2 * BATCH + kBlendThreads * CP + (kBlendThreads / 32) * kWarpScratch);
 }
 
 template <int CP, int BATCH, bool kVec>
 __global__ void __launch_bounds__(kBlendThreads)
 blend_bwd_kernel(const BlendArgs a) {
     extern __shared__ __align__(16) float smem[];
-    float* geo_sm = smem;
-    float* col_sm = smem + 2 * BATCH * 8;
-    int* ids_sm = reinterpret_cast<int*>(smem + 2 * BATCH * (8 + CP));  // [2][BATCH]
+    float* geo_sm = smem;                                                  // [2][BATCH][8]
+    float* col_sm = geo_sm + 2 * BATCH * 8;                                // [2][BATCH][CP]
+    int* ids_sm = reinterpret_cast<int*>(col_sm + 2 * BATCH * CP);         // [2][BATCH]
+    float* vo_sm = reinterpret_cast<float*>(ids_sm + 2 * BATCH);           // [256][CP]
     __shared__ int s_max[kBlendThreads / 32];
     const int view = blockIdx.y;
     const int tile = blockIdx.x;
@@ -264,15 +269,20 @@ blend_bwd_kernel(const BlendArgs a) {
     int tx, ty;
     tile_pixel(tx, ty);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* facm = vo_sm + kBlendThreads * CP + warp * kWarpScratch;        // [32][33]
+    float* wm = facm + 32 * kHitRow;                                       // [32][33]
+    int* hit_g = reinterpret_cast<int*>(wm + 32 * kHitRow);                // [32]
     const int px = tile_x * GG_TILE + tx, py = tile_y * GG_TILE + ty;
     const bool inside = px < a.img_w && py < a.img_h;
     const float fpx = (float)px, fpy = (float)py;
+    const float rx0 = (float)(tile_x * GG_TILE + ((warp & 1) << 3)), ry0 = (float)(tile_y * GG_TILE + ((warp >> 1) << 2));
+    const float rx1 = rx0 + 7.0f, ry1 = ry0 + 3.0f;
     const int2 range = __ldg(reinterpret_cast<const int2*>(a.tile_ranges) + (long long)view * a.tiles_x * a.tiles_y + tile);
     const long long geo_base = (long long)view * a.geo_view_stride;
     const long long color_base = (long long)view * a.color_view_stride;
     const long long pix = ((long long)view * a.img_h + py) * a.img_w + px;
 
-    // padding lanes of the staged colour rows are read by the gradient sums: keep them finite
+    // padding lanes of the staged colour rows are read by the dot product: keep them finite
     for (int k = threadIdx.x; k < 2 * BATCH * CP; k += kBlendThreads) col_sm[k] = 0.0f;
 
     float vo[CP];
@@ -288,11 +298,13 @@ blend_bwd_kernel(const BlendArgs a) {
         for (int c = 0; c < CP; ++c)
             if (c < a.channels) { vo[c] = __ldg(v + c); bgdot = fmaf(__ldg(a.bg + c), vo[c], bgdot); }
     }
+    {
+        float4* row = reinterpret_cast<float4*>(vo_sm + threadIdx.x * CP);
+#pragma unroll
+        for (int q = 0; q < CP / 4; ++q) row[q] = make_float4(vo[4 * q], vo[4 * q + 1], vo[4 * q + 2], vo[4 * q + 3]);
+    }
     float T = T_final;
-    // R = T_final * <bg, v_out> + sum over the entries behind the current one of fac * <colour, v_out>:
-    // the only state the alpha gradient needs from "behind" (replaces C running colour sums)
     float R = T_final * bgdot;
-    // tile-wide last contributing index
     int wmax = last;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
@@ -304,6 +316,60 @@ blend_bwd_kernel(const BlendArgs a) {
     const int total = bmax - range.x;
     const int nb = (total + BATCH - 1) / BATCH;
     if (nb == 0) return;
+
+    const float* vo_warp = vo_sm + warp * 32 * CP;
+    int nhit = 0;
+    // phase B: lane = stored entry; sums over the warp's 32 pixels, then one red per component
+    auto flush = [&](int count) {
+        __syncwarp();
+        const bool live = lane < count;
+        const int g = live ? hit_g[lane] : 0;
+        float4 ga = make_float4(0.f, 0.f, 0.f, 0.f), gb = ga;
+        if (live) {
+            ga = __ldg(reinterpret_cast<const float4*>(a.geo) + 2 * (geo_base + g));
+            gb = __ldg(reinterpret_cast<const float4*>(a.geo) + 2 * (geo_base + g) + 1);
+        }
+        float acc[CP];
+#pragma unroll
+        for (int c = 0; c < CP; ++c) acc[c] = 0.0f;
+        float m0 = 0.f, mx = 0.f, my = 0.f, mxx = 0.f, mxy = 0.f, myy = 0.f;
+        const float* fr = facm + lane * kHitRow;
+        const float* wr = wm + lane * kHitRow;
+        const float bx = ga.x - rx0, by = ga.y - ry0;
+#pragma unroll 4
+        for (int p = 0; p < 32; ++p) {
+            const float f = live ? fr[p] : 0.0f;
+            const float wv = live ? wr[p] : 0.0f;
+            const float4* vrow = reinterpret_cast<const float4*>(vo_warp + p * CP);
+#pragma unroll
+            for (int q = 0; q < CP / 4; ++q) {
+                const float4 v = vrow[q];
+                acc[4 * q] = fmaf(f, v.x, acc[4 * q]);
+                acc[4 * q + 1] = fmaf(f, v.y, acc[4 * q + 1]);
+                acc[4 * q + 2] = fmaf(f, v.z, acc[4 * q + 2]);
+                acc[4 * q + 3] = fmaf(f, v.w, acc[4 * q + 3]);
+            }
+            const float dx = bx - (float)(p & 7), dy = by - (float)(p >> 3);
+            const float wdx = wv * dx, wdy = wv * dy;
+            m0 += wv; mx += wdx; my += wdy;
+            mxx = fmaf(wdx, dx, mxx); mxy = fmaf(wdx, dy, mxy); myy = fmaf(wdy, dy, myy);
+        }
+        if (live) {
+            const float o = gb.y, A = 2.0f * ga.z, B = ga.w, C = 2.0f * gb.x;
+            float* vg = a.v_geo + (geo_base + g) * 8;
+            atomicAdd(vg + 0, -o * fmaf(A, mx, B * my));
+            atomicAdd(vg + 1, -o * fmaf(B, mx, C * my));
+            atomicAdd(vg + 2, -0.5f * o * mxx);
+            atomicAdd(vg + 3, -o * mxy);
+            atomicAdd(vg + 4, -0.5f * o * myy);
+            atomicAdd(vg + 5, m0);
+            float* vc = a.v_colors + (color_base + g) * (long long)a.color_stride;
+#pragma unroll
+            for (int c = 0; c < CP; ++c)
+                if (c < a.channels) atomicAdd(vc + c, acc[c]);
+        }
+        __syncwarp();
+    };
 
     auto stage = [&](int b, int buf) {
         const int first = range.x + b * BATCH;
@@ -320,69 +386,63 @@ blend_bwd_kernel(const BlendArgs a) {
         __syncthreads();
         const int first = range.x + b * BATCH;
         const int cnt = min(BATCH, bmax - first);
-        const float4* g4 = reinterpret_cast<const float4*>(geo_sm + buf * BATCH * 8);
-        const float4* c4 = reinterpret_cast<const float4*>(col_sm + buf * BATCH * CP);
-        const int* idb = ids_sm + buf * BATCH;
         // entries at or beyond the warp's own last contributor are dead for the whole warp
         const int e_hi = min(cnt, wmax - first);
-        for (int e = e_hi - 1; e >= 0; --e) {
-            const float4 ga = g4[2 * e], gb = g4[2 * e + 1];
-            const float dx = ga.x - fpx, dy = ga.y - fpy;
-            const float sigma = eval_sigma(dx, dy, ga.z, ga.w, gb.x);
-            // branch-free replay of the forward test (same arithmetic as blend_fwd_kernel)
-            const float vis = __expf(-sigma);
-            const float araw = gb.y * vis;
-            const float alpha = fminf(kAlphaMax, araw);
-            const bool valid = (first + e < last) && !(sigma < 0.0f || sigma > gb.z) && (alpha >= kAlphaMin);
-            if (!__any_sync(0xffffffffu, valid)) continue;
-            constexpr int NV0 = (CP + 6 <= 32) ? next_pow2(CP + 6) : 32;  // first tree: 6 geo + channels
-            constexpr int C0 = (CP + 6 <= 32) ? CP : 26;                  // channels carried by tree 0
-            float r[NV0];
+        if (e_hi > 0) {
+            const float* gbuf = geo_sm + buf * BATCH * 8;
+            const float4* g4 = reinterpret_cast<const float4*>(gbuf);
+            const float4* c4 = reinterpret_cast<const float4*>(col_sm + buf * BATCH * CP);
+            const int* idb = ids_sm + buf * BATCH;
+            unsigned mask[BATCH / 32];
+            cull_batch<BATCH>(gbuf, e_hi, rx0, ry0, rx1, ry1, mask);
 #pragma unroll
-            for (int k = 0; k < NV0; ++k) r[k] = 0.0f;
-            float fac = 0.0f;
-            if (valid) {
-                const float ra = 1.0f / (1.0f - alpha);
-                T *= ra;  // transmittance in front of this entry
-                fac = alpha * T;
-                float dot = 0.0f;
+            for (int k = BATCH / 32 - 1; k >= 0; --k) {
+                unsigned m = mask[k];
+                while (m) {
+                    const int bit = 31 - __clz(m);
+                    m &= ~(1u << bit);
+                    const int e = k * 32 + bit;
+                    const float4 ga = g4[2 * e], gb = g4[2 * e + 1];
+                    const float dx = ga.x - fpx, dy = ga.y - fpy;
+                    const float sigma = eval_sigma(dx, dy, ga.z, ga.w, gb.x);
+                    // branch-free replay of the forward test (same arithmetic as blend_fwd_kernel)
+                    const float vis = __expf(-sigma);
+                    const float araw = gb.y * vis;
+                    const float alpha = fminf(kAlphaMax, araw);
+                    const bool valid = (first + e < last) && !(sigma < 0.0f || sigma > gb.z) && (alpha >= kAlphaMin);
+                    if (!__any_sync(0xffffffffu, valid)) continue;
+                    float fac = 0.0f, w = 0.0f;
+                    if (valid) {
+                        const float ra = 1.0f / (1.0f - alpha);
+                        T *= ra;  // transmittance in front of this entry
+                        fac = alpha * T;
+                        float dot = 0.0f;
 #pragma unroll
-                for (int q = 0; q < CP / 4; ++q) {
-                    const float4 cc = c4[e * (CP / 4) + q];
-                    dot = fmaf(cc.x, vo[4 * q], dot);
-                    dot = fmaf(cc.y, vo[4 * q + 1], dot);
-                    dot = fmaf(cc.z, vo[4 * q + 2], dot);
-                    dot = fmaf(cc.w, vo[4 * q + 3], dot);
-                }
-                const float v_alpha = fmaf(dot, T, -R * ra);
-                R = fmaf(fac, dot, R);
-                if (araw <= kAlphaMax) {  // a clamped alpha passes no gradient to sigma / opacity
-                    const float v_sigma = -alpha * v_alpha;
-                    // conic as stored by the caller is (A, B, C); geo holds (A/2, B, C/2)
-                    r[0] = v_sigma * fmaf(2.0f * ga.z, dx, ga.w * dy);
-                    r[1] = v_sigma * fmaf(ga.w, dx, 2.0f * gb.x * dy);
-                    r[2] = 0.5f * v_sigma * dx * dx;
-                    r[3] = v_sigma * dx * dy;
-                    r[4] = 0.5f * v_sigma * dy * dy;
-                    r[5] = vis * v_alpha;
+                        for (int q = 0; q < CP / 4; ++q) {
+                            const float4 cc = c4[e * (CP / 4) + q];
+                            dot = fmaf(cc.x, vo[4 * q], dot);
+                            dot = fmaf(cc.y, vo[4 * q + 1], dot);
+                            dot = fmaf(cc.z, vo[4 * q + 2], dot);
+                            dot = fmaf(cc.w, vo[4 * q + 3], dot);
+                        }
+                        const float v_alpha = fmaf(dot, T, -R * ra);
+                        R = fmaf(fac, dot, R);
+                        // a clamped alpha passes no gradient to sigma / opacity
+                        w = (araw <= kAlphaMax) ? vis * v_alpha : 0.0f;
+                    }
+                    facm[nhit * kHitRow + lane] = fac;
+                    wm[nhit * kHitRow + lane] = w;
+                    if (lane == 0) hit_g[nhit] = idb[e];
+                    if (++nhit == 32) { flush(32); nhit = 0; }
                 }
             }
-#pragma unroll
-            for (int c = 0; c < C0; ++c) r[6 + c] = fac * vo[c];
-            const int g = idb[e];
-            float* vg = a.v_geo + (geo_base + g) * 8;
-            float* vc = a.v_colors + (color_base + g) * (long long)a.color_stride;
-            const int nch = a.channels;
-            reduce_and_add<C0 + 6>(r, lane, [&](int k) -> float* {
-                return k < 6 ? vg + k : (k - 6 < nch ? vc + (k - 6) : nullptr);
-            });
-            reduce_rest<C0, CP>(vo, fac, lane, vc, nch);
         }
         __syncthreads();
     }
+    if (nhit) flush(nhit);
 }
 
-// geo[g] = {x, y, A/2, B, C/2, o, tau, 0};  one thread per row
+// geo[g] = {x, y, A/2, B, C/2, o, tau, rcut2};  one thread per row
 __global__ void __launch_bounds__(256)
 pack_geo_kernel(long long rows, long long n, const float* __restrict__ xys, const float* __restrict__ conics,
                 const float* __restrict__ opac, int opac_per_view, float* __restrict__ geo) {
@@ -391,10 +451,11 @@ pack_geo_kernel(long long rows, long long n, const float* __restrict__ xys, cons
     const float2 c = __ldg(reinterpret_cast<const float2*>(xys) + i);
     const float A = __ldg(conics + 3 * i), B = __ldg(conics + 3 * i + 1), C = __ldg(conics + 3 * i + 2);
     const float o = __ldg(opac + (opac_per_view ? i : i % n));
-    const float tau = (o * 255.0f > 1.0f) ? __logf(o * 255.0f) + kTauMargin : -1.0f;
+    float tau, rcut2;
+    geo_tau_rcut(o, A, B, C, tau, rcut2);
     float4* dst = reinterpret_cast<float4*>(geo) + 2 * i;
     dst[0] = make_float4(c.x, c.y, 0.5f * A, B);
-    dst[1] = make_float4(0.5f * C, o, tau, 0.0f);
+    dst[1] = make_float4(0.5f * C, o, tau, rcut2);
 }
 
 // v_geo[V*N, 8] -> v_xys [V*N,2], v_conics [V*N,3] (per view) and v_opac [N] (summed over views)
@@ -416,19 +477,32 @@ unpack_vgeo_kernel(long long n, int n_views, const float* __restrict__ v_geo, fl
 }
 
 template <int CP, int BATCH>
-static int launch_blend(bool backward, const BlendArgs& a, int n_views, bool vec, cudaStream_t st) {
+static int launch_blend_impl(bool backward, const BlendArgs& a, int n_views, bool vec, cudaStream_t st) {
     dim3 grid(a.tiles_x * a.tiles_y, n_views);
     size_t smem = sizeof(float) * 2 * BATCH * (8 + CP);
-    if (backward) smem += sizeof(int) * 2 * BATCH;
     if (backward) {
-        if (vec) blend_bwd_kernel<CP, BATCH, true><<<grid, kBlendThreads, smem, st>>>(a);
-        else blend_bwd_kernel<CP, BATCH, false><<<grid, kBlendThreads, smem, st>>>(a);
+        smem = blend_bwd_smem<CP, BATCH>();
+        if (vec) {
+            GG_CUDA(cudaFuncSetAttribute(blend_bwd_kernel<CP, BATCH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            blend_bwd_kernel<CP, BATCH, true><<<grid, kBlendThreads, smem, st>>>(a);
+        } else {
+            GG_CUDA(cudaFuncSetAttribute(blend_bwd_kernel<CP, BATCH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            blend_bwd_kernel<CP, BATCH, false><<<grid, kBlendThreads, smem, st>>>(a);
+        }
     } else {
         if (vec) blend_fwd_kernel<CP, BATCH, true><<<grid, kBlendThreads, smem, st>>>(a);
         else blend_fwd_kernel<CP, BATCH, false><<<grid, kBlendThreads, smem, st>>>(a);
     }
     count_launch();
     return check_launch(backward ? "blend_bwd_kernel" : "blend_fwd_kernel");
+}
+
+// forward stages BATCH entries per round; the backward also keeps v_out and the per-warp hit
+// matrices in shared memory, so it stages 64
+template <int CP, int BATCH>
+static int launch_blend(bool backward, const BlendArgs& a, int n_views, bool vec, cudaStream_t st) {
+    if (backward) return launch_blend_impl<CP, 64>(true, a, n_views, vec, st);
+    return launch_blend_impl<CP, BATCH>(false, a, n_views, vec, st);
 }
 
 static int dispatch_blend(bool backward, const BlendArgs& a, int n_views, cudaStream_t st) {

@@ -1,7 +1,7 @@
 // Fused per-(view, Gaussian) preparation for the multi-view entry point (render_views):
 //   activation (exp / normalise / sigmoid) + EWA projection + SH->RGB (+0.5, clamp) + smallest-axis
 //   normal + feature copy, written straight into the packed records the blend kernels gather:
-//       geo [V*N, 8]   = {x, y, A/2, B, C/2, opacity, tau, 0}
+//       geo [V*N, 8]   = {x, y, A/2, B, C/2, opacity, tau, rcut2}
 //       chan[V*N, CP]  = {r, g, b, depth, nx, ny, nz, feature[0..D), 0-pad}
 // and its exact backward (sum over views) to the raw model parameters.  This replaces, in one
 // launch each way, the reference's ProjectGaussians + SphericalHarmonics + ~10 ATen elementwise
@@ -10,6 +10,7 @@
 // Compiled with -fmad=false: radii / num_tiles_hit / depth bits must equal what the stand-alone
 // projection kernel (and the CPU oracle) produce from the same activated inputs.
 #include "gg_common.cuh"
+#include "gg_geo.cuh"
 #include "gg_math.cuh"
 #include "gg_b200.h"
 
@@ -101,10 +102,11 @@ prepare_views_kernel(const PrepArgs a, float* __restrict__ geo, float* __restric
         radii[vrow] = o.radius;
         num_tiles_hit[vrow] = o.tiles;
         const bool vis = o.tiles > 0;
-        const float tau = (vis && g.opacity * 255.0f > 1.0f) ? __logf(g.opacity * 255.0f) + GG_TAU_MARGIN : -1.0f;
+        float tau = -1.0f, rcut2 = -1.0f;
+        if (vis) geo_tau_rcut(g.opacity, o.conic[0], o.conic[1], o.conic[2], tau, rcut2);
         float4* gd = reinterpret_cast<float4*>(geo) + 2 * vrow;
         gd[0] = make_float4(o.ux, o.uy, 0.5f * o.conic[0], o.conic[1]);
-        gd[1] = make_float4(0.5f * o.conic[2], vis ? g.opacity : 0.0f, tau, 0.0f);
+        gd[1] = make_float4(0.5f * o.conic[2], vis ? g.opacity : 0.0f, tau, rcut2);
         if (view == 0 && scales_out) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) scales_out[3 * i + k] = g.s[k];
