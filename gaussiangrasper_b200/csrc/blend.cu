@@ -25,6 +25,7 @@ constexpr int kBlendThreads = 256;
 constexpr float kAlphaMin = 1.0f / 255.0f;
 constexpr float kAlphaMax = 0.999f;
 constexpr float kTStop = 1e-4f;
+constexpr int kStages = 3;  // staging ring depth of the blend kernels
 
 
 struct BlendArgs {
@@ -127,11 +128,11 @@ __device__ __forceinline__ void cull_batch(const float* __restrict__ geo_buf, in
 }
 
 template <int CP, int BATCH, bool kVec>
-__global__ void __launch_bounds__(kBlendThreads)
+__global__ void __launch_bounds__(kBlendThreads, (CP <= 24) ? 4 : ((CP <= 48) ? 2 : 1))
 blend_fwd_kernel(const BlendArgs a) {
     extern __shared__ __align__(16) float smem[];
-    float* geo_sm = smem;                      // [2][BATCH][8]
-    float* col_sm = smem + 2 * BATCH * 8;      // [2][BATCH][CP]
+    float* geo_sm = smem;                            // [kStages][BATCH][8]
+    float* col_sm = smem + kStages * BATCH * 8;      // [kStages][BATCH][CP]
     const int view = blockIdx.y;
     const int tile = blockIdx.x;
     const int tile_y = tile / a.tiles_x, tile_x = tile - tile_y * a.tiles_x;
@@ -158,22 +159,22 @@ blend_fwd_kernel(const BlendArgs a) {
 
     const int total = range.y - range.x;
     const int nb = (total + BATCH - 1) / BATCH;
-    if (nb > 0) {
-        stage_batch<CP, BATCH, kVec>(a, geo_base, color_base, range.x, min(BATCH, total), geo_sm, col_sm);
+    // kStages-deep ring of staging buffers: batch b+2 is issued while batch b is blended, and one
+    // barrier per batch both publishes batch b and retires the buffer batch b+2 will overwrite
+    auto stage = [&](int b) {
+        const int first = range.x + b * BATCH;
+        const int buf = b % kStages;
+        stage_batch<CP, BATCH, kVec>(a, geo_base, color_base, first, min(BATCH, range.y - first),
+                                     geo_sm + buf * BATCH * 8, col_sm + buf * BATCH * CP);
         cp_async_commit();
-    }
+    };
+    if (nb > 0) stage(0);
+    if (nb > 1) stage(1);
     for (int b = 0; b < nb; ++b) {
-        const int buf = b & 1;
-        if (b + 1 < nb) {
-            const int first = range.x + (b + 1) * BATCH;
-            stage_batch<CP, BATCH, kVec>(a, geo_base, color_base, first, min(BATCH, range.y - first),
-                                         geo_sm + (buf ^ 1) * BATCH * 8, col_sm + (buf ^ 1) * BATCH * CP);
-            cp_async_commit();
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
-        __syncthreads();
+        const int buf = b % kStages;
+        if (b + 1 < nb) cp_async_wait<1>(); else cp_async_wait<0>();
+        if (__syncthreads_count(warp_done) == kBlendThreads) break;
+        if (b + 2 < nb) stage(b + 2);
         const int first = range.x + b * BATCH;
         const int cnt = min(BATCH, range.y - first);
         if (!warp_done) {
@@ -182,37 +183,46 @@ blend_fwd_kernel(const BlendArgs a) {
             const float4* c4 = reinterpret_cast<const float4*>(col_sm + buf * BATCH * CP);
             unsigned mask[BATCH / 32];
             cull_batch<BATCH>(gbuf, cnt, rx0, ry0, rx1, ry1, mask);
+            auto blend = [&](int e, float alpha) {
+                const float next_T = T * (1.0f - alpha);
+                if (next_T <= kTStop) { done = true; stop = first + e + 1; return; }
+                const float vis = alpha * T;
+#pragma unroll
+                for (int q = 0; q < CP / 4; ++q) {
+                    const float4 cc = c4[e * (CP / 4) + q];
+                    acc[4 * q] = fmaf(vis, cc.x, acc[4 * q]);
+                    acc[4 * q + 1] = fmaf(vis, cc.y, acc[4 * q + 1]);
+                    acc[4 * q + 2] = fmaf(vis, cc.z, acc[4 * q + 2]);
+                    acc[4 * q + 3] = fmaf(vis, cc.w, acc[4 * q + 3]);
+                }
+                T = next_T;
+                last = first + e + 1;
+            };
 #pragma unroll
             for (int k = 0; k < BATCH / 32; ++k) {
                 unsigned m = mask[k];
                 while (m) {
-                    const int e = k * 32 + __ffs(m) - 1;
+                    // two surviving entries per round: their alpha chains are independent, only the
+                    // transmittance update is sequential
+                    const int e0 = k * 32 + __ffs(m) - 1;
                     m &= m - 1;
-                    if (done) continue;
-                    const float4 ga = g4[2 * e], gb = g4[2 * e + 1];
-                    const float dx = ga.x - fpx, dy = ga.y - fpy;
-                    const float sigma = eval_sigma(dx, dy, ga.z, ga.w, gb.x);
-                    if (sigma < 0.0f || sigma > gb.z) continue;
-                    const float alpha = fminf(kAlphaMax, gb.y * __expf(-sigma));
-                    if (alpha < kAlphaMin) continue;
-                    const float next_T = T * (1.0f - alpha);
-                    if (next_T <= kTStop) { done = true; stop = first + e + 1; continue; }
-                    const float vis = alpha * T;
-#pragma unroll
-                    for (int q = 0; q < CP / 4; ++q) {
-                        const float4 cc = c4[e * (CP / 4) + q];
-                        acc[4 * q] = fmaf(vis, cc.x, acc[4 * q]);
-                        acc[4 * q + 1] = fmaf(vis, cc.y, acc[4 * q + 1]);
-                        acc[4 * q + 2] = fmaf(vis, cc.z, acc[4 * q + 2]);
-                        acc[4 * q + 3] = fmaf(vis, cc.w, acc[4 * q + 3]);
-                    }
-                    T = next_T;
-                    last = first + e + 1;
+                    const bool two = m != 0;
+                    const int e1 = two ? k * 32 + __ffs(m) - 1 : e0;
+                    m &= m - 1;
+                    const float4 ga0 = g4[2 * e0], gb0 = g4[2 * e0 + 1];
+                    const float4 ga1 = g4[2 * e1], gb1 = g4[2 * e1 + 1];
+                    const float s0 = eval_sigma(ga0.x - fpx, ga0.y - fpy, ga0.z, ga0.w, gb0.x);
+                    const float s1 = eval_sigma(ga1.x - fpx, ga1.y - fpy, ga1.z, ga1.w, gb1.x);
+                    const float a0 = fminf(kAlphaMax, gb0.y * __expf(-s0));
+                    const float a1 = fminf(kAlphaMax, gb1.y * __expf(-s1));
+                    const bool ok0 = !(s0 < 0.0f || s0 > gb0.z) && a0 >= kAlphaMin;
+                    const bool ok1 = two && !(s1 < 0.0f || s1 > gb1.z) && a1 >= kAlphaMin;
+                    if (ok0 && !done) blend(e0, a0);
+                    if (ok1 && !done) blend(e1, a1);
                 }
                 if (__all_sync(0xffffffffu, done)) { warp_done = true; break; }
             }
         }
-        if (__syncthreads_count(warp_done) == kBlendThreads) break;
     }
     cp_async_wait<0>();
     if (inside) {
@@ -251,17 +261,18 @@ constexpr int kWarpScratch = 2 * 32 * kHitRow + 32;          // facm, wm, hit id
 
 template <int CP, int BATCH>
 constexpr size_t blend_bwd_smem() {
-    return sizeof(float) * (2 * BATCH * (8 + CP) + 2 * BATCH + kBlendThreads * CP + (kBlendThreads / 32) * kWarpScratch);
+    return sizeof(float) * (kStages * BATCH * (8 + CP) + kStages * BATCH + kBlendThreads * CP +
+                            (kBlendThreads / 32) * kWarpScratch);
 }
 
 template <int CP, int BATCH, bool kVec>
 __global__ void __launch_bounds__(kBlendThreads)
 blend_bwd_kernel(const BlendArgs a) {
     extern __shared__ __align__(16) float smem[];
-    float* geo_sm = smem;                                                  // [2][BATCH][8]
-    float* col_sm = geo_sm + 2 * BATCH * 8;                                // [2][BATCH][CP]
-    int* ids_sm = reinterpret_cast<int*>(col_sm + 2 * BATCH * CP);         // [2][BATCH]
-    float* vo_sm = reinterpret_cast<float*>(ids_sm + 2 * BATCH);           // [256][CP]
+    float* geo_sm = smem;                                                  // [kStages][BATCH][8]
+    float* col_sm = geo_sm + kStages * BATCH * 8;                          // [kStages][BATCH][CP]
+    int* ids_sm = reinterpret_cast<int*>(col_sm + kStages * BATCH * CP);   // [kStages][BATCH]
+    float* vo_sm = reinterpret_cast<float*>(ids_sm + kStages * BATCH);     // [256][CP]
     __shared__ int s_max[kBlendThreads / 32];
     const int view = blockIdx.y;
     const int tile = blockIdx.x;
@@ -283,7 +294,7 @@ blend_bwd_kernel(const BlendArgs a) {
     const long long pix = ((long long)view * a.img_h + py) * a.img_w + px;
 
     // padding lanes of the staged colour rows are read by the dot product: keep them finite
-    for (int k = threadIdx.x; k < 2 * BATCH * CP; k += kBlendThreads) col_sm[k] = 0.0f;
+    for (int k = threadIdx.x; k < kStages * BATCH * CP; k += kBlendThreads) col_sm[k] = 0.0f;
 
     float vo[CP];
     float T_final = 1.0f, bgdot = 0.0f;
@@ -371,19 +382,22 @@ blend_bwd_kernel(const BlendArgs a) {
         __syncwarp();
     };
 
-    auto stage = [&](int b, int buf) {
+    auto stage = [&](int b) {
         const int first = range.x + b * BATCH;
         const int cnt = min(BATCH, bmax - first);
+        const int buf = b % kStages;
         if (threadIdx.x < cnt) ids_sm[buf * BATCH + threadIdx.x] = __ldg(a.ids_sorted + first + threadIdx.x);
         stage_batch<CP, BATCH, kVec>(a, geo_base, color_base, first, cnt, geo_sm + buf * BATCH * 8,
                                      col_sm + buf * BATCH * CP);
         cp_async_commit();
     };
-    stage(nb - 1, (nb - 1) & 1);
+    stage(nb - 1);
+    if (nb > 1) stage(nb - 2);
     for (int b = nb - 1; b >= 0; --b) {
-        const int buf = b & 1;
-        if (b > 0) { stage(b - 1, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
-        __syncthreads();
+        const int buf = b % kStages;
+        if (b > 0) cp_async_wait<1>(); else cp_async_wait<0>();
+        __syncthreads();  // batch b is visible; everyone is done with the buffer batch b-2 reuses
+        if (b > 1) stage(b - 2);
         const int first = range.x + b * BATCH;
         const int cnt = min(BATCH, bmax - first);
         // entries at or beyond the warp's own last contributor are dead for the whole warp
@@ -395,49 +409,65 @@ blend_bwd_kernel(const BlendArgs a) {
             const int* idb = ids_sm + buf * BATCH;
             unsigned mask[BATCH / 32];
             cull_batch<BATCH>(gbuf, e_hi, rx0, ry0, rx1, ry1, mask);
+            auto colour_dot = [&](int e) {
+                float d0 = 0.0f, d1 = 0.0f;
+#pragma unroll
+                for (int q = 0; q < CP / 4; ++q) {
+                    const float4 cc = c4[e * (CP / 4) + q];
+                    d0 = fmaf(cc.x, vo[4 * q], d0);
+                    d1 = fmaf(cc.y, vo[4 * q + 1], d1);
+                    d0 = fmaf(cc.z, vo[4 * q + 2], d0);
+                    d1 = fmaf(cc.w, vo[4 * q + 3], d1);
+                }
+                return d0 + d1;
+            };
+            // sequential part of one entry: transmittance, alpha gradient, row of the hit matrices
+            auto record = [&](int e, bool valid, float alpha, float araw, float vis, float dot) {
+                float fac = 0.0f, w = 0.0f;
+                if (valid) {
+                    const float ra = 1.0f / (1.0f - alpha);
+                    T *= ra;  // transmittance in front of this entry
+                    fac = alpha * T;
+                    const float v_alpha = fmaf(dot, T, -R * ra);
+                    R = fmaf(fac, dot, R);
+                    // a clamped alpha passes no gradient to sigma / opacity
+                    w = (araw <= kAlphaMax) ? vis * v_alpha : 0.0f;
+                }
+                facm[nhit * kHitRow + lane] = fac;
+                wm[nhit * kHitRow + lane] = w;
+                if (lane == 0) hit_g[nhit] = idb[e];
+                if (++nhit == 32) { flush(32); nhit = 0; }
+            };
 #pragma unroll
             for (int k = BATCH / 32 - 1; k >= 0; --k) {
                 unsigned m = mask[k];
                 while (m) {
-                    const int bit = 31 - __clz(m);
-                    m &= ~(1u << bit);
-                    const int e = k * 32 + bit;
-                    const float4 ga = g4[2 * e], gb = g4[2 * e + 1];
-                    const float dx = ga.x - fpx, dy = ga.y - fpy;
-                    const float sigma = eval_sigma(dx, dy, ga.z, ga.w, gb.x);
+                    // two surviving entries per round (independent alpha / dot chains)
+                    const int bit0 = 31 - __clz(m);
+                    m &= ~(1u << bit0);
+                    const bool two = m != 0;
+                    const int bit1 = two ? 31 - __clz(m) : bit0;
+                    m &= ~(1u << bit1);
+                    const int e0 = k * 32 + bit0, e1 = k * 32 + bit1;
+                    const float4 ga0 = g4[2 * e0], gb0 = g4[2 * e0 + 1];
+                    const float4 ga1 = g4[2 * e1], gb1 = g4[2 * e1 + 1];
                     // branch-free replay of the forward test (same arithmetic as blend_fwd_kernel)
-                    const float vis = __expf(-sigma);
-                    const float araw = gb.y * vis;
-                    const float alpha = fminf(kAlphaMax, araw);
-                    const bool valid = (first + e < last) && !(sigma < 0.0f || sigma > gb.z) && (alpha >= kAlphaMin);
-                    if (!__any_sync(0xffffffffu, valid)) continue;
-                    float fac = 0.0f, w = 0.0f;
-                    if (valid) {
-                        const float ra = 1.0f / (1.0f - alpha);
-                        T *= ra;  // transmittance in front of this entry
-                        fac = alpha * T;
-                        float dot = 0.0f;
-#pragma unroll
-                        for (int q = 0; q < CP / 4; ++q) {
-                            const float4 cc = c4[e * (CP / 4) + q];
-                            dot = fmaf(cc.x, vo[4 * q], dot);
-                            dot = fmaf(cc.y, vo[4 * q + 1], dot);
-                            dot = fmaf(cc.z, vo[4 * q + 2], dot);
-                            dot = fmaf(cc.w, vo[4 * q + 3], dot);
-                        }
-                        const float v_alpha = fmaf(dot, T, -R * ra);
-                        R = fmaf(fac, dot, R);
-                        // a clamped alpha passes no gradient to sigma / opacity
-                        w = (araw <= kAlphaMax) ? vis * v_alpha : 0.0f;
-                    }
-                    facm[nhit * kHitRow + lane] = fac;
-                    wm[nhit * kHitRow + lane] = w;
-                    if (lane == 0) hit_g[nhit] = idb[e];
-                    if (++nhit == 32) { flush(32); nhit = 0; }
+                    const float s0 = eval_sigma(ga0.x - fpx, ga0.y - fpy, ga0.z, ga0.w, gb0.x);
+                    const float s1 = eval_sigma(ga1.x - fpx, ga1.y - fpy, ga1.z, ga1.w, gb1.x);
+                    const float vis0 = __expf(-s0), vis1 = __expf(-s1);
+                    const float araw0 = gb0.y * vis0, araw1 = gb1.y * vis1;
+                    const float al0 = fminf(kAlphaMax, araw0), al1 = fminf(kAlphaMax, araw1);
+                    const bool v0 = (first + e0 < last) && !(s0 < 0.0f || s0 > gb0.z) && (al0 >= kAlphaMin);
+                    const bool v1 = two && (first + e1 < last) && !(s1 < 0.0f || s1 > gb1.z) && (al1 >= kAlphaMin);
+                    const bool any0 = __any_sync(0xffffffffu, v0), any1 = __any_sync(0xffffffffu, v1);
+                    if (!(any0 || any1)) continue;
+                    const float dot0 = v0 ? colour_dot(e0) : 0.0f;
+                    const float dot1 = v1 ? colour_dot(e1) : 0.0f;
+                    if (any0) record(e0, v0, al0, araw0, vis0, dot0);
+                    if (any1) record(e1, v1, al1, araw1, vis1, dot1);
                 }
             }
         }
-        __syncthreads();
     }
     if (nhit) flush(nhit);
 }
@@ -479,7 +509,7 @@ unpack_vgeo_kernel(long long n, int n_views, const float* __restrict__ v_geo, fl
 template <int CP, int BATCH>
 static int launch_blend_impl(bool backward, const BlendArgs& a, int n_views, bool vec, cudaStream_t st) {
     dim3 grid(a.tiles_x * a.tiles_y, n_views);
-    size_t smem = sizeof(float) * 2 * BATCH * (8 + CP);
+    size_t smem = sizeof(float) * kStages * BATCH * (8 + CP);
     if (backward) {
         smem = blend_bwd_smem<CP, BATCH>();
         if (vec) {
@@ -490,8 +520,13 @@ static int launch_blend_impl(bool backward, const BlendArgs& a, int n_views, boo
             blend_bwd_kernel<CP, BATCH, false><<<grid, kBlendThreads, smem, st>>>(a);
         }
     } else {
-        if (vec) blend_fwd_kernel<CP, BATCH, true><<<grid, kBlendThreads, smem, st>>>(a);
-        else blend_fwd_kernel<CP, BATCH, false><<<grid, kBlendThreads, smem, st>>>(a);
+        if (vec) {
+            GG_CUDA(cudaFuncSetAttribute(blend_fwd_kernel<CP, BATCH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            blend_fwd_kernel<CP, BATCH, true><<<grid, kBlendThreads, smem, st>>>(a);
+        } else {
+            GG_CUDA(cudaFuncSetAttribute(blend_fwd_kernel<CP, BATCH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            blend_fwd_kernel<CP, BATCH, false><<<grid, kBlendThreads, smem, st>>>(a);
+        }
     }
     count_launch();
     return check_launch(backward ? "blend_bwd_kernel" : "blend_fwd_kernel");
