@@ -257,7 +257,8 @@ blend_fwd_kernel(const BlendArgs a) {
 // memory turns the per-Gaussian reduction into register accumulation at full lane occupancy.
 // ---------------------------------------------------------------------------------------------
 constexpr int kHitRow = 33;                                  // padded row: conflict-free both ways
-constexpr int kWarpScratch = 2 * 32 * kHitRow + 32;          // facm, wm, hit ids (floats)
+constexpr int kHitRows = 16;                                 // entries stored before a flush
+constexpr int kWarpScratch = 2 * kHitRows * kHitRow + kHitRows;  // facm, wm, hit ids (floats)
 
 template <int CP, int BATCH>
 constexpr size_t blend_bwd_smem() {
@@ -280,9 +281,9 @@ blend_bwd_kernel(const BlendArgs a) {
     int tx, ty;
     tile_pixel(tx, ty);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* facm = vo_sm + kBlendThreads * CP + warp * kWarpScratch;        // [32][33]
-    float* wm = facm + 32 * kHitRow;                                       // [32][33]
-    int* hit_g = reinterpret_cast<int*>(wm + 32 * kHitRow);                // [32]
+    float* facm = vo_sm + kBlendThreads * CP + warp * kWarpScratch;        // [kHitRows][33]
+    float* wm = facm + kHitRows * kHitRow;                                 // [kHitRows][33]
+    int* hit_g = reinterpret_cast<int*>(wm + kHitRows * kHitRow);          // [kHitRows]
     const int px = tile_x * GG_TILE + tx, py = tile_y * GG_TILE + ty;
     const bool inside = px < a.img_w && py < a.img_h;
     const float fpx = (float)px, fpy = (float)py;
@@ -330,11 +331,14 @@ blend_bwd_kernel(const BlendArgs a) {
 
     const float* vo_warp = vo_sm + warp * 32 * CP;
     int nhit = 0;
-    // phase B: lane = stored entry; sums over the warp's 32 pixels, then one red per component
+    // phase B: lane = (stored entry j = lane & 15, pixel half h = lane >> 4); each half-warp sums
+    // its 16 pixels, the halves are combined with one shuffle per value, then the 6 + C reds of an
+    // entry are split between its two lanes
     auto flush = [&](int count) {
         __syncwarp();
-        const bool live = lane < count;
-        const int g = live ? hit_g[lane] : 0;
+        const int j = lane & (kHitRows - 1), h = lane >> 4;
+        const bool live = j < count;
+        const int g = live ? hit_g[j] : 0;
         float4 ga = make_float4(0.f, 0.f, 0.f, 0.f), gb = ga;
         if (live) {
             ga = __ldg(reinterpret_cast<const float4*>(a.geo) + 2 * (geo_base + g));
@@ -344,14 +348,14 @@ blend_bwd_kernel(const BlendArgs a) {
 #pragma unroll
         for (int c = 0; c < CP; ++c) acc[c] = 0.0f;
         float m0 = 0.f, mx = 0.f, my = 0.f, mxx = 0.f, mxy = 0.f, myy = 0.f;
-        const float* fr = facm + lane * kHitRow;
-        const float* wr = wm + lane * kHitRow;
-        const float bx = ga.x - rx0, by = ga.y - ry0;
+        const float* fr = facm + j * kHitRow + 16 * h;
+        const float* wr = wm + j * kHitRow + 16 * h;
+        const float bx = ga.x - rx0, by = ga.y - ry0 - (float)(2 * h);
 #pragma unroll 4
-        for (int p = 0; p < 32; ++p) {
+        for (int p = 0; p < 16; ++p) {
             const float f = live ? fr[p] : 0.0f;
             const float wv = live ? wr[p] : 0.0f;
-            const float4* vrow = reinterpret_cast<const float4*>(vo_warp + p * CP);
+            const float4* vrow = reinterpret_cast<const float4*>(vo_warp + (16 * h + p) * CP);
 #pragma unroll
             for (int q = 0; q < CP / 4; ++q) {
                 const float4 v = vrow[q];
@@ -365,19 +369,31 @@ blend_bwd_kernel(const BlendArgs a) {
             m0 += wv; mx += wdx; my += wdy;
             mxx = fmaf(wdx, dx, mxx); mxy = fmaf(wdx, dy, mxy); myy = fmaf(wdy, dy, myy);
         }
+#pragma unroll
+        for (int c = 0; c < CP; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 16);
+        m0 += __shfl_xor_sync(0xffffffffu, m0, 16);
+        mx += __shfl_xor_sync(0xffffffffu, mx, 16);
+        my += __shfl_xor_sync(0xffffffffu, my, 16);
+        mxx += __shfl_xor_sync(0xffffffffu, mxx, 16);
+        mxy += __shfl_xor_sync(0xffffffffu, mxy, 16);
+        myy += __shfl_xor_sync(0xffffffffu, myy, 16);
         if (live) {
-            const float o = gb.y, A = 2.0f * ga.z, B = ga.w, C = 2.0f * gb.x;
-            float* vg = a.v_geo + (geo_base + g) * 8;
-            atomicAdd(vg + 0, -o * fmaf(A, mx, B * my));
-            atomicAdd(vg + 1, -o * fmaf(B, mx, C * my));
-            atomicAdd(vg + 2, -0.5f * o * mxx);
-            atomicAdd(vg + 3, -o * mxy);
-            atomicAdd(vg + 4, -0.5f * o * myy);
-            atomicAdd(vg + 5, m0);
             float* vc = a.v_colors + (color_base + g) * (long long)a.color_stride;
+            if (h == 0) {
+                const float o = gb.y, A = 2.0f * ga.z, B = ga.w, C = 2.0f * gb.x;
+                float* vg = a.v_geo + (geo_base + g) * 8;
+                atomicAdd(vg + 0, -o * fmaf(A, mx, B * my));
+                atomicAdd(vg + 1, -o * fmaf(B, mx, C * my));
+                atomicAdd(vg + 2, -0.5f * o * mxx);
+                atomicAdd(vg + 3, -o * mxy);
+                atomicAdd(vg + 4, -0.5f * o * myy);
+                atomicAdd(vg + 5, m0);
+            }
+            // lane h==0 takes the low channels (fewer, it also did the geometry), h==1 the rest
+            constexpr int kSplit = (CP > 6) ? (CP - 6) / 2 : 0;
 #pragma unroll
             for (int c = 0; c < CP; ++c)
-                if (c < a.channels) atomicAdd(vc + c, acc[c]);
+                if (c < a.channels && ((c < kSplit) == (h == 0))) atomicAdd(vc + c, acc[c]);
         }
         __syncwarp();
     };
@@ -436,7 +452,7 @@ blend_bwd_kernel(const BlendArgs a) {
                 facm[nhit * kHitRow + lane] = fac;
                 wm[nhit * kHitRow + lane] = w;
                 if (lane == 0) hit_g[nhit] = idb[e];
-                if (++nhit == 32) { flush(32); nhit = 0; }
+                if (++nhit == kHitRows) { flush(kHitRows); nhit = 0; }
             };
 #pragma unroll
             for (int k = BATCH / 32 - 1; k >= 0; --k) {
