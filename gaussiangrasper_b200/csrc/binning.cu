@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(256) radix_scan_hist_kernel(uint32_t* __restri
     h[threadIdx.x] = (uint32_t)block_excl_scan_256(v, sm, total);
 }
 
-__global__ void __launch_bounds__(kRsThreads)
+__global__ void __launch_bounds__(kRsThreads, 3)
 radix_pass_kernel(const uint64_t* __restrict__ kin, const uint32_t* __restrict__ vin, uint64_t* __restrict__ kout,
                   uint32_t* __restrict__ vout, long long m, int shift, const uint32_t* __restrict__ ghist_excl,
                   volatile uint64_t* tile_state, uint32_t* ticket, uint32_t generation) {
@@ -412,8 +412,9 @@ extern "C" int gg_sort_pairs(long long m, int key_bits, const int64_t* keys_in, 
     GG_CUDA(cudaFuncSetAttribute(radix_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     // histograms + tickets are contiguous at the start of the workspace
     GG_CUDA(cudaMemsetAsync(ws, 0, L.off_state, st));
-    int hist_blocks = div_up(m, 256 * 8);
-    if (hist_blocks > 148 * 8) hist_blocks = 148 * 8;
+    // few, fat blocks: every block ends with passes*256 global atomics onto the same bins
+    int hist_blocks = div_up(m, 256 * 16);
+    if (hist_blocks > 148 * 2) hist_blocks = 148 * 2;
     radix_hist_kernel<<<hist_blocks, 256, 0, st>>>(reinterpret_cast<const uint64_t*>(keys_in), m, passes, ghist);
     radix_scan_hist_kernel<<<passes, 256, 0, st>>>(ghist);
     const uint64_t* kin = reinterpret_cast<const uint64_t*>(keys_in);

@@ -79,7 +79,10 @@ __device__ __forceinline__ Activated load_activated(const PrepArgs& a, long long
 __global__ void __launch_bounds__(kPrepThreads)
 prepare_views_kernel(const PrepArgs a, float* __restrict__ geo, float* __restrict__ chan,
                      float* __restrict__ depths, int32_t* __restrict__ radii, int32_t* __restrict__ num_tiles_hit,
-                     float* __restrict__ scales_out, float* __restrict__ quats_out, int slab_row) {
+                     float* __restrict__ scales_out, float* __restrict__ quats_out, int slab_row, int phase) {
+    // phase 0: everything; 1: geometry only (geo, depths, radii, num_tiles_hit); 2: channel rows
+    // only, from the radii / depths phase 1 left behind.  The split lets the host read the number
+    // of intersections (needed to size the sort) while phase 2 keeps the GPU busy.
     extern __shared__ __align__(16) float sm[];
     const int view = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -95,7 +98,11 @@ prepare_views_kernel(const PrepArgs a, float* __restrict__ geo, float* __restric
     Activated g;
     ProjOut o;
     o.tiles = 0;
-    if (active) {
+    if (active && phase == 2) {
+        g = load_activated(a, i);
+        o.tiles = radii[vrow] > 0 ? 1 : 0;
+        o.depth = depths[vrow];
+    } else if (active) {
         g = load_activated(a, i);
         o = project_one(g.p, g.s, 1.0f, g.qh, cam, a.img_h, a.img_w, a.tiles_x, a.tiles_y, a.clip);
         depths[vrow] = o.depth;
@@ -115,7 +122,7 @@ prepare_views_kernel(const PrepArgs a, float* __restrict__ geo, float* __restric
             reinterpret_cast<float4*>(quats_out)[i] = make_float4(g.qh[0], g.qh[1], g.qh[2], g.qh[3]);
     }
     const bool vis = active && o.tiles > 0;
-    if (!__any_sync(0xffffffffu, vis)) return;  // nothing of this warp reaches a tile list
+    if (phase == 1 || !__any_sync(0xffffffffu, vis)) return;  // nothing of this warp reaches a tile list
 
     // ---- SH coefficients of the warp's 32 Gaussians: one contiguous span, 16-byte loads ----
     const int row = a.nb * 3;
@@ -303,8 +310,10 @@ extern "C" int gg_prepare_views(int n, int n_views, int feat_dim, int cp, int de
                                 const float* viewmats, const float* fullmats, const float* intrins,
                                 const float* positions, int img_h, int img_w, int tiles_x, int tiles_y,
                                 float clip_thresh, float* geo, float* chan, float* depths, int32_t* radii,
-                                int32_t* num_tiles_hit, float* scales_out, float* quats_out, void* stream) {
+                                int32_t* num_tiles_hit, float* scales_out, float* quats_out, int phase,
+                                void* stream) {
     PrepArgs a;
+    GG_REQUIRE(phase >= 0 && phase <= 2, "gg_prepare_views: phase must be 0, 1 or 2");
     const int rc = fill_args(a, n, n_views, feat_dim, cp, degree, degrees_to_use, means, log_scales, quats,
                              opacity_logit, sh_coeffs, features, viewmats, fullmats, intrins, positions, img_h, img_w,
                              tiles_x, tiles_y, clip_thresh);
@@ -317,7 +326,7 @@ extern "C" int gg_prepare_views(int n, int n_views, int feat_dim, int cp, int de
     dim3 grid(div_up(n, kPrepThreads), n_views);
     prepare_views_kernel<<<grid, kPrepThreads, smem, (cudaStream_t)stream>>>(a, geo, chan, depths, radii,
                                                                              num_tiles_hit, scales_out, quats_out,
-                                                                             slab_row);
+                                                                             slab_row, phase);
     count_launch();
     return check_launch("prepare_views_kernel");
 }

@@ -33,6 +33,8 @@ class _Workspace:
         self.ids = None
         self.keys_sorted = None
         self.total = torch.zeros(1, dtype=torch.int32, device=device)
+        self.total_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.total_event = torch.cuda.Event()
 
     def scan_ws(self, n):
         need = int(_lib.load().gg_cumsum_workspace_bytes(n))
@@ -198,7 +200,8 @@ class Binning:
     tile_bounds: Tuple[int, int, int]
 
 
-def bin_views(n, n_views, xys, depths, radii, num_tiles_hit, tile_bounds, xy_from_geo=False) -> Binning:
+def bin_views(n, n_views, xys, depths, radii, num_tiles_hit, tile_bounds, xy_from_geo=False,
+              while_waiting=None) -> Binning:
     """cumsum -> (one host read of M) -> key emission -> radix sort -> tile ranges.
     xy_from_geo: `xys` is the packed [V*n, 8] geo table (pixel centres in columns 0..1)."""
     dev = require_cuda(xys, depths, radii, num_tiles_hit)
@@ -206,7 +209,14 @@ def bin_views(n, n_views, xys, depths, radii, num_tiles_hit, tile_bounds, xy_fro
     xys, depths = f32c(xys), f32c(depths)
     radii, num_tiles_hit = radii.contiguous(), num_tiles_hit.contiguous()
     cum = cumsum_i32(num_tiles_hit.reshape(-1), ws.total)
-    m = int(ws.total.item())
+    # the one device->host read of the path (the reference has five per view): M sizes the sort.
+    # Work passed as `while_waiting` is enqueued behind the copy so the GPU stays busy meanwhile.
+    ws.total_host.copy_(ws.total, non_blocking=True)
+    ws.total_event.record(torch.cuda.current_stream(dev))
+    if while_waiting is not None:
+        while_waiting()
+    ws.total_event.synchronize()
+    m = int(ws.total_host[0])
     if m < 0:
         raise _lib.GGError("number of tile intersections overflows int32")
     num_tiles = int(tile_bounds[0]) * int(tile_bounds[1]) * n_views

@@ -114,14 +114,19 @@ class _RenderViews(Function):
         dbg = holder.get("debug_activations") if holder is not None else None
         s_out = torch.empty((n, 3), dtype=torch.float32, device=dev) if dbg else None
         q_out = torch.empty((n, 4), dtype=torch.float32, device=dev) if dbg else None
-        with torch.cuda.device(dev):
-            _lib.call("gg_prepare_views", n, V, D, CP, degree, int(degrees_to_use), ops.ptr(means), ops.ptr(log_scales),
-                      ops.ptr(quats), ops.ptr(opacity_logit), ops.ptr(sh_coeffs), ops.ptr(features),
-                      ops.ptr(views.viewmats), ops.ptr(views.fullmats), ops.ptr(views.intrins),
-                      ops.ptr(views.positions), H, W, tb[0], tb[1], float(clip_thresh), ops.ptr(geo), ops.ptr(chan),
-                      ops.ptr(depths), ops.ptr(radii), ops.ptr(nth), ops.ptr(s_out), ops.ptr(q_out),
-                      ops.stream_ptr(dev))
-        binning = ops.bin_views(n, V, geo, depths, radii, nth, tb, xy_from_geo=True)
+        def prepare(phase):
+            with torch.cuda.device(dev):
+                _lib.call("gg_prepare_views", n, V, D, CP, degree, int(degrees_to_use), ops.ptr(means),
+                          ops.ptr(log_scales), ops.ptr(quats), ops.ptr(opacity_logit), ops.ptr(sh_coeffs),
+                          ops.ptr(features), ops.ptr(views.viewmats), ops.ptr(views.fullmats), ops.ptr(views.intrins),
+                          ops.ptr(views.positions), H, W, tb[0], tb[1], float(clip_thresh), ops.ptr(geo),
+                          ops.ptr(chan), ops.ptr(depths), ops.ptr(radii), ops.ptr(nth), ops.ptr(s_out), ops.ptr(q_out),
+                          phase, ops.stream_ptr(dev))
+
+        # geometry first; the channel rows (SH, normals, features) are produced while the host waits
+        # for the intersection count that sizes the sort
+        prepare(1)
+        binning = ops.bin_views(n, V, geo, depths, radii, nth, tb, xy_from_geo=True, while_waiting=lambda: prepare(2))
         bg = torch.zeros(CP, dtype=torch.float32, device=dev)
         bg[3] = depth_background
         out, final_T, final_idx = ops.blend_fwd(binning, geo, chan, bg, H, W, colors_per_view=True,

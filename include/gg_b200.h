@@ -130,13 +130,15 @@ int gg_unpack_vgeo(long long n, int n_views, const float* v_geo, float* v_xys, f
  * [n,(degree+1)^2,3], features [n,D].  Out, per (view, Gaussian): the packed geo record, the
  * channel row chan[V*n, cp] = {r,g,b (SH+0.5 clamped), depth, normal(3), feature(D), 0-pad},
  * depths, radii, num_tiles_hit.  cp is a multiple of 4, >= 7 + D.  scales_out [n,3] / quats_out
- * [n,4] (nullable) receive the activated inputs of the projection (used by the parity tests). */
+ * [n,4] (nullable) receive the activated inputs of the projection (used by the parity tests).
+ * phase: 0 = everything; 1 = geometry only (geo, depths, radii, num_tiles_hit); 2 = channel rows
+ * only, reusing phase 1's radii / depths -- the host reads the intersection count in between. */
 int gg_prepare_views(int n, int n_views, int feat_dim, int cp, int degree, int degrees_to_use, const float* means,
                      const float* log_scales, const float* quats, const float* opacity_logit,
                      const float* sh_coeffs, const float* features, const float* viewmats, const float* fullmats,
                      const float* intrins, const float* positions, int img_h, int img_w, int tiles_x, int tiles_y,
                      float clip_thresh, float* geo, float* chan, float* depths, int32_t* radii,
-                     int32_t* num_tiles_hit, float* scales_out, float* quats_out, void* stream);
+                     int32_t* num_tiles_hit, float* scales_out, float* quats_out, int phase, void* stream);
 /* exact backward, summed over the views: v_geo [V*n,8] = {v_x, v_y, v_A, v_B, v_C, v_opacity,.,.}
  * and v_chan [V*n,cp] in; gradients of the raw parameters out (overwritten). */
 int gg_prepare_views_bwd(int n, int n_views, int feat_dim, int cp, int degree, int degrees_to_use,
