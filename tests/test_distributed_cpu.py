@@ -1,0 +1,93 @@
+"""world_size-2 gloo tests of the view-sharding host logic (no GPU): partition of views and the
+single flat gradient all-reduce."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from gaussiangrasper_b200 import distributed as ggd
+
+
+def test_views_partition_is_a_partition():
+    for world in (1, 2, 4, 8):
+        for n in (1, 7, 8, 64):
+            seen = []
+            for r in range(world):
+                mine = ggd.views_for_rank(n, r, world)
+                assert all(ggd.owner_of_view(v, world) == r for v in mine)
+                seen += mine
+            assert sorted(seen) == list(range(n))
+    with pytest.raises(ValueError):
+        ggd.views_for_rank(4, 2, 2)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _make_params(n=50, D=4, K=25):
+    g = torch.Generator().manual_seed(0)
+    shapes = dict(means=(n, 3), log_scales=(n, 3), quats=(n, 4), opacity_logit=(n, 1), sh_coeffs=(n, K, 3),
+                  features=(n, D))
+    return {k: torch.randn(s, generator=g).requires_grad_(True) for k, s in shapes.items()}
+
+
+def _per_view_grad(params, view):
+    """A stand-in for "gradient of the loss of one view": deterministic function of (param, view)."""
+    return {k: torch.sin(p.detach() * (view + 1)) * (0.5 + view) for k, p in params.items()}
+
+
+def _worker(rank, world, port, n_views, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        params = _make_params()
+        # accumulate the local views' gradients into .grad, as a training step would
+        for k in params:
+            params[k].grad = torch.zeros_like(params[k])
+        for v in ggd.views_for_rank(n_views, rank, world):
+            for k, g in _per_view_grad(params, v).items():
+                params[k].grad += g
+        bucket = ggd.all_reduce_gradients(params)
+        assert bucket.numel == sum(p.numel() for p in params.values())
+        # a second step reuses the persistent flat buffer
+        ggd.all_reduce_gradients({k: p for k, p in params.items()}, bucket)
+        if rank == 0:
+            torch.save({k: p.grad.clone() for k, p in params.items()}, out)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_allreduce_two_ranks_equals_sum_over_views(tmp_path):
+    world, n_views = 2, 5
+    out = str(tmp_path / "grads.pt")
+    mp.spawn(_worker, args=(world, _free_port(), n_views, out), nprocs=world, join=True)
+    got = torch.load(out)
+    params = _make_params()
+    once = {k: sum(_per_view_grad(params, v)[k] for v in range(n_views)) for k in params}
+    for k in params:
+        # the worker all-reduces twice (the second call sums the already-reduced grads of both ranks)
+        assert torch.allclose(got[k], once[k] * world, rtol=1e-5, atol=1e-6), k
+
+
+def test_bucket_layout_single_process():
+    params = _make_params(n=7, D=3, K=4)
+    b = ggd.GradientBucket(params)
+    assert b.numel == 7 * (3 + 3 + 4 + 1 + 12 + 3)
+    grads = {k: torch.full_like(p, i + 1.0) for i, (k, p) in enumerate(params.items())}
+    grads["quats"] = None
+    flat = b.pack(grads)
+    assert b.all_reduce() is None  # no process group: no-op
+    un = b.unpack()
+    assert float(un["means"].mean()) == 1.0 and float(un["quats"].abs().sum()) == 0.0
+    assert un["sh_coeffs"].shape == (7, 4, 3) and flat.numel() == b.numel
+    with pytest.raises(ValueError):
+        ggd.GradientBucket({"bogus": torch.zeros(3)})
