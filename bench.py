@@ -95,9 +95,10 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # the reference's CPU maths (oracle/torch_oracle.py is the port of gsplat's _torch_impl)
 # ---------------------------------------------------------------------------------------------
-def cpu_reference_step(sc, cam, D, tiles, threads):
+def cpu_reference_step(sc, cam, D, n_tiles, threads):
     """One fwd+bwd of the reference maths on the host: full SH + projection + binning for all
-    Gaussians (timed), blend fwd+bwd on the sampled tiles (timed); returns (t_geom, t_blend)."""
+    Gaussians (timed), blend fwd+bwd on `n_tiles` sampled tiles (timed); returns
+    (t_geom, t_blend_sample, scale, n_sampled, n_total) with scale = frame pairs / sample pairs."""
     from oracle import torch_oracle as to
     torch.set_num_threads(threads)
     P = {k: v.clone().requires_grad_(True) for k, v in sc.items()}
@@ -116,6 +117,8 @@ def cpu_reference_step(sc, cam, D, tiles, threads):
     cols = torch.cat([rgbs, depths[:, None], normals, P["features"]], dim=1)
     _, _, ids_s, ranges = to.bin_and_sort(xys, depths, radii, nth, cam.tile_bounds)
     t1 = time.perf_counter()
+    tiles, scale = sample_tiles(ranges, n_tiles)
+    t1b = time.perf_counter()
     bg = torch.zeros(cols.shape[1]); bg[3] = 10.0
     g = torch.Generator().manual_seed(0)
     v_out = torch.randn((cam.H, cam.W, cols.shape[1]), generator=g)
@@ -124,14 +127,20 @@ def cpu_reference_step(sc, cam, D, tiles, threads):
     t2 = time.perf_counter()
     torch.autograd.backward([xys, conics, op, cols], [v_xys, v_con, v_op, v_col])
     t3 = time.perf_counter()
-    return (t1 - t0) + (t3 - t2), (t2 - t1)
+    return (t1 - t0) + (t3 - t2), (t2 - t1b), scale, len(tiles), int(ranges.shape[0])
 
 
-def sample_tiles(cam, count):
-    tx, ty = cam.tile_bounds[0], cam.tile_bounds[1]
-    total = tx * ty
-    stride = max(1, total // count)
-    return list(range(stride // 2, total, stride))[:count], total
+def sample_tiles(ranges, count):
+    """Tiles at evenly spaced quantiles of the tile-list length; returns (tile ids, scale) where
+    scale = total pixel-Gaussian pairs of the frame / pairs of the sample (the vectorised CPU blend
+    costs time proportional to the list length of a tile)."""
+    lens = (ranges[:, 1] - ranges[:, 0]).to(torch.float64)
+    order = torch.argsort(lens)
+    nz = order[lens[order] > 0]
+    if nz.numel() == 0:
+        return [0], 1.0
+    pick = nz[torch.linspace(0, nz.numel() - 1, min(count, nz.numel())).round().long()]
+    return pick.tolist(), float(lens.sum() / lens[pick].sum())
 
 
 def run_reference(args):
@@ -143,17 +152,17 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     sc = scenes.random_scene(cfg["n"], feature_dim=cfg["D"], seed=1235)
     cam = scenes.orbit_cameras(1, cfg["W"], cfg["H"])[0]
-    tiles, total_tiles = sample_tiles(cam, 12)
     times = []
     for s in range(args.warmup + args.steps):
-        tg, tb = cpu_reference_step(sc, cam, cfg["D"], tiles, threads)
+        tg, tb, scale, ns, nt = cpu_reference_step(sc, cam, cfg["D"], 8, threads)
         if s >= args.warmup:
-            times.append(tg + tb * total_tiles / len(tiles))
+            times.append(tg + tb * scale)
     t = sum(times) / len(times)
     mpix = cfg["W"] * cfg["H"] / 1e6
     val = mpix / t
     sample = (f"each step: SH+projection+binning of all {cfg['n']} Gaussians fwd+bwd (timed in full) + blend "
-              f"fwd+bwd of {len(tiles)} of {total_tiles} tiles, blend time scaled by {total_tiles}/{len(tiles)}")
+              f"fwd+bwd of {ns} of {nt} tiles (length quantiles), blend time scaled by frame pairs / sample pairs "
+              f"= {scale:.1f}")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -195,7 +204,8 @@ def run_ours(args):
     views = ViewBatch.from_cameras(cams, dev)
     g = torch.Generator().manual_seed(100 + rank)
     v_img = torch.randn((V, H, W, CP), generator=g).to(dev)
-    flat_grads = None
+    from gaussiangrasper_b200.distributed import GradientBucket
+    bucket = GradientBucket(P) if (world > 1 and cfg["backward"]) else None
 
     def step():
         for p in P.values():
@@ -204,10 +214,10 @@ def run_ours(args):
                            P["features"], views)
         if cfg["backward"]:
             out["image"].backward(v_img)
-            if world > 1:
-                flat = torch.cat([P[k].grad.reshape(-1) for k in names])
-                dist.all_reduce(flat)
-                return flat
+            if bucket is not None:
+                bucket.pack({k: P[k].grad for k in names})
+                bucket.all_reduce()
+                return bucket.flat
         return out["image"]
 
     for _ in range(max(args.warmup, 3)):
@@ -258,9 +268,9 @@ def run_ours(args):
         loss = ((out["image"] - target) ** 2).mean()
         if cfg["backward"]:
             loss.backward()
-            if world > 1:
-                flat = torch.cat([P[k].grad.reshape(-1) for k in names])
-                dist.all_reduce(flat)
+            if bucket is not None:
+                bucket.pack({k: P[k].grad for k in names})
+                bucket.all_reduce()
         rgb_host.copy_(out["rgb"].detach(), non_blocking=True)      # D2H: rendered rgb
         loss_host.copy_(loss.detach().reshape(1), non_blocking=True)  # D2H: loss
         torch.cuda.synchronize()
@@ -323,17 +333,15 @@ def run_ours(args):
         roof = {"kernel": dom, "bound": "hbm", "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None,
                 "traffic": None, "peak_source": peak_src, "avg_launch_ms": avg[dom]}
     # HBM-bound stages against the measured copy bandwidth
-    nuse = 25
-    bytes_model = {
-        "gg_sh_fwd": n * (12 + 12 * nuse + 12) * V, "gg_sh_bwd": n * (12 + 12 + 12 * nuse) * V,
-        "gg_project_fwd_views": n * V * 96, "gg_project_bwd_views": n * V * 180,
-    }
+    # algorithmic bytes per (view, Gaussian) of the HBM-bound stages
+    prep_b = (12 + 12 + 16 + 4 + 300 + 4 * D) + (32 + 4 * CP + 12) + 44      # in + out + phase-2 re-read
+    prep_bwd_b = (44 + 32 + 12 + 4 + 32 + 4 * CP) + (12 + 12 + 16 + 4 + 300 + 4 * D)
+    bytes_model = {"gg_prepare_views": n * V * prep_b, "gg_prepare_views_bwd": n * V * prep_bwd_b}
     hbm_stages = {}
     for k, bts in bytes_model.items():
-        if k in avg:
-            per_launch = bts / (len(per_call[k]) / args.steps)
-            gbs = per_launch / (avg[k] * 1e-3) / 1e9
-            hbm_stages[k] = {"GB/s": gbs, "frac": gbs / hbm_peak, "avg_launch_ms": avg[k]}
+        if k in share:
+            gbs = bts / (share[k] * 1e-3) / 1e9   # all launches of the stage in one step
+            hbm_stages[k] = {"GB/s": gbs, "frac": gbs / hbm_peak, "ms_per_step": share[k], "bytes_per_step": bts}
 
     # --- CPU baseline (rank 0, N=1 only): the reference maths on the host cores ---------------
     cpu = None
@@ -341,13 +349,12 @@ def run_ours(args):
         threads = os.cpu_count() or 1
         sc_cpu = {k: sc[k] for k in names}
         cam0 = cams[0]
-        tiles, total_tiles = sample_tiles(cam0, 8)
-        tg, tb = cpu_reference_step(sc_cpu, cam0, D, tiles, threads)
-        t_full = tg + tb * total_tiles / len(tiles)
+        tg, tb, scale, ns, nt = cpu_reference_step(sc_cpu, cam0, D, 8, threads)
+        t_full = tg + tb * scale
         cpu = {"value": (W * H / 1e6) / t_full, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": (f"torch-CPU port of the reference maths, 1 step: SH+projection+binning fwd+bwd of all {n} "
-                          f"Gaussians ({tg:.2f} s) + blend fwd+bwd of {len(tiles)}/{total_tiles} tiles ({tb:.2f} s, "
-                          f"scaled to the frame)")}
+                          f"Gaussians ({tg:.2f} s) + blend fwd+bwd of {ns}/{nt} tiles at length quantiles ({tb:.2f} s, "
+                          f"scaled by frame pairs / sample pairs = {scale:.1f})")}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
