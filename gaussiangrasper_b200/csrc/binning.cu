@@ -314,6 +314,45 @@ tile_ranges_kernel(long long m, const int64_t* __restrict__ keys_sorted, int32_t
     if (i == m - 1 || (int32_t)(keys_sorted[i + 1] >> 32) != t) tile_ranges[2 * (size_t)t + 1] = (int32_t)(i + 1);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Longest-first tile order for the blend kernels: CTAs are dispatched in blockIdx order, so
+// visiting the tiles by descending list length keeps the tail of the launch short (the lists
+// vary by two orders of magnitude).  Counting sort on 1024 length buckets; the order inside a
+// bucket is whatever the atomics give (it only affects scheduling, never results).
+// ---------------------------------------------------------------------------------------------
+constexpr int kOrderBins = 1024;
+__device__ __forceinline__ int tile_len_bucket(int len) { return min(kOrderBins - 1, len >> 3); }
+
+__global__ void __launch_bounds__(256)
+tile_len_hist_kernel(long long num_tiles, const int32_t* __restrict__ tile_ranges, int* __restrict__ bins) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= num_tiles) return;
+    const int2 r = __ldg(reinterpret_cast<const int2*>(tile_ranges) + t);
+    atomicAdd(&bins[tile_len_bucket(r.y - r.x)], 1);
+}
+// bins[b] <- number of tiles in buckets above b (descending exclusive scan); one block of 1024
+__global__ void __launch_bounds__(kOrderBins) tile_order_scan_kernel(int* __restrict__ bins) {
+    __shared__ int sm[kOrderBins];
+    const int b = threadIdx.x;
+    sm[b] = bins[kOrderBins - 1 - b];  // reversed: ascending index = descending length
+    __syncthreads();
+    for (int o = 1; o < kOrderBins; o <<= 1) {
+        const int v = b >= o ? sm[b - o] : 0;
+        __syncthreads();
+        sm[b] += v;
+        __syncthreads();
+    }
+    bins[kOrderBins - 1 - b] = sm[b] - bins[kOrderBins - 1 - b];
+}
+__global__ void __launch_bounds__(256)
+tile_order_scatter_kernel(long long num_tiles, const int32_t* __restrict__ tile_ranges, int* __restrict__ cursor,
+                          int32_t* __restrict__ order) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= num_tiles) return;
+    const int2 r = __ldg(reinterpret_cast<const int2*>(tile_ranges) + t);
+    order[atomicAdd(&cursor[tile_len_bucket(r.y - r.x)], 1)] = (int32_t)t;
+}
+
 static std::atomic<uint32_t> g_generation{1};
 
 struct SortLayout {
@@ -445,4 +484,22 @@ extern "C" int gg_tile_ranges(long long m, const int64_t* keys_sorted, long long
         count_launch();
     }
     return check_launch("tile_ranges_kernel");
+}
+
+extern "C" size_t gg_tile_order_workspace_bytes(void) { return sizeof(int) * kOrderBins; }
+
+extern "C" int gg_tile_order(long long num_tiles, const int32_t* tile_ranges, int32_t* tile_order, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+    GG_REQUIRE(num_tiles >= 1 && num_tiles < (1ll << 31), "gg_tile_order: bad tile count");
+    GG_REQUIRE(tile_ranges && tile_order && workspace, "gg_tile_order: null pointer");
+    GG_REQUIRE(workspace_bytes >= gg_tile_order_workspace_bytes(), "gg_tile_order: workspace too small");
+    GG_REQUIRE(((uintptr_t)tile_ranges & 7) == 0, "gg_tile_order: tile_ranges misaligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    int* bins = reinterpret_cast<int*>(workspace);
+    GG_CUDA(cudaMemsetAsync(bins, 0, sizeof(int) * kOrderBins, st));
+    tile_len_hist_kernel<<<div_up(num_tiles, 256), 256, 0, st>>>(num_tiles, tile_ranges, bins);
+    tile_order_scan_kernel<<<1, kOrderBins, 0, st>>>(bins);
+    tile_order_scatter_kernel<<<div_up(num_tiles, 256), 256, 0, st>>>(num_tiles, tile_ranges, bins, tile_order);
+    count_launch(3);
+    return check_launch("gg_tile_order");
 }

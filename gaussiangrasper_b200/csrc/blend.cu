@@ -37,6 +37,7 @@ struct BlendArgs {
     long long color_view_stride;  // rows between views in colors / v_colors (0: shared by all views)
     const int32_t* ids_sorted;
     const int32_t* tile_ranges;  // [V*T, 2]
+    const int32_t* tile_order;   // [V*T] visiting order of the tiles (nullable: identity)
     const float* geo;            // [V*N, 8]
     const float* colors;
     const float* bg;             // [channels]
@@ -133,8 +134,11 @@ blend_fwd_kernel(const BlendArgs a) {
     extern __shared__ __align__(16) float smem[];
     float* geo_sm = smem;                            // [kStages][BATCH][8]
     float* col_sm = smem + kStages * BATCH * 8;      // [kStages][BATCH][CP]
-    const int view = blockIdx.y;
-    const int tile = blockIdx.x;
+    const int n_tiles = a.tiles_x * a.tiles_y;
+    const int lin = blockIdx.y * n_tiles + blockIdx.x;
+    const int gtile = a.tile_order ? __ldg(a.tile_order + lin) : lin;  // longest lists first
+    const int view = gtile / n_tiles;
+    const int tile = gtile - view * n_tiles;
     const int tile_y = tile / a.tiles_x, tile_x = tile - tile_y * a.tiles_x;
     int tx, ty;
     tile_pixel(tx, ty);
@@ -267,7 +271,7 @@ constexpr size_t blend_bwd_smem() {
 }
 
 template <int CP, int BATCH, bool kVec>
-__global__ void __launch_bounds__(kBlendThreads)
+__global__ void __launch_bounds__(kBlendThreads, (CP <= 24) ? 3 : ((CP <= 40) ? 2 : 1))
 blend_bwd_kernel(const BlendArgs a) {
     extern __shared__ __align__(16) float smem[];
     float* geo_sm = smem;                                                  // [kStages][BATCH][8]
@@ -275,8 +279,11 @@ blend_bwd_kernel(const BlendArgs a) {
     int* ids_sm = reinterpret_cast<int*>(col_sm + kStages * BATCH * CP);   // [kStages][BATCH]
     float* vo_sm = reinterpret_cast<float*>(ids_sm + kStages * BATCH);     // [256][CP]
     __shared__ int s_max[kBlendThreads / 32];
-    const int view = blockIdx.y;
-    const int tile = blockIdx.x;
+    const int n_tiles = a.tiles_x * a.tiles_y;
+    const int lin = blockIdx.y * n_tiles + blockIdx.x;
+    const int gtile = a.tile_order ? __ldg(a.tile_order + lin) : lin;  // longest lists first
+    const int view = gtile / n_tiles;
+    const int tile = gtile - view * n_tiles;
     const int tile_y = tile / a.tiles_x, tile_x = tile - tile_y * a.tiles_x;
     int tx, ty;
     tile_pixel(tx, ty);
@@ -331,6 +338,14 @@ blend_bwd_kernel(const BlendArgs a) {
 
     const float* vo_warp = vo_sm + warp * 32 * CP;
     int nhit = 0;
+    auto reload_vo = [&]() {
+        const float4* row = reinterpret_cast<const float4*>(vo_sm + threadIdx.x * CP);
+#pragma unroll
+        for (int q = 0; q < CP / 4; ++q) {
+            const float4 v = row[q];
+            vo[4 * q] = v.x; vo[4 * q + 1] = v.y; vo[4 * q + 2] = v.z; vo[4 * q + 3] = v.w;
+        }
+    };
     // phase B: lane = (stored entry j = lane & 15, pixel half h = lane >> 4); each half-warp sums
     // its 16 pixels, the halves are combined with one shuffle per value, then the 6 + C reds of an
     // entry are split between its two lanes
@@ -452,7 +467,11 @@ blend_bwd_kernel(const BlendArgs a) {
                 facm[nhit * kHitRow + lane] = fac;
                 wm[nhit * kHitRow + lane] = w;
                 if (lane == 0) hit_g[nhit] = idb[e];
-                if (++nhit == kHitRows) { flush(kHitRows); nhit = 0; }
+                if (++nhit == kHitRows) {
+                    flush(kHitRows);
+                    nhit = 0;
+                    reload_vo();  // vo[] was dead across the flush: its registers held the accumulators
+                }
             };
 #pragma unroll
             for (int k = BATCH / 32 - 1; k >= 0; --k) {
@@ -549,10 +568,10 @@ static int launch_blend_impl(bool backward, const BlendArgs& a, int n_views, boo
 }
 
 // forward stages BATCH entries per round; the backward also keeps v_out and the per-warp hit
-// matrices in shared memory, so it stages 64
+// matrices in shared memory, so it stages 32 (3 CTAs per SM at C <= 24)
 template <int CP, int BATCH>
 static int launch_blend(bool backward, const BlendArgs& a, int n_views, bool vec, cudaStream_t st) {
-    if (backward) return launch_blend_impl<CP, 64>(true, a, n_views, vec, st);
+    if (backward) return launch_blend_impl<CP, 32>(true, a, n_views, vec, st);
     return launch_blend_impl<CP, BATCH>(false, a, n_views, vec, st);
 }
 
@@ -601,9 +620,9 @@ extern "C" int gg_unpack_vgeo(long long n, int n_views, const float* v_geo, floa
 
 extern "C" int gg_blend_fwd(int n_views, long long n, int channels, int color_stride, int colors_per_view,
                             int out_stride, int img_h, int img_w, int tiles_x, int tiles_y,
-                            const int32_t* ids_sorted, const int32_t* tile_ranges, const float* geo,
-                            const float* colors, const float* bg, float* out, float* final_T, int32_t* final_idx,
-                            unsigned long long* pair_counter, void* stream) {
+                            const int32_t* ids_sorted, const int32_t* tile_ranges, const int32_t* tile_order,
+                            const float* geo, const float* colors, const float* bg, float* out, float* final_T,
+                            int32_t* final_idx, unsigned long long* pair_counter, void* stream) {
     GG_REQUIRE(n_views >= 1 && n >= 1 && channels >= 1, "gg_blend_fwd: bad sizes");
     GG_REQUIRE(color_stride >= channels && out_stride >= channels, "gg_blend_fwd: stride smaller than channels");
     GG_REQUIRE(img_h > 0 && img_w > 0 && tiles_x == (img_w + GG_TILE - 1) / GG_TILE &&
@@ -616,16 +635,17 @@ extern "C" int gg_blend_fwd(int n_views, long long n, int channels, int color_st
     a.channels = channels; a.color_stride = color_stride; a.out_stride = out_stride;
     a.img_h = img_h; a.img_w = img_w; a.tiles_x = tiles_x; a.tiles_y = tiles_y;
     a.geo_view_stride = n; a.color_view_stride = colors_per_view ? n : 0;
-    a.ids_sorted = ids_sorted; a.tile_ranges = tile_ranges; a.geo = geo; a.colors = colors; a.bg = bg;
+    a.ids_sorted = ids_sorted; a.tile_ranges = tile_ranges; a.tile_order = tile_order; a.geo = geo; a.colors = colors; a.bg = bg;
     a.out = out; a.final_T = final_T; a.final_idx = final_idx; a.pair_counter = pair_counter;
     return dispatch_blend(false, a, n_views, (cudaStream_t)stream);
 }
 
 extern "C" int gg_blend_bwd(int n_views, long long n, int channels, int color_stride, int colors_per_view,
                             int out_stride, int img_h, int img_w, int tiles_x, int tiles_y,
-                            const int32_t* ids_sorted, const int32_t* tile_ranges, const float* geo,
-                            const float* colors, const float* bg, const float* final_T, const int32_t* final_idx,
-                            const float* v_out, float* v_geo, float* v_colors, void* stream) {
+                            const int32_t* ids_sorted, const int32_t* tile_ranges, const int32_t* tile_order,
+                            const float* geo, const float* colors, const float* bg, const float* final_T,
+                            const int32_t* final_idx, const float* v_out, float* v_geo, float* v_colors,
+                            void* stream) {
     GG_REQUIRE(n_views >= 1 && n >= 1 && channels >= 1, "gg_blend_bwd: bad sizes");
     GG_REQUIRE(color_stride >= channels && out_stride >= channels, "gg_blend_bwd: stride smaller than channels");
     GG_REQUIRE(img_h > 0 && img_w > 0 && tiles_x == (img_w + GG_TILE - 1) / GG_TILE &&
@@ -638,7 +658,7 @@ extern "C" int gg_blend_bwd(int n_views, long long n, int channels, int color_st
     a.channels = channels; a.color_stride = color_stride; a.out_stride = out_stride;
     a.img_h = img_h; a.img_w = img_w; a.tiles_x = tiles_x; a.tiles_y = tiles_y;
     a.geo_view_stride = n; a.color_view_stride = colors_per_view ? n : 0;
-    a.ids_sorted = ids_sorted; a.tile_ranges = tile_ranges; a.geo = geo; a.colors = colors; a.bg = bg;
+    a.ids_sorted = ids_sorted; a.tile_ranges = tile_ranges; a.tile_order = tile_order; a.geo = geo; a.colors = colors; a.bg = bg;
     a.final_T = const_cast<float*>(final_T); a.final_idx = const_cast<int32_t*>(final_idx);
     a.v_out = v_out; a.v_geo = v_geo; a.v_colors = v_colors;
     return dispatch_blend(true, a, n_views, (cudaStream_t)stream);

@@ -32,6 +32,7 @@ class _Workspace:
         self.keys = None
         self.ids = None
         self.keys_sorted = None
+        self.order_ws = None
         self.total = torch.zeros(1, dtype=torch.int32, device=device)
         self.total_host = torch.zeros(1, dtype=torch.int32).pin_memory()
         self.total_event = torch.cuda.Event()
@@ -189,6 +190,18 @@ def tile_ranges(m, keys_sorted, num_tiles):
     return ranges
 
 
+def tile_order(ranges: torch.Tensor) -> torch.Tensor:
+    dev = ranges.device
+    ws = workspace(dev)
+    if ws.order_ws is None:
+        ws.order_ws = torch.empty(int(_lib.load().gg_tile_order_workspace_bytes()), dtype=torch.uint8, device=dev)
+    order = torch.empty((ranges.shape[0],), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.call("gg_tile_order", int(ranges.shape[0]), ptr(ranges), ptr(order), ptr(ws.order_ws), ws.order_ws.numel(),
+                  stream_ptr(dev))
+    return order
+
+
 @dataclass
 class Binning:
     """Sorted intersection list of one batch of views (what the blend kernels consume)."""
@@ -198,6 +211,7 @@ class Binning:
     ids_sorted: torch.Tensor    # [M] int32
     tile_ranges: torch.Tensor   # [V*T, 2] int32
     tile_bounds: Tuple[int, int, int]
+    tile_order: Optional[torch.Tensor] = None  # [V*T] int32, tiles by descending list length
 
 
 def bin_views(n, n_views, xys, depths, radii, num_tiles_hit, tile_bounds, xy_from_geo=False,
@@ -228,7 +242,8 @@ def bin_views(n, n_views, xys, depths, radii, num_tiles_hit, tile_bounds, xy_fro
         ranges = tile_ranges(m, keys_sorted, num_tiles)
     else:
         ranges = torch.zeros((num_tiles, 2), dtype=torch.int32, device=dev)
-    return Binning(n, n_views, m, ids_sorted[:m] if m > 0 else ids_sorted[:0], ranges, tuple(tile_bounds))
+    order = tile_order(ranges) if m > 0 else None
+    return Binning(n, n_views, m, ids_sorted[:m] if m > 0 else ids_sorted[:0], ranges, tuple(tile_bounds), order)
 
 
 # ------------------------------------------------------------------------------------------
@@ -269,8 +284,8 @@ def blend_fwd(binning: Binning, geo, colors, background, img_height, img_width, 
             c1 = min(C, c0 + step)
             _lib.call("gg_blend_fwd", 
                 V, n, c1 - c0, C, 1 if colors_per_view else 0, C, int(img_height), int(img_width), tb[0], tb[1],
-                ptr(binning.ids_sorted), ptr(binning.tile_ranges), ptr(geo), colors.data_ptr() + 4 * c0,
-                background.data_ptr() + 4 * c0, out.data_ptr() + 4 * c0, ptr(final_T), ptr(final_idx),
+                ptr(binning.ids_sorted), ptr(binning.tile_ranges), ptr(binning.tile_order), ptr(geo),
+                colors.data_ptr() + 4 * c0, background.data_ptr() + 4 * c0, out.data_ptr() + 4 * c0, ptr(final_T), ptr(final_idx),
                 ptr(pair_counter) if c0 == 0 else None, stream_ptr(dev))
     return out, final_T, final_idx
 
@@ -291,8 +306,8 @@ def blend_bwd(binning: Binning, geo, colors, background, final_T, final_idx, v_o
             c1 = min(C, c0 + step)
             _lib.call("gg_blend_bwd", 
                 V, n, c1 - c0, C, 1 if colors_per_view else 0, C, int(img_height), int(img_width), tb[0], tb[1],
-                ptr(binning.ids_sorted), ptr(binning.tile_ranges), ptr(geo), colors.data_ptr() + 4 * c0,
-                background.data_ptr() + 4 * c0, ptr(final_T), ptr(final_idx), v_out.data_ptr() + 4 * c0, ptr(v_geo),
+                ptr(binning.ids_sorted), ptr(binning.tile_ranges), ptr(binning.tile_order), ptr(geo),
+                colors.data_ptr() + 4 * c0, background.data_ptr() + 4 * c0, ptr(final_T), ptr(final_idx), v_out.data_ptr() + 4 * c0, ptr(v_geo),
                 v_colors.data_ptr() + 4 * c0, stream_ptr(dev))
     return v_geo, v_colors
 

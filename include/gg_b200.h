@@ -100,6 +100,12 @@ int gg_sort_pairs(long long m, int key_bits, const int64_t* keys_in, const int32
 int gg_tile_ranges(long long m, const int64_t* keys_sorted, long long num_tiles, int32_t* tile_ranges,
                    void* stream);
 
+/* visiting order of the tiles for the blend kernels: tile ids by descending list length (only
+ * scheduling depends on it, never results); tile_order [num_tiles] int32 */
+size_t gg_tile_order_workspace_bytes(void);
+int gg_tile_order(long long num_tiles, const int32_t* tile_ranges, int32_t* tile_order, void* workspace,
+                  size_t workspace_bytes, void* stream);
+
 /* ---- blending: replaces gsplat.cuda.rasterize_forward / nd_rasterize_forward and backward ---
  * (RasterizeGaussians / NDRasterizeGaussians, gaussian_splatting.py:735,747,759,773).
  * geo is the packed per-Gaussian record {x, y, A/2, B, C/2, opacity, tau, 0} built by gg_pack_geo.
@@ -111,13 +117,15 @@ int gg_pack_geo(long long n, int n_views, const float* xys, const float* conics,
                 int opac_per_view, float* geo /*[V*n,8]*/, void* stream);
 int gg_blend_fwd(int n_views, long long n, int channels, int color_stride, int colors_per_view, int out_stride,
                  int img_h, int img_w, int tiles_x, int tiles_y, const int32_t* ids_sorted,
-                 const int32_t* tile_ranges, const float* geo, const float* colors, const float* bg,
+                 const int32_t* tile_ranges, const int32_t* tile_order /*nullable*/, const float* geo,
+                 const float* colors, const float* bg,
                  float* out /*[V,H,W,out_stride]*/, float* final_T /*[V,H,W]*/, int32_t* final_idx /*[V,H,W]*/,
                  unsigned long long* pair_counter /*nullable*/, void* stream);
 /* v_geo [V*n,8] and v_colors (indexed like colors) are accumulated into: zero them first */
 int gg_blend_bwd(int n_views, long long n, int channels, int color_stride, int colors_per_view, int out_stride,
                  int img_h, int img_w, int tiles_x, int tiles_y, const int32_t* ids_sorted,
-                 const int32_t* tile_ranges, const float* geo, const float* colors, const float* bg,
+                 const int32_t* tile_ranges, const int32_t* tile_order /*nullable*/, const float* geo,
+                 const float* colors, const float* bg,
                  const float* final_T, const int32_t* final_idx, const float* v_out, float* v_geo,
                  float* v_colors, void* stream);
 /* v_geo -> v_xys [V*n,2], v_conics [V*n,3], v_opac [n] (summed over views; nullable) */
