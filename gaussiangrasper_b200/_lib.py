@@ -41,6 +41,10 @@ _SIGNATURES = {
     "gg_pack_geo": (C.c_int, [_ll, _i, _p, _p, _p, _i, _p, _p]),
     "gg_blend_fwd": (C.c_int, [_i, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "gg_blend_bwd": (C.c_int, [_i, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "gg_depth_keys": (C.c_int, [_ll, _i, _p, _p, _p, _p]),
+    "gg_gather_counts": (C.c_int, [_ll, _p, _p, _p, _p]),
+    "gg_emit_tiles_sorted": (C.c_int, [_i, _i, _p, _p, _i, _p, _p, _i, _i, _p, _p, _p]),
+    "gg_tile_ranges_lowkey": (C.c_int, [_ll, _p, _ll, _p, _p]),
     "gg_tile_order_workspace_bytes": (C.c_size_t, []),
     "gg_tile_order": (C.c_int, [_ll, _p, _p, _p, _sz, _p]),
     "gg_unpack_vgeo": (C.c_int, [_ll, _i, _p, _p, _p, _p, _i, _p]),

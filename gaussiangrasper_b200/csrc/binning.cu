@@ -306,12 +306,63 @@ radix_pass_kernel(const uint64_t* __restrict__ kin, const uint32_t* __restrict__
 // tile_ranges[t] = (first, last+1) of the run of sorted keys whose high word is t; must be
 // zero-initialised (empty tiles stay (0,0)).
 __global__ void __launch_bounds__(256)
-tile_ranges_kernel(long long m, const int64_t* __restrict__ keys_sorted, int32_t* __restrict__ tile_ranges) {
+tile_ranges_kernel(long long m, const int64_t* __restrict__ keys_sorted, int shift,
+                   int32_t* __restrict__ tile_ranges) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
-    const int32_t t = (int32_t)(keys_sorted[i] >> 32);
-    if (i == 0 || (int32_t)(keys_sorted[i - 1] >> 32) != t) tile_ranges[2 * (size_t)t] = (int32_t)i;
-    if (i == m - 1 || (int32_t)(keys_sorted[i + 1] >> 32) != t) tile_ranges[2 * (size_t)t + 1] = (int32_t)(i + 1);
+    const int32_t t = (int32_t)(keys_sorted[i] >> shift);
+    if (i == 0 || (int32_t)(keys_sorted[i - 1] >> shift) != t) tile_ranges[2 * (size_t)t] = (int32_t)i;
+    if (i == m - 1 || (int32_t)(keys_sorted[i + 1] >> shift) != t) tile_ranges[2 * (size_t)t + 1] = (int32_t)(i + 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Depth-first binning (used by the internal path; the gsplat-compatible entry points above keep
+// the reference's one-sort formulation).  The (tile, depth, id) order is obtained as
+//   1. stable sort of the V*N Gaussians by (view, depth)            -- 4-5 passes over N items
+//   2. emission of the tile entries in that order                    -- key = view*T + tile only
+//   3. stable sort of the M entries by that tile key                 -- 2-3 passes over M items
+// which yields bit for bit the same sorted id list as sorting M 64-bit (tile|depth) keys with
+// ties broken by id, at a third of the M-sized passes.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+depth_keys_kernel(long long total, long long n, const float* __restrict__ depths, int64_t* __restrict__ keys,
+                  int32_t* __restrict__ rows) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const uint64_t view = (uint64_t)(i / n);
+    keys[i] = (int64_t)((view << 32) | (uint64_t)__float_as_uint(depths[i]));
+    rows[i] = (int32_t)i;
+}
+
+__global__ void __launch_bounds__(256)
+gather_counts_kernel(long long total, const int32_t* __restrict__ order, const int32_t* __restrict__ num_tiles_hit,
+                     int32_t* __restrict__ counts) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    counts[i] = __ldg(num_tiles_hit + order[i]);
+}
+
+__global__ void __launch_bounds__(256)
+emit_tiles_sorted_kernel(long long total, int n, const int32_t* __restrict__ order, const float* __restrict__ xys,
+                         int xy_stride, const int32_t* __restrict__ radii, const int32_t* __restrict__ cum,
+                         int tiles_x, int tiles_y, int64_t* __restrict__ keys, int32_t* __restrict__ ids) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long long row = order[i];
+    const int r = radii[row];
+    if (r <= 0) return;
+    const int view = (int)(row / n);
+    const int g = (int)(row - (long long)view * n);
+    const float2 c = __ldg(reinterpret_cast<const float2*>(xys + row * xy_stride));
+    const TileBox tb = tile_box(c.x, c.y, (float)r, tiles_x, tiles_y);
+    long long cur = i == 0 ? 0 : cum[i - 1];
+    const long long tile0 = (long long)view * tiles_x * tiles_y;
+    for (int ty = tb.y0; ty < tb.y1; ++ty)
+        for (int tx = tb.x0; tx < tb.x1; ++tx) {
+            keys[cur] = tile0 + (long long)ty * tiles_x + tx;
+            ids[cur] = g;
+            ++cur;
+        }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -473,14 +524,28 @@ extern "C" int gg_sort_pairs(long long m, int key_bits, const int64_t* keys_in, 
     return check_launch("gg_sort_pairs");
 }
 
+static int tile_ranges_impl(long long m, const int64_t* keys_sorted, int key_shift, long long num_tiles,
+                            int32_t* tile_ranges, void* stream);
+
 extern "C" int gg_tile_ranges(long long m, const int64_t* keys_sorted, long long num_tiles, int32_t* tile_ranges,
                               void* stream) {
+    return tile_ranges_impl(m, keys_sorted, 32, num_tiles, tile_ranges, stream);
+}
+
+// same for keys that hold the tile id in their low bits (depth-first binning)
+extern "C" int gg_tile_ranges_lowkey(long long m, const int64_t* keys_sorted, long long num_tiles,
+                                     int32_t* tile_ranges, void* stream) {
+    return tile_ranges_impl(m, keys_sorted, 0, num_tiles, tile_ranges, stream);
+}
+
+static int tile_ranges_impl(long long m, const int64_t* keys_sorted, int key_shift, long long num_tiles,
+                            int32_t* tile_ranges, void* stream) {
     GG_REQUIRE(m >= 0 && num_tiles >= 1, "gg_tile_ranges: bad sizes");
     GG_REQUIRE(tile_ranges && (m == 0 || keys_sorted), "gg_tile_ranges: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     GG_CUDA(cudaMemsetAsync(tile_ranges, 0, sizeof(int32_t) * 2 * (size_t)num_tiles, st));
     if (m > 0) {
-        tile_ranges_kernel<<<div_up(m, 256), 256, 0, st>>>(m, keys_sorted, tile_ranges);
+        tile_ranges_kernel<<<div_up(m, 256), 256, 0, st>>>(m, keys_sorted, key_shift, tile_ranges);
         count_launch();
     }
     return check_launch("tile_ranges_kernel");
@@ -502,4 +567,37 @@ extern "C" int gg_tile_order(long long num_tiles, const int32_t* tile_ranges, in
     tile_order_scatter_kernel<<<div_up(num_tiles, 256), 256, 0, st>>>(num_tiles, tile_ranges, bins, tile_order);
     count_launch(3);
     return check_launch("gg_tile_order");
+}
+
+extern "C" int gg_depth_keys(long long n, int n_views, const float* depths, int64_t* keys, int32_t* rows,
+                             void* stream) {
+    GG_REQUIRE(n >= 1 && n_views >= 1 && n * n_views < (1ll << 31), "gg_depth_keys: bad sizes");
+    GG_REQUIRE(depths && keys && rows, "gg_depth_keys: null pointer");
+    const long long total = n * n_views;
+    depth_keys_kernel<<<div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(total, n, depths, keys, rows);
+    count_launch();
+    return check_launch("depth_keys_kernel");
+}
+
+extern "C" int gg_gather_counts(long long total, const int32_t* order, const int32_t* num_tiles_hit, int32_t* counts,
+                                void* stream) {
+    GG_REQUIRE(total >= 1, "gg_gather_counts: bad size");
+    GG_REQUIRE(order && num_tiles_hit && counts, "gg_gather_counts: null pointer");
+    gather_counts_kernel<<<div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(total, order, num_tiles_hit, counts);
+    count_launch();
+    return check_launch("gather_counts_kernel");
+}
+
+extern "C" int gg_emit_tiles_sorted(int n, int n_views, const int32_t* order, const float* xys, int xy_stride,
+                                    const int32_t* radii, const int32_t* cum_sorted, int tiles_x, int tiles_y,
+                                    int64_t* keys, int32_t* ids, void* stream) {
+    GG_REQUIRE(n >= 1 && n_views >= 1, "gg_emit_tiles_sorted: need n >= 1");
+    GG_REQUIRE(order && xys && radii && cum_sorted && keys && ids, "gg_emit_tiles_sorted: null pointer");
+    GG_REQUIRE((xy_stride == 2 || xy_stride == 8) && ((uintptr_t)xys & 7) == 0, "gg_emit_tiles_sorted: bad xys");
+    GG_REQUIRE((long long)n_views * tiles_x * tiles_y < (1ll << 31), "gg_emit_tiles_sorted: too many tiles");
+    const long long total = (long long)n * n_views;
+    emit_tiles_sorted_kernel<<<div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        total, n, order, xys, xy_stride, radii, cum_sorted, tiles_x, tiles_y, keys, ids);
+    count_launch();
+    return check_launch("emit_tiles_sorted_kernel");
 }

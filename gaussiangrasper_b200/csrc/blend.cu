@@ -271,7 +271,7 @@ constexpr size_t blend_bwd_smem() {
 }
 
 template <int CP, int BATCH, bool kVec>
-__global__ void __launch_bounds__(kBlendThreads, (CP <= 24) ? 3 : ((CP <= 40) ? 2 : 1))
+__global__ void __launch_bounds__(kBlendThreads)
 blend_bwd_kernel(const BlendArgs a) {
     extern __shared__ __align__(16) float smem[];
     float* geo_sm = smem;                                                  // [kStages][BATCH][8]
@@ -568,10 +568,11 @@ static int launch_blend_impl(bool backward, const BlendArgs& a, int n_views, boo
 }
 
 // forward stages BATCH entries per round; the backward also keeps v_out and the per-warp hit
-// matrices in shared memory, so it stages 32 (3 CTAs per SM at C <= 24)
+// matrices in shared memory, so it stages 64 (2 CTAs per SM at C <= 24; 3 CTAs with 32-entry
+// batches measured slower: twice the barriers)
 template <int CP, int BATCH>
 static int launch_blend(bool backward, const BlendArgs& a, int n_views, bool vec, cudaStream_t st) {
-    if (backward) return launch_blend_impl<CP, 32>(true, a, n_views, vec, st);
+    if (backward) return launch_blend_impl<CP, 64>(true, a, n_views, vec, st);
     return launch_blend_impl<CP, BATCH>(false, a, n_views, vec, st);
 }
 

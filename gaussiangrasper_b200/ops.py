@@ -33,6 +33,7 @@ class _Workspace:
         self.ids = None
         self.keys_sorted = None
         self.order_ws = None
+        self.depth = None
         self.total = torch.zeros(1, dtype=torch.int32, device=device)
         self.total_host = torch.zeros(1, dtype=torch.int32).pin_memory()
         self.total_event = torch.cuda.Event()
@@ -49,6 +50,14 @@ class _Workspace:
             # zero-filled once: the library owns the look-back status words afterwards
             self.sort = torch.zeros(int(need * 1.5) + 256, dtype=torch.uint8, device=self.device)
         return self.sort
+
+    def depth_buffers(self, total):
+        if self.depth is None or self.depth[0].numel() < total:
+            cap = int(total * 1.25) + 1024
+            i64 = lambda: torch.empty(cap, dtype=torch.int64, device=self.device)
+            i32 = lambda: torch.empty(cap, dtype=torch.int32, device=self.device)
+            self.depth = (i64(), i32(), i64(), i32(), i32())   # keys, rows, keys_sorted, order, counts
+        return self.depth
 
     def key_buffers(self, m):
         if self.keys is None or self.keys.numel() < m:
@@ -215,14 +224,32 @@ class Binning:
 
 
 def bin_views(n, n_views, xys, depths, radii, num_tiles_hit, tile_bounds, xy_from_geo=False,
-              while_waiting=None) -> Binning:
-    """cumsum -> (one host read of M) -> key emission -> radix sort -> tile ranges.
-    xy_from_geo: `xys` is the packed [V*n, 8] geo table (pixel centres in columns 0..1)."""
+              while_waiting=None, depth_first=True) -> Binning:
+    """Sorted (tile, depth, id) intersection list of a batch of views.
+
+    depth_first (default): sort the V*n Gaussians by (view, depth), emit their tile entries in that
+    order, stable-sort the M entries by tile id -- 4-5 small passes + 2-3 M-sized passes.  Otherwise the
+    reference's formulation: emit 64-bit tile|depth keys in id order and sort all M of them (6-7
+    M-sized passes).  Both give bit-identical ids_sorted / tile_ranges.
+    xy_from_geo: `xys` is the packed [V*n, 8] geo table (pixel centres in columns 0..1).
+    while_waiting: callable run after the M read-back is enqueued and before the host waits for it."""
     dev = require_cuda(xys, depths, radii, num_tiles_hit)
     ws = workspace(dev)
+    lib_call = _lib.call
     xys, depths = f32c(xys), f32c(depths)
-    radii, num_tiles_hit = radii.contiguous(), num_tiles_hit.contiguous()
-    cum = cumsum_i32(num_tiles_hit.reshape(-1), ws.total)
+    radii, num_tiles_hit = radii.contiguous().reshape(-1), num_tiles_hit.contiguous().reshape(-1)
+    total = n * n_views
+    num_tiles = int(tile_bounds[0]) * int(tile_bounds[1]) * n_views
+    order = None
+    with torch.cuda.device(dev):
+        if depth_first:
+            dkeys, rows, dkeys_sorted, order, counts = ws.depth_buffers(total)
+            lib_call("gg_depth_keys", int(n), int(n_views), ptr(depths), ptr(dkeys), ptr(rows), stream_ptr(dev))
+            sort_pairs(total, 32 + max(0, (n_views - 1).bit_length()), dkeys, rows, dkeys_sorted, order)
+            lib_call("gg_gather_counts", int(total), ptr(order), ptr(num_tiles_hit), ptr(counts), stream_ptr(dev))
+            cum = cumsum_i32(counts[:total], ws.total)
+        else:
+            cum = cumsum_i32(num_tiles_hit, ws.total)
     # the one device->host read of the path (the reference has five per view): M sizes the sort.
     # Work passed as `while_waiting` is enqueued behind the copy so the GPU stays busy meanwhile.
     ws.total_host.copy_(ws.total, non_blocking=True)
@@ -233,17 +260,25 @@ def bin_views(n, n_views, xys, depths, radii, num_tiles_hit, tile_bounds, xy_fro
     m = int(ws.total_host[0])
     if m < 0:
         raise _lib.GGError("number of tile intersections overflows int32")
-    num_tiles = int(tile_bounds[0]) * int(tile_bounds[1]) * n_views
     ids_sorted = torch.empty((max(m, 1),), dtype=torch.int32, device=dev)
     if m > 0:
         keys, ids, keys_sorted = ws.key_buffers(m)
-        map_to_intersects(n, n_views, xys, depths, radii, cum, tile_bounds, keys, ids, xy_from_geo)
-        sort_pairs(m, key_bits_for(num_tiles), keys, ids, keys_sorted, ids_sorted)
-        ranges = tile_ranges(m, keys_sorted, num_tiles)
+        with torch.cuda.device(dev):
+            if depth_first:
+                lib_call("gg_emit_tiles_sorted", int(n), int(n_views), ptr(order), ptr(xys), 8 if xy_from_geo else 2,
+                         ptr(radii), ptr(cum), int(tile_bounds[0]), int(tile_bounds[1]), ptr(keys), ptr(ids),
+                         stream_ptr(dev))
+                sort_pairs(m, max(1, (num_tiles - 1).bit_length()), keys, ids, keys_sorted, ids_sorted)
+                ranges = torch.empty((num_tiles, 2), dtype=torch.int32, device=dev)
+                lib_call("gg_tile_ranges_lowkey", int(m), ptr(keys_sorted), int(num_tiles), ptr(ranges), stream_ptr(dev))
+            else:
+                map_to_intersects(n, n_views, xys, depths, radii, cum, tile_bounds, keys, ids, xy_from_geo)
+                sort_pairs(m, key_bits_for(num_tiles), keys, ids, keys_sorted, ids_sorted)
+                ranges = tile_ranges(m, keys_sorted, num_tiles)
     else:
         ranges = torch.zeros((num_tiles, 2), dtype=torch.int32, device=dev)
-    order = tile_order(ranges) if m > 0 else None
-    return Binning(n, n_views, m, ids_sorted[:m] if m > 0 else ids_sorted[:0], ranges, tuple(tile_bounds), order)
+    order_t = tile_order(ranges) if m > 0 else None
+    return Binning(n, n_views, m, ids_sorted[:m] if m > 0 else ids_sorted[:0], ranges, tuple(tile_bounds), order_t)
 
 
 # ------------------------------------------------------------------------------------------

@@ -100,6 +100,19 @@ int gg_sort_pairs(long long m, int key_bits, const int64_t* keys_in, const int32
 int gg_tile_ranges(long long m, const int64_t* keys_sorted, long long num_tiles, int32_t* tile_ranges,
                    void* stream);
 
+/* ---- depth-first binning (internal fast path; same sorted ids / tile ranges as the entry points
+ * above, with 2-3 M-sized sort passes instead of 6-7): sort the V*n Gaussians by (view, depth),
+ * emit their tile entries in that order with key = view*tiles + tile, stable-sort by that key. */
+int gg_depth_keys(long long n, int n_views, const float* depths, int64_t* keys /*[V*n]*/, int32_t* rows /*[V*n]*/,
+                  void* stream);
+int gg_gather_counts(long long total, const int32_t* order, const int32_t* num_tiles_hit, int32_t* counts,
+                     void* stream);
+int gg_emit_tiles_sorted(int n, int n_views, const int32_t* order, const float* xys, int xy_stride /*2 or 8*/,
+                         const int32_t* radii, const int32_t* cum_sorted, int tiles_x, int tiles_y, int64_t* keys,
+                         int32_t* ids, void* stream);
+int gg_tile_ranges_lowkey(long long m, const int64_t* keys_sorted, long long num_tiles, int32_t* tile_ranges,
+                          void* stream);
+
 /* visiting order of the tiles for the blend kernels: tile ids by descending list length (only
  * scheduling depends on it, never results); tile_order [num_tiles] int32 */
 size_t gg_tile_order_workspace_bytes(void);

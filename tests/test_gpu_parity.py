@@ -174,6 +174,38 @@ def test_binning_bit_exact(dev, n, W, H, seed, big):
     assert torch.equal(gbins.cpu(), torch.from_numpy(ranges))
 
 
+@pytest.mark.parametrize("n,W,H,seed,big,views", [(3000, 96, 64, 7, True, 1), (50_000, 640, 480, 1234, False, 1),
+                                                  (20_000, 320, 240, 5, True, 3)])
+def test_depth_first_binning_equals_reference_formulation(dev, n, W, H, seed, big, views):
+    """Internal fast path (sort Gaussians by depth, emit, stable-sort by tile) == one 64-bit sort."""
+    from gaussiangrasper_b200 import ops
+    sc, _, scales, quats = make_inputs(n, W, H, seed, big)
+    cams = scenes.orbit_cameras(views, W, H, total=5)
+    outs = [oracle_project(sc, c, scales, quats) for c in cams]
+    cat = lambda k: torch.from_numpy(np.concatenate([o[k] for o in outs])).to(dev)
+    xys, depths, radii, nth = cat(0), cat(1), cat(2), cat(4)
+    tb = cams[0].tile_bounds
+    a = ops.bin_views(n, views, xys, depths, radii, nth, tb, depth_first=True)
+    b = ops.bin_views(n, views, xys, depths, radii, nth, tb, depth_first=False)
+    assert a.num_intersects == b.num_intersects > 0
+    assert torch.equal(a.ids_sorted, b.ids_sorted) and torch.equal(a.tile_ranges, b.tile_ranges)
+    # against the oracle, view by view
+    T = tb[0] * tb[1]
+    off = 0
+    for v, o in enumerate(outs):
+        _, _, _, _, ids_s, ranges = c_oracle.bin_and_sort(o[0], o[1], o[2], o[4], tb)
+        assert np.array_equal(a.ids_sorted[off:off + len(ids_s)].cpu().numpy(), ids_s)
+        got = a.tile_ranges[v * T:(v + 1) * T].cpu().numpy()
+        ne = ranges[:, 1] > ranges[:, 0]
+        assert np.array_equal(got[ne], ranges[ne] + off) and not got[~ne].any()
+        off += len(ids_s)
+    # the tile order is a permutation sorted by (bucketed) descending length
+    order = a.tile_order.cpu().numpy()
+    assert sorted(order.tolist()) == list(range(T * views))
+    lens = (a.tile_ranges[:, 1] - a.tile_ranges[:, 0]).cpu().numpy()[order] >> 3
+    assert (np.diff(np.minimum(lens, 1023)) <= 0).all()
+
+
 def test_binning_empty(dev):
     from gaussiangrasper_b200 import ops
     n = 100
