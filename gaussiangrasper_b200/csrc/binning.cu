@@ -166,6 +166,7 @@ constexpr int kMaxPasses = 8;
 constexpr uint32_t kFlagAgg = 1u << 30;
 constexpr uint32_t kFlagIncl = 1u << 31;
 constexpr uint32_t kValueMask = (1u << 30) - 1;
+constexpr int kLookback = 16;  // status words fetched per look-back round
 
 __global__ void __launch_bounds__(256)
 radix_hist_kernel(const uint64_t* __restrict__ keys, long long m, int passes, uint32_t* __restrict__ ghist) {
@@ -200,7 +201,7 @@ __global__ void __launch_bounds__(256) radix_scan_hist_kernel(uint32_t* __restri
     h[threadIdx.x] = (uint32_t)block_excl_scan_256(v, sm, total);
 }
 
-__global__ void __launch_bounds__(kRsThreads, 3)
+__global__ void __launch_bounds__(kRsThreads, 2)
 radix_pass_kernel(const uint64_t* __restrict__ kin, const uint32_t* __restrict__ vin, uint64_t* __restrict__ kout,
                   uint32_t* __restrict__ vout, long long m, int shift, const uint32_t* __restrict__ ghist_excl,
                   volatile uint64_t* tile_state, uint32_t* ticket, uint32_t generation) {
@@ -261,15 +262,30 @@ radix_pass_kernel(const uint64_t* __restrict__ kin, const uint32_t* __restrict__
         *my_state = gen | kFlagIncl | count;
     } else {
         *my_state = gen | kFlagAgg | count;
+        // Windowed look-back: kLookback status words are fetched at once (independent loads), then
+        // consumed front to back until one is not published yet or carries an inclusive prefix.
+        // A serial walk costs one L2 round trip per predecessor, i.e. ~0.3 us x (tiles in flight),
+        // which is what bounds a pass on the few-hundred-tile sorts of this workload.
         long long prev = (long long)tile - 1;
-        while (true) {
-            uint64_t s;
-            do {
-                s = tile_state[(size_t)prev * kRadix + tid];
-            } while ((s >> 32) != generation || ((uint32_t)s & (kFlagAgg | kFlagIncl)) == 0);
-            excl += (uint32_t)s & kValueMask;
-            if ((uint32_t)s & kFlagIncl) break;
-            --prev;
+        bool found = false;
+        while (!found) {
+            uint64_t w[kLookback];
+#pragma unroll
+            for (int i = 0; i < kLookback; ++i) {
+                const long long idx = prev - i;
+                w[i] = idx >= 0 ? tile_state[(size_t)idx * kRadix + tid] : (gen | kFlagIncl);
+            }
+            int consumed = 0;
+#pragma unroll
+            for (int i = 0; i < kLookback; ++i) {
+                if (found || consumed < i) continue;  // stop at the first word that is not ready
+                const uint64_t sw = w[i];
+                if ((sw >> 32) != generation || ((uint32_t)sw & (kFlagAgg | kFlagIncl)) == 0) continue;
+                excl += (uint32_t)sw & kValueMask;
+                ++consumed;
+                if ((uint32_t)sw & kFlagIncl) found = true;
+            }
+            prev -= consumed;
         }
         *my_state = gen | kFlagIncl | ((excl + count) & kValueMask);
     }
