@@ -280,9 +280,11 @@ def run_ours(args):
             copy_stream.wait_event(fwd_done)
             rgb_host.copy_(out["rgb"].detach(), non_blocking=True)      # D2H: rendered rgb, overlaps backward
         main.wait_event(target_ready)
-        loss = ((out["image"] - target_dev) ** 2).mean()
+        img = out["image"]
+        diff = img.detach() - target_dev                                 # L2 loss against the host-fed targets
+        loss = (diff * diff).mean()
         if cfg["backward"]:
-            loss.backward()
+            img.backward(diff * (2.0 / diff.numel()))
             if bucket is not None:
                 bucket.pack({k: P[k].grad for k in names})
                 bucket.all_reduce()

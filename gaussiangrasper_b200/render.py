@@ -19,6 +19,9 @@ from ._torch_impl import quat_to_rotmat
 from .sh import SphericalHarmonics
 
 
+_pinned_ring = {}
+
+
 @dataclass
 class ViewBatch:
     """Cameras of one batch of views, already on the device (same image size for all)."""
@@ -40,7 +43,15 @@ class ViewBatch:
         intr = torch.tensor([[c.fx, c.fy, c.cx, c.cy] for c in cams], dtype=torch.float32)
         pos = torch.stack([c.position for c in cams]).float()
         packed = torch.cat([vm, fm, intr, pos], dim=1)  # one H2D copy for the whole batch
-        packed = packed.pin_memory().to(device, non_blocking=True) if device.type == "cuda" else packed
+        if device.type == "cuda":
+            # a small ring of reusable pinned staging buffers per batch size (pinning memory per call
+            # costs more than the render's whole prepare stage; the ring keeps a buffer untouched
+            # until the asynchronous copy that reads it has long completed)
+            ring = _pinned_ring.setdefault(tuple(packed.shape), [0, [torch.empty(packed.shape).pin_memory() for _ in range(8)]])
+            ring[0] = (ring[0] + 1) % len(ring[1])
+            stage = ring[1][ring[0]]
+            stage.copy_(packed)
+            packed = stage.to(device, non_blocking=True)
         return ViewBatch(packed[:, :12].contiguous(), packed[:, 12:28].contiguous(), packed[:, 28:32].contiguous(),
                          packed[:, 32:35].contiguous(), cams[0].H, cams[0].W)
 
