@@ -107,9 +107,18 @@ __device__ __forceinline__ void stage_batch(const BlendArgs& a, long long geo_ba
 }
 
 // Conservative per-warp culling of a staged batch: lane l tests entries l, l+32, ... against the
-// warp's 8x4 pixel rectangle using geo[7] = rcut2, a bound on the squared distance at which the
-// Gaussian can still reach alpha >= 1/255 (sigma >= lambda_min(Q)/2 * d^2).  Entries that fail
-// would be skipped by the per-pixel test anyway, so results are unchanged; only their cost goes.
+// warp's 8x4 pixel rectangle.  The test is the exact minimum of sigma(d) = d^T Q d / 2 over the
+// (continuous) rectangle: 0 if the centre is inside, otherwise the smallest of the four edge
+// minima (sigma is convex, so the minimum sits on the boundary; on an edge it is a clamped 1-D
+// parabola).  An entry is kept iff that minimum is <= tau, i.e. iff some pixel of the warp could
+// pass the per-pixel test -- so results are unchanged, only the cost of hopeless entries goes.
+__device__ __forceinline__ float edge_min_sigma(float d_fixed, float lo, float hi, float h_fixed, float B, float h_free) {
+    // minimise  h_fixed*d_fixed^2 + B*d_fixed*t + h_free*t^2  over t in [lo, hi]
+    const float t_opt = (h_free > 0.0f) ? -0.5f * B * d_fixed / h_free : lo;
+    const float t = fminf(hi, fmaxf(lo, t_opt));
+    return fmaf(t, fmaf(h_free, t, B * d_fixed), h_fixed * d_fixed * d_fixed);
+}
+
 template <int BATCH>
 __device__ __forceinline__ void cull_batch(const float* __restrict__ geo_buf, int cnt, float rx0, float ry0,
                                            float rx1, float ry1, unsigned (&mask)[BATCH / 32]) {
@@ -119,10 +128,20 @@ __device__ __forceinline__ void cull_batch(const float* __restrict__ geo_buf, in
         const int e = k * 32 + lane;
         bool pass = false;
         if (e < cnt) {
-            const float gx = geo_buf[e * 8], gy = geo_buf[e * 8 + 1], rc = geo_buf[e * 8 + 7];
-            const float ddx = fmaxf(fmaxf(rx0 - gx, gx - rx1), 0.0f);
-            const float ddy = fmaxf(fmaxf(ry0 - gy, gy - ry1), 0.0f);
-            pass = ddx * ddx + ddy * ddy <= rc;
+            const float4 ga = reinterpret_cast<const float4*>(geo_buf)[2 * e];
+            const float4 gb = reinterpret_cast<const float4*>(geo_buf)[2 * e + 1];
+            const float hA = ga.z, B = ga.w, hC = gb.x, tau = gb.z;
+            // rectangle relative to the Gaussian centre (d = pixel - centre; sigma is even in d)
+            const float x0 = rx0 - ga.x, x1 = rx1 - ga.x, y0 = ry0 - ga.y, y1 = ry1 - ga.y;
+            float smin = 0.0f;
+            if (!(x0 <= 0.0f && x1 >= 0.0f && y0 <= 0.0f && y1 >= 0.0f)) {
+                smin = fminf(fminf(edge_min_sigma(x0, y0, y1, hA, B, hC), edge_min_sigma(x1, y0, y1, hA, B, hC)),
+                             fminf(edge_min_sigma(y0, x0, x1, hC, B, hA), edge_min_sigma(y1, x0, x1, hC, B, hA)));
+            }
+            // 1e-4 relative slack covers the rounding difference to the per-pixel evaluation
+            pass = (tau >= 0.0f) && (smin <= tau + 1e-4f * (1.0f + tau)) ;
+            // conics that are not safely positive definite (or NaN) are never culled
+            if (!(hA > 0.0f && hC > 0.0f && 4.0f * hA * hC - B * B > 0.0f) || !(smin == smin)) pass = tau >= 0.0f;
         }
         mask[k] = __ballot_sync(0xffffffffu, pass);
     }
