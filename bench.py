@@ -193,7 +193,10 @@ def run_ours(args):
 
     cfg = scenes.CONFIGS[args.config]
     n, W, H, D = cfg["n"], cfg["W"], cfg["H"], cfg["D"]
-    V = args.views if args.views else (1 if args.config == 1 else cfg["views"])
+    # config 2 is a fixed 64-view batch split over the ranks (strong scaling); the others fix the work per GPU
+    strong = args.config == 2
+    V = args.views if args.views else (1 if args.config == 1 else (max(1, cfg["views"] // world) if strong else cfg["views"]))
+    chunk = min(V, args.chunk)
     C = 7 + D
     CP = (C + 3) // 4 * 4
     sc = scenes.random_scene(n, feature_dim=D, seed=1234 + args.config)
@@ -201,23 +204,28 @@ def run_ours(args):
     P = {k: sc[k].to(dev).requires_grad_(cfg["backward"]) for k in names}
     total_views = V * world
     cams = scenes.orbit_cameras(V, W, H, first=rank * V, total=max(total_views, 8))
-    views = ViewBatch.from_cameras(cams, dev)
+    views = ViewBatch.from_cameras(cams[:chunk], dev)
     g = torch.Generator().manual_seed(100 + rank)
-    v_img = torch.randn((V, H, W, CP), generator=g).to(dev)
+    v_img = torch.randn((chunk, H, W, CP), generator=g).to(dev) if cfg["backward"] else None
+    # views are rendered `chunk` at a time (one projection + one sort + one blend launch per chunk)
+    chunks = [ViewBatch.from_cameras(cams[i:i + chunk], dev) for i in range(0, V, chunk)]
     from gaussiangrasper_b200.distributed import GradientBucket
     bucket = GradientBucket(P) if (world > 1 and cfg["backward"]) else None
 
     def step():
         for p in P.values():
             p.grad = None
-        out = render_views(P["means"], P["log_scales"], P["quats"], P["opacity_logit"], P["sh_coeffs"],
-                           P["features"], views)
-        if cfg["backward"]:
-            out["image"].backward(v_img)
-            if bucket is not None:
-                bucket.pack({k: P[k].grad for k in names})
-                bucket.all_reduce()
-                return bucket.flat
+        out = None
+        for vb in chunks:
+            with torch.set_grad_enabled(cfg["backward"]):
+                out = render_views(P["means"], P["log_scales"], P["quats"], P["opacity_logit"], P["sh_coeffs"],
+                                   P["features"], vb)
+            if cfg["backward"]:
+                out["image"].backward(v_img[:vb.n_views])  # leaf gradients accumulate over the chunks
+        if bucket is not None:
+            bucket.pack({k: P[k].grad for k in names})
+            bucket.all_reduce()
+            return bucket.flat
         return out["image"]
 
     for _ in range(max(args.warmup, 3)):
@@ -254,12 +262,12 @@ def run_ours(args):
     value = mpix_per_step / (ms_per_step * 1e-3)
 
     # --- e2e: host buffers in, host results out, every step ---------------------------------
-    target_host = torch.randn((V, H, W, CP), generator=g).pin_memory()
-    rgb_host = torch.empty((V, H, W, 3)).pin_memory()
+    target_host = torch.randn((chunk, H, W, CP), generator=g).pin_memory() if cfg["backward"] else None
+    rgb_host = torch.empty((chunk, H, W, 3)).pin_memory()
     loss_host = torch.empty((1,)).pin_memory()
 
     copy_stream = torch.cuda.Stream(device=dev)
-    target_dev = torch.empty((V, H, W, CP), dtype=torch.float32, device=dev)
+    target_dev = torch.empty((chunk, H, W, CP), dtype=torch.float32, device=dev) if cfg["backward"] else None
 
     def e2e_step():
         """One user-level training step from HOST buffers: cameras + supervision images go host->device,
@@ -268,26 +276,35 @@ def run_ours(args):
         for p in P.values():
             p.grad = None
         main = torch.cuda.current_stream(dev)
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_stream(main)                               # previous step is done with target_dev
-            target_dev.copy_(target_host, non_blocking=True)            # H2D: supervision images (pinned)
-            target_ready = copy_stream.record_event()
-        vb = ViewBatch.from_cameras(cams, dev)                          # H2D: cameras (pinned)
-        out = render_views(P["means"], P["log_scales"], P["quats"], P["opacity_logit"], P["sh_coeffs"],
-                           P["features"], vb)
-        fwd_done = main.record_event()
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(fwd_done)
-            rgb_host.copy_(out["rgb"].detach(), non_blocking=True)      # D2H: rendered rgb, overlaps backward
-        main.wait_event(target_ready)
-        img = out["image"]
-        diff = img.detach() - target_dev                                 # L2 loss against the host-fed targets
-        loss = (diff * diff).mean()
-        if cfg["backward"]:
-            img.backward(diff * (2.0 / diff.numel()))
-            if bucket is not None:
-                bucket.pack({k: P[k].grad for k in names})
-                bucket.all_reduce()
+        loss = torch.zeros((), device=dev)
+        for ci in range(0, V, chunk):
+            cc = cams[ci:ci + chunk]
+            nv = len(cc)
+            if cfg["backward"]:
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_stream(main)                           # previous use of target_dev is over
+                    target_dev[:nv].copy_(target_host[:nv], non_blocking=True)  # H2D: supervision images (pinned)
+                    target_ready = copy_stream.record_event()
+            vb = ViewBatch.from_cameras(cc, dev)                            # H2D: cameras (pinned)
+            with torch.set_grad_enabled(cfg["backward"]):
+                out = render_views(P["means"], P["log_scales"], P["quats"], P["opacity_logit"], P["sh_coeffs"],
+                                   P["features"], vb)
+            fwd_done = main.record_event()
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(fwd_done)
+                rgb_host[:nv].copy_(out["rgb"].detach(), non_blocking=True)  # D2H: rendered rgb, overlaps backward
+                out["rgb"].record_stream(copy_stream)
+            if cfg["backward"]:
+                main.wait_event(target_ready)
+                img = out["image"]
+                diff = img.detach() - target_dev[:nv]                       # L2 loss against the host-fed targets
+                loss = loss + (diff * diff).mean()
+                img.backward(diff * (2.0 / diff.numel()))
+            else:
+                loss = loss + out["alpha"].mean()
+        if bucket is not None:
+            bucket.pack({k: P[k].grad for k in names})
+            bucket.all_reduce()
         loss_host.copy_(loss.detach().reshape(1), non_blocking=True)    # D2H: loss
         torch.cuda.synchronize()
         return float(loss_host[0])
@@ -305,8 +322,8 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_val = mpix_per_step * args.steps / float(t_e2e.item())
-    h2d = target_host.numel() * 4 + V * 35 * 4
-    d2h = rgb_host.numel() * 4 + 4
+    h2d = (chunk * H * W * CP * 4 if cfg["backward"] else 0) * (V // chunk) + V * 35 * 4
+    d2h = V * H * W * 3 * 4 + 4
 
     if rank != 0:
         if world > 1:
@@ -319,7 +336,7 @@ def run_ours(args):
     share = {k: sum(v) / args.steps for k, v in per_call.items()}
     stats = torch.zeros(1, dtype=torch.int64, device=dev)
     with torch.no_grad():
-        o = render_views(*(P[k].detach() for k in names), views, stats=stats)
+        o = render_views(*(P[k].detach() for k in names), views, stats=stats)  # first chunk only
     torch.cuda.synchronize()
     pairs = int(stats.item())
     binning_m = None
@@ -380,9 +397,9 @@ def run_ours(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": cfg["name"], "gaussians": n, "image": [W, H], "views_per_gpu": V,
+        "config": {"workload": cfg["name"], "gaussians": n, "image": [W, H], "views_per_gpu": V, "views_per_launch": chunk,
                    "channels": C, "backward": cfg["backward"], "parallelism": f"view-sharded x{world}",
                    "l2": "inputs larger than L2 (parameters+gradients 2x%.0f MB per step)" % (n * (86 + D) * 4 / 1e6)},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -407,6 +424,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=1, help="index into BASELINE.json configs (default 1)")
     ap.add_argument("--views", type=int, default=0, help="views per GPU per step (default: config's)")
+    ap.add_argument("--chunk", type=int, default=8, help="views rendered per launch group")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
