@@ -166,10 +166,13 @@ constexpr int kMaxPasses = 8;
 constexpr uint32_t kFlagAgg = 1u << 30;
 constexpr uint32_t kFlagIncl = 1u << 31;
 constexpr uint32_t kValueMask = (1u << 30) - 1;
-constexpr int kLookback = 16;  // status words fetched per look-back round
+constexpr int kLookback = 4;   // status words fetched per look-back round
 
 __global__ void __launch_bounds__(256)
 radix_hist_kernel(const uint64_t* __restrict__ keys, long long m, int passes, uint32_t* __restrict__ ghist) {
+    // Block-shared histograms, plain shared-memory atomics.  Digits on which a whole warp agrees
+    // (the high bytes of tile|depth keys are nearly constant) would serialise 32-fold on one
+    // address, so those take a match.all fast path: one add of the warp's population.
     __shared__ uint32_t sh[kMaxPasses * kRadix];
     for (int i = threadIdx.x; i < passes * kRadix; i += blockDim.x) sh[i] = 0;
     __syncthreads();
@@ -179,11 +182,20 @@ radix_hist_kernel(const uint64_t* __restrict__ keys, long long m, int passes, ui
     for (long long r = 0; r < rounds; ++r) {
         const long long i = r * stride + (long long)blockIdx.x * blockDim.x + threadIdx.x;
         const bool valid = i < m;
-        const uint64_t k = valid ? __ldg(keys + i) : 0;
+        const unsigned active = __ballot_sync(0xffffffffu, valid);
+        if (!valid) continue;
+        const uint64_t k = __ldg(keys + i);
+        const int leader = __ffs(active) - 1;
+        const uint32_t pop = (uint32_t)__popc(active);
         for (int p = 0; p < passes; ++p) {
-            const uint32_t d = valid ? (uint32_t)(k >> (8 * p)) & 255u : 256u + lane;
-            const uint32_t mask = __match_any_sync(0xffffffffu, d);
-            if (valid && lane == __ffs(mask) - 1) atomicAdd(&sh[p * kRadix + d], (uint32_t)__popc(mask));
+            const uint32_t d = (uint32_t)(k >> (8 * p)) & 255u;
+            int same;
+            __match_all_sync(active, d, &same);
+            if (same) {
+                if (lane == leader) atomicAdd(&sh[p * kRadix + d], pop);
+            } else {
+                atomicAdd(&sh[p * kRadix + d], 1u);
+            }
         }
     }
     __syncthreads();
@@ -201,7 +213,7 @@ __global__ void __launch_bounds__(256) radix_scan_hist_kernel(uint32_t* __restri
     h[threadIdx.x] = (uint32_t)block_excl_scan_256(v, sm, total);
 }
 
-__global__ void __launch_bounds__(kRsThreads, 2)
+__global__ void __launch_bounds__(kRsThreads, 3)
 radix_pass_kernel(const uint64_t* __restrict__ kin, const uint32_t* __restrict__ vin, uint64_t* __restrict__ kout,
                   uint32_t* __restrict__ vout, long long m, int shift, const uint32_t* __restrict__ ghist_excl,
                   volatile uint64_t* tile_state, uint32_t* ticket, uint32_t generation) {
@@ -358,27 +370,54 @@ gather_counts_kernel(long long total, const int32_t* __restrict__ order, const i
     counts[i] = __ldg(num_tiles_hit + order[i]);
 }
 
+// Warp-cooperative emission: a warp owns 32 consecutive slots of the depth order; their tile
+// entries form one contiguous output span, written 32 entries per step with coalesced stores (a
+// thread-per-Gaussian loop scatters 8+4 byte writes and stalls on the store queue).  Each output
+// entry finds its Gaussian by a 5-step binary search over the warp's exclusive offsets.
 __global__ void __launch_bounds__(256)
 emit_tiles_sorted_kernel(long long total, int n, const int32_t* __restrict__ order, const float* __restrict__ xys,
                          int xy_stride, const int32_t* __restrict__ radii, const int32_t* __restrict__ cum,
                          int tiles_x, int tiles_y, int64_t* __restrict__ keys, int32_t* __restrict__ ids) {
+    __shared__ int s_off[8][33];
+    __shared__ int4 s_box[8][32];  // x0, y0, width, view * tiles
+    __shared__ int s_g[8][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const long long row = order[i];
-    const int r = radii[row];
-    if (r <= 0) return;
-    const int view = (int)(row / n);
-    const int g = (int)(row - (long long)view * n);
-    const float2 c = __ldg(reinterpret_cast<const float2*>(xys + row * xy_stride));
-    const TileBox tb = tile_box(c.x, c.y, (float)r, tiles_x, tiles_y);
-    long long cur = i == 0 ? 0 : cum[i - 1];
-    const long long tile0 = (long long)view * tiles_x * tiles_y;
-    for (int ty = tb.y0; ty < tb.y1; ++ty)
-        for (int tx = tb.x0; tx < tb.x1; ++tx) {
-            keys[cur] = tile0 + (long long)ty * tiles_x + tx;
-            ids[cur] = g;
-            ++cur;
+    const long long i0 = i - lane;
+    if (i0 >= total) return;
+    int cnt = 0, g = 0;
+    int4 box = make_int4(0, 0, 1, 0);
+    if (i < total) {
+        const long long row = order[i];
+        const int r = radii[row];
+        if (r > 0) {
+            const int view = (int)(row / n);
+            g = (int)(row - (long long)view * n);
+            const float2 c = __ldg(reinterpret_cast<const float2*>(xys + row * xy_stride));
+            const TileBox tb = tile_box(c.x, c.y, (float)r, tiles_x, tiles_y);
+            cnt = tb.area();
+            box = make_int4(tb.x0, tb.y0, max(tb.x1 - tb.x0, 1), view * tiles_x * tiles_y);
         }
+    }
+    const int incl = warp_incl_scan(cnt);
+    s_off[warp][lane] = incl - cnt;
+    if (lane == 31) s_off[warp][32] = incl;
+    s_box[warp][lane] = box;
+    s_g[warp][lane] = g;
+    __syncwarp();
+    const int total_w = s_off[warp][32];
+    const long long wbase = i0 == 0 ? 0 : (long long)cum[i0 - 1];
+    for (int j = lane; j < total_w; j += 32) {
+        int lo = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1)
+            if (s_off[warp][lo + step] <= j) lo += step;
+        const int k = j - s_off[warp][lo];
+        const int4 bx = s_box[warp][lo];
+        const int ty = bx.y + k / bx.z, tx = bx.x + k - (k / bx.z) * bx.z;
+        keys[wbase + j] = (int64_t)bx.w + (int64_t)ty * tiles_x + tx;
+        ids[wbase + j] = s_g[warp][lo];
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
