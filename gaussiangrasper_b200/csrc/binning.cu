@@ -242,12 +242,16 @@ radix_pass_kernel(const uint64_t* __restrict__ kin, const uint32_t* __restrict__
         const long long idx = wbase + j * 32 + lane;
         key[j] = idx < m ? __ldg(kin + idx) : ~0ull;
     }
-    // stable rank inside the warp: items are ordered (j, lane)
+    // stable rank inside the warp: items are ordered (j, lane).  All 16 match.any are issued first
+    // (they are independent and have a long latency); only the counter updates form a chain.
+    uint32_t peers[kRsIpt];
+#pragma unroll
+    for (int j = 0; j < kRsIpt; ++j) peers[j] = __match_any_sync(0xffffffffu, (uint32_t)(key[j] >> shift) & 255u);
     uint32_t rank[kRsIpt];
 #pragma unroll
     for (int j = 0; j < kRsIpt; ++j) {
         const uint32_t d = (uint32_t)(key[j] >> shift) & 255u;
-        const uint32_t mask = __match_any_sync(0xffffffffu, d);
+        const uint32_t mask = peers[j];
         const int leader = __ffs(mask) - 1;
         uint32_t prev = 0;
         if (lane == leader) {

@@ -184,6 +184,85 @@ prepare_views_kernel(const PrepArgs a, float* __restrict__ geo, float* __restric
     }
 }
 
+// Channel rows for ALL views of a batch in one pass over the Gaussians (phase 2 of the fused
+// path): the 300-byte SH row, the feature row and the quaternion are read once per Gaussian and
+// reused for every view, instead of once per (view, Gaussian).  Per view only radii/depths are read
+// and the CP-float row is written (coalesced through shared memory).
+__global__ void __launch_bounds__(kPrepThreads)
+prepare_chan_kernel(const PrepArgs a, float* __restrict__ chan, const float* __restrict__ depths,
+                    const int32_t* __restrict__ radii) {
+    extern __shared__ __align__(16) float sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = a.nb * 3, D = a.feat_dim, cp = a.cp;
+    const int per_warp = 32 * (row + D + cp);
+    float* slab = sm + (size_t)warp * per_warp;   // [32][row]  SH coefficients
+    float* fslab = slab + 32 * row;               // [32][D]    features
+    float* rbuf = fslab + 32 * D;                 // [32][cp]   channel rows of the current view
+    const long long first = ((long long)blockIdx.x * kPrepWarps + warp) * 32;
+    if (first >= a.n) return;
+    const long long i = first + lane;
+    const bool active = i < a.n;
+    const int rows_here = (int)min((long long)32, a.n - first);
+    // visibility of this Gaussian in each view (bit v); warps that are invisible everywhere stop here
+    unsigned vismask = 0;
+    if (active)
+        for (int v = 0; v < a.n_views; ++v)
+            if (radii[(long long)v * a.n + i] > 0) vismask |= 1u << (v & 31);
+    const bool many_views = a.n_views > 32;  // the bit mask is only a hint then
+    if (!many_views && !__any_sync(0xffffffffu, vismask != 0)) return;
+    {
+        const float* gspan = a.sh + first * row;
+        const int span = rows_here * row, nvec = span >> 2;
+        const float4* g4 = reinterpret_cast<const float4*>(gspan);
+        float4* s4 = reinterpret_cast<float4*>(slab);
+        for (int k = lane; k < nvec; k += 32) s4[k] = __ldg(g4 + k);
+        for (int k = (nvec << 2) + lane; k < span; k += 32) slab[k] = __ldg(gspan + k);
+        const float* fspan = a.features + first * D;
+        for (int k = lane; k < rows_here * D; k += 32) fslab[k] = __ldg(fspan + k);
+    }
+    float p[3] = {0.f, 0.f, 0.f}, nrm[3] = {0.f, 0.f, 0.f};
+    if (active) {
+        const Activated g = load_activated(a, i);
+        p[0] = g.p[0]; p[1] = g.p[1]; p[2] = g.p[2];
+        const Rot3 R = quat_to_rot(g.qh[0], g.qh[1], g.qh[2], g.qh[3]);
+        nrm[0] = R.m[g.kmin]; nrm[1] = R.m[3 + g.kmin]; nrm[2] = R.m[6 + g.kmin];
+    }
+    __syncwarp();
+    const int nuse = sh_num_bases(a.deg_use);
+    const float* cf = slab + lane * row;
+    const float* fr = fslab + lane * D;
+    float* r = rbuf + lane * cp;
+    for (int v = 0; v < a.n_views; ++v) {
+        const long long vrow = (long long)v * a.n + i;
+        const bool vis = active && radii[vrow] > 0;
+        if (!__any_sync(0xffffffffu, vis)) continue;
+        if (vis) {
+            float Y[25];
+            sh_basis(a.deg_use, p[0] - __ldg(a.positions + 3 * v), p[1] - __ldg(a.positions + 3 * v + 1),
+                     p[2] - __ldg(a.positions + 3 * v + 2), Y);
+            float rgb[3] = {0.f, 0.f, 0.f};
+            for (int b = 0; b < nuse; ++b) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) rgb[c] = rgb[c] + Y[b] * cf[3 * b + c];
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) r[c] = fminf(1.0f, fmaxf(0.0f, rgb[c] + 0.5f));
+            r[3] = depths[vrow];
+            r[4] = nrm[0]; r[5] = nrm[1]; r[6] = nrm[2];
+            for (int d = 0; d < D; ++d) r[7 + d] = fr[d];
+            for (int d = 7 + D; d < cp; ++d) r[d] = 0.0f;
+        } else {
+            for (int d = 0; d < cp; ++d) r[d] = 0.0f;
+        }
+        __syncwarp();
+        float4* g4 = reinterpret_cast<float4*>(chan + ((long long)v * a.n + first) * cp);
+        const float4* s4 = reinterpret_cast<const float4*>(rbuf);
+        const int nvec = (rows_here * cp) >> 2;
+        for (int k = lane; k < nvec; k += 32) g4[k] = s4[k];
+        __syncwarp();
+    }
+}
+
 // Sum over views of the vector-Jacobian product of prepare_views_kernel.
 //   v_geo [V*N, 8] : v_x, v_y, v_A, v_B, v_C (w.r.t. the conic, not its halves), v_opacity
 //   v_chan[V*N, CP]: v_rgb(3), v_depth, v_normal(3), v_feature(D)
@@ -346,6 +425,14 @@ extern "C" int gg_prepare_views(int n, int n_views, int feat_dim, int cp, int de
     if (rc != GG_OK) return rc;
     GG_REQUIRE(geo && chan && depths && radii && num_tiles_hit, "gg_prepare_views: null output pointer");
     GG_REQUIRE(((uintptr_t)geo & 15) == 0 && ((uintptr_t)chan & 15) == 0, "gg_prepare_views: geo/chan misaligned");
+    if (phase == 2) {
+        const size_t smem2 = sizeof(float) * kPrepWarps * 32 * (size_t)(a.nb * 3 + feat_dim + cp);
+        GG_CUDA(cudaFuncSetAttribute(prepare_chan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        prepare_chan_kernel<<<div_up(n, kPrepThreads), kPrepThreads, smem2, (cudaStream_t)stream>>>(a, chan, depths,
+                                                                                                   radii);
+        count_launch();
+        return check_launch("prepare_chan_kernel");
+    }
     const int slab_row = a.nb * 3 > cp ? a.nb * 3 : cp;
     const size_t smem = sizeof(float) * kPrepWarps * 32 * (size_t)slab_row;
     GG_CUDA(cudaFuncSetAttribute(prepare_views_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
