@@ -425,7 +425,7 @@ extern "C" int gg_prepare_views(int n, int n_views, int feat_dim, int cp, int de
     if (rc != GG_OK) return rc;
     GG_REQUIRE(geo && chan && depths && radii && num_tiles_hit, "gg_prepare_views: null output pointer");
     GG_REQUIRE(((uintptr_t)geo & 15) == 0 && ((uintptr_t)chan & 15) == 0, "gg_prepare_views: geo/chan misaligned");
-    if (phase == 2) {
+    if (phase == 2 && n_views > 1) {  // one view: the per-view kernel below has the better occupancy
         const size_t smem2 = sizeof(float) * kPrepWarps * 32 * (size_t)(a.nb * 3 + feat_dim + cp);
         GG_CUDA(cudaFuncSetAttribute(prepare_chan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         prepare_chan_kernel<<<div_up(n, kPrepThreads), kPrepThreads, smem2, (cudaStream_t)stream>>>(a, chan, depths,
