@@ -237,17 +237,10 @@ radix_pass_kernel(const uint64_t* __restrict__ kin, const uint32_t* __restrict__
     const long long wbase = base + (long long)warp * (32 * kRsIpt);
 
     uint64_t key[kRsIpt];
-    uint32_t val[kRsIpt];
 #pragma unroll
     for (int j = 0; j < kRsIpt; ++j) {
         const long long idx = wbase + j * 32 + lane;
         key[j] = idx < m ? __ldg(kin + idx) : ~0ull;
-    }
-    // payloads are fetched together with the keys: one memory round trip per tile instead of two
-#pragma unroll
-    for (int j = 0; j < kRsIpt; ++j) {
-        const long long idx = wbase + j * 32 + lane;
-        val[j] = idx < m ? __ldg(vin + idx) : 0u;
     }
     // stable rank inside the warp: items are ordered (j, lane).  All 16 match.any are issued first
     // (they are independent and have a long latency); only the counter updates form a chain.
@@ -322,8 +315,9 @@ radix_pass_kernel(const uint64_t* __restrict__ kin, const uint32_t* __restrict__
     for (int j = 0; j < kRsIpt; ++j) {
         const uint32_t d = (uint32_t)(key[j] >> shift) & 255u;
         const uint32_t pos = local_start[d] + warp_hist[warp][d] + rank[j];
+        const long long idx = wbase + j * 32 + lane;
         keys_sm[pos] = key[j];
-        vals_sm[pos] = val[j];
+        vals_sm[pos] = idx < m ? __ldg(vin + idx) : 0u;
     }
     __syncthreads();
     const long long remain = m - base;
