@@ -216,14 +216,18 @@ def run_ours(args):
         for p in P.values():
             p.grad = None
         out = None
+        # one launch group per step: the backward writes the leaf gradients straight into the flat
+        # all-reduce buffer; several chunks accumulate in .grad and are packed afterwards
+        direct = bucket is not None and len(chunks) == 1
         for vb in chunks:
             with torch.set_grad_enabled(cfg["backward"]):
                 out = render_views(P["means"], P["log_scales"], P["quats"], P["opacity_logit"], P["sh_coeffs"],
-                                   P["features"], vb)
+                                   P["features"], vb, holder={"grad_out": bucket.unpack()} if direct else None)
             if cfg["backward"]:
                 out["image"].backward(v_img[:vb.n_views])  # leaf gradients accumulate over the chunks
         if bucket is not None:
-            bucket.pack({k: P[k].grad for k in names})
+            if not direct:
+                bucket.pack({k: P[k].grad for k in names})
             bucket.all_reduce()
             return bucket.flat
         return out["image"]

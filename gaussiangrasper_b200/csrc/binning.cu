@@ -151,7 +151,6 @@ emit_keys_kernel(int n, int n_views, const float* __restrict__ xys, int xy_strid
 // ---------------------------------------------------------------------------------------------
 // Onesweep LSD radix sort, 8-bit digits, 256 threads x 16 keys per tile.
 //   1 upfront kernel  : digit histograms of every pass
-//   1 tiny kernel     : exclusive scan of each 256-bin histogram
 //   P pass kernels    : rank (warp match), decoupled look-back across tiles, shared-memory
 //                       reorder, coalesced scatter
 // Tile status words are 64 bit: [generation:32 | flag:2 | count:30]; a per-process generation
@@ -203,14 +202,6 @@ radix_hist_kernel(const uint64_t* __restrict__ keys, long long m, int passes, ui
         const uint32_t v = sh[i];
         if (v) atomicAdd(&ghist[i], v);
     }
-}
-
-__global__ void __launch_bounds__(256) radix_scan_hist_kernel(uint32_t* __restrict__ ghist) {
-    __shared__ int sm[8];
-    uint32_t* h = ghist + blockIdx.x * kRadix;
-    int total;
-    const int v = (int)h[threadIdx.x];
-    h[threadIdx.x] = (uint32_t)block_excl_scan_256(v, sm, total);
 }
 
 __global__ void __launch_bounds__(kRsThreads, 3)
@@ -307,8 +298,11 @@ radix_pass_kernel(const uint64_t* __restrict__ kin, const uint32_t* __restrict__
     }
     int total;
     const uint32_t lstart = (uint32_t)block_excl_scan_256((int)count, scan_sm, total);
+    // global digit offsets: exclusive scan of this pass's 256-bin histogram, redone by every tile
+    // (256 values; cheaper than a separate launch per sort)
+    const uint32_t gstart = (uint32_t)block_excl_scan_256((int)ghist_excl[tid], scan_sm, total);
     local_start[tid] = lstart;
-    global_base[tid] = ghist_excl[tid] + excl - lstart;
+    global_base[tid] = gstart + excl - lstart;
     __syncthreads();
     // reorder through shared memory so that the scatter writes runs of consecutive addresses
 #pragma unroll
@@ -463,6 +457,37 @@ tile_order_scatter_kernel(long long num_tiles, const int32_t* __restrict__ tile_
     order[atomicAdd(&cursor[tile_len_bucket(r.y - r.x)], 1)] = (int32_t)t;
 }
 
+// single-block variant for up to a few thousand tiles: histogram, scan and scatter in one launch
+__global__ void __launch_bounds__(kOrderBins)
+tile_order_small_kernel(int num_tiles, const int32_t* __restrict__ tile_ranges, int32_t* __restrict__ order) {
+    __shared__ int bins[kOrderBins];
+    __shared__ int sm[kOrderBins];
+    const int b = threadIdx.x;
+    bins[b] = 0;
+    __syncthreads();
+    for (int t = b; t < num_tiles; t += kOrderBins) {
+        const int2 r = __ldg(reinterpret_cast<const int2*>(tile_ranges) + t);
+        atomicAdd(&bins[tile_len_bucket(r.y - r.x)], 1);
+    }
+    __syncthreads();
+    sm[b] = bins[kOrderBins - 1 - b];
+    __syncthreads();
+    for (int o = 1; o < kOrderBins; o <<= 1) {
+        const int v = b >= o ? sm[b - o] : 0;
+        __syncthreads();
+        sm[b] += v;
+        __syncthreads();
+    }
+    const int start = sm[b] - bins[kOrderBins - 1 - b];
+    __syncthreads();
+    bins[kOrderBins - 1 - b] = start;
+    __syncthreads();
+    for (int t = b; t < num_tiles; t += kOrderBins) {
+        const int2 r = __ldg(reinterpret_cast<const int2*>(tile_ranges) + t);
+        order[atomicAdd(&bins[tile_len_bucket(r.y - r.x)], 1)] = t;
+    }
+}
+
 static std::atomic<uint32_t> g_generation{1};
 
 struct SortLayout {
@@ -565,7 +590,6 @@ extern "C" int gg_sort_pairs(long long m, int key_bits, const int64_t* keys_in, 
     int hist_blocks = div_up(m, 256 * 16);
     if (hist_blocks > 148 * 2) hist_blocks = 148 * 2;
     radix_hist_kernel<<<hist_blocks, 256, 0, st>>>(reinterpret_cast<const uint64_t*>(keys_in), m, passes, ghist);
-    radix_scan_hist_kernel<<<passes, 256, 0, st>>>(ghist);
     const uint64_t* kin = reinterpret_cast<const uint64_t*>(keys_in);
     const uint32_t* vin = reinterpret_cast<const uint32_t*>(vals_in);
     for (int p = 0; p < passes; ++p) {
@@ -579,7 +603,7 @@ extern "C" int gg_sort_pairs(long long m, int key_bits, const int64_t* keys_in, 
         kin = ko;
         vin = vo;
     }
-    count_launch(2 + passes);
+    count_launch(1 + passes);
     return check_launch("gg_sort_pairs");
 }
 
@@ -619,6 +643,11 @@ extern "C" int gg_tile_order(long long num_tiles, const int32_t* tile_ranges, in
     GG_REQUIRE(workspace_bytes >= gg_tile_order_workspace_bytes(), "gg_tile_order: workspace too small");
     GG_REQUIRE(((uintptr_t)tile_ranges & 7) == 0, "gg_tile_order: tile_ranges misaligned");
     cudaStream_t st = (cudaStream_t)stream;
+    if (num_tiles <= 8 * kOrderBins) {
+        tile_order_small_kernel<<<1, kOrderBins, 0, st>>>((int)num_tiles, tile_ranges, tile_order);
+        count_launch();
+        return check_launch("tile_order_small_kernel");
+    }
     int* bins = reinterpret_cast<int*>(workspace);
     GG_CUDA(cudaMemsetAsync(bins, 0, sizeof(int) * kOrderBins, st));
     tile_len_hist_kernel<<<div_up(num_tiles, 256), 256, 0, st>>>(num_tiles, tile_ranges, bins);

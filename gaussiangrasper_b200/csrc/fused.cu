@@ -277,10 +277,8 @@ prepare_views_bwd_kernel(const PrepArgs a, const float* __restrict__ geo, const 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = a.nb * 3;
     const int D = a.feat_dim;
-    const int vrow_pad = a.cp + 1;  // odd row length: conflict-free per-lane row reads
-    float* slab = sm + (size_t)warp * 32 * (row + D + vrow_pad);  // [32][row] SH grads, [32][D] feature grads, v_chan stage
+    float* slab = sm + (size_t)warp * 32 * (row + D);  // [32][row] SH grads, then [32][D] feature grads
     float* fslab = slab + 32 * row;
-    float* vstage = fslab + 32 * D;
     const long long first = ((long long)blockIdx.x * kPrepWarps + warp) * 32;
     if (first >= a.n) return;
     const long long i = first + lane;
@@ -295,30 +293,15 @@ prepare_views_bwd_kernel(const PrepArgs a, const float* __restrict__ geo, const 
     const int nuse = sh_num_bases(a.deg_use);
     for (int view = 0; view < a.n_views; ++view) {
         const long long vrow = (long long)view * a.n + i;
-        const bool vis = active && radii[vrow] > 0;
-        if (!__any_sync(0xffffffffu, vis)) continue;
-        // v_chan rows of the warp's Gaussians: one contiguous span, 16-byte coalesced loads
-        __syncwarp();
-        {
-            const float4* g4 = reinterpret_cast<const float4*>(v_chan + ((long long)view * a.n + first) * a.cp);
-            const int nvec = (rows_here * a.cp) >> 2, per_row = a.cp >> 2;
-            for (int k = lane; k < nvec; k += 32) {
-                const float4 v = __ldg(g4 + k);
-                const int l = k / per_row, q = k - l * per_row;
-                float* dst = vstage + l * vrow_pad + 4 * q;
-                dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
-            }
-        }
-        __syncwarp();
-        if (!vis) continue;
+        if (!(active && radii[vrow] > 0)) continue;
         const Camera cam = load_camera_regs(a, view);
         const float4 ga = __ldg(reinterpret_cast<const float4*>(geo) + 2 * vrow);
         const float4 gb = __ldg(reinterpret_cast<const float4*>(geo) + 2 * vrow + 1);
         const float4 va = __ldg(reinterpret_cast<const float4*>(v_geo) + 2 * vrow);
         const float4 vb = __ldg(reinterpret_cast<const float4*>(v_geo) + 2 * vrow + 1);
-        const float* vc = vstage + lane * vrow_pad;
-        const float4 c0 = make_float4(vc[0], vc[1], vc[2], vc[3]);
-        const float4 c1 = make_float4(vc[4], vc[5], vc[6], vc[7]);
+        const float* vc = v_chan + vrow * a.cp;
+        const float4 c0 = __ldg(reinterpret_cast<const float4*>(vc));
+        const float4 c1 = __ldg(reinterpret_cast<const float4*>(vc) + 1);
         const float conic[3] = {2.0f * ga.z, ga.w, 2.0f * gb.x};
         const float v_xy[2] = {va.x, va.y};
         const float v_conic[3] = {va.z, va.w, vb.x};
@@ -350,7 +333,7 @@ prepare_views_bwd_kernel(const PrepArgs a, const float* __restrict__ geo, const 
             for (int c = 0; c < 3; ++c) sr[3 * b + c] += Y[b] * vrgb[c];
         }
         float* fr = fslab + lane * D;
-        for (int d = 0; d < D; ++d) fr[d] += vc[7 + d];
+        for (int d = 0; d < D; ++d) fr[d] += __ldg(vc + 7 + d);
     }
     if (active) {
 #pragma unroll
@@ -463,7 +446,7 @@ extern "C" int gg_prepare_views_bwd(int n, int n_views, int feat_dim, int cp, in
                "gg_prepare_views_bwd: null output pointer");
     GG_REQUIRE(((uintptr_t)v_quats & 15) == 0 && ((uintptr_t)v_geo & 15) == 0 && ((uintptr_t)v_chan & 15) == 0,
                "gg_prepare_views_bwd: misaligned");
-    const size_t smem = sizeof(float) * kPrepWarps * 32 * (size_t)(a.nb * 3 + feat_dim + cp + 1);
+    const size_t smem = sizeof(float) * kPrepWarps * 32 * (size_t)(a.nb * 3 + feat_dim);
     GG_CUDA(cudaFuncSetAttribute(prepare_views_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     prepare_views_bwd_kernel<<<div_up(n, kPrepThreads), kPrepThreads, smem, (cudaStream_t)stream>>>(
         a, geo, chan, radii, v_geo, v_chan, v_means, v_log_scales, v_quats, v_opacity_logit, v_sh_coeffs, v_features);

@@ -20,6 +20,18 @@ from .sh import SphericalHarmonics
 
 
 _pinned_ring = {}
+_bg_cache = {}
+
+
+def _background(cp: int, depth_background: float, dev) -> torch.Tensor:
+    """[0,0,0, depth_background, 0, ...]: the model's backgrounds (gaussian_splatting.py:745,757,769,783)."""
+    key = (cp, depth_background, dev.type, dev.index)
+    t = _bg_cache.get(key)
+    if t is None:
+        host = torch.zeros(cp, dtype=torch.float32)
+        host[3] = depth_background
+        t = _bg_cache[key] = host.to(dev)
+    return t
 
 
 @dataclass
@@ -138,8 +150,7 @@ class _RenderViews(Function):
         # for the intersection count that sizes the sort
         prepare(1)
         binning = ops.bin_views(n, V, geo, depths, radii, nth, tb, xy_from_geo=True, while_waiting=lambda: prepare(2))
-        bg = torch.zeros(CP, dtype=torch.float32, device=dev)
-        bg[3] = depth_background
+        bg = _background(CP, float(depth_background), dev)
         out, final_T, final_idx = ops.blend_fwd(binning, geo, chan, bg, H, W, colors_per_view=True,
                                                 pair_counter=stats)
         ctx.binning, ctx.views, ctx.dims = binning, views, (n, V, D, CP, degree, int(degrees_to_use), H, W)
@@ -160,12 +171,16 @@ class _RenderViews(Function):
         v_geo, v_chan = ops.blend_bwd(ctx.binning, geo, chan, bg, final_T, final_idx, v_out, H, W,
                                       colors_per_view=True)
         nb = (degree + 1) ** 2
-        v_means = torch.empty((n, 3), dtype=torch.float32, device=dev)
-        v_ls = torch.empty((n, 3), dtype=torch.float32, device=dev)
-        v_q = torch.empty((n, 4), dtype=torch.float32, device=dev)
-        v_op = torch.empty((n,), dtype=torch.float32, device=dev)
-        v_sh = torch.empty((n, nb, 3), dtype=torch.float32, device=dev)
-        v_f = torch.empty((n, D), dtype=torch.float32, device=dev)
+        go = (ctx.holder or {}).get("grad_out")  # optional caller-owned buffers (views of a flat bucket)
+
+        def buf(name, shape):
+            t = go.get(name) if go else None
+            if t is not None and t.numel() == int(torch.Size(shape).numel()) and t.is_contiguous() and t.dtype == torch.float32:
+                return t.view(shape)
+            return torch.empty(shape, dtype=torch.float32, device=dev)
+
+        v_means, v_ls, v_q = buf("means", (n, 3)), buf("log_scales", (n, 3)), buf("quats", (n, 4))
+        v_op, v_sh, v_f = buf("opacity_logit", (n,)), buf("sh_coeffs", (n, nb, 3)), buf("features", (n, D))
         with torch.cuda.device(dev):
             _lib.call("gg_prepare_views_bwd", n, V, D, CP, degree, deg_use, ops.ptr(means), ops.ptr(log_scales),
                       ops.ptr(quats), ops.ptr(opacity_logit), ops.ptr(features), ops.ptr(views.viewmats),
@@ -195,7 +210,9 @@ def render_views(means, log_scales, quats, opacity_logit, sh_coeffs, features, v
     `holder` (a dict, optional) receives the per-view projection by-products -- packed geo records
     (pixel centres in columns 0..1), radii, num_tiles_hit, depths, the binning -- and, after
     backward, `v_geo` whose first two columns are d loss / d xys, the statistic the model's
-    densification reads from `xys.grad` (gaussian_splatting.py:725,377).
+    densification reads from `xys.grad` (gaussian_splatting.py:725,377).  If it carries
+    `grad_out` (name -> preallocated fp32 tensor, e.g. `GradientBucket.unpack()`), the backward
+    writes the leaf gradients of a single-launch step straight into those buffers.
     """
     out, final_T = _RenderViews.apply(means, log_scales, quats, opacity_logit, sh_coeffs, features, views,
                                       int(degrees_to_use), float(depth_background), float(clip_thresh), stats, holder)
