@@ -192,7 +192,7 @@ def run_ours(args):
     _lib.check(_lib.load().gg_check_device(), "gg_check_device")
 
     cfg = scenes.CONFIGS[args.config]
-    n, W, H, D = cfg["n"], cfg["W"], cfg["H"], cfg["D"]
+    n, W, H, D = cfg["n"], cfg["W"], cfg["H"], (cfg["D"] if args.feat < 0 else args.feat)
     # config 2 is a fixed 64-view batch split over the ranks (strong scaling); the others fix the work per GPU
     strong = args.config == 2
     V = args.views if args.views else (1 if args.config == 1 else (max(1, cfg["views"] // world) if strong else cfg["views"]))
@@ -212,7 +212,22 @@ def run_ours(args):
     from gaussiangrasper_b200.distributed import GradientBucket
     bucket = GradientBucket(P) if (world > 1 and cfg["backward"]) else None
 
+    def step_dropin():
+        from gaussiangrasper_b200.reference_flow import get_outputs
+        for p in P.values():
+            p.grad = None
+        for cam_i in cams:
+            o = get_outputs(P["means"], P["log_scales"], P["quats"], P["opacity_logit"], P["sh_coeffs"], P["features"],
+                            cam_i)
+            if cfg["backward"]:
+                loss = ((o["rgb"] * v_img[0, ..., 0:3]).sum() + (o["depth"] * v_img[0, ..., 3:4]).sum() +
+                        (o["normal"] * v_img[0, ..., 4:7]).sum() + (o["feature"] * v_img[0, ..., 7:7 + D]).sum())
+                loss.backward()
+        return o["rgb"]
+
     def step():
+        if args.path == "dropin":
+            return step_dropin()
         for p in P.values():
             p.grad = None
         out = None
@@ -404,7 +419,7 @@ def run_ours(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": cfg["name"], "gaussians": n, "image": [W, H], "views_per_gpu": V, "views_per_launch": chunk,
-                   "channels": C, "backward": cfg["backward"], "parallelism": f"view-sharded x{world}",
+                   "channels": C, "backward": cfg["backward"], "parallelism": f"view-sharded x{world}", "path": args.path,
                    "l2": "inputs larger than L2 (parameters+gradients 2x%.0f MB per step)" % (n * (86 + D) * 4 / 1e6)},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
@@ -429,6 +444,9 @@ def main():
     ap.add_argument("--config", type=int, default=1, help="index into BASELINE.json configs (default 1)")
     ap.add_argument("--views", type=int, default=0, help="views per GPU per step (default: config's)")
     ap.add_argument("--chunk", type=int, default=8, help="views rendered per launch group")
+    ap.add_argument("--feat", type=int, default=-1, help="feature channels D (default: the config's)")
+    ap.add_argument("--path", default="fused", choices=["fused", "dropin"],
+                    help="fused: render_views; dropin: the reference's 1 projection + SH + 4 rasterize calls")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

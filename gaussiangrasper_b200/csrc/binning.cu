@@ -137,10 +137,11 @@ emit_keys_kernel(int n, int n_views, const float* __restrict__ xys, int xy_strid
     const float2 c = __ldg(reinterpret_cast<const float2*>(xys + gi * xy_stride));
     const TileBox tb = tile_box(c.x, c.y, (float)r, tiles_x, tiles_y);
     long long cur = gi == 0 ? 0 : cum[gi - 1];
+    const long long end = cum[gi];  // never write past this Gaussian's slot, whatever the caller's counts say
     const uint64_t dbits = (uint64_t)__float_as_uint(depths[gi]);
     const long long tile0 = (long long)view * tiles_x * tiles_y;
     for (int ty = tb.y0; ty < tb.y1; ++ty)
-        for (int tx = tb.x0; tx < tb.x1; ++tx) {
+        for (int tx = tb.x0; tx < tb.x1 && cur < end; ++tx) {
             const uint64_t tile = (uint64_t)(tile0 + (long long)ty * tiles_x + tx);
             keys[cur] = (int64_t)((tile << 32) | dbits);
             ids[cur] = g;
@@ -403,8 +404,10 @@ emit_tiles_sorted_kernel(long long total, int n, const int32_t* __restrict__ ord
     s_box[warp][lane] = box;
     s_g[warp][lane] = g;
     __syncwarp();
-    const int total_w = s_off[warp][32];
     const long long wbase = i0 == 0 ? 0 : (long long)cum[i0 - 1];
+    const long long ilast = min(i0 + 31, total - 1);
+    // the span this warp may write is fixed by the scanned counts, whatever the recomputed boxes say
+    const int total_w = min(s_off[warp][32], (int)((long long)cum[ilast] - wbase));
     for (int j = lane; j < total_w; j += 32) {
         int lo = 0;
 #pragma unroll

@@ -339,31 +339,6 @@ def test_alpha_clamp_has_zero_gradient(dev):
 
 
 # ---------------------------------------------------------------------------------------------
-def model_forward(P, RG, NDRG, SH, means, log_scales, quats, opac_logit, sh_coeffs, feats, cam, dev, sh_deg=4):
-    """The render of gaussian_splatting.py:699-784 (rgb, feature, depth, normal), written against
-    whatever operator set is passed in."""
-    from gaussiangrasper_b200 import quat_to_rotmat
-    tb = cam.tile_bounds
-    xys, depths, radii, conics, nth, cov3d = P.apply(
-        means, torch.exp(log_scales), 1, quats / quats.norm(dim=-1, keepdim=True), cam.viewmat[:3].to(dev),
-        cam.fullmat.to(dev), cam.fx, cam.fy, cam.cx, cam.cy, cam.H, cam.W, tb)
-    xys.retain_grad()
-    viewdirs = means.detach() - cam.position.to(dev)
-    viewdirs = viewdirs / viewdirs.norm(dim=-1, keepdim=True)
-    rgbs = torch.clamp(SH.apply(sh_deg, viewdirs, sh_coeffs) + 0.5, 0.0, 1.0)
-    op = torch.sigmoid(opac_logit)
-    rgb = RG.apply(xys, depths, radii, conics, nth, rgbs, op, cam.H, cam.W, torch.zeros(3, device=dev))
-    feature = NDRG.apply(xys, depths, radii, conics, nth, feats, op, cam.H, cam.W,
-                         torch.zeros(feats.shape[1], device=dev))
-    depth_im = RG.apply(xys, depths, radii, conics, nth, depths[:, None].repeat(1, 3), op, cam.H, cam.W,
-                        torch.ones(3, device=dev) * 10)[..., 0:1]
-    R = quat_to_rotmat(quats)
-    idx = torch.exp(log_scales).min(dim=-1)[1][..., None, None].expand(-1, 3, -1)
-    normals = R.gather(2, idx).squeeze(dim=2)
-    normal_im = RG.apply(xys, depths, radii, conics, nth, normals, op, cam.H, cam.W, torch.zeros(3, device=dev))
-    return dict(rgb=rgb, feature=feature, depth=depth_im, normal=normal_im, xys=xys)
-
-
 def oracle_model(sc, cam, v, dtype=torch.float64):
     """Same render with the torch oracle in fp64 + autograd; binning taken from the fp32 C oracle so
     both sides blend identical lists."""
@@ -410,8 +385,8 @@ def test_model_render_end_to_end_gradients(dev):
 
     P = {k: sc[k].to(dev).clone().requires_grad_(True) for k in
          ("means", "log_scales", "quats", "opacity_logit", "sh_coeffs", "features")}
-    outs = model_forward(ProjectGaussians, RasterizeGaussians, NDRasterizeGaussians, SphericalHarmonics, P["means"],
-                         P["log_scales"], P["quats"], P["opacity_logit"], P["sh_coeffs"], P["features"], cam, dev)
+    from gaussiangrasper_b200.reference_flow import get_outputs
+    outs = get_outputs(P["means"], P["log_scales"], P["quats"], P["opacity_logit"], P["sh_coeffs"], P["features"], cam)
     for k in ("rgb", "feature", "depth", "normal"):
         err = (outs[k].detach().cpu().double() - ref_out[k].detach()).abs()
         # fp32 pipeline vs fp64 oracle: a few threshold pixels may differ; the bulk must be tight
