@@ -12,6 +12,7 @@
 #include "gg_common.cuh"
 #include "gg_geo.cuh"
 #include "gg_math.cuh"
+#include "gg_tma.cuh"
 #include "gg_b200.h"
 
 namespace gg {
@@ -124,23 +125,32 @@ prepare_views_kernel(const PrepArgs a, float* __restrict__ geo, float* __restric
     const bool vis = active && o.tiles > 0;
     if (phase == 1 || !__any_sync(0xffffffffu, vis)) return;  // nothing of this warp reaches a tile list
 
-    // ---- SH coefficients of the warp's 32 Gaussians: one contiguous span, 16-byte loads ----
+    // ---- SH coefficients of the warp's 32 Gaussians: one contiguous span.  A full warp moves it
+    // with a single bulk copy (TMA engine) and evaluates the SH basis while it lands ----
     const int row = a.nb * 3;
-    {
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + (size_t)kPrepWarps * 32 * slab_row) + warp;
+    const bool bulk = rows_here == 32;
+    if (bulk) {
+        if (lane == 0) {
+            mbar_init(bar, 1);
+            bulk_load(slab, a.sh + first * row, (uint32_t)(32 * row * sizeof(float)), bar);
+        }
+        __syncwarp();
+    } else {
         const float* gspan = a.sh + first * row;
         const int span = rows_here * row;
-        const int nvec = span >> 2;
-        const float4* g4 = reinterpret_cast<const float4*>(gspan);
-        float4* s4 = reinterpret_cast<float4*>(slab);
-        for (int k = lane; k < nvec; k += 32) s4[k] = __ldg(g4 + k);
-        for (int k = (nvec << 2) + lane; k < span; k += 32) slab[k] = __ldg(gspan + k);
+        for (int k = lane; k < span; k += 32) slab[k] = __ldg(gspan + k);
     }
-    __syncwarp();
     float rgb[3] = {0.f, 0.f, 0.f}, nrm[3] = {0.f, 0.f, 0.f};
+    float Y[25];
     if (vis) {
-        float Y[25];
         sh_basis(a.deg_use, g.p[0] - __ldg(a.positions + 3 * view), g.p[1] - __ldg(a.positions + 3 * view + 1),
                  g.p[2] - __ldg(a.positions + 3 * view + 2), Y);
+        const Rot3 R = quat_to_rot(g.qh[0], g.qh[1], g.qh[2], g.qh[3]);
+        nrm[0] = R.m[g.kmin]; nrm[1] = R.m[3 + g.kmin]; nrm[2] = R.m[6 + g.kmin];
+    }
+    if (bulk) mbar_wait(bar, 0); else __syncwarp();
+    if (vis) {
         const int nuse = sh_num_bases(a.deg_use);
         const float* cf = slab + lane * row;
         for (int b = 0; b < nuse; ++b) {
@@ -149,8 +159,6 @@ prepare_views_kernel(const PrepArgs a, float* __restrict__ geo, float* __restric
         }
 #pragma unroll
         for (int c = 0; c < 3; ++c) rgb[c] = fminf(1.0f, fmaxf(0.0f, rgb[c] + 0.5f));
-        const Rot3 R = quat_to_rot(g.qh[0], g.qh[1], g.qh[2], g.qh[3]);
-        nrm[0] = R.m[g.kmin]; nrm[1] = R.m[3 + g.kmin]; nrm[2] = R.m[6 + g.kmin];
     }
     __syncwarp();
     // ---- assemble the channel rows in shared memory, store them as one coalesced span ----
@@ -210,13 +218,18 @@ prepare_chan_kernel(const PrepArgs a, float* __restrict__ chan, const float* __r
             if (radii[(long long)v * a.n + i] > 0) vismask |= 1u << (v & 31);
     const bool many_views = a.n_views > 32;  // the bit mask is only a hint then
     if (!many_views && !__any_sync(0xffffffffu, vismask != 0)) return;
-    {
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + (size_t)kPrepWarps * per_warp) + warp;
+    const bool bulk = rows_here == 32;
+    if (bulk) {
+        if (lane == 0) {
+            mbar_init(bar, 1);
+            bulk_load(slab, a.sh + first * row, (uint32_t)(32 * row * sizeof(float)), bar);
+        }
+    } else {
         const float* gspan = a.sh + first * row;
-        const int span = rows_here * row, nvec = span >> 2;
-        const float4* g4 = reinterpret_cast<const float4*>(gspan);
-        float4* s4 = reinterpret_cast<float4*>(slab);
-        for (int k = lane; k < nvec; k += 32) s4[k] = __ldg(g4 + k);
-        for (int k = (nvec << 2) + lane; k < span; k += 32) slab[k] = __ldg(gspan + k);
+        for (int k = lane; k < rows_here * row; k += 32) slab[k] = __ldg(gspan + k);
+    }
+    {
         const float* fspan = a.features + first * D;
         for (int k = lane; k < rows_here * D; k += 32) fslab[k] = __ldg(fspan + k);
     }
@@ -228,6 +241,7 @@ prepare_chan_kernel(const PrepArgs a, float* __restrict__ chan, const float* __r
         nrm[0] = R.m[g.kmin]; nrm[1] = R.m[3 + g.kmin]; nrm[2] = R.m[6 + g.kmin];
     }
     __syncwarp();
+    if (bulk) mbar_wait(bar, 0);
     const int nuse = sh_num_bases(a.deg_use);
     const float* cf = slab + lane * row;
     const float* fr = fslab + lane * D;
@@ -349,14 +363,13 @@ prepare_views_bwd_kernel(const PrepArgs a, const float* __restrict__ geo, const 
         v_opacity_logit[i] = go * g.opacity * (1.0f - g.opacity);
     }
     __syncwarp();
-    {
+    if (rows_here == 32) {
+        // the warp's [32, 3*nb] gradient rows are one contiguous, 16-byte aligned span: one bulk store
+        if (lane == 0) bulk_store_and_wait(v_sh + first * row, slab, (uint32_t)(32 * row * sizeof(float)));
+        __syncwarp();
+    } else {
         float* gspan = v_sh + first * row;
-        const int span = rows_here * row;
-        const int nvec = span >> 2;
-        float4* g4 = reinterpret_cast<float4*>(gspan);
-        const float4* s4 = reinterpret_cast<const float4*>(slab);
-        for (int k = lane; k < nvec; k += 32) g4[k] = s4[k];
-        for (int k = (nvec << 2) + lane; k < span; k += 32) gspan[k] = slab[k];
+        for (int k = lane; k < rows_here * row; k += 32) gspan[k] = slab[k];
     }
     if (D > 0) {
         float* gspan = v_features + first * D;
@@ -409,7 +422,7 @@ extern "C" int gg_prepare_views(int n, int n_views, int feat_dim, int cp, int de
     GG_REQUIRE(geo && chan && depths && radii && num_tiles_hit, "gg_prepare_views: null output pointer");
     GG_REQUIRE(((uintptr_t)geo & 15) == 0 && ((uintptr_t)chan & 15) == 0, "gg_prepare_views: geo/chan misaligned");
     if (phase == 2 && n_views > 1) {  // one view: the per-view kernel below has the better occupancy
-        const size_t smem2 = sizeof(float) * kPrepWarps * 32 * (size_t)(a.nb * 3 + feat_dim + cp);
+        const size_t smem2 = sizeof(float) * kPrepWarps * 32 * (size_t)(a.nb * 3 + feat_dim + cp) + sizeof(uint64_t) * kPrepWarps;
         GG_CUDA(cudaFuncSetAttribute(prepare_chan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         prepare_chan_kernel<<<div_up(n, kPrepThreads), kPrepThreads, smem2, (cudaStream_t)stream>>>(a, chan, depths,
                                                                                                    radii);
@@ -417,7 +430,7 @@ extern "C" int gg_prepare_views(int n, int n_views, int feat_dim, int cp, int de
         return check_launch("prepare_chan_kernel");
     }
     const int slab_row = a.nb * 3 > cp ? a.nb * 3 : cp;
-    const size_t smem = sizeof(float) * kPrepWarps * 32 * (size_t)slab_row;
+    const size_t smem = sizeof(float) * kPrepWarps * 32 * (size_t)slab_row + sizeof(uint64_t) * kPrepWarps;
     GG_CUDA(cudaFuncSetAttribute(prepare_views_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(div_up(n, kPrepThreads), n_views);
     prepare_views_kernel<<<grid, kPrepThreads, smem, (cudaStream_t)stream>>>(a, geo, chan, depths, radii,
