@@ -24,6 +24,7 @@ UNITS = [
     ("binning.cu", ["-fmad=false"]),
     ("blend.cu", []),
     ("fused.cu", ["-fmad=false"]),
+    ("train.cu", ["-fmad=false"]),
 ]
 
 

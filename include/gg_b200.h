@@ -170,6 +170,22 @@ int gg_prepare_views_bwd(int n, int n_views, int feat_dim, int cp, int degree, i
                          const float* v_chan, float* v_means, float* v_log_scales, float* v_quats,
                          float* v_opacity_logit, float* v_sh_coeffs, float* v_features, void* stream);
 
+/* ---- next rows: the streaming steps directly behind the backward -----------------
+ * gg_adam_step: fused torch.optim.Adam (no amsgrad / weight decay) over a flat gradient buffer that
+ * is tiled by up to 8 segments, each with its own parameter tensor and learning rate (replaces the
+ * reference's per-group optimizers, method_configs.py:618-664).  params/offsets/counts/lrs are HOST
+ * arrays of n_segments entries; `step` is the 1-based update count used for the bias corrections. */
+int gg_adam_step(int n_segments, float* const* params, const long long* offsets, const long long* counts,
+                 const float* lrs, const float* grad_flat, float* exp_avg_flat, float* exp_avg_sq_flat, float beta1,
+                 float beta2, float eps, int step, void* stream);
+/* gg_densify_stats: GaussianSplattingModel.after_train (gaussian_splatting.py:373-393) from the
+ * blend gradient table: xys_grad_norm += |d loss / d xy|, vis_counts += 1, max_2dsize =
+ * max(., radius / max(H, W)) for the Gaussians visible in each view; first_call != 0 initialises
+ * (norms of every Gaussian, counts of one) the way the model does on its first step. */
+int gg_densify_stats(long long n, int n_views, const float* v_geo /*[V*n,8]*/, const int32_t* radii /*[V*n]*/,
+                     int img_h, int img_w, int first_call, float* xys_grad_norm, float* vis_counts,
+                     float* max_2dsize, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
