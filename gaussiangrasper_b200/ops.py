@@ -294,6 +294,14 @@ def pack_geo(n, n_views, xys, conics, opacity, opac_per_view=False):
     return geo
 
 
+def _ids_ptr(binning: "Binning"):
+    """Pointer of the sorted id list; an empty list (nothing visible) still needs a valid address
+    for the C ABI's null checks -- no kernel dereferences it, every tile range is (0,0)."""
+    if binning.ids_sorted.numel() > 0:
+        return ptr(binning.ids_sorted)
+    return ptr(workspace(binning.tile_ranges.device).total)
+
+
 def max_channels() -> int:
     return int(_lib.load().gg_blend_max_channels())
 
@@ -319,7 +327,7 @@ def blend_fwd(binning: Binning, geo, colors, background, img_height, img_width, 
             c1 = min(C, c0 + step)
             _lib.call("gg_blend_fwd", 
                 V, n, c1 - c0, C, 1 if colors_per_view else 0, C, int(img_height), int(img_width), tb[0], tb[1],
-                ptr(binning.ids_sorted), ptr(binning.tile_ranges), ptr(binning.tile_order), ptr(geo),
+                _ids_ptr(binning), ptr(binning.tile_ranges), ptr(binning.tile_order), ptr(geo),
                 colors.data_ptr() + 4 * c0, background.data_ptr() + 4 * c0, out.data_ptr() + 4 * c0, ptr(final_T), ptr(final_idx),
                 ptr(pair_counter) if c0 == 0 else None, stream_ptr(dev))
     return out, final_T, final_idx
@@ -341,7 +349,7 @@ def blend_bwd(binning: Binning, geo, colors, background, final_T, final_idx, v_o
             c1 = min(C, c0 + step)
             _lib.call("gg_blend_bwd", 
                 V, n, c1 - c0, C, 1 if colors_per_view else 0, C, int(img_height), int(img_width), tb[0], tb[1],
-                ptr(binning.ids_sorted), ptr(binning.tile_ranges), ptr(binning.tile_order), ptr(geo),
+                _ids_ptr(binning), ptr(binning.tile_ranges), ptr(binning.tile_order), ptr(geo),
                 colors.data_ptr() + 4 * c0, background.data_ptr() + 4 * c0, ptr(final_T), ptr(final_idx), v_out.data_ptr() + 4 * c0, ptr(v_geo),
                 v_colors.data_ptr() + 4 * c0, stream_ptr(dev))
     return v_geo, v_colors
