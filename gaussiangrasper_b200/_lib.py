@@ -39,8 +39,9 @@ _SIGNATURES = {
     "gg_tile_ranges": (C.c_int, [_ll, _p, _ll, _p, _p]),
     "gg_blend_max_channels": (C.c_int, []),
     "gg_pack_geo": (C.c_int, [_ll, _i, _p, _p, _p, _i, _p, _p]),
-    "gg_blend_fwd": (C.c_int, [_i, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
-    "gg_blend_bwd": (C.c_int, [_i, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "gg_blend_fwd": (C.c_int, [_i, _ll, _i, _i, _i, _i, _i, _i, _i, _i] + [_p] * 12),
+    "gg_blend_bwd": (C.c_int, [_i, _ll, _i, _i, _i, _i, _i, _i, _i, _i] + [_p] * 13),
+    "gg_blend_hit_words": (C.c_size_t, [_ll, _ll, _i]),
     "gg_depth_keys": (C.c_int, [_ll, _i, _p, _p, _p, _p]),
     "gg_gather_counts": (C.c_int, [_ll, _p, _p, _p, _p]),
     "gg_emit_tiles_sorted": (C.c_int, [_i, _i, _p, _p, _i, _p, _p, _i, _i, _p, _p, _p]),

@@ -56,8 +56,9 @@ def rasterize_forward(ctx, xys, depths, radii, conics, num_tiles_hit, colors, op
     geo = ops.pack_geo(n, 1, xys.detach(), conics.detach(), opacity.detach())
     colors_c = ops.f32c(colors.detach())
     background = ops.f32c(background.detach())
-    out, final_T, final_idx = ops.blend_fwd(binning, geo, colors_c, background, img_height, img_width,
-                                            single_image=True)
+    out, final_T, final_idx, hit_words = ops.blend_fwd(binning, geo, colors_c, background, img_height, img_width,
+                                                       single_image=True)
+    ctx.hit_words = hit_words
     ctx.binning = binning
     ctx.img_size = (int(img_height), int(img_width))
     ctx.opacity_shape = tuple(opacity.shape)
@@ -72,6 +73,6 @@ def rasterize_backward(ctx, v_out):
     binning = ctx.binning
     h, w = ctx.img_size
     v_geo, v_colors = ops.blend_bwd(binning, geo, colors, background, final_T, final_idx,
-                                    v_out.reshape(1, h, w, -1), h, w)
+                                    v_out.reshape(1, h, w, -1), h, w, hit_words=ctx.hit_words)
     v_xys, v_conics, v_opac = ops.unpack_vgeo(binning.n, 1, v_geo)
     return v_xys, v_conics, v_colors, v_opac.reshape(ctx.opacity_shape)

@@ -45,6 +45,13 @@ struct BlendArgs {
     float* final_T;              // [V, H, W]
     int32_t* final_idx;          // [V, H, W]
     unsigned long long* pair_counter;  // optional: += pixel-Gaussian pairs visited
+    // Per (tile batch, warp) bit masks of the entries to which at least one pixel of the warp's 8x4
+    // block contributed, written by the forward and consumed by the backward (which then neither
+    // culls nor tests the others).  Record r = range.x / fwd_batch + global tile + batch holds
+    // 8 warps x (fwd_batch / 32) words; the index is collision free because
+    // floor(a) + ceil(b) <= floor(a + b) + 1.  Nullable: the backward then culls on its own.
+    uint32_t* hit_words;
+    int fwd_batch;
     // backward only
     const float* v_out;
     float* v_geo;     // [V*N, 8]  (+= v_x, v_y, v_A, v_B, v_C, v_opacity)
@@ -206,9 +213,12 @@ blend_fwd_kernel(const BlendArgs a) {
             const float4* c4 = reinterpret_cast<const float4*>(col_sm + buf * BATCH * CP);
             unsigned mask[BATCH / 32];
             cull_batch<BATCH>(gbuf, cnt, rx0, ry0, rx1, ry1, mask);
-            auto blend = [&](int e, float alpha) {
+            unsigned hits[BATCH / 32];
+#pragma unroll
+            for (int k = 0; k < BATCH / 32; ++k) hits[k] = 0u;
+            auto blend = [&](int e, float alpha) -> bool {
                 const float next_T = T * (1.0f - alpha);
-                if (next_T <= kTStop) { done = true; stop = first + e + 1; return; }
+                if (next_T <= kTStop) { done = true; stop = first + e + 1; return false; }
                 const float vis = alpha * T;
 #pragma unroll
                 for (int q = 0; q < CP / 4; ++q) {
@@ -220,6 +230,7 @@ blend_fwd_kernel(const BlendArgs a) {
                 }
                 T = next_T;
                 last = first + e + 1;
+                return true;
             };
 #pragma unroll
             for (int k = 0; k < BATCH / 32; ++k) {
@@ -227,10 +238,12 @@ blend_fwd_kernel(const BlendArgs a) {
                 while (m) {
                     // two surviving entries per round: their alpha chains are independent, only the
                     // transmittance update is sequential
-                    const int e0 = k * 32 + __ffs(m) - 1;
+                    const int b0 = __ffs(m) - 1;
+                    const int e0 = k * 32 + b0;
                     m &= m - 1;
                     const bool two = m != 0;
-                    const int e1 = two ? k * 32 + __ffs(m) - 1 : e0;
+                    const int b1 = two ? __ffs(m) - 1 : b0;
+                    const int e1 = k * 32 + b1;
                     m &= m - 1;
                     const float4 ga0 = g4[2 * e0], gb0 = g4[2 * e0 + 1];
                     const float4 ga1 = g4[2 * e1], gb1 = g4[2 * e1 + 1];
@@ -240,10 +253,21 @@ blend_fwd_kernel(const BlendArgs a) {
                     const float a1 = fminf(kAlphaMax, gb1.y * __expf(-s1));
                     const bool ok0 = !(s0 < 0.0f || s0 > gb0.z) && a0 >= kAlphaMin;
                     const bool ok1 = two && !(s1 < 0.0f || s1 > gb1.z) && a1 >= kAlphaMin;
-                    if (ok0 && !done) blend(e0, a0);
-                    if (ok1 && !done) blend(e1, a1);
+                    const bool c0 = (ok0 && !done) ? blend(e0, a0) : false;
+                    const bool c1 = (ok1 && !done) ? blend(e1, a1) : false;
+                    if (__any_sync(0xffffffffu, c0)) hits[k] |= 1u << b0;
+                    if (__any_sync(0xffffffffu, c1)) hits[k] |= 1u << b1;
                 }
                 if (__all_sync(0xffffffffu, done)) { warp_done = true; break; }
+            }
+            if (a.hit_words) {
+                // record index: see BlendArgs::hit_words (a.fwd_batch == BATCH in the forward)
+                const long long rec = (long long)(range.x / BATCH) + gtile + b;
+                uint32_t* dst = a.hit_words + (rec * (kBlendThreads / 32) + warp) * (BATCH / 32);
+                const int lane_id = threadIdx.x & 31;
+#pragma unroll
+                for (int k = 0; k < BATCH / 32; ++k)
+                    if (lane_id == k) dst[k] = hits[k];
             }
         }
     }
@@ -458,7 +482,23 @@ blend_bwd_kernel(const BlendArgs a) {
             const float4* c4 = reinterpret_cast<const float4*>(col_sm + buf * BATCH * CP);
             const int* idb = ids_sm + buf * BATCH;
             unsigned mask[BATCH / 32];
-            cull_batch<BATCH>(gbuf, e_hi, rx0, ry0, rx1, ry1, mask);
+            if (a.hit_words) {
+                // entries the forward recorded as contributing for this warp (bwd batches are 64 wide,
+                // forward records fwd_batch wide: pick the matching words)
+                const int fb = a.fwd_batch;
+                const int e_abs = b * BATCH;  // offset of this batch inside the tile's list
+                const long long rec = (long long)(range.x / fb) + gtile + e_abs / fb;
+                const uint32_t* src = a.hit_words + (rec * (kBlendThreads / 32) + warp) * (fb / 32) + (e_abs % fb) / 32;
+#pragma unroll
+                for (int k = 0; k < BATCH / 32; ++k) {
+                    const int lo = k * 32;
+                    unsigned w = lo < e_hi ? __ldg(src + k) : 0u;
+                    if (e_hi - lo < 32 && e_hi > lo) w &= (1u << (e_hi - lo)) - 1u;
+                    mask[k] = w;
+                }
+            } else {
+                cull_batch<BATCH>(gbuf, e_hi, rx0, ry0, rx1, ry1, mask);
+            }
             auto colour_dot = [&](int e) {
                 float d0 = 0.0f, d1 = 0.0f;
 #pragma unroll
@@ -617,6 +657,16 @@ using namespace gg;
 
 extern "C" int gg_blend_max_channels(void) { return 64; }
 
+// entries staged per round by the forward kernel for a given channel count (see dispatch_blend)
+static int fwd_batch_for(int channels) { return channels <= 32 ? 128 : 64; }
+
+// number of uint32 words of the forward's hit-mask table for m intersections over num_tiles tiles
+extern "C" size_t gg_blend_hit_words(long long m, long long num_tiles, int channels) {
+    const long long fb = fwd_batch_for(channels);
+    const long long records = m / fb + num_tiles + 2;
+    return (size_t)(records * (kBlendThreads / 32) * (fb / 32));
+}
+
 extern "C" int gg_pack_geo(long long n, int n_views, const float* xys, const float* conics, const float* opac,
                            int opac_per_view, float* geo, void* stream) {
     GG_REQUIRE(n >= 1 && n_views >= 1, "gg_pack_geo: need n >= 1");
@@ -642,7 +692,8 @@ extern "C" int gg_blend_fwd(int n_views, long long n, int channels, int color_st
                             int out_stride, int img_h, int img_w, int tiles_x, int tiles_y,
                             const int32_t* ids_sorted, const int32_t* tile_ranges, const int32_t* tile_order,
                             const float* geo, const float* colors, const float* bg, float* out, float* final_T,
-                            int32_t* final_idx, unsigned long long* pair_counter, void* stream) {
+                            int32_t* final_idx, unsigned long long* pair_counter, uint32_t* hit_words,
+                            void* stream) {
     GG_REQUIRE(n_views >= 1 && n >= 1 && channels >= 1, "gg_blend_fwd: bad sizes");
     GG_REQUIRE(color_stride >= channels && out_stride >= channels, "gg_blend_fwd: stride smaller than channels");
     GG_REQUIRE(img_h > 0 && img_w > 0 && tiles_x == (img_w + GG_TILE - 1) / GG_TILE &&
@@ -657,6 +708,7 @@ extern "C" int gg_blend_fwd(int n_views, long long n, int channels, int color_st
     a.geo_view_stride = n; a.color_view_stride = colors_per_view ? n : 0;
     a.ids_sorted = ids_sorted; a.tile_ranges = tile_ranges; a.tile_order = tile_order; a.geo = geo; a.colors = colors; a.bg = bg;
     a.out = out; a.final_T = final_T; a.final_idx = final_idx; a.pair_counter = pair_counter;
+    a.hit_words = hit_words; a.fwd_batch = fwd_batch_for(channels);
     return dispatch_blend(false, a, n_views, (cudaStream_t)stream);
 }
 
@@ -664,8 +716,8 @@ extern "C" int gg_blend_bwd(int n_views, long long n, int channels, int color_st
                             int out_stride, int img_h, int img_w, int tiles_x, int tiles_y,
                             const int32_t* ids_sorted, const int32_t* tile_ranges, const int32_t* tile_order,
                             const float* geo, const float* colors, const float* bg, const float* final_T,
-                            const int32_t* final_idx, const float* v_out, float* v_geo, float* v_colors,
-                            void* stream) {
+                            const int32_t* final_idx, const float* v_out, const uint32_t* hit_words, float* v_geo,
+                            float* v_colors, void* stream) {
     GG_REQUIRE(n_views >= 1 && n >= 1 && channels >= 1, "gg_blend_bwd: bad sizes");
     GG_REQUIRE(color_stride >= channels && out_stride >= channels, "gg_blend_bwd: stride smaller than channels");
     GG_REQUIRE(img_h > 0 && img_w > 0 && tiles_x == (img_w + GG_TILE - 1) / GG_TILE &&
@@ -681,5 +733,6 @@ extern "C" int gg_blend_bwd(int n_views, long long n, int channels, int color_st
     a.ids_sorted = ids_sorted; a.tile_ranges = tile_ranges; a.tile_order = tile_order; a.geo = geo; a.colors = colors; a.bg = bg;
     a.final_T = const_cast<float*>(final_T); a.final_idx = const_cast<int32_t*>(final_idx);
     a.v_out = v_out; a.v_geo = v_geo; a.v_colors = v_colors;
+    a.hit_words = const_cast<uint32_t*>(hit_words); a.fwd_batch = fwd_batch_for(channels);
     return dispatch_blend(true, a, n_views, (cudaStream_t)stream);
 }

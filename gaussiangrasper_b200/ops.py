@@ -307,9 +307,10 @@ def max_channels() -> int:
 
 
 def blend_fwd(binning: Binning, geo, colors, background, img_height, img_width, colors_per_view=False,
-              pair_counter: Optional[torch.Tensor] = None, single_image: bool = False):
+              pair_counter: Optional[torch.Tensor] = None, single_image: bool = False, record_hits: bool = True):
     """colors [rows, C] (C arbitrary; split into launches of <= 64 channels).  Returns
-    (out [V,H,W,C], final_T [V,H,W], final_idx [V,H,W])."""
+    (out [V,H,W,C], final_T [V,H,W], final_idx [V,H,W], hit_words or None).  hit_words is the forward's
+    table of contributing entries per (tile batch, warp); give it to blend_bwd."""
     dev = require_cuda(geo, colors, background)
     colors, background = f32c(colors), f32c(background)
     V, n, C = binning.n_views, binning.n, colors.shape[1]
@@ -321,20 +322,23 @@ def blend_fwd(binning: Binning, geo, colors, background, img_height, img_width, 
     final_idx = torch.empty((V, img_height, img_width), dtype=torch.int32, device=dev)
     tb = binning.tile_bounds
     step = max_channels()
-    lib = _lib.load()
+    hit_words = None
+    if record_hits and C <= step and binning.num_intersects > 0:
+        nwords = int(_lib.load().gg_blend_hit_words(binning.num_intersects, binning.tile_ranges.shape[0], C))
+        hit_words = torch.zeros(nwords, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         for c0 in range(0, C, step):
             c1 = min(C, c0 + step)
-            _lib.call("gg_blend_fwd", 
+            _lib.call("gg_blend_fwd",
                 V, n, c1 - c0, C, 1 if colors_per_view else 0, C, int(img_height), int(img_width), tb[0], tb[1],
                 _ids_ptr(binning), ptr(binning.tile_ranges), ptr(binning.tile_order), ptr(geo),
-                colors.data_ptr() + 4 * c0, background.data_ptr() + 4 * c0, out.data_ptr() + 4 * c0, ptr(final_T), ptr(final_idx),
-                ptr(pair_counter) if c0 == 0 else None, stream_ptr(dev))
-    return out, final_T, final_idx
+                colors.data_ptr() + 4 * c0, background.data_ptr() + 4 * c0, out.data_ptr() + 4 * c0, ptr(final_T),
+                ptr(final_idx), ptr(pair_counter) if c0 == 0 else None, ptr(hit_words), stream_ptr(dev))
+    return out, final_T, final_idx, hit_words
 
 
 def blend_bwd(binning: Binning, geo, colors, background, final_T, final_idx, v_out, img_height, img_width,
-              colors_per_view=False):
+              colors_per_view=False, hit_words: Optional[torch.Tensor] = None):
     """Returns (v_geo [V*n, 8], v_colors like colors)."""
     dev = require_cuda(geo, colors, background, v_out)
     colors, background, v_out = f32c(colors), f32c(background), f32c(v_out)
@@ -343,15 +347,16 @@ def blend_bwd(binning: Binning, geo, colors, background, final_T, final_idx, v_o
     v_colors = torch.zeros_like(colors)
     tb = binning.tile_bounds
     step = max_channels()
-    lib = _lib.load()
+    if C > step:
+        hit_words = None
     with torch.cuda.device(dev):
         for c0 in range(0, C, step):
             c1 = min(C, c0 + step)
-            _lib.call("gg_blend_bwd", 
+            _lib.call("gg_blend_bwd",
                 V, n, c1 - c0, C, 1 if colors_per_view else 0, C, int(img_height), int(img_width), tb[0], tb[1],
                 _ids_ptr(binning), ptr(binning.tile_ranges), ptr(binning.tile_order), ptr(geo),
-                colors.data_ptr() + 4 * c0, background.data_ptr() + 4 * c0, ptr(final_T), ptr(final_idx), v_out.data_ptr() + 4 * c0, ptr(v_geo),
-                v_colors.data_ptr() + 4 * c0, stream_ptr(dev))
+                colors.data_ptr() + 4 * c0, background.data_ptr() + 4 * c0, ptr(final_T), ptr(final_idx),
+                v_out.data_ptr() + 4 * c0, ptr(hit_words), ptr(v_geo), v_colors.data_ptr() + 4 * c0, stream_ptr(dev))
     return v_geo, v_colors
 
 

@@ -151,8 +151,10 @@ class _RenderViews(Function):
         prepare(1)
         binning = ops.bin_views(n, V, geo, depths, radii, nth, tb, xy_from_geo=True, while_waiting=lambda: prepare(2))
         bg = _background(CP, float(depth_background), dev)
-        out, final_T, final_idx = ops.blend_fwd(binning, geo, chan, bg, H, W, colors_per_view=True,
-                                                pair_counter=stats)
+        out, final_T, final_idx, hit_words = ops.blend_fwd(binning, geo, chan, bg, H, W, colors_per_view=True,
+                                                           pair_counter=stats,
+                                                           record_hits=any(ctx.needs_input_grad))
+        ctx.hit_words = hit_words
         ctx.binning, ctx.views, ctx.dims = binning, views, (n, V, D, CP, degree, int(degrees_to_use), H, W)
         ctx.holder = holder
         ctx.save_for_backward(means, log_scales, quats, opacity_logit, features, geo, chan, radii, bg, final_T,
@@ -169,7 +171,7 @@ class _RenderViews(Function):
         n, V, D, CP, degree, deg_use, H, W = ctx.dims
         views, dev = ctx.views, means.device
         v_geo, v_chan = ops.blend_bwd(ctx.binning, geo, chan, bg, final_T, final_idx, v_out, H, W,
-                                      colors_per_view=True)
+                                      colors_per_view=True, hit_words=ctx.hit_words)
         nb = (degree + 1) ** 2
         go = (ctx.holder or {}).get("grad_out")  # optional caller-owned buffers (views of a flat bucket)
 

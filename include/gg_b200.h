@@ -133,14 +133,19 @@ int gg_blend_fwd(int n_views, long long n, int channels, int color_stride, int c
                  const int32_t* tile_ranges, const int32_t* tile_order /*nullable*/, const float* geo,
                  const float* colors, const float* bg,
                  float* out /*[V,H,W,out_stride]*/, float* final_T /*[V,H,W]*/, int32_t* final_idx /*[V,H,W]*/,
-                 unsigned long long* pair_counter /*nullable*/, void* stream);
+                 unsigned long long* pair_counter /*nullable*/, uint32_t* hit_words /*nullable*/, void* stream);
+/* hit_words: table of gg_blend_hit_words(m, V*tiles, channels) uint32, ZERO-FILLED by the caller before
+ * gg_blend_fwd, in which the forward records per (tile batch, 8x4-pixel warp) the entries that
+ * contributed; handed to gg_blend_bwd (same channel count) it spares the backward the culling and
+ * the alpha test of every other entry.  Results are identical with or without it. */
+size_t gg_blend_hit_words(long long m, long long num_tiles, int channels);
 /* v_geo [V*n,8] and v_colors (indexed like colors) are accumulated into: zero them first */
 int gg_blend_bwd(int n_views, long long n, int channels, int color_stride, int colors_per_view, int out_stride,
                  int img_h, int img_w, int tiles_x, int tiles_y, const int32_t* ids_sorted,
                  const int32_t* tile_ranges, const int32_t* tile_order /*nullable*/, const float* geo,
                  const float* colors, const float* bg,
-                 const float* final_T, const int32_t* final_idx, const float* v_out, float* v_geo,
-                 float* v_colors, void* stream);
+                 const float* final_T, const int32_t* final_idx, const float* v_out,
+                 const uint32_t* hit_words /*nullable*/, float* v_geo, float* v_colors, void* stream);
 /* v_geo -> v_xys [V*n,2], v_conics [V*n,3], v_opac [n] (summed over views; nullable) */
 int gg_unpack_vgeo(long long n, int n_views, const float* v_geo, float* v_xys, float* v_conics, float* v_opac,
                    int accumulate_opac, void* stream);
