@@ -566,6 +566,274 @@ blend_bwd_kernel(const BlendArgs a) {
     if (nhit) flush(nhit);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Warp-autonomous backward (used whenever the forward's hit masks are available).
+// Every warp owns one 8x4 pixel block and walks, back to front, ONLY the entries the forward
+// recorded as contributing to that block.  It gathers their geo/channel rows itself (cp.async
+// into a warp-private double buffer), so there is no CTA-wide staging, no __syncthreads and no
+// coupling between the eight blocks of a tile: a warp's time is the sum of its own work instead
+// of, per staged batch, the maximum over the tile's warps.  CTAs are 4 warps = half a tile.
+// ---------------------------------------------------------------------------------------------
+constexpr int kBwdWarps = 4;
+constexpr int kChunk = 16;  // entries gathered per round (= kHitRows)
+
+template <int CP>
+constexpr size_t blend_bwd_warp_smem() {
+    return sizeof(float) * kBwdWarps * (2 * kChunk * (8 + CP) + 2 * kHitRows * kHitRow + kHitRows + 2 * kChunk + 32 * CP);
+}
+
+template <int CP, bool kVec>
+__global__ void __launch_bounds__(kBwdWarps * 32)
+blend_bwd_warp_kernel(const BlendArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    constexpr int kRow = 8 + CP;                                   // staged row: geo then channels
+    constexpr int kPerWarp = 2 * kChunk * kRow + 2 * kHitRows * kHitRow + kHitRows + 2 * kChunk + 32 * CP;
+    float* wsm = smem + wib * kPerWarp;
+    float* rows = wsm;                                             // [2][kChunk][kRow]
+    float* facm = rows + 2 * kChunk * kRow;                        // [kHitRows][33]
+    float* wm = facm + kHitRows * kHitRow;                         // [kHitRows][33]
+    int* hit_g = reinterpret_cast<int*>(wm + kHitRows * kHitRow);  // [kHitRows]
+    int* chunk_g = hit_g + kHitRows;                               // [2][kChunk] Gaussian ids of the staged rows
+    float* vo_warp = reinterpret_cast<float*>(chunk_g + 2 * kChunk);  // [32][CP]
+
+    const int n_tiles = a.tiles_x * a.tiles_y;
+    const int lin = blockIdx.y * n_tiles + (blockIdx.x >> 1);
+    const int gtile = a.tile_order ? __ldg(a.tile_order + lin) : lin;
+    const int view = gtile / n_tiles;
+    const int tile = gtile - view * n_tiles;
+    const int tile_y = tile / a.tiles_x, tile_x = tile - tile_y * a.tiles_x;
+    const int warp = (blockIdx.x & 1) * kBwdWarps + wib;           // 0..7: which 8x4 block of the tile
+    const int tx = (lane & 7) | ((warp & 1) << 3), ty = (lane >> 3) | ((warp >> 1) << 2);
+    const int px = tile_x * GG_TILE + tx, py = tile_y * GG_TILE + ty;
+    const bool inside = px < a.img_w && py < a.img_h;
+    const float fpx = (float)px, fpy = (float)py;
+    const float rx0 = (float)(tile_x * GG_TILE + ((warp & 1) << 3)), ry0 = (float)(tile_y * GG_TILE + ((warp >> 1) << 2));
+    const int2 range = __ldg(reinterpret_cast<const int2*>(a.tile_ranges) + gtile);
+    const long long geo_base = (long long)view * a.geo_view_stride;
+    const long long color_base = (long long)view * a.color_view_stride;
+    const long long pix = ((long long)view * a.img_h + py) * a.img_w + px;
+
+    float vo[CP];
+    float T_final = 1.0f, bgdot = 0.0f;
+    int last = range.x;
+#pragma unroll
+    for (int c = 0; c < CP; ++c) vo[c] = 0.0f;
+    if (inside) {
+        T_final = a.final_T[pix];
+        last = a.final_idx[pix];
+        const float* v = a.v_out + pix * a.out_stride;
+#pragma unroll
+        for (int c = 0; c < CP; ++c)
+            if (c < a.channels) { vo[c] = __ldg(v + c); bgdot = fmaf(__ldg(a.bg + c), vo[c], bgdot); }
+    }
+    {
+        float4* row = reinterpret_cast<float4*>(vo_warp + lane * CP);
+#pragma unroll
+        for (int q = 0; q < CP / 4; ++q) row[q] = make_float4(vo[4 * q], vo[4 * q + 1], vo[4 * q + 2], vo[4 * q + 3]);
+    }
+    // zero the staged rows once: padding channels are read by the dot product
+    for (int k = lane; k < 2 * kChunk * kRow; k += 32) rows[k] = 0.0f;
+    float T = T_final;
+    float R = T_final * bgdot;
+    int wmax = last;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+    __syncwarp();
+    const int e_top = wmax - range.x;  // entries [0, e_top) of the tile's list can matter to this warp
+    if (e_top <= 0) return;
+
+    int nhit = 0;
+    auto reload_vo = [&]() {
+        const float4* row = reinterpret_cast<const float4*>(vo_warp + lane * CP);
+#pragma unroll
+        for (int q = 0; q < CP / 4; ++q) {
+            const float4 v = row[q];
+            vo[4 * q] = v.x; vo[4 * q + 1] = v.y; vo[4 * q + 2] = v.z; vo[4 * q + 3] = v.w;
+        }
+    };
+    // phase B: lane = (stored entry j = lane & 15, pixel half h = lane >> 4), see blend_bwd_kernel
+    auto flush = [&](int count) {
+        __syncwarp();
+        const int j = lane & (kHitRows - 1), h = lane >> 4;
+        const bool live = j < count;
+        const int g = live ? hit_g[j] : 0;
+        float4 ga = make_float4(0.f, 0.f, 0.f, 0.f), gb = ga;
+        if (live) {
+            ga = __ldg(reinterpret_cast<const float4*>(a.geo) + 2 * (geo_base + g));
+            gb = __ldg(reinterpret_cast<const float4*>(a.geo) + 2 * (geo_base + g) + 1);
+        }
+        float acc[CP];
+#pragma unroll
+        for (int c = 0; c < CP; ++c) acc[c] = 0.0f;
+        float m0 = 0.f, mx = 0.f, my = 0.f, mxx = 0.f, mxy = 0.f, myy = 0.f;
+        const float* fr = facm + j * kHitRow + 16 * h;
+        const float* wr = wm + j * kHitRow + 16 * h;
+        const float bx = ga.x - rx0, by = ga.y - ry0 - (float)(2 * h);
+#pragma unroll 4
+        for (int p = 0; p < 16; ++p) {
+            const float f = live ? fr[p] : 0.0f;
+            const float wv = live ? wr[p] : 0.0f;
+            const float4* vrow = reinterpret_cast<const float4*>(vo_warp + (16 * h + p) * CP);
+#pragma unroll
+            for (int q = 0; q < CP / 4; ++q) {
+                const float4 v = vrow[q];
+                acc[4 * q] = fmaf(f, v.x, acc[4 * q]);
+                acc[4 * q + 1] = fmaf(f, v.y, acc[4 * q + 1]);
+                acc[4 * q + 2] = fmaf(f, v.z, acc[4 * q + 2]);
+                acc[4 * q + 3] = fmaf(f, v.w, acc[4 * q + 3]);
+            }
+            const float dx = bx - (float)(p & 7), dy = by - (float)(p >> 3);
+            const float wdx = wv * dx, wdy = wv * dy;
+            m0 += wv; mx += wdx; my += wdy;
+            mxx = fmaf(wdx, dx, mxx); mxy = fmaf(wdx, dy, mxy); myy = fmaf(wdy, dy, myy);
+        }
+#pragma unroll
+        for (int c = 0; c < CP; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 16);
+        m0 += __shfl_xor_sync(0xffffffffu, m0, 16);
+        mx += __shfl_xor_sync(0xffffffffu, mx, 16);
+        my += __shfl_xor_sync(0xffffffffu, my, 16);
+        mxx += __shfl_xor_sync(0xffffffffu, mxx, 16);
+        mxy += __shfl_xor_sync(0xffffffffu, mxy, 16);
+        myy += __shfl_xor_sync(0xffffffffu, myy, 16);
+        if (live) {
+            float* vc = a.v_colors + (color_base + g) * (long long)a.color_stride;
+            if (h == 0) {
+                const float o = gb.y, A = 2.0f * ga.z, B = ga.w, C = 2.0f * gb.x;
+                float* vg = a.v_geo + (geo_base + g) * 8;
+                atomicAdd(vg + 0, -o * fmaf(A, mx, B * my));
+                atomicAdd(vg + 1, -o * fmaf(B, mx, C * my));
+                atomicAdd(vg + 2, -0.5f * o * mxx);
+                atomicAdd(vg + 3, -o * mxy);
+                atomicAdd(vg + 4, -0.5f * o * myy);
+                atomicAdd(vg + 5, m0);
+            }
+            constexpr int kSplit = (CP > 6) ? (CP - 6) / 2 : 0;
+#pragma unroll
+            for (int c = 0; c < CP; ++c)
+                if (c < a.channels && ((c < kSplit) == (h == 0))) atomicAdd(vc + c, acc[c]);
+        }
+        __syncwarp();
+    };
+
+    // Gather the rows of up to kChunk hit entries of word `wi` (bits taken from the top of `bits`):
+    // lane l serves entry j = l & 15 and copies half of its row.
+    auto gather = [&](unsigned bits, int wi, int buf) {
+        const int j = lane & (kChunk - 1), half = lane >> 4;
+        const unsigned bit = __fns(bits, 31, -(j + 1));  // (j+1)-th set bit from the top, or 0xffffffff
+        if (bit != 0xffffffffu) {
+            const int g = __ldg(a.ids_sorted + range.x + wi * 32 + (int)bit);
+            if (half == 0) chunk_g[buf * kChunk + j] = g;
+            const float* grow = a.geo + (geo_base + g) * 8;
+            const float* crow = a.colors + (color_base + g) * (long long)a.color_stride;
+            float* dst = rows + (buf * kChunk + j) * kRow;
+            if (kVec) {
+                constexpr int kChunks16 = 2 + CP / 4;
+                const int cchunks = 2 + ((a.channels + 3) >> 2);
+                for (int q = half; q < kChunks16; q += 2) {
+                    if (q < 2) cp_async16(dst + 4 * q, grow + 4 * q);
+                    else if (q < cchunks) cp_async16(dst + 4 * q, crow + 4 * (q - 2));
+                }
+            } else {
+                if (half == 0) { cp_async16(dst, grow); cp_async16(dst + 4, grow + 4); }
+                for (int c = half; c < a.channels; c += 2) cp_async4(dst + 8 + c, crow + c);
+            }
+        }
+        cp_async_commit();
+    };
+
+    const int fb = a.fwd_batch;
+    const long long rec0 = (long long)(range.x / fb) + gtile;
+    auto hit_word = [&](int wi) -> unsigned {
+        // word wi covers entries [32 wi, 32 wi + 32) of the tile's list
+        const int e0 = wi * 32;
+        const long long rec = rec0 + e0 / fb;
+        unsigned w = __ldg(a.hit_words + (rec * (kBlendThreads / 32) + warp) * (fb / 32) + (e0 % fb) / 32);
+        if (e_top - e0 < 32) w &= (1u << (e_top - e0)) - 1u;
+        return w;
+    };
+
+    // chunk iterator: walks the hit words from the top, handing out up to kChunk bits at a time
+    int wi = (e_top - 1) >> 5;
+    unsigned bits = hit_word(wi);
+    auto next_chunk = [&](unsigned& cbits, int& cwi) -> bool {
+        while (bits == 0u) {
+            if (--wi < 0) return false;
+            bits = hit_word(wi);
+        }
+        cwi = wi;
+        if (__popc(bits) <= kChunk) {
+            cbits = bits;
+            bits = 0u;
+        } else {
+            // keep the kChunk highest bits for this chunk
+            const unsigned kth = __fns(bits, 31, -kChunk);
+            cbits = bits & ~((1u << kth) - 1u);
+            bits &= (1u << kth) - 1u;
+        }
+        return true;
+    };
+
+    unsigned cbits = 0u, nbits = 0u;
+    int cwi = 0, nwi = 0;
+    bool have = next_chunk(cbits, cwi);
+    int buf = 0;
+    if (have) gather(cbits, cwi, buf);
+    while (have) {
+        const bool have_next = next_chunk(nbits, nwi);
+        if (have_next) { gather(nbits, nwi, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+        __syncwarp();
+        const int k = __popc(cbits);
+        const float* rbuf = rows + buf * kChunk * kRow;
+        const int* gbuf = chunk_g + buf * kChunk;
+        for (int j = 0; j < k; ++j) {
+            const unsigned bit = __fns(cbits, 31, -(j + 1));
+            const int e = cwi * 32 + (int)bit;
+            const float4 ga = *reinterpret_cast<const float4*>(rbuf + j * kRow);
+            const float4 gb = *reinterpret_cast<const float4*>(rbuf + j * kRow + 4);
+            const float s = eval_sigma(ga.x - fpx, ga.y - fpy, ga.z, ga.w, gb.x);
+            const float vis = __expf(-s);
+            const float araw = gb.y * vis;
+            const float alpha = fminf(kAlphaMax, araw);
+            const bool valid = (range.x + e < last) && !(s < 0.0f || s > gb.z) && (alpha >= kAlphaMin);
+            float fac = 0.0f, w = 0.0f;
+            if (valid) {
+                const float4* c4 = reinterpret_cast<const float4*>(rbuf + j * kRow + 8);
+                float d0 = 0.0f, d1 = 0.0f;
+#pragma unroll
+                for (int q = 0; q < CP / 4; ++q) {
+                    const float4 cc = c4[q];
+                    d0 = fmaf(cc.x, vo[4 * q], d0);
+                    d1 = fmaf(cc.y, vo[4 * q + 1], d1);
+                    d0 = fmaf(cc.z, vo[4 * q + 2], d0);
+                    d1 = fmaf(cc.w, vo[4 * q + 3], d1);
+                }
+                const float dot = d0 + d1;
+                const float ra = 1.0f / (1.0f - alpha);
+                T *= ra;
+                fac = alpha * T;
+                const float v_alpha = fmaf(dot, T, -R * ra);
+                R = fmaf(fac, dot, R);
+                w = (araw <= kAlphaMax) ? vis * v_alpha : 0.0f;
+            }
+            facm[nhit * kHitRow + lane] = fac;
+            wm[nhit * kHitRow + lane] = w;
+            if (lane == 0) hit_g[nhit] = gbuf[j];
+            if (++nhit == kHitRows) {
+                flush(kHitRows);
+                nhit = 0;
+                reload_vo();
+            }
+        }
+        __syncwarp();
+        have = have_next;
+        cbits = nbits;
+        cwi = nwi;
+        buf ^= 1;
+    }
+    if (nhit) flush(nhit);
+}
+
 // geo[g] = {x, y, A/2, B, C/2, o, tau, rcut2};  one thread per row
 __global__ void __launch_bounds__(256)
 pack_geo_kernel(long long rows, long long n, const float* __restrict__ xys, const float* __restrict__ conics,
@@ -604,6 +872,19 @@ template <int CP, int BATCH>
 static int launch_blend_impl(bool backward, const BlendArgs& a, int n_views, bool vec, cudaStream_t st) {
     dim3 grid(a.tiles_x * a.tiles_y, n_views);
     size_t smem = sizeof(float) * kStages * BATCH * (8 + CP);
+    if (backward && a.hit_words) {
+        const size_t wsmem = blend_bwd_warp_smem<CP>();
+        dim3 wgrid(2 * a.tiles_x * a.tiles_y, n_views);
+        if (vec) {
+            GG_CUDA(cudaFuncSetAttribute(blend_bwd_warp_kernel<CP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+            blend_bwd_warp_kernel<CP, true><<<wgrid, kBwdWarps * 32, wsmem, st>>>(a);
+        } else {
+            GG_CUDA(cudaFuncSetAttribute(blend_bwd_warp_kernel<CP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+            blend_bwd_warp_kernel<CP, false><<<wgrid, kBwdWarps * 32, wsmem, st>>>(a);
+        }
+        count_launch();
+        return check_launch("blend_bwd_warp_kernel");
+    }
     if (backward) {
         smem = blend_bwd_smem<CP, BATCH>();
         if (vec) {
