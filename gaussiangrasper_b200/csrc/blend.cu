@@ -786,28 +786,18 @@ blend_bwd_warp_kernel(const BlendArgs a) {
         const int k = __popc(cbits);
         const float* rbuf = rows + buf * kChunk * kRow;
         const int* gbuf = chunk_g + buf * kChunk;
-        // kIlp entries per round: everything that does not depend on the running transmittance
-        // (sigma, exp, alpha, 1/(1-alpha), <colour, v_out>) is evaluated for the whole group first, so
-        // that the serial part per entry is four dependent FMAs.  The heaviest warps of a frame walk
-        // thousands of entries one after the other: their latency chain, not the instruction count,
-        // bounds the kernel.
-        constexpr int kIlp = 4;
-        for (int j0 = 0; j0 < k; j0 += kIlp) {
-            float alpha[kIlp], vis[kIlp], araw[kIlp], dot[kIlp], ra[kIlp];
-            bool valid[kIlp];
-#pragma unroll
-            for (int u = 0; u < kIlp; ++u) {
-                const int j = min(j0 + u, k - 1);
-                const unsigned bit = __fns(cbits, 31, -(j + 1));
-                const int e = cwi * 32 + (int)bit;
-                const float4 ga = *reinterpret_cast<const float4*>(rbuf + j * kRow);
-                const float4 gb = *reinterpret_cast<const float4*>(rbuf + j * kRow + 4);
-                const float s = eval_sigma(ga.x - fpx, ga.y - fpy, ga.z, ga.w, gb.x);
-                vis[u] = __expf(-s);
-                araw[u] = gb.y * vis[u];
-                alpha[u] = fminf(kAlphaMax, araw[u]);
-                valid[u] = (j0 + u < k) && (range.x + e < last) && !(s < 0.0f || s > gb.z) && (alpha[u] >= kAlphaMin);
-                ra[u] = 1.0f / (1.0f - alpha[u]);
+        for (int j = 0; j < k; ++j) {
+            const unsigned bit = __fns(cbits, 31, -(j + 1));
+            const int e = cwi * 32 + (int)bit;
+            const float4 ga = *reinterpret_cast<const float4*>(rbuf + j * kRow);
+            const float4 gb = *reinterpret_cast<const float4*>(rbuf + j * kRow + 4);
+            const float s = eval_sigma(ga.x - fpx, ga.y - fpy, ga.z, ga.w, gb.x);
+            const float vis = __expf(-s);
+            const float araw = gb.y * vis;
+            const float alpha = fminf(kAlphaMax, araw);
+            const bool valid = (range.x + e < last) && !(s < 0.0f || s > gb.z) && (alpha >= kAlphaMin);
+            float fac = 0.0f, w = 0.0f;
+            if (valid) {
                 const float4* c4 = reinterpret_cast<const float4*>(rbuf + j * kRow + 8);
                 float d0 = 0.0f, d1 = 0.0f;
 #pragma unroll
@@ -818,28 +808,21 @@ blend_bwd_warp_kernel(const BlendArgs a) {
                     d0 = fmaf(cc.z, vo[4 * q + 2], d0);
                     d1 = fmaf(cc.w, vo[4 * q + 3], d1);
                 }
-                dot[u] = d0 + d1;
+                const float dot = d0 + d1;
+                const float ra = 1.0f / (1.0f - alpha);
+                T *= ra;
+                fac = alpha * T;
+                const float v_alpha = fmaf(dot, T, -R * ra);
+                R = fmaf(fac, dot, R);
+                w = (araw <= kAlphaMax) ? vis * v_alpha : 0.0f;
             }
-#pragma unroll
-            for (int u = 0; u < kIlp; ++u) {
-                if (j0 + u < k) {
-                    float fac = 0.0f, w = 0.0f;
-                    if (valid[u]) {
-                        T *= ra[u];
-                        fac = alpha[u] * T;
-                        const float v_alpha = fmaf(dot[u], T, -R * ra[u]);
-                        R = fmaf(fac, dot[u], R);
-                        w = (araw[u] <= kAlphaMax) ? vis[u] * v_alpha : 0.0f;
-                    }
-                    facm[nhit * kHitRow + lane] = fac;
-                    wm[nhit * kHitRow + lane] = w;
-                    if (lane == 0) hit_g[nhit] = gbuf[j0 + u];
-                    if (++nhit == kHitRows) {
-                        flush(kHitRows);
-                        nhit = 0;
-                        reload_vo();
-                    }
-                }
+            facm[nhit * kHitRow + lane] = fac;
+            wm[nhit * kHitRow + lane] = w;
+            if (lane == 0) hit_g[nhit] = gbuf[j];
+            if (++nhit == kHitRows) {
+                flush(kHitRows);
+                nhit = 0;
+                reload_vo();
             }
         }
         __syncwarp();
