@@ -783,22 +783,25 @@ blend_bwd_warp_kernel(const BlendArgs a) {
         const bool have_next = next_chunk(nbits, nwi);
         if (have_next) { gather(nbits, nwi, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
         __syncwarp();
-        const int k = __popc(cbits);
         const float* rbuf = rows + buf * kChunk * kRow;
         const int* gbuf = chunk_g + buf * kChunk;
-        for (int j = 0; j < k; ++j) {
-            const unsigned bit = __fns(cbits, 31, -(j + 1));
-            const int e = cwi * 32 + (int)bit;
-            const float4 ga = *reinterpret_cast<const float4*>(rbuf + j * kRow);
-            const float4 gb = *reinterpret_cast<const float4*>(rbuf + j * kRow + 4);
+        unsigned rem = cbits;             // warp-uniform: the staged entries, highest bit first
+        const float* rp = rbuf;           // row of the current entry
+        const int* gp = gbuf;
+        const int rel_last = last - range.x - cwi * 32;   // this pixel contributed to bits < rel_last
+        for (; rem != 0u; rp += kRow, ++gp) {
+            const int bit = 31 - __clz(rem);
+            rem &= ~(1u << bit);
+            const float4 ga = *reinterpret_cast<const float4*>(rp);
+            const float4 gb = *reinterpret_cast<const float4*>(rp + 4);
             const float s = eval_sigma(ga.x - fpx, ga.y - fpy, ga.z, ga.w, gb.x);
             const float vis = __expf(-s);
             const float araw = gb.y * vis;
             const float alpha = fminf(kAlphaMax, araw);
-            const bool valid = (range.x + e < last) && !(s < 0.0f || s > gb.z) && (alpha >= kAlphaMin);
+            const bool valid = (bit < rel_last) && !(s < 0.0f || s > gb.z) && (alpha >= kAlphaMin);
             float fac = 0.0f, w = 0.0f;
             if (valid) {
-                const float4* c4 = reinterpret_cast<const float4*>(rbuf + j * kRow + 8);
+                const float4* c4 = reinterpret_cast<const float4*>(rp + 8);
                 float d0 = 0.0f, d1 = 0.0f;
 #pragma unroll
                 for (int q = 0; q < CP / 4; ++q) {
@@ -818,7 +821,7 @@ blend_bwd_warp_kernel(const BlendArgs a) {
             }
             facm[nhit * kHitRow + lane] = fac;
             wm[nhit * kHitRow + lane] = w;
-            if (lane == 0) hit_g[nhit] = gbuf[j];
+            if (lane == 0) hit_g[nhit] = *gp;
             if (++nhit == kHitRows) {
                 flush(kHitRows);
                 nhit = 0;
