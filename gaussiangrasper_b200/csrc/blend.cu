@@ -579,23 +579,21 @@ constexpr int kChunk = 16;  // entries gathered per round (= kHitRows)
 
 template <int CP>
 constexpr size_t blend_bwd_warp_smem() {
-    return sizeof(float) * kBwdWarps * (2 * kChunk * (8 + CP) + 2 * kHitRows * kHitRow + kHitRows + 2 * kChunk + 32 * CP);
+    return sizeof(float) * kBwdWarps * (2 * kChunk * (8 + CP) + 2 * kHitRows * kHitRow + 32 * CP);
 }
 
 template <int CP, bool kVec>
-__global__ void __launch_bounds__(kBwdWarps * 32)
+__global__ void __launch_bounds__(kBwdWarps * 32, (CP <= 24) ? 5 : 1)
 blend_bwd_warp_kernel(const BlendArgs a) {
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     constexpr int kRow = 8 + CP;                                   // staged row: geo then channels
-    constexpr int kPerWarp = 2 * kChunk * kRow + 2 * kHitRows * kHitRow + kHitRows + 2 * kChunk + 32 * CP;
+    constexpr int kPerWarp = 2 * kChunk * kRow + 2 * kHitRows * kHitRow + 32 * CP;
     float* wsm = smem + wib * kPerWarp;
     float* rows = wsm;                                             // [2][kChunk][kRow]
     float* facm = rows + 2 * kChunk * kRow;                        // [kHitRows][33]
     float* wm = facm + kHitRows * kHitRow;                         // [kHitRows][33]
-    int* hit_g = reinterpret_cast<int*>(wm + kHitRows * kHitRow);  // [kHitRows]
-    int* chunk_g = hit_g + kHitRows;                               // [2][kChunk] Gaussian ids of the staged rows
-    float* vo_warp = reinterpret_cast<float*>(chunk_g + 2 * kChunk);  // [32][CP]
+    float* vo_warp = wm + kHitRows * kHitRow;                      // [32][CP]
 
     const int n_tiles = a.tiles_x * a.tiles_y;
     const int lin = blockIdx.y * n_tiles + (blockIdx.x >> 1);
@@ -644,6 +642,7 @@ blend_bwd_warp_kernel(const BlendArgs a) {
     if (e_top <= 0) return;
 
     int nhit = 0;
+    int fg = 0;  // Gaussian id of the stored entry (lane & 15) waiting in the hit matrices
     auto reload_vo = [&]() {
         const float4* row = reinterpret_cast<const float4*>(vo_warp + lane * CP);
 #pragma unroll
@@ -657,7 +656,7 @@ blend_bwd_warp_kernel(const BlendArgs a) {
         __syncwarp();
         const int j = lane & (kHitRows - 1), h = lane >> 4;
         const bool live = j < count;
-        const int g = live ? hit_g[j] : 0;
+        const int g = live ? fg : 0;
         float4 ga = make_float4(0.f, 0.f, 0.f, 0.f), gb = ga;
         if (live) {
             ga = __ldg(reinterpret_cast<const float4*>(a.geo) + 2 * (geo_base + g));
@@ -716,14 +715,47 @@ blend_bwd_warp_kernel(const BlendArgs a) {
         __syncwarp();
     };
 
-    // Gather the rows of up to kChunk hit entries of word `wi` (bits taken from the top of `bits`):
-    // lane l serves entry j = l & 15 and copies half of its row.
-    auto gather = [&](unsigned bits, int wi, int buf) {
+    const int fb = a.fwd_batch;
+    const long long rec0 = (long long)(range.x / fb) + gtile;
+    auto hit_word = [&](int w) -> unsigned {
+        // word w covers entries [32 w, 32 w + 32) of the tile's list
+        const int e0 = w * 32;
+        const long long rec = rec0 + e0 / fb;
+        unsigned v = __ldg(a.hit_words + (rec * (kBlendThreads / 32) + warp) * (fb / 32) + (e0 % fb) / 32);
+        if (e_top - e0 < 32) v &= (1u << (e_top - e0)) - 1u;
+        return v;
+    };
+    // hit-entry iterator (warp-uniform): highest entry first, the next mask word prefetched
+    int wi = (e_top - 1) >> 5;
+    unsigned cur = hit_word(wi);
+    unsigned nxt = wi > 0 ? hit_word(wi - 1) : 0u;
+    auto take = [&](int& e) -> bool {
+        while (cur == 0u) {
+            if (wi == 0) return false;
+            --wi;
+            cur = nxt;
+            nxt = wi > 0 ? hit_word(wi - 1) : 0u;
+        }
+        const int bit = 31 - __clz(cur);
+        cur &= ~(1u << bit);
+        e = wi * 32 + bit;
+        return true;
+    };
+    // up to kChunk entries (they may span several mask words); lanes j and j+16 keep entry j
+    auto build_chunk = [&](int& my_e) -> int {
+        int k = 0, e = 0;
+        while (k < kChunk && take(e)) {
+            if ((lane & (kChunk - 1)) == k) my_e = e;
+            ++k;
+        }
+        return k;
+    };
+    // gather the rows of a chunk: lane l serves entry j = l & 15 and copies half of its row
+    auto gather = [&](int k, int my_e, int& my_g, int buf) {
         const int j = lane & (kChunk - 1), half = lane >> 4;
-        const unsigned bit = __fns(bits, 31, -(j + 1));  // (j+1)-th set bit from the top, or 0xffffffff
-        if (bit != 0xffffffffu) {
-            const int g = __ldg(a.ids_sorted + range.x + wi * 32 + (int)bit);
-            if (half == 0) chunk_g[buf * kChunk + j] = g;
+        if (j < k) {
+            const int g = __ldg(a.ids_sorted + range.x + my_e);
+            my_g = g;
             const float* grow = a.geo + (geo_base + g) * 8;
             const float* crow = a.colors + (color_base + g) * (long long)a.color_stride;
             float* dst = rows + (buf * kChunk + j) * kRow;
@@ -742,63 +774,26 @@ blend_bwd_warp_kernel(const BlendArgs a) {
         cp_async_commit();
     };
 
-    const int fb = a.fwd_batch;
-    const long long rec0 = (long long)(range.x / fb) + gtile;
-    auto hit_word = [&](int wi) -> unsigned {
-        // word wi covers entries [32 wi, 32 wi + 32) of the tile's list
-        const int e0 = wi * 32;
-        const long long rec = rec0 + e0 / fb;
-        unsigned w = __ldg(a.hit_words + (rec * (kBlendThreads / 32) + warp) * (fb / 32) + (e0 % fb) / 32);
-        if (e_top - e0 < 32) w &= (1u << (e_top - e0)) - 1u;
-        return w;
-    };
-
-    // chunk iterator: walks the hit words from the top, handing out up to kChunk bits at a time
-    int wi = (e_top - 1) >> 5;
-    unsigned bits = hit_word(wi);
-    auto next_chunk = [&](unsigned& cbits, int& cwi) -> bool {
-        while (bits == 0u) {
-            if (--wi < 0) return false;
-            bits = hit_word(wi);
-        }
-        cwi = wi;
-        if (__popc(bits) <= kChunk) {
-            cbits = bits;
-            bits = 0u;
-        } else {
-            // keep the kChunk highest bits for this chunk
-            const unsigned kth = __fns(bits, 31, -kChunk);
-            cbits = bits & ~((1u << kth) - 1u);
-            bits &= (1u << kth) - 1u;
-        }
-        return true;
-    };
-
-    unsigned cbits = 0u, nbits = 0u;
-    int cwi = 0, nwi = 0;
-    bool have = next_chunk(cbits, cwi);
+    int cur_e = 0, nxt_e = 0, cur_g = 0, nxt_g = 0;
+    int cur_k = build_chunk(cur_e);
     int buf = 0;
-    if (have) gather(cbits, cwi, buf);
-    while (have) {
-        const bool have_next = next_chunk(nbits, nwi);
-        if (have_next) { gather(nbits, nwi, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    if (cur_k) gather(cur_k, cur_e, cur_g, buf);
+    while (cur_k) {
+        const int nxt_k = build_chunk(nxt_e);
+        if (nxt_k) { gather(nxt_k, nxt_e, nxt_g, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
         __syncwarp();
-        const float* rbuf = rows + buf * kChunk * kRow;
-        const int* gbuf = chunk_g + buf * kChunk;
-        unsigned rem = cbits;             // warp-uniform: the staged entries, highest bit first
-        const float* rp = rbuf;           // row of the current entry
-        const int* gp = gbuf;
-        const int rel_last = last - range.x - cwi * 32;   // this pixel contributed to bits < rel_last
-        for (; rem != 0u; rp += kRow, ++gp) {
-            const int bit = 31 - __clz(rem);
-            rem &= ~(1u << bit);
+        const float* rp = rows + buf * kChunk * kRow;  // row of the current entry
+        const int rel_last = last - range.x;            // this pixel contributed to entries < rel_last
+        for (int j = 0; j < cur_k; ++j, rp += kRow) {
+            const int e = __shfl_sync(0xffffffffu, cur_e, j);
+            const int g = __shfl_sync(0xffffffffu, cur_g, j);
             const float4 ga = *reinterpret_cast<const float4*>(rp);
             const float4 gb = *reinterpret_cast<const float4*>(rp + 4);
             const float s = eval_sigma(ga.x - fpx, ga.y - fpy, ga.z, ga.w, gb.x);
             const float vis = __expf(-s);
             const float araw = gb.y * vis;
             const float alpha = fminf(kAlphaMax, araw);
-            const bool valid = (bit < rel_last) && !(s < 0.0f || s > gb.z) && (alpha >= kAlphaMin);
+            const bool valid = (e < rel_last) && !(s < 0.0f || s > gb.z) && (alpha >= kAlphaMin);
             float fac = 0.0f, w = 0.0f;
             if (valid) {
                 const float4* c4 = reinterpret_cast<const float4*>(rp + 8);
@@ -821,7 +816,7 @@ blend_bwd_warp_kernel(const BlendArgs a) {
             }
             facm[nhit * kHitRow + lane] = fac;
             wm[nhit * kHitRow + lane] = w;
-            if (lane == 0) hit_g[nhit] = *gp;
+            if ((lane & (kHitRows - 1)) == nhit) fg = g;
             if (++nhit == kHitRows) {
                 flush(kHitRows);
                 nhit = 0;
@@ -829,9 +824,9 @@ blend_bwd_warp_kernel(const BlendArgs a) {
             }
         }
         __syncwarp();
-        have = have_next;
-        cbits = nbits;
-        cwi = nwi;
+        cur_k = nxt_k;
+        cur_e = nxt_e;
+        cur_g = nxt_g;
         buf ^= 1;
     }
     if (nhit) flush(nhit);
