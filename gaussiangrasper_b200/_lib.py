@@ -46,6 +46,11 @@ _SIGNATURES = {
     "gg_gather_counts": (C.c_int, [_ll, _p, _p, _p, _p]),
     "gg_emit_tiles_sorted": (C.c_int, [_i, _i, _p, _p, _i, _p, _p, _i, _i, _p, _p, _p]),
     "gg_tile_ranges_lowkey": (C.c_int, [_ll, _p, _ll, _p, _p]),
+    "gg_bin_begin_scratch_bytes": (C.c_size_t, [_ll]),
+    "gg_bin_finish_scratch_bytes": (C.c_size_t, [_ll]),
+    "gg_bin_begin": (C.c_int, [_i, _i, _p, _p, _p, _sz, _p, _p]),
+    "gg_bin_wait": (C.c_int, []),
+    "gg_bin_finish": (C.c_int, [_i, _i, _ll, _p, _i, _p, _i, _i, _p, _p, _sz, _p, _p, _p, _p]),
     "gg_tile_order_workspace_bytes": (C.c_size_t, []),
     "gg_tile_order": (C.c_int, [_ll, _p, _p, _p, _sz, _p]),
     "gg_unpack_vgeo": (C.c_int, [_ll, _i, _p, _p, _p, _p, _i, _p]),
@@ -109,20 +114,25 @@ def check(rc: int, what: str = "") -> None:
 
 # optional per-call CUDA-event timing (bench.py: "measured live inside the timed region")
 _profile = None
+_profile_only = None
 
 
 class profile:
-    """with _lib.profile() as prof: ...  ->  prof.ms() = {entry point: [ms per call]}"""
+    """with _lib.profile() as prof: ...  ->  prof.ms() = {entry point: [ms per call]}
+    only: restrict the event pairs to these entry points (every pair perturbs the stream a little)."""
+
+    def __init__(self, only=None):
+        self.only = frozenset(only) if only else None
 
     def __enter__(self):
-        global _profile
+        global _profile, _profile_only
         self.records = {}
-        _profile = self.records
+        _profile, _profile_only = self.records, self.only
         return self
 
     def __exit__(self, *exc):
-        global _profile
-        _profile = None
+        global _profile, _profile_only
+        _profile = _profile_only = None
         return False
 
     def ms(self):
@@ -133,7 +143,7 @@ class profile:
 def call(name: str, *args) -> None:
     """Invoke a C-ABI entry point on torch's current stream and raise on a non-zero status."""
     fn = getattr(load(), name)
-    if _profile is None:
+    if _profile is None or (_profile_only is not None and name not in _profile_only):
         rc = fn(*args)
     else:
         a = torch.cuda.Event(enable_timing=True)
@@ -155,6 +165,26 @@ def ptr(t):
     if t is None:
         return None
     return t.data_ptr()
+
+
+class _NoGuard:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def device_guard(device):
+    """`with torch.cuda.device(device)` only when `device` is not current already (the context
+    manager costs microseconds per use, which adds up over the calls of one render)."""
+    idx = device.index
+    if idx is None or idx == torch.cuda.current_device():
+        return _NO_GUARD
+    return torch.cuda.device(device)
 
 
 def stream_ptr(device) -> int:

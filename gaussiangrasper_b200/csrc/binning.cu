@@ -154,9 +154,12 @@ emit_keys_kernel(int n, int n_views, const float* __restrict__ xys, int xy_strid
 //   1 upfront kernel  : digit histograms of every pass
 //   P pass kernels    : rank (warp match), decoupled look-back across tiles, shared-memory
 //                       reorder, coalesced scatter
+// Digits are balanced: a b-bit key takes ceil(b/8) passes of b/passes (+1) bits each -- an 11-bit tile
+// key sorts as 6+5 bits, whose 64/32-bin scatters write 4-8x longer runs than an 8+3 split.
 // Tile status words are 64 bit: [generation:32 | flag:2 | count:30]; a per-process generation
 // counter makes stale words from earlier passes/calls invisible, so the status array is zeroed
-// only once, by whoever allocates the workspace.
+// only once, by whoever allocates the workspace.  Generations carry bit 31, which the high word of
+// nothing else this workspace ever holds (keys, ids, counts) has.
 // ---------------------------------------------------------------------------------------------
 constexpr int kRsThreads = 256;
 constexpr int kRsIpt = 16;
@@ -168,8 +171,29 @@ constexpr uint32_t kFlagIncl = 1u << 31;
 constexpr uint32_t kValueMask = (1u << 30) - 1;
 constexpr int kLookback = 4;   // status words fetched per look-back round
 
+struct DigitPlan {
+    int passes;
+    int shift[kMaxPasses];
+    uint32_t mask[kMaxPasses];
+};
+
+static DigitPlan digit_plan(int key_bits) {
+    DigitPlan P;
+    P.passes = (key_bits + 7) / 8;
+    const int base = key_bits / P.passes, rem = key_bits % P.passes;
+    int shift = 0;
+    for (int p = 0; p < kMaxPasses; ++p) {
+        const int bits = p < P.passes ? base + (p < rem ? 1 : 0) : 0;
+        P.shift[p] = shift;
+        P.mask[p] = (1u << bits) - 1u;
+        shift += bits;
+    }
+    return P;
+}
+
 __global__ void __launch_bounds__(256)
-radix_hist_kernel(const uint64_t* __restrict__ keys, long long m, int passes, uint32_t* __restrict__ ghist) {
+radix_hist_kernel(const uint64_t* __restrict__ keys, long long m, const DigitPlan plan, uint32_t* __restrict__ ghist) {
+    const int passes = plan.passes;
     // Block-shared histograms, plain shared-memory atomics.  Digits on which a whole warp agrees
     // (the high bytes of tile|depth keys are nearly constant) would serialise 32-fold on one
     // address, so those take a match.all fast path: one add of the warp's population.
@@ -188,7 +212,7 @@ radix_hist_kernel(const uint64_t* __restrict__ keys, long long m, int passes, ui
         const int leader = __ffs(active) - 1;
         const uint32_t pop = (uint32_t)__popc(active);
         for (int p = 0; p < passes; ++p) {
-            const uint32_t d = (uint32_t)(k >> (8 * p)) & 255u;
+            const uint32_t d = (uint32_t)(k >> plan.shift[p]) & plan.mask[p];
             int same;
             __match_all_sync(active, d, &same);
             if (same) {
@@ -207,7 +231,7 @@ radix_hist_kernel(const uint64_t* __restrict__ keys, long long m, int passes, ui
 
 __global__ void __launch_bounds__(kRsThreads, 3)
 radix_pass_kernel(const uint64_t* __restrict__ kin, const uint32_t* __restrict__ vin, uint64_t* __restrict__ kout,
-                  uint32_t* __restrict__ vout, long long m, int shift, const uint32_t* __restrict__ ghist_excl,
+                  uint32_t* __restrict__ vout, long long m, int shift, uint32_t dmask, const uint32_t* __restrict__ ghist_excl,
                   volatile uint64_t* tile_state, uint32_t* ticket, uint32_t generation) {
     // everything lives in dynamic shared memory (59.5 KB > the 48 KB static limit)
     extern __shared__ __align__(16) unsigned char dyn[];
@@ -238,11 +262,11 @@ radix_pass_kernel(const uint64_t* __restrict__ kin, const uint32_t* __restrict__
     // (they are independent and have a long latency); only the counter updates form a chain.
     uint32_t peers[kRsIpt];
 #pragma unroll
-    for (int j = 0; j < kRsIpt; ++j) peers[j] = __match_any_sync(0xffffffffu, (uint32_t)(key[j] >> shift) & 255u);
+    for (int j = 0; j < kRsIpt; ++j) peers[j] = __match_any_sync(0xffffffffu, (uint32_t)(key[j] >> shift) & dmask);
     uint32_t rank[kRsIpt];
 #pragma unroll
     for (int j = 0; j < kRsIpt; ++j) {
-        const uint32_t d = (uint32_t)(key[j] >> shift) & 255u;
+        const uint32_t d = (uint32_t)(key[j] >> shift) & dmask;
         const uint32_t mask = peers[j];
         const int leader = __ffs(mask) - 1;
         uint32_t prev = 0;
@@ -308,7 +332,7 @@ radix_pass_kernel(const uint64_t* __restrict__ kin, const uint32_t* __restrict__
     // reorder through shared memory so that the scatter writes runs of consecutive addresses
 #pragma unroll
     for (int j = 0; j < kRsIpt; ++j) {
-        const uint32_t d = (uint32_t)(key[j] >> shift) & 255u;
+        const uint32_t d = (uint32_t)(key[j] >> shift) & dmask;
         const uint32_t pos = local_start[d] + warp_hist[warp][d] + rank[j];
         const long long idx = wbase + j * 32 + lane;
         keys_sm[pos] = key[j];
@@ -322,7 +346,7 @@ radix_pass_kernel(const uint64_t* __restrict__ kin, const uint32_t* __restrict__
         const int pos = k * kRsThreads + tid;
         if (pos < valid) {
             const uint64_t kk = keys_sm[pos];
-            const uint32_t d = (uint32_t)(kk >> shift) & 255u;
+            const uint32_t d = (uint32_t)(kk >> shift) & dmask;
             const uint32_t gpos = global_base[d] + (uint32_t)pos;
             kout[gpos] = kk;
             vout[gpos] = vals_sm[pos];
@@ -582,7 +606,8 @@ extern "C" int gg_sort_pairs(long long m, int key_bits, const int64_t* keys_in, 
     uint64_t* state = reinterpret_cast<uint64_t*>(ws + L.off_state);
     uint64_t* kalt = reinterpret_cast<uint64_t*>(ws + L.off_keys);
     uint32_t* valt = reinterpret_cast<uint32_t*>(ws + L.off_vals);
-    const int passes = (key_bits + 7) / 8;
+    const DigitPlan plan = digit_plan(key_bits);
+    const int passes = plan.passes;
 
     const size_t dyn = (sizeof(uint64_t) + sizeof(uint32_t)) * kRsTile +
                        sizeof(uint32_t) * ((kRsThreads / 32) * kRadix + 2 * kRadix) + sizeof(int) * 8 + 16;
@@ -592,7 +617,7 @@ extern "C" int gg_sort_pairs(long long m, int key_bits, const int64_t* keys_in, 
     // few, fat blocks: every block ends with passes*256 global atomics onto the same bins
     int hist_blocks = div_up(m, 256 * 16);
     if (hist_blocks > 148 * 2) hist_blocks = 148 * 2;
-    radix_hist_kernel<<<hist_blocks, 256, 0, st>>>(reinterpret_cast<const uint64_t*>(keys_in), m, passes, ghist);
+    radix_hist_kernel<<<hist_blocks, 256, 0, st>>>(reinterpret_cast<const uint64_t*>(keys_in), m, plan, ghist);
     const uint64_t* kin = reinterpret_cast<const uint64_t*>(keys_in);
     const uint32_t* vin = reinterpret_cast<const uint32_t*>(vals_in);
     for (int p = 0; p < passes; ++p) {
@@ -601,8 +626,9 @@ extern "C" int gg_sort_pairs(long long m, int key_bits, const int64_t* keys_in, 
         uint64_t* ko = to_out ? reinterpret_cast<uint64_t*>(keys_out) : kalt;
         uint32_t* vo = to_out ? reinterpret_cast<uint32_t*>(vals_out) : valt;
         const uint32_t gen = g_generation.fetch_add(1);
-        radix_pass_kernel<<<(unsigned)L.tiles, kRsThreads, dyn, st>>>(kin, vin, ko, vo, m, 8 * p, ghist + p * kRadix,
-                                                                      state, tickets + p, gen == 0 ? 1u : gen);
+        radix_pass_kernel<<<(unsigned)L.tiles, kRsThreads, dyn, st>>>(kin, vin, ko, vo, m, plan.shift[p], plan.mask[p],
+                                                                      ghist + p * kRadix, state, tickets + p,
+                                                                      gen | 0x80000000u);
         kin = ko;
         vin = vo;
     }
@@ -691,4 +717,134 @@ extern "C" int gg_emit_tiles_sorted(int n, int n_views, const int32_t* order, co
         total, n, order, xys, xy_stride, radii, cum_sorted, tiles_x, tiles_y, keys, ids);
     count_launch();
     return check_launch("emit_tiles_sorted_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------
+// Whole depth-first binning in two host calls (the sequences above, enqueued from C so that the
+// host spends microseconds, not a Python call per kernel, between launches).
+// ---------------------------------------------------------------------------------------------
+namespace gg {
+
+struct BeginLayout {
+    size_t dkeys, rows, dkeys_sorted, order, counts, cum, total_dev, scan, sort, bytes;
+};
+
+static BeginLayout begin_layout(long long total) {
+    BeginLayout L;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~(size_t)255; return r; };
+    const size_t t = (size_t)(total > 0 ? total : 1);
+    // the sort workspace comes first: its look-back words must sit at offsets that do not move
+    // with `total` more than the workspace itself does (the caller zero-fills the scratch once)
+    L.sort = take(gg_sort_workspace_bytes(total));
+    L.scan = take(gg_cumsum_workspace_bytes(total));
+    L.total_dev = take(sizeof(int32_t));
+    L.dkeys = take(sizeof(int64_t) * t);
+    L.dkeys_sorted = take(sizeof(int64_t) * t);
+    L.rows = take(sizeof(int32_t) * t);
+    L.order = take(sizeof(int32_t) * t);
+    L.counts = take(sizeof(int32_t) * t);
+    L.cum = take(sizeof(int32_t) * t);
+    L.bytes = o;
+    return L;
+}
+
+struct FinishLayout {
+    size_t sort, order_ws, keys, keys_sorted, ids, bytes;
+};
+
+static FinishLayout finish_layout(long long m) {
+    FinishLayout L;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~(size_t)255; return r; };
+    const size_t t = (size_t)(m > 0 ? m : 1);
+    L.sort = take(gg_sort_workspace_bytes(m));
+    L.order_ws = take(gg_tile_order_workspace_bytes());
+    L.keys = take(sizeof(int64_t) * t);
+    L.keys_sorted = take(sizeof(int64_t) * t);
+    L.ids = take(sizeof(int32_t) * t);
+    L.bytes = o;
+    return L;
+}
+
+constexpr int kMaxDevices = 64;
+static cudaEvent_t g_count_event[kMaxDevices] = {};
+
+}  // namespace gg
+
+extern "C" size_t gg_bin_begin_scratch_bytes(long long total) { return begin_layout(total).bytes; }
+extern "C" size_t gg_bin_finish_scratch_bytes(long long m) { return finish_layout(m).bytes; }
+
+extern "C" int gg_bin_begin(int n, int n_views, const float* depths, const int32_t* num_tiles_hit, void* scratch,
+                            size_t scratch_bytes, int32_t* m_host, void* stream) {
+    GG_REQUIRE(n >= 1 && n_views >= 1 && (long long)n * n_views < (1ll << 31), "gg_bin_begin: bad sizes");
+    GG_REQUIRE(depths && num_tiles_hit && scratch && m_host, "gg_bin_begin: null pointer");
+    const long long total = (long long)n * n_views;
+    const BeginLayout L = begin_layout(total);
+    GG_REQUIRE(scratch_bytes >= L.bytes, "gg_bin_begin: scratch too small");
+    GG_REQUIRE(((uintptr_t)scratch & 255) == 0, "gg_bin_begin: scratch must be 256-byte aligned");
+    unsigned char* s = reinterpret_cast<unsigned char*>(scratch);
+    int64_t* dkeys = reinterpret_cast<int64_t*>(s + L.dkeys);
+    int64_t* dkeys_sorted = reinterpret_cast<int64_t*>(s + L.dkeys_sorted);
+    int32_t* rows = reinterpret_cast<int32_t*>(s + L.rows);
+    int32_t* order = reinterpret_cast<int32_t*>(s + L.order);
+    int32_t* counts = reinterpret_cast<int32_t*>(s + L.counts);
+    int32_t* cum = reinterpret_cast<int32_t*>(s + L.cum);
+    int32_t* total_dev = reinterpret_cast<int32_t*>(s + L.total_dev);
+    int view_bits = 0;
+    while ((1 << view_bits) < n_views) ++view_bits;
+    int rc;
+    if ((rc = gg_depth_keys(n, n_views, depths, dkeys, rows, stream))) return rc;
+    if ((rc = gg_sort_pairs(total, 32 + view_bits, dkeys, rows, dkeys_sorted, order, s + L.sort,
+                            gg_sort_workspace_bytes(total), stream)))
+        return rc;
+    if ((rc = gg_gather_counts(total, order, num_tiles_hit, counts, stream))) return rc;
+    if ((rc = gg_cumsum(total, counts, cum, total_dev, s + L.scan, gg_cumsum_workspace_bytes(total), stream))) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    GG_CUDA(cudaMemcpyAsync(m_host, total_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    int dev = 0;
+    GG_CUDA(cudaGetDevice(&dev));
+    GG_REQUIRE(dev >= 0 && dev < kMaxDevices, "gg_bin_begin: device index out of range");
+    if (!g_count_event[dev]) GG_CUDA(cudaEventCreateWithFlags(&g_count_event[dev], cudaEventDisableTiming));
+    GG_CUDA(cudaEventRecord(g_count_event[dev], st));
+    return GG_OK;
+}
+
+extern "C" int gg_bin_wait(void) {
+    int dev = 0;
+    GG_CUDA(cudaGetDevice(&dev));
+    GG_REQUIRE(dev >= 0 && dev < kMaxDevices && g_count_event[dev], "gg_bin_wait: no gg_bin_begin on this device");
+    GG_CUDA(cudaEventSynchronize(g_count_event[dev]));
+    return GG_OK;
+}
+
+extern "C" int gg_bin_finish(int n, int n_views, long long m, const float* xys, int xy_stride, const int32_t* radii,
+                             int tiles_x, int tiles_y, const void* begin_scratch, void* scratch, size_t scratch_bytes,
+                             int32_t* ids_sorted, int32_t* tile_ranges, int32_t* tile_order, void* stream) {
+    GG_REQUIRE(n >= 1 && n_views >= 1 && m >= 1 && m < (1ll << 30), "gg_bin_finish: bad sizes");
+    GG_REQUIRE(xys && radii && begin_scratch && scratch && ids_sorted && tile_ranges && tile_order,
+               "gg_bin_finish: null pointer");
+    const long long total = (long long)n * n_views;
+    const BeginLayout B = begin_layout(total);
+    const FinishLayout L = finish_layout(m);
+    GG_REQUIRE(scratch_bytes >= L.bytes, "gg_bin_finish: scratch too small");
+    GG_REQUIRE(((uintptr_t)scratch & 255) == 0, "gg_bin_finish: scratch must be 256-byte aligned");
+    const unsigned char* b = reinterpret_cast<const unsigned char*>(begin_scratch);
+    unsigned char* s = reinterpret_cast<unsigned char*>(scratch);
+    const int32_t* order = reinterpret_cast<const int32_t*>(b + B.order);
+    const int32_t* cum = reinterpret_cast<const int32_t*>(b + B.cum);
+    int64_t* keys = reinterpret_cast<int64_t*>(s + L.keys);
+    int64_t* keys_sorted = reinterpret_cast<int64_t*>(s + L.keys_sorted);
+    int32_t* ids = reinterpret_cast<int32_t*>(s + L.ids);
+    const long long num_tiles = (long long)n_views * tiles_x * tiles_y;
+    int tile_bits = 1;
+    while ((1ll << tile_bits) < num_tiles) ++tile_bits;
+    int rc;
+    if ((rc = gg_emit_tiles_sorted(n, n_views, order, xys, xy_stride, radii, cum, tiles_x, tiles_y, keys, ids, stream)))
+        return rc;
+    if ((rc = gg_sort_pairs(m, tile_bits, keys, ids, keys_sorted, ids_sorted, s + L.sort, gg_sort_workspace_bytes(m),
+                            stream)))
+        return rc;
+    if ((rc = gg_tile_ranges_lowkey(m, keys_sorted, num_tiles, tile_ranges, stream))) return rc;
+    return gg_tile_order(num_tiles, tile_ranges, tile_order, s + L.order_ws, gg_tile_order_workspace_bytes(), stream);
 }

@@ -34,6 +34,8 @@ class _Workspace:
         self.keys_sorted = None
         self.order_ws = None
         self.depth = None
+        self.begin = None
+        self.finish = None
         self.total = torch.zeros(1, dtype=torch.int32, device=device)
         self.total_host = torch.zeros(1, dtype=torch.int32).pin_memory()
         self.total_event = torch.cuda.Event()
@@ -50,6 +52,18 @@ class _Workspace:
             # zero-filled once: the library owns the look-back status words afterwards
             self.sort = torch.zeros(int(need * 1.5) + 256, dtype=torch.uint8, device=self.device)
         return self.sort
+
+    def begin_scratch(self, total):
+        need = int(_lib.load().gg_bin_begin_scratch_bytes(total))
+        if self.begin is None or self.begin.numel() < need:
+            self.begin = torch.zeros(int(need * 1.25) + 4096, dtype=torch.uint8, device=self.device)
+        return self.begin
+
+    def finish_scratch(self, m):
+        need = int(_lib.load().gg_bin_finish_scratch_bytes(m))
+        if self.finish is None or self.finish.numel() < need:
+            self.finish = torch.zeros(int(need * 1.5) + 4096, dtype=torch.uint8, device=self.device)
+        return self.finish
 
     def depth_buffers(self, total):
         if self.depth is None or self.depth[0].numel() < total:
@@ -97,7 +111,7 @@ def project_fwd(means3d, scales, glob_scale, quats, viewmat, fullmat, fx, fy, cx
     radii = torch.empty((n,), dtype=torch.int32, device=dev)
     conics = torch.empty((n, 3), dtype=torch.float32, device=dev)
     nth = torch.empty((n,), dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev):
+    with _lib.device_guard(dev):
         _lib.call("gg_project_fwd", 
             n, ptr(means3d), ptr(scales), float(glob_scale), ptr(quats), ptr(vm), ptr(fm), float(fx), float(fy),
             float(cx), float(cy), int(img_height), int(img_width), int(tile_bounds[0]), int(tile_bounds[1]),
@@ -117,7 +131,7 @@ def project_bwd(means3d, scales, glob_scale, quats, viewmat, fullmat, fx, fy, cx
     v_means = torch.empty((n, 3), dtype=torch.float32, device=dev)
     v_scales = torch.empty((n, 3), dtype=torch.float32, device=dev)
     v_quats = torch.empty((n, 4), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with _lib.device_guard(dev):
         _lib.call("gg_project_bwd", 
             n, ptr(means3d), ptr(scales), float(glob_scale), ptr(quats), ptr(vm), ptr(fm), float(fx), float(fy),
             float(cx), float(cy), int(img_height), int(img_width), ptr(radii), ptr(conics), ptr(v_xys),
@@ -138,7 +152,7 @@ def sh_fwd(degrees_to_use, viewdirs, coeffs):
     n = coeffs.shape[0]
     degree = sh_degree_from_bases(coeffs.shape[-2])
     colors = torch.empty((n, 3), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with _lib.device_guard(dev):
         _lib.call("gg_sh_fwd", n, degree, int(degrees_to_use), ptr(viewdirs), ptr(coeffs), ptr(colors),
                                     stream_ptr(dev))
     return colors
@@ -150,7 +164,7 @@ def sh_bwd(degree, degrees_to_use, viewdirs, v_colors):
     n = viewdirs.shape[0]
     nb = (degree + 1) ** 2
     v_coeffs = torch.empty((n, nb, 3), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with _lib.device_guard(dev):
         _lib.call("gg_sh_bwd", n, int(degree), int(degrees_to_use), ptr(viewdirs), ptr(v_colors), ptr(v_coeffs),
                                     stream_ptr(dev))
     return v_coeffs
@@ -165,7 +179,7 @@ def cumsum_i32(x: torch.Tensor, total_out: Optional[torch.Tensor] = None) -> tor
     assert x.dtype == torch.int32
     out = torch.empty_like(x)
     ws = workspace(dev).scan_ws(x.numel())
-    with torch.cuda.device(dev):
+    with _lib.device_guard(dev):
         _lib.call("gg_cumsum", x.numel(), ptr(x), ptr(out), ptr(total_out), ptr(ws), ws.numel(),
                                     stream_ptr(dev))
     return out
@@ -177,7 +191,7 @@ def key_bits_for(num_tiles_total: int) -> int:
 
 def map_to_intersects(n, n_views, xys, depths, radii, cum, tile_bounds, keys, ids, xy_from_geo=False):
     dev = xys.device
-    with torch.cuda.device(dev):
+    with _lib.device_guard(dev):
         _lib.call("gg_map_to_intersects_geo" if xy_from_geo else "gg_map_to_intersects", int(n), int(n_views), ptr(xys), ptr(depths), ptr(radii), ptr(cum),
                                                int(tile_bounds[0]), int(tile_bounds[1]), ptr(keys), ptr(ids),
                                                stream_ptr(dev))
@@ -186,7 +200,7 @@ def map_to_intersects(n, n_views, xys, depths, radii, cum, tile_bounds, keys, id
 def sort_pairs(m, key_bits, keys_in, ids_in, keys_out, ids_out):
     dev = keys_in.device
     ws = workspace(dev).sort_ws(m)
-    with torch.cuda.device(dev):
+    with _lib.device_guard(dev):
         _lib.call("gg_sort_pairs", int(m), int(key_bits), ptr(keys_in), ptr(ids_in), ptr(keys_out), ptr(ids_out),
                                         ptr(ws), ws.numel(), stream_ptr(dev))
 
@@ -194,7 +208,7 @@ def sort_pairs(m, key_bits, keys_in, ids_in, keys_out, ids_out):
 def tile_ranges(m, keys_sorted, num_tiles):
     dev = keys_sorted.device
     ranges = torch.empty((num_tiles, 2), dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev):
+    with _lib.device_guard(dev):
         _lib.call("gg_tile_ranges", int(m), ptr(keys_sorted), int(num_tiles), ptr(ranges), stream_ptr(dev))
     return ranges
 
@@ -205,7 +219,7 @@ def tile_order(ranges: torch.Tensor) -> torch.Tensor:
     if ws.order_ws is None:
         ws.order_ws = torch.empty(int(_lib.load().gg_tile_order_workspace_bytes()), dtype=torch.uint8, device=dev)
     order = torch.empty((ranges.shape[0],), dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev):
+    with _lib.device_guard(dev):
         _lib.call("gg_tile_order", int(ranges.shape[0]), ptr(ranges), ptr(order), ptr(ws.order_ws), ws.order_ws.numel(),
                   stream_ptr(dev))
     return order
@@ -239,46 +253,46 @@ def bin_views(n, n_views, xys, depths, radii, num_tiles_hit, tile_bounds, xy_fro
     xys, depths = f32c(xys), f32c(depths)
     radii, num_tiles_hit = radii.contiguous().reshape(-1), num_tiles_hit.contiguous().reshape(-1)
     total = n * n_views
-    num_tiles = int(tile_bounds[0]) * int(tile_bounds[1]) * n_views
-    order = None
-    with torch.cuda.device(dev):
+    tiles_x, tiles_y = int(tile_bounds[0]), int(tile_bounds[1])
+    num_tiles = tiles_x * tiles_y * n_views
+    with _lib.device_guard(dev):
+        st = stream_ptr(dev)
+        # the one device->host read of the path (the reference has five per view): M sizes the sort.
+        # Work passed as `while_waiting` is enqueued behind the copy so the GPU stays busy meanwhile.
         if depth_first:
-            dkeys, rows, dkeys_sorted, order, counts = ws.depth_buffers(total)
-            lib_call("gg_depth_keys", int(n), int(n_views), ptr(depths), ptr(dkeys), ptr(rows), stream_ptr(dev))
-            sort_pairs(total, 32 + max(0, (n_views - 1).bit_length()), dkeys, rows, dkeys_sorted, order)
-            lib_call("gg_gather_counts", int(total), ptr(order), ptr(num_tiles_hit), ptr(counts), stream_ptr(dev))
-            cum = cumsum_i32(counts[:total], ws.total)
+            begin = ws.begin_scratch(total)
+            lib_call("gg_bin_begin", int(n), int(n_views), ptr(depths), ptr(num_tiles_hit), ptr(begin), begin.numel(),
+                     ws.total_host.data_ptr(), st)
+            if while_waiting is not None:
+                while_waiting()
+            lib_call("gg_bin_wait")
         else:
             cum = cumsum_i32(num_tiles_hit, ws.total)
-    # the one device->host read of the path (the reference has five per view): M sizes the sort.
-    # Work passed as `while_waiting` is enqueued behind the copy so the GPU stays busy meanwhile.
-    ws.total_host.copy_(ws.total, non_blocking=True)
-    ws.total_event.record(torch.cuda.current_stream(dev))
-    if while_waiting is not None:
-        while_waiting()
-    ws.total_event.synchronize()
-    m = int(ws.total_host[0])
-    if m < 0:
-        raise _lib.GGError("number of tile intersections overflows int32")
-    ids_sorted = torch.empty((max(m, 1),), dtype=torch.int32, device=dev)
-    if m > 0:
-        keys, ids, keys_sorted = ws.key_buffers(m)
-        with torch.cuda.device(dev):
-            if depth_first:
-                lib_call("gg_emit_tiles_sorted", int(n), int(n_views), ptr(order), ptr(xys), 8 if xy_from_geo else 2,
-                         ptr(radii), ptr(cum), int(tile_bounds[0]), int(tile_bounds[1]), ptr(keys), ptr(ids),
-                         stream_ptr(dev))
-                sort_pairs(m, max(1, (num_tiles - 1).bit_length()), keys, ids, keys_sorted, ids_sorted)
-                ranges = torch.empty((num_tiles, 2), dtype=torch.int32, device=dev)
-                lib_call("gg_tile_ranges_lowkey", int(m), ptr(keys_sorted), int(num_tiles), ptr(ranges), stream_ptr(dev))
-            else:
-                map_to_intersects(n, n_views, xys, depths, radii, cum, tile_bounds, keys, ids, xy_from_geo)
-                sort_pairs(m, key_bits_for(num_tiles), keys, ids, keys_sorted, ids_sorted)
-                ranges = tile_ranges(m, keys_sorted, num_tiles)
-    else:
-        ranges = torch.zeros((num_tiles, 2), dtype=torch.int32, device=dev)
-    order_t = tile_order(ranges) if m > 0 else None
-    return Binning(n, n_views, m, ids_sorted[:m] if m > 0 else ids_sorted[:0], ranges, tuple(tile_bounds), order_t)
+            ws.total_host.copy_(ws.total, non_blocking=True)
+            ws.total_event.record(torch.cuda.current_stream(dev))
+            if while_waiting is not None:
+                while_waiting()
+            ws.total_event.synchronize()
+        m = int(ws.total_host[0])
+        if m < 0:
+            raise _lib.GGError("number of tile intersections overflows int32")
+        if m == 0:
+            ranges = torch.zeros((num_tiles, 2), dtype=torch.int32, device=dev)
+            return Binning(n, n_views, 0, torch.empty((0,), dtype=torch.int32, device=dev), ranges, tuple(tile_bounds), None)
+        ids_sorted = torch.empty((m,), dtype=torch.int32, device=dev)
+        if depth_first:
+            ranges = torch.empty((num_tiles, 2), dtype=torch.int32, device=dev)
+            order_t = torch.empty((num_tiles,), dtype=torch.int32, device=dev)
+            fin = ws.finish_scratch(m)
+            lib_call("gg_bin_finish", int(n), int(n_views), m, ptr(xys), 8 if xy_from_geo else 2, ptr(radii), tiles_x,
+                     tiles_y, ptr(begin), ptr(fin), fin.numel(), ptr(ids_sorted), ptr(ranges), ptr(order_t), st)
+        else:
+            keys, ids, keys_sorted = ws.key_buffers(m)
+            map_to_intersects(n, n_views, xys, depths, radii, cum, tile_bounds, keys, ids, xy_from_geo)
+            sort_pairs(m, key_bits_for(num_tiles), keys, ids, keys_sorted, ids_sorted)
+            ranges = tile_ranges(m, keys_sorted, num_tiles)
+            order_t = tile_order(ranges)
+    return Binning(n, n_views, m, ids_sorted, ranges, tuple(tile_bounds), order_t)
 
 
 # ------------------------------------------------------------------------------------------
@@ -288,7 +302,7 @@ def pack_geo(n, n_views, xys, conics, opacity, opac_per_view=False):
     dev = require_cuda(xys, conics, opacity)
     xys, conics, opacity = f32c(xys), f32c(conics), f32c(opacity).reshape(-1)
     geo = torch.empty((n * n_views, 8), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with _lib.device_guard(dev):
         _lib.call("gg_pack_geo", int(n), int(n_views), ptr(xys), ptr(conics), ptr(opacity),
                                       1 if opac_per_view else 0, ptr(geo), stream_ptr(dev))
     return geo
@@ -326,7 +340,7 @@ def blend_fwd(binning: Binning, geo, colors, background, img_height, img_width, 
     if record_hits and C <= step and binning.num_intersects > 0:
         nwords = int(_lib.load().gg_blend_hit_words(binning.num_intersects, binning.tile_ranges.shape[0], C))
         hit_words = torch.zeros(nwords, dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev):
+    with _lib.device_guard(dev):
         for c0 in range(0, C, step):
             c1 = min(C, c0 + step)
             _lib.call("gg_blend_fwd",
@@ -343,13 +357,16 @@ def blend_bwd(binning: Binning, geo, colors, background, final_T, final_idx, v_o
     dev = require_cuda(geo, colors, background, v_out)
     colors, background, v_out = f32c(colors), f32c(background), f32c(v_out)
     V, n, C = binning.n_views, binning.n, colors.shape[1]
-    v_geo = torch.zeros((V * n, 8), dtype=torch.float32, device=dev)
-    v_colors = torch.zeros_like(colors)
+    # one zero fill for both accumulation targets (the kernels add into them with red.global)
+    rows_g, rows_c = V * n * 8, colors.numel()
+    acc = torch.zeros(rows_g + rows_c, dtype=torch.float32, device=dev)
+    v_geo = acc[:rows_g].view(V * n, 8)
+    v_colors = acc[rows_g:].view(colors.shape)
     tb = binning.tile_bounds
     step = max_channels()
     if C > step:
         hit_words = None
-    with torch.cuda.device(dev):
+    with _lib.device_guard(dev):
         for c0 in range(0, C, step):
             c1 = min(C, c0 + step)
             _lib.call("gg_blend_bwd",
@@ -365,7 +382,7 @@ def unpack_vgeo(n, n_views, v_geo):
     v_xys = torch.empty((n_views * n, 2), dtype=torch.float32, device=dev)
     v_conics = torch.empty((n_views * n, 3), dtype=torch.float32, device=dev)
     v_opac = torch.empty((n,), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with _lib.device_guard(dev):
         _lib.call("gg_unpack_vgeo", int(n), int(n_views), ptr(v_geo), ptr(v_xys), ptr(v_conics), ptr(v_opac), 0,
                                          stream_ptr(dev))
     return v_xys, v_conics, v_opac

@@ -50,20 +50,37 @@ class ViewBatch:
 
     @staticmethod
     def from_cameras(cams: Sequence, device) -> "ViewBatch":
-        vm = torch.stack([c.viewmat[:3].reshape(-1) for c in cams]).float()
-        fm = torch.stack([c.fullmat.reshape(-1) for c in cams]).float()
-        intr = torch.tensor([[c.fx, c.fy, c.cx, c.cy] for c in cams], dtype=torch.float32)
-        pos = torch.stack([c.position for c in cams]).float()
-        packed = torch.cat([vm, fm, intr, pos], dim=1)  # one H2D copy for the whole batch
+        # one packed row of 35 floats per camera, built once and kept on the camera object
+        rows = []
+        for c in cams:
+            r = getattr(c, "_gg_row", None)
+            if r is None:
+                r = torch.cat([c.viewmat[:3].reshape(-1).float(), c.fullmat.reshape(-1).float(),
+                               torch.tensor([c.fx, c.fy, c.cx, c.cy], dtype=torch.float32), c.position.reshape(-1).float()])
+                try:
+                    c._gg_row = r
+                except AttributeError:
+                    pass
+            rows.append(r)
+        V = len(rows)
         if device.type == "cuda":
             # a small ring of reusable pinned staging buffers per batch size (pinning memory per call
             # costs more than the render's whole prepare stage; the ring keeps a buffer untouched
-            # until the asynchronous copy that reads it has long completed)
-            ring = _pinned_ring.setdefault(tuple(packed.shape), [0, [torch.empty(packed.shape).pin_memory() for _ in range(8)]])
+            # until the asynchronous copy that reads it has long completed); one H2D copy per batch
+            ring = _pinned_ring.get(V)
+            if ring is None:
+                ring = _pinned_ring[V] = [0, [torch.empty((V, 35)).pin_memory() for _ in range(8)]]
             ring[0] = (ring[0] + 1) % len(ring[1])
             stage = ring[1][ring[0]]
-            stage.copy_(packed)
+            if V == 1:
+                stage[0].copy_(rows[0])
+            else:
+                torch.stack(rows, out=stage)
             packed = stage.to(device, non_blocking=True)
+        else:
+            packed = torch.stack(rows)
+        if V == 1:  # slices of a single row are contiguous already
+            return ViewBatch(packed[:, :12], packed[:, 12:28], packed[:, 28:32], packed[:, 32:35], cams[0].H, cams[0].W)
         return ViewBatch(packed[:, :12].contiguous(), packed[:, 12:28].contiguous(), packed[:, 28:32].contiguous(),
                          packed[:, 32:35].contiguous(), cams[0].H, cams[0].W)
 
@@ -81,7 +98,7 @@ class _ProjectViews(Function):
         radii = torch.empty((V, n), dtype=torch.int32, device=dev)
         conics = torch.empty((V, n, 3), dtype=torch.float32, device=dev)
         nth = torch.empty((V, n), dtype=torch.int32, device=dev)
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             _lib.call("gg_project_fwd_views", 
                 n, V, ops.ptr(means), ops.ptr(scales), 1.0, ops.ptr(quats), ops.ptr(viewmats), ops.ptr(fullmats),
                 ops.ptr(intrins), 0.0, 0.0, 0.0, 0.0, int(H), int(W), tb[0], tb[1], float(clip_thresh),
@@ -104,7 +121,7 @@ class _ProjectViews(Function):
         v_means = torch.empty((n, 3), dtype=torch.float32, device=dev)
         v_scales = torch.empty((n, 3), dtype=torch.float32, device=dev)
         v_quats = torch.empty((n, 4), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             _lib.call("gg_project_bwd_views", 
                 n, V, ops.ptr(means), ops.ptr(scales), 1.0, ops.ptr(quats), ops.ptr(viewmats), ops.ptr(fullmats),
                 ops.ptr(intrins), 0.0, 0.0, 0.0, 0.0, H, W, ops.ptr(radii), ops.ptr(conics), ops.ptr(v_xys),
@@ -138,7 +155,7 @@ class _RenderViews(Function):
         s_out = torch.empty((n, 3), dtype=torch.float32, device=dev) if dbg else None
         q_out = torch.empty((n, 4), dtype=torch.float32, device=dev) if dbg else None
         def prepare(phase):
-            with torch.cuda.device(dev):
+            with _lib.device_guard(dev):
                 _lib.call("gg_prepare_views", n, V, D, CP, degree, int(degrees_to_use), ops.ptr(means),
                           ops.ptr(log_scales), ops.ptr(quats), ops.ptr(opacity_logit), ops.ptr(sh_coeffs),
                           ops.ptr(features), ops.ptr(views.viewmats), ops.ptr(views.fullmats), ops.ptr(views.intrins),
@@ -183,7 +200,7 @@ class _RenderViews(Function):
 
         v_means, v_ls, v_q = buf("means", (n, 3)), buf("log_scales", (n, 3)), buf("quats", (n, 4))
         v_op, v_sh, v_f = buf("opacity_logit", (n,)), buf("sh_coeffs", (n, nb, 3)), buf("features", (n, D))
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             _lib.call("gg_prepare_views_bwd", n, V, D, CP, degree, deg_use, ops.ptr(means), ops.ptr(log_scales),
                       ops.ptr(quats), ops.ptr(opacity_logit), ops.ptr(features), ops.ptr(views.viewmats),
                       ops.ptr(views.fullmats), ops.ptr(views.intrins), ops.ptr(views.positions), H, W, ops.ptr(geo),

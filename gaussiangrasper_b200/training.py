@@ -46,7 +46,7 @@ class FusedAdam:
         cnts = (C.c_longlong * n)(*[b.sizes[k] for k in names])
         lr = (C.c_float * n)(*[float(self.lrs[k]) for k in names])
         dev = b.flat.device
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             _lib.call("gg_adam_step", n, ptrs, offs, cnts, lr, b.flat.data_ptr(), self.exp_avg.data_ptr(),
                       self.exp_avg_sq.data_ptr(), float(self.betas[0]), float(self.betas[1]), float(self.eps), self.t,
                       _lib.stream_ptr(dev))
@@ -68,7 +68,7 @@ class DensifyStats:
         n_views = radii.numel() // self.n
         dev = v_geo.device
         radii = radii.contiguous()
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             _lib.call("gg_densify_stats", self.n, n_views, v_geo.data_ptr(), radii.data_ptr(), int(img_height),
                       int(img_width), 1 if self.first else 0, self.xys_grad_norm.data_ptr(), self.vis_counts.data_ptr(),
                       self.max_2Dsize.data_ptr(), _lib.stream_ptr(dev))

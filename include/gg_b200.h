@@ -113,6 +113,24 @@ int gg_emit_tiles_sorted(int n, int n_views, const int32_t* order, const float* 
 int gg_tile_ranges_lowkey(long long m, const int64_t* keys_sorted, long long num_tiles, int32_t* tile_ranges,
                           void* stream);
 
+/* The same depth-first binning as two host calls (every kernel above enqueued from C).
+ *   gg_bin_begin : depth keys -> sort by (view, depth) -> per-Gaussian tile counts in that order ->
+ *                  inclusive scan; the total M is copied to *m_host (pinned host memory) and an event is
+ *                  recorded behind the copy.  Work enqueued after this call overlaps the read-back.
+ *   gg_bin_wait  : blocks the host until *m_host is valid (one outstanding gg_bin_begin per device).
+ *   gg_bin_finish: emission in depth order -> stable sort by tile -> tile ranges -> tile order (m >= 1).
+ * `scratch` buffers are caller-owned, 256-byte aligned and ZERO-FILLED when allocated (the sort's look-back
+ * words live in them); begin_scratch must stay untouched between gg_bin_begin and gg_bin_finish. */
+size_t gg_bin_begin_scratch_bytes(long long total /* n * n_views */);
+size_t gg_bin_finish_scratch_bytes(long long m);
+int gg_bin_begin(int n, int n_views, const float* depths /*[V*n]*/, const int32_t* num_tiles_hit /*[V*n]*/,
+                 void* scratch, size_t scratch_bytes, int32_t* m_host, void* stream);
+int gg_bin_wait(void);
+int gg_bin_finish(int n, int n_views, long long m, const float* xys, int xy_stride /*2 or 8*/, const int32_t* radii,
+                  int tiles_x, int tiles_y, const void* begin_scratch, void* scratch, size_t scratch_bytes,
+                  int32_t* ids_sorted /*[m]*/, int32_t* tile_ranges /*[V*tiles, 2]*/, int32_t* tile_order /*[V*tiles]*/,
+                  void* stream);
+
 /* visiting order of the tiles for the blend kernels: tile ids by descending list length (only
  * scheduling depends on it, never results); tile_order [num_tiles] int32 */
 size_t gg_tile_order_workspace_bytes(void);
