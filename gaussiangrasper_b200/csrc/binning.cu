@@ -262,7 +262,21 @@ radix_pass_kernel(const uint64_t* __restrict__ kin, const uint32_t* __restrict__
     // (they are independent and have a long latency); only the counter updates form a chain.
     uint32_t peers[kRsIpt];
 #pragma unroll
-    for (int j = 0; j < kRsIpt; ++j) peers[j] = __match_any_sync(0xffffffffu, (uint32_t)(key[j] >> shift) & dmask);
+    for (int j = 0; j < kRsIpt; ++j) {
+        // lanes holding the same digit, from one ballot per digit bit: match.any serialises over the
+        // distinct values of a warp (~30 for an 8-bit digit of spread keys) and bounded the whole pass
+        const uint32_t d = (uint32_t)(key[j] >> shift) & dmask;
+        uint32_t same = 0xffffffffu;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            if ((dmask >> b) & 1u) {  // warp-uniform
+                const bool bit = (d >> b) & 1u;
+                const uint32_t v = __ballot_sync(0xffffffffu, bit);
+                same &= bit ? v : ~v;
+            }
+        }
+        peers[j] = same;
+    }
     uint32_t rank[kRsIpt];
 #pragma unroll
     for (int j = 0; j < kRsIpt; ++j) {

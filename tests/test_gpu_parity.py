@@ -144,6 +144,28 @@ def test_radix_sort_pairs_stable(dev, m):
     assert torch.equal(ko.cpu(), ks2) and torch.equal(io.cpu(), ids[order2])
 
 
+def test_radix_sort_every_key_width(dev):
+    """Digits are balanced over the passes (b bits -> ceil(b/8) passes of b/passes or one more bit):
+    every width from 1 to 64 must sort, stably, keys that use exactly that many bits."""
+    from gaussiangrasper_b200 import ops
+    m = 20_011
+    g = torch.Generator().manual_seed(7)
+    ids = torch.arange(m, dtype=torch.int32)
+    ko = torch.empty(m, dtype=torch.int64, device=dev)
+    io = torch.empty(m, dtype=torch.int32, device=dev)
+    for bits in range(1, 65):
+        hi = 2 ** min(bits, 62)
+        keys = torch.randint(0, hi, (m,), generator=g, dtype=torch.int64)
+        if bits >= 63:  # reach the top bits too (int64 sign bit: compare as unsigned below)
+            keys = keys | (torch.randint(0, 2 ** (bits - 62), (m,), generator=g, dtype=torch.int64) << 62)
+        keys[::3] = keys[0]  # ties
+        ops.sort_pairs(m, bits, keys.to(dev), ids.to(dev), ko, io)
+        ukeys = keys.numpy().view(np.uint64)
+        order = np.argsort(ukeys, kind="stable")
+        assert np.array_equal(ko.cpu().numpy().view(np.uint64), ukeys[order]), bits
+        assert np.array_equal(io.cpu().numpy(), order.astype(np.int32)), bits
+
+
 @pytest.mark.parametrize("n", [1, 4095, 4096, 4097, 1_000_003])
 def test_cumsum(dev, n):
     from gaussiangrasper_b200 import ops
@@ -204,6 +226,23 @@ def test_depth_first_binning_equals_reference_formulation(dev, n, W, H, seed, bi
     assert sorted(order.tolist()) == list(range(T * views))
     lens = (a.tile_ranges[:, 1] - a.tile_ranges[:, 0]).cpu().numpy()[order] >> 3
     assert (np.diff(np.minimum(lens, 1023)) <= 0).all()
+
+
+def test_binning_scratch_reuse_across_sizes(dev):
+    """The binning scratch is laid out per call inside grow-only buffers: a sequence of larger and smaller
+    problems (the layout shifts under stale data of the previous call) must keep matching the oracle."""
+    from gaussiangrasper_b200 import ops
+    for n, W, H, seed in [(40_000, 640, 480, 3), (2_000, 96, 64, 4), (90_000, 1280, 720, 5), (2_500, 160, 120, 6),
+                          (40_000, 320, 240, 7)]:
+        sc, cam, scales, quats = make_inputs(n, W, H, seed, True)
+        xys, depths, radii, conics, nth, _ = oracle_project(sc, cam, scales, quats)
+        _, _, _, _, ids_s, ranges = c_oracle.bin_and_sort(xys, depths, radii, nth, cam.tile_bounds)
+        t = lambda a: torch.from_numpy(a).to(dev)
+        b = ops.bin_views(n, 1, t(xys), t(depths), t(radii), t(nth), cam.tile_bounds)
+        assert np.array_equal(b.ids_sorted.cpu().numpy(), ids_s)
+        got = b.tile_ranges.cpu().numpy()
+        ne = ranges[:, 1] > ranges[:, 0]
+        assert np.array_equal(got[ne], ranges[ne]) and not got[~ne].any()
 
 
 def test_binning_empty(dev):

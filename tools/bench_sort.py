@@ -5,12 +5,12 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from gaussiangrasper_b200 import ops
 
 dev = torch.device("cuda:0")
-for m in (4096, 65536, 500_000, 2_170_000, 8_000_000, 35_000_000):
+for m in (500_000, 1_400_000, 8_000_000, 35_000_000):
     g = torch.Generator(device="cpu").manual_seed(1)
     keys = torch.randint(0, 2**40, (m,), generator=g, dtype=torch.int64).to(dev)
     ids = torch.arange(m, dtype=torch.int32, device=dev)
     ko, io = torch.empty_like(keys), torch.empty_like(ids)
-    for bits in (8, 16, 32, 40):
+    for bits in (8, 32):
         for _ in range(3):
             ops.sort_pairs(m, bits, keys, ids, ko, io)
         torch.cuda.synchronize()
