@@ -153,9 +153,12 @@ prepare_views_kernel(const PrepArgs a, float* __restrict__ geo, float* __restric
     if (vis) {
         const int nuse = sh_num_bases(a.deg_use);
         const float* cf = slab + lane * row;
-        for (int b = 0; b < nuse; ++b) {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) rgb[c] = rgb[c] + Y[b] * cf[3 * b + c];
+        for (int b = 0; b < 25; ++b) {  // fully unrolled: Y stays in registers
+            if (b < nuse) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) rgb[c] = rgb[c] + Y[b] * cf[3 * b + c];
+            }
         }
 #pragma unroll
         for (int c = 0; c < 3; ++c) rgb[c] = fminf(1.0f, fmaxf(0.0f, rgb[c] + 0.5f));
@@ -280,7 +283,7 @@ prepare_chan_kernel(const PrepArgs a, float* __restrict__ chan, const float* __r
 // Sum over views of the vector-Jacobian product of prepare_views_kernel.
 //   v_geo [V*N, 8] : v_x, v_y, v_A, v_B, v_C (w.r.t. the conic, not its halves), v_opacity
 //   v_chan[V*N, CP]: v_rgb(3), v_depth, v_normal(3), v_feature(D)
-__global__ void __launch_bounds__(kPrepThreads)
+__global__ void __launch_bounds__(kPrepThreads, 4)
 prepare_views_bwd_kernel(const PrepArgs a, const float* __restrict__ geo, const float* __restrict__ chan,
                          const int32_t* __restrict__ radii, const float* __restrict__ v_geo,
                          const float* __restrict__ v_chan, float* __restrict__ v_means,
@@ -291,14 +294,15 @@ prepare_views_bwd_kernel(const PrepArgs a, const float* __restrict__ geo, const 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = a.nb * 3;
     const int D = a.feat_dim;
-    float* slab = sm + (size_t)warp * 32 * (row + D);  // [32][row] SH grads, then [32][D] feature grads
+    const int Dp = D | 1;  // odd row stride: lane-per-row accumulation hits 32 different banks
+    float* slab = sm + (size_t)warp * 32 * (row + Dp);  // [32][row] SH grads, then [32][Dp] feature grads
     float* fslab = slab + 32 * row;
     const long long first = ((long long)blockIdx.x * kPrepWarps + warp) * 32;
     if (first >= a.n) return;
     const long long i = first + lane;
     const bool active = i < a.n;
     const int rows_here = (int)min((long long)32, a.n - first);
-    for (int k = lane; k < 32 * (row + D); k += 32) slab[k] = 0.0f;
+    for (int k = lane; k < 32 * (row + Dp); k += 32) slab[k] = 0.0f;
     __syncwarp();
 
     Activated g;
@@ -346,8 +350,18 @@ prepare_views_bwd_kernel(const PrepArgs a, const float* __restrict__ geo, const 
 #pragma unroll
             for (int c = 0; c < 3; ++c) sr[3 * b + c] += Y[b] * vrgb[c];
         }
-        float* fr = fslab + lane * D;
-        for (int d = 0; d < D; ++d) fr[d] += __ldg(vc + 7 + d);
+        // feature gradients: columns 7.. of the row, fetched as aligned 16-byte pieces
+        float* fr = fslab + lane * Dp;
+        if (D > 0) fr[0] += c1.w;
+        for (int q = 2; 4 * q < 7 + D; ++q) {
+            const float4 c = __ldg(reinterpret_cast<const float4*>(vc) + q);
+            const float e[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int d = 4 * q + t - 7;
+                if (d < D) fr[d] += e[t];
+            }
+        }
     }
     if (active) {
 #pragma unroll
@@ -374,7 +388,10 @@ prepare_views_bwd_kernel(const PrepArgs a, const float* __restrict__ geo, const 
     if (D > 0) {
         float* gspan = v_features + first * D;
         const int span = rows_here * D;
-        for (int k = lane; k < span; k += 32) gspan[k] = fslab[k];
+        for (int k = lane; k < span; k += 32) {
+            const int l = k / D;
+            gspan[k] = fslab[l * Dp + (k - l * D)];
+        }
     }
 }
 
@@ -459,7 +476,7 @@ extern "C" int gg_prepare_views_bwd(int n, int n_views, int feat_dim, int cp, in
                "gg_prepare_views_bwd: null output pointer");
     GG_REQUIRE(((uintptr_t)v_quats & 15) == 0 && ((uintptr_t)v_geo & 15) == 0 && ((uintptr_t)v_chan & 15) == 0,
                "gg_prepare_views_bwd: misaligned");
-    const size_t smem = sizeof(float) * kPrepWarps * 32 * (size_t)(a.nb * 3 + feat_dim);
+    const size_t smem = sizeof(float) * kPrepWarps * 32 * (size_t)(a.nb * 3 + (feat_dim | 1));
     GG_CUDA(cudaFuncSetAttribute(prepare_views_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     prepare_views_bwd_kernel<<<div_up(n, kPrepThreads), kPrepThreads, smem, (cudaStream_t)stream>>>(
         a, geo, chan, radii, v_geo, v_chan, v_means, v_log_scales, v_quats, v_opacity_logit, v_sh_coeffs, v_features);
