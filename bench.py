@@ -299,63 +299,71 @@ def run_ours(args):
     rgb_host = torch.empty((chunk, H, W, 3)).pin_memory()
     loss_host = torch.empty((1,)).pin_memory()
 
-    copy_stream = torch.cuda.Stream(device=dev)
-    # supervision images are double-buffered on the device: the copy for chunk q+1 is issued when chunk q
-    # starts (what a prefetching data loader does), so every step still moves its full H2D bytes inside
-    # the timed region, but behind the render instead of in front of the loss
+    h2d_stream = torch.cuda.Stream(device=dev)
+    d2h_stream = torch.cuda.Stream(device=dev)
+    # Supervision images are double-buffered on the device.  The copy for chunk q+1 is enqueued after chunk
+    # q's backward has been launched (what a prefetching data loader does): every step still moves its full
+    # H2D bytes inside the timed region, but while the GPU runs the two long blend kernels -- a 30 MB PCIe
+    # read that overlaps the launch-bound front of the forward costs ~0.14 ms per step of launch latency.
     target_dev = [torch.empty((chunk, H, W, CP), dtype=torch.float32, device=dev) for _ in range(2)] if cfg["backward"] else None
     pf = {"q": 0, "ready": [None, None], "consumed": [None, None]}
 
     def prefetch_target(q, nv):
         b = q & 1
-        with torch.cuda.stream(copy_stream):
+        with torch.cuda.stream(h2d_stream):
             if pf["consumed"][b] is not None:
-                copy_stream.wait_event(pf["consumed"][b])                    # chunk q-2 has read this buffer
+                h2d_stream.wait_event(pf["consumed"][b])                     # chunk q-2 has read this buffer
             target_dev[b][:nv].copy_(target_host[:nv], non_blocking=True)   # H2D: supervision images (pinned)
-            pf["ready"][b] = copy_stream.record_event()
+            pf["ready"][b] = h2d_stream.record_event()
 
     def e2e_step():
         """One user-level training step from HOST buffers: cameras + supervision images go host->device,
         the rendered rgb and the loss come back device->host, all inside the timed region.  The big
-        copies run on a side stream so they overlap the render (as a data loader would prefetch)."""
+        copies run on side streams so they overlap the render (as a data loader would prefetch); the
+        step returns when its loss and its rgb image are in host memory."""
         for p in P.values():
             p.grad = None
         main = torch.cuda.current_stream(dev)
-        loss = torch.zeros((), device=dev)
+        loss = None
+        rgb_done = None
         for ci in range(0, V, chunk):
             cc = cams[ci:ci + chunk]
             nv = len(cc)
             q = pf["q"]
-            if cfg["backward"]:
-                if pf["ready"][q & 1] is None:
-                    prefetch_target(q, nv)                                  # very first chunk only
-                nxt = ci + chunk if ci + chunk < V else 0
-                prefetch_target(q + 1, min(chunk, V - nxt))                 # next chunk (of this or the next step)
+            if cfg["backward"] and pf["ready"][q & 1] is None:
+                prefetch_target(q, nv)                                      # very first chunk only
             vb = ViewBatch.from_cameras(cc, dev)                            # H2D: cameras (pinned)
             with torch.set_grad_enabled(cfg["backward"]):
                 out = render_views(P["means"], P["log_scales"], P["quats"], P["opacity_logit"], P["sh_coeffs"],
                                    P["features"], vb)
             fwd_done = main.record_event()
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(fwd_done)
-                rgb_host[:nv].copy_(out["rgb"].detach(), non_blocking=True)  # D2H: rendered rgb, overlaps backward
-                out["rgb"].record_stream(copy_stream)
             if cfg["backward"]:
                 main.wait_event(pf["ready"][q & 1])
                 img = out["image"]
                 diff = img.detach() - target_dev[q & 1][:nv]                # L2 loss against the host-fed targets
                 pf["consumed"][q & 1] = main.record_event()
                 pf["ready"][q & 1] = None
-                loss = loss + (diff * diff).mean()
+                l = (diff * diff).mean()
                 img.backward(diff * (2.0 / diff.numel()))
             else:
-                loss = loss + out["alpha"].mean()
+                l = out["alpha"].mean()
+            loss = l if loss is None else loss + l
+            # the copies are enqueued once the step's kernels are: they run under the backward
+            with torch.cuda.stream(d2h_stream):
+                d2h_stream.wait_event(fwd_done)
+                rgb_host[:nv].copy_(out["rgb"].detach(), non_blocking=True)  # D2H: rendered rgb
+                out["rgb"].record_stream(d2h_stream)
+                rgb_done = d2h_stream.record_event()
+            if cfg["backward"]:
+                nxt = ci + chunk if ci + chunk < V else 0
+                prefetch_target(q + 1, min(chunk, V - nxt))                 # next chunk (of this or the next step)
             pf["q"] = q + 1
         if bucket is not None:
             bucket.pack({k: P[k].grad for k in names})
             bucket.all_reduce()
         loss_host.copy_(loss.detach().reshape(1), non_blocking=True)    # D2H: loss
-        torch.cuda.synchronize()
+        main.synchronize()
+        rgb_done.synchronize()
         return float(loss_host[0])
 
     for _ in range(2):

@@ -65,3 +65,44 @@ for it in range(40):
 for k in sorted(HT):
     v = sorted(HT[k][5:]); g = sorted(GT[k][5:]) if k in GT else None
     print(f"{k:20s} host {v[len(v)//2]:8.1f}   gpu-event {g[len(g)//2] if g else float('nan'):8.1f}")
+
+# ---- which part of bench.py's e2e step costs what: add the side-stream copies one at a time ----
+print("--- e2e variants: ms per step (sync'd every step)")
+copy_stream = torch.cuda.Stream(device=dev)
+target_host = torch.randn((1, H, W, CP)).pin_memory()
+tbuf = [torch.empty((1, H, W, CP), device=dev) for _ in range(2)]
+rgb_host = torch.empty((1, H, W, 3)).pin_memory()
+def run_variant(h2d, d2h, steps=30):
+    main = torch.cuda.current_stream(dev)
+    ready = [None, None]
+    def one(q):
+        for p in P.values():
+            p.grad = None
+        if h2d:
+            with torch.cuda.stream(copy_stream):
+                tbuf[(q + 1) & 1].copy_(target_host, non_blocking=True)
+                ready[(q + 1) & 1] = copy_stream.record_event()
+        vb = ViewBatch.from_cameras(cams, dev)
+        out = render_views(*(P[k] for k in names), vb)
+        if d2h:
+            fwd_done = main.record_event()
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(fwd_done)
+                rgb_host.copy_(out["rgb"].detach(), non_blocking=True)
+                out["rgb"].record_stream(copy_stream)
+        if h2d and ready[q & 1] is not None:
+            main.wait_event(ready[q & 1])
+        img = out["image"]
+        diff = img.detach() - tbuf[q & 1]
+        loss = (diff * diff).mean()
+        img.backward(diff * (2.0 / diff.numel()))
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        torch.cuda.synchronize()
+    for q in range(5):
+        one(q)
+    t0 = time.perf_counter()
+    for q in range(steps):
+        one(q)
+    return (time.perf_counter() - t0) / steps * 1e3
+for h2d, d2h in ((False, False), (True, False), (False, True), (True, True)):
+    print(f"h2d_prefetch={h2d!s:5} rgb_d2h={d2h!s:5}  {run_variant(h2d, d2h):.3f} ms/step")
