@@ -212,8 +212,14 @@ def run_ours(args):
     v_img = torch.randn((chunk, H, W, CP), generator=g).to(dev) if cfg["backward"] else None
     # views are rendered `chunk` at a time (one projection + one sort + one blend launch per chunk)
     chunks = [ViewBatch.from_cameras(cams[i:i + chunk], dev) for i in range(0, V, chunk)]
-    from gaussiangrasper_b200.distributed import GradientBucket
-    bucket = GradientBucket(P) if (world > 1 and cfg["backward"]) else None
+    from gaussiangrasper_b200.distributed import FactoredExchange, GradientBucket
+    from gaussiangrasper_b200 import ops as _ops
+    sh_degree = _ops.sh_degree_from_bases(P["sh_coeffs"].shape[1])
+    # gradient exchange of a multi-GPU training step: SH gradient as per-view factors (all-gather) + one
+    # all-reduce of the other leaves; --exchange allreduce = one all-reduce of everything
+    factored = world > 1 and cfg["backward"] and len(chunks) == 1 and args.exchange == "factored"
+    ex = FactoredExchange(P, chunks[0].n_views) if factored else None
+    bucket = GradientBucket(P) if (world > 1 and cfg["backward"] and not factored) else None
 
     def step_dropin():
         from gaussiangrasper_b200.reference_flow import get_outputs
@@ -238,11 +244,14 @@ def run_ours(args):
         # all-reduce buffer; several chunks accumulate in .grad and are packed afterwards
         direct = bucket is not None and len(chunks) == 1
         for vb in chunks:
+            holder = ex.holder() if ex is not None else ({"grad_out": bucket.unpack()} if direct else None)
             with torch.set_grad_enabled(cfg["backward"]):
                 out = render_views(P["means"], P["log_scales"], P["quats"], P["opacity_logit"], P["sh_coeffs"],
-                                   P["features"], vb, holder={"grad_out": bucket.unpack()} if direct else None)
+                                   P["features"], vb, holder=holder)
             if cfg["backward"]:
                 out["image"].backward(v_img[:vb.n_views])  # leaf gradients accumulate over the chunks
+        if ex is not None:
+            return ex.exchange(P["means"], chunks[0].positions, sh_degree, 4, holder)["sh_coeffs"]
         if bucket is not None:
             if not direct:
                 bucket.pack({k: P[k].grad for k in names})
@@ -333,9 +342,10 @@ def run_ours(args):
             if cfg["backward"] and pf["ready"][q & 1] is None:
                 prefetch_target(q, nv)                                      # very first chunk only
             vb = ViewBatch.from_cameras(cc, dev)                            # H2D: cameras (pinned)
+            holder = ex.holder() if ex is not None else None
             with torch.set_grad_enabled(cfg["backward"]):
                 out = render_views(P["means"], P["log_scales"], P["quats"], P["opacity_logit"], P["sh_coeffs"],
-                                   P["features"], vb)
+                                   P["features"], vb, holder=holder)
             fwd_done = main.record_event()
             if cfg["backward"]:
                 main.wait_event(pf["ready"][q & 1])
@@ -358,7 +368,9 @@ def run_ours(args):
                 nxt = ci + chunk if ci + chunk < V else 0
                 prefetch_target(q + 1, min(chunk, V - nxt))                 # next chunk (of this or the next step)
             pf["q"] = q + 1
-        if bucket is not None:
+        if ex is not None:
+            ex.exchange(P["means"], vb.positions, sh_degree, 4, holder)
+        elif bucket is not None:
             bucket.pack({k: P[k].grad for k in names})
             bucket.all_reduce()
         loss_host.copy_(loss.detach().reshape(1), non_blocking=True)    # D2H: loss
@@ -460,6 +472,8 @@ def run_ours(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": cfg["name"], "gaussians": n, "image": [W, H], "views_per_gpu": V, "views_per_launch": chunk,
                    "channels": C, "backward": cfg["backward"], "parallelism": f"view-sharded x{world}", "path": args.path,
+                   "gradient_exchange": ("sh factors all-gather + all-reduce of the other leaves" if ex is not None else
+                                         "all-reduce" if bucket is not None else "none"),
                    "l2": "inputs larger than L2 (parameters+gradients 2x%.0f MB per step)" % (n * (86 + D) * 4 / 1e6)},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
@@ -514,6 +528,9 @@ def main():
     ap.add_argument("--feat", type=int, default=-1, help="feature channels D (default: the config's)")
     ap.add_argument("--path", default="fused", choices=["fused", "dropin"],
                     help="fused: render_views; dropin: the reference's 1 projection + SH + 4 rasterize calls")
+    ap.add_argument("--exchange", default="factored", choices=["factored", "allreduce"],
+                    help="N>1 training steps: SH gradient exchanged as per-view factors (default) or one all-reduce of "
+                         "every leaf gradient")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--trace", default="", help="diagnostic: write a GPU timeline (kernels + idle gaps) of one e2e and one "
                                                 "device-timed step to this file (torch.profiler; not part of the measurement)")

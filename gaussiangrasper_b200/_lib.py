@@ -57,7 +57,8 @@ _SIGNATURES = {
     "gg_adam_step": (C.c_int, [_i, _p, _p, _p, _p, _p, _p, _p, _f, _f, _f, _i, _p]),
     "gg_densify_stats": (C.c_int, [_ll, _i, _p, _p, _i, _i, _i, _p, _p, _p, _p]),
     "gg_prepare_views": (C.c_int, [_i] * 6 + [_p] * 10 + [_i] * 4 + [_f] + [_p] * 7 + [_i, _p]),
-    "gg_prepare_views_bwd": (C.c_int, [_i] * 6 + [_p] * 9 + [_i] * 2 + [_p] * 12),
+    "gg_prepare_views_bwd": (C.c_int, [_i] * 6 + [_p] * 9 + [_i] * 2 + [_p] * 13),
+    "gg_sh_grad_from_views": (C.c_int, [_i] * 4 + [_p] * 5),
 }
 
 # optional symbols of later translation units (bound when present)

@@ -289,10 +289,13 @@ prepare_views_bwd_kernel(const PrepArgs a, const float* __restrict__ geo, const 
                          const float* __restrict__ v_chan, float* __restrict__ v_means,
                          float* __restrict__ v_log_scales, float* __restrict__ v_quats,
                          float* __restrict__ v_opacity_logit, float* __restrict__ v_sh,
-                         float* __restrict__ v_features) {
+                         float* __restrict__ v_features, float* __restrict__ v_rgb_views) {
+    // v_rgb_views != nullptr: the SH gradient is left to sh_grad_views_kernel; this kernel only emits its
+    // per-view factor, the clamp-masked colour gradient [V*N, 3] (and needs no SH slab)
     extern __shared__ __align__(16) float sm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row = a.nb * 3;
+    const bool defer_sh = v_rgb_views != nullptr;
+    const int row = defer_sh ? 0 : a.nb * 3;
     const int D = a.feat_dim;
     const int Dp = D | 1;  // odd row stride: lane-per-row accumulation hits 32 different banks
     float* slab = sm + (size_t)warp * 32 * (row + Dp);  // [32][row] SH grads, then [32][Dp] feature grads
@@ -311,7 +314,12 @@ prepare_views_bwd_kernel(const PrepArgs a, const float* __restrict__ geo, const 
     const int nuse = sh_num_bases(a.deg_use);
     for (int view = 0; view < a.n_views; ++view) {
         const long long vrow = (long long)view * a.n + i;
-        if (!(active && radii[vrow] > 0)) continue;
+        if (!(active && radii[vrow] > 0)) {
+            if (defer_sh && active) {
+                v_rgb_views[3 * vrow] = 0.0f; v_rgb_views[3 * vrow + 1] = 0.0f; v_rgb_views[3 * vrow + 2] = 0.0f;
+            }
+            continue;
+        }
         const Camera cam = load_camera_regs(a, view);
         const float4 ga = __ldg(reinterpret_cast<const float4*>(geo) + 2 * vrow);
         const float4 gb = __ldg(reinterpret_cast<const float4*>(geo) + 2 * vrow + 1);
@@ -342,13 +350,17 @@ prepare_views_bwd_kernel(const PrepArgs a, const float* __restrict__ geo, const 
             const float v = __ldg(cr + c);
             if (!(v > 0.0f && v < 1.0f)) vrgb[c] = 0.0f;
         }
-        float Y[25];
-        sh_basis(a.deg_use, g.p[0] - __ldg(a.positions + 3 * view), g.p[1] - __ldg(a.positions + 3 * view + 1),
-                 g.p[2] - __ldg(a.positions + 3 * view + 2), Y);
-        float* sr = slab + lane * row;
-        for (int b = 0; b < nuse; ++b) {
+        if (defer_sh) {
+            v_rgb_views[3 * vrow] = vrgb[0]; v_rgb_views[3 * vrow + 1] = vrgb[1]; v_rgb_views[3 * vrow + 2] = vrgb[2];
+        } else {
+            float Y[25];
+            sh_basis(a.deg_use, g.p[0] - __ldg(a.positions + 3 * view), g.p[1] - __ldg(a.positions + 3 * view + 1),
+                     g.p[2] - __ldg(a.positions + 3 * view + 2), Y);
+            float* sr = slab + lane * row;
+            for (int b = 0; b < nuse; ++b) {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) sr[3 * b + c] += Y[b] * vrgb[c];
+                for (int c = 0; c < 3; ++c) sr[3 * b + c] += Y[b] * vrgb[c];
+            }
         }
         // feature gradients: columns 7.. of the row, fetched as aligned 16-byte pieces
         float* fr = fslab + lane * Dp;
@@ -377,7 +389,9 @@ prepare_views_bwd_kernel(const PrepArgs a, const float* __restrict__ geo, const 
         v_opacity_logit[i] = go * g.opacity * (1.0f - g.opacity);
     }
     __syncwarp();
-    if (rows_here == 32) {
+    if (defer_sh) {
+        // nothing to store for the SH table
+    } else if (rows_here == 32) {
         // the warp's [32, 3*nb] gradient rows are one contiguous, 16-byte aligned span: one bulk store
         if (lane == 0) bulk_store_and_wait(v_sh + first * row, slab, (uint32_t)(32 * row * sizeof(float)));
         __syncwarp();
@@ -392,6 +406,50 @@ prepare_views_bwd_kernel(const PrepArgs a, const float* __restrict__ geo, const 
             const int l = k / D;
             gspan[k] = fslab[l * Dp + (k - l * D)];
         }
+    }
+}
+
+// SH-coefficient gradient from its per-view factors: v_sh[i] = sum_v Y(dir_v(i)) (x) v_rgb[v][i].
+// The gradient of the 3*nb coefficients is an outer product per view, so a data-parallel step only has
+// to exchange the 3 floats per (view, Gaussian) -- all-gathered with the camera centres -- instead of
+// all-reducing 3*nb floats per Gaussian (75 at degree 4); every rank then rebuilds the full sum here.
+__global__ void __launch_bounds__(kPrepThreads)
+sh_grad_views_kernel(int n, int n_views, int nb, int deg_use, const float* __restrict__ means,
+                     const float* __restrict__ positions, const float* __restrict__ v_rgb, float* __restrict__ v_sh) {
+    extern __shared__ __align__(16) float sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = nb * 3;
+    float* slab = sm + (size_t)warp * 32 * row;
+    const long long first = ((long long)blockIdx.x * kPrepWarps + warp) * 32;
+    if (first >= n) return;
+    const long long i = first + lane;
+    const bool active = i < n;
+    const int rows_here = (int)min((long long)32, n - first);
+    for (int k = lane; k < 32 * row; k += 32) slab[k] = 0.0f;
+    __syncwarp();
+    if (active) {
+        const float px = __ldg(means + 3 * i), py = __ldg(means + 3 * i + 1), pz = __ldg(means + 3 * i + 2);
+        const int nuse = sh_num_bases(deg_use);
+        float* sr = slab + lane * row;
+        for (int v = 0; v < n_views; ++v) {
+            const float* g = v_rgb + 3 * ((long long)v * n + i);
+            const float vr = __ldg(g), vg = __ldg(g + 1), vb = __ldg(g + 2);
+            if (vr == 0.0f && vg == 0.0f && vb == 0.0f) continue;  // culled in this view, or clamped / unlit
+            float Y[25];
+            sh_basis(deg_use, px - __ldg(positions + 3 * v), py - __ldg(positions + 3 * v + 1),
+                     pz - __ldg(positions + 3 * v + 2), Y);
+            for (int b = 0; b < nuse; ++b) {
+                sr[3 * b] += Y[b] * vr; sr[3 * b + 1] += Y[b] * vg; sr[3 * b + 2] += Y[b] * vb;
+            }
+        }
+    }
+    __syncwarp();
+    if (rows_here == 32) {
+        if (lane == 0) bulk_store_and_wait(v_sh + first * row, slab, (uint32_t)(32 * row * sizeof(float)));
+        __syncwarp();
+    } else {
+        float* gspan = v_sh + first * row;
+        for (int k = lane; k < rows_here * row; k += 32) gspan[k] = slab[k];
     }
 }
 
@@ -464,22 +522,41 @@ extern "C" int gg_prepare_views_bwd(int n, int n_views, int feat_dim, int cp, in
                                     int img_w, const float* geo, const float* chan, const int32_t* radii,
                                     const float* v_geo, const float* v_chan, float* v_means, float* v_log_scales,
                                     float* v_quats, float* v_opacity_logit, float* v_sh_coeffs, float* v_features,
-                                    void* stream) {
+                                    float* v_rgb_views, void* stream) {
     PrepArgs a;
-    // the SH table itself is not read by the backward; pass v_sh_coeffs for the alignment check
+    // the SH table itself is not read by the backward; pass a gradient buffer for the alignment check
+    GG_REQUIRE(v_sh_coeffs || v_rgb_views, "gg_prepare_views_bwd: need v_sh_coeffs or v_rgb_views");
     const int rc = fill_args(a, n, n_views, feat_dim, cp, degree, degrees_to_use, means, log_scales, quats,
-                             opacity_logit, v_sh_coeffs, features, viewmats, fullmats, intrins, positions, img_h,
-                             img_w, 1, 1, 0.0f);
+                             opacity_logit, v_rgb_views ? quats : v_sh_coeffs, features, viewmats, fullmats, intrins,
+                             positions, img_h, img_w, 1, 1, 0.0f);
     if (rc != GG_OK) return rc;
     GG_REQUIRE(geo && chan && radii && v_geo && v_chan, "gg_prepare_views_bwd: null input pointer");
-    GG_REQUIRE(v_means && v_log_scales && v_quats && v_opacity_logit && v_sh_coeffs && (v_features || feat_dim == 0),
+    GG_REQUIRE(v_means && v_log_scales && v_quats && v_opacity_logit && (v_features || feat_dim == 0),
                "gg_prepare_views_bwd: null output pointer");
     GG_REQUIRE(((uintptr_t)v_quats & 15) == 0 && ((uintptr_t)v_geo & 15) == 0 && ((uintptr_t)v_chan & 15) == 0,
                "gg_prepare_views_bwd: misaligned");
-    const size_t smem = sizeof(float) * kPrepWarps * 32 * (size_t)(a.nb * 3 + (feat_dim | 1));
+    const size_t smem = sizeof(float) * kPrepWarps * 32 * (size_t)((v_rgb_views ? 0 : a.nb * 3) + (feat_dim | 1));
     GG_CUDA(cudaFuncSetAttribute(prepare_views_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     prepare_views_bwd_kernel<<<div_up(n, kPrepThreads), kPrepThreads, smem, (cudaStream_t)stream>>>(
-        a, geo, chan, radii, v_geo, v_chan, v_means, v_log_scales, v_quats, v_opacity_logit, v_sh_coeffs, v_features);
+        a, geo, chan, radii, v_geo, v_chan, v_means, v_log_scales, v_quats, v_opacity_logit, v_sh_coeffs, v_features,
+        v_rgb_views);
     count_launch();
     return check_launch("prepare_views_bwd_kernel");
+}
+
+extern "C" int gg_sh_grad_from_views(int n, int n_views, int degree, int degrees_to_use, const float* means,
+                                     const float* positions, const float* v_rgb_views, float* v_sh_coeffs,
+                                     void* stream) {
+    GG_REQUIRE(n >= 1 && n_views >= 1, "gg_sh_grad_from_views: need n >= 1 and n_views >= 1");
+    GG_REQUIRE(degree >= 0 && degree <= 4 && degrees_to_use >= 0 && degrees_to_use <= degree,
+               "gg_sh_grad_from_views: need 0 <= degrees_to_use <= degree <= 4");
+    GG_REQUIRE(means && positions && v_rgb_views && v_sh_coeffs, "gg_sh_grad_from_views: null pointer");
+    GG_REQUIRE(((uintptr_t)v_sh_coeffs & 15) == 0, "gg_sh_grad_from_views: v_sh_coeffs misaligned");
+    const int nb = sh_num_bases(degree);
+    const size_t smem = sizeof(float) * kPrepWarps * 32 * (size_t)(nb * 3);
+    GG_CUDA(cudaFuncSetAttribute(sh_grad_views_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sh_grad_views_kernel<<<div_up(n, kPrepThreads), kPrepThreads, smem, (cudaStream_t)stream>>>(
+        n, n_views, nb, degrees_to_use, means, positions, v_rgb_views, v_sh_coeffs);
+    count_launch();
+    return check_launch("sh_grad_views_kernel");
 }

@@ -146,6 +146,22 @@ def sh_degree_from_bases(num_bases: int) -> int:
     return table[num_bases]
 
 
+def sh_grad_from_views(degree: int, degrees_to_use: int, means, positions, v_rgb_views, out=None):
+    """v_sh [N,(degree+1)^2,3] = sum over views of Y(dir) (x) v_rgb: positions [Vt,3], v_rgb_views [Vt,N,3]."""
+    dev = require_cuda(means, positions, v_rgb_views)
+    means, positions, v_rgb_views = f32c(means), f32c(positions), f32c(v_rgb_views)
+    n, vt = means.shape[0], positions.shape[0]
+    if v_rgb_views.numel() != vt * n * 3:
+        raise ValueError("v_rgb_views must hold [views, N, 3] floats for the views in `positions`")
+    nb = (degree + 1) ** 2
+    if out is None:
+        out = torch.empty((n, nb, 3), dtype=torch.float32, device=dev)
+    with _lib.device_guard(dev):
+        _lib.call("gg_sh_grad_from_views", int(n), int(vt), int(degree), int(degrees_to_use), ptr(means), ptr(positions),
+                  ptr(v_rgb_views), ptr(out), stream_ptr(dev))
+    return out
+
+
 def sh_fwd(degrees_to_use, viewdirs, coeffs):
     dev = require_cuda(viewdirs, coeffs)
     viewdirs, coeffs = f32c(viewdirs), f32c(coeffs)

@@ -199,15 +199,21 @@ class _RenderViews(Function):
             return torch.empty(shape, dtype=torch.float32, device=dev)
 
         v_means, v_ls, v_q = buf("means", (n, 3)), buf("log_scales", (n, 3)), buf("quats", (n, 4))
-        v_op, v_sh, v_f = buf("opacity_logit", (n,)), buf("sh_coeffs", (n, nb, 3)), buf("features", (n, D))
+        v_op, v_f = buf("opacity_logit", (n,)), buf("features", (n, D))
+        # view-sharded training: leave the SH gradient as its per-view factor (distributed.FactoredExchange)
+        defer = bool((ctx.holder or {}).get("defer_sh_grad"))
+        v_sh = None if defer else buf("sh_coeffs", (n, nb, 3))
+        v_rgb = buf("v_rgb_views", (V, n, 3)) if defer else None
         with _lib.device_guard(dev):
             _lib.call("gg_prepare_views_bwd", n, V, D, CP, degree, deg_use, ops.ptr(means), ops.ptr(log_scales),
                       ops.ptr(quats), ops.ptr(opacity_logit), ops.ptr(features), ops.ptr(views.viewmats),
                       ops.ptr(views.fullmats), ops.ptr(views.intrins), ops.ptr(views.positions), H, W, ops.ptr(geo),
                       ops.ptr(chan), ops.ptr(radii), ops.ptr(v_geo), ops.ptr(v_chan), ops.ptr(v_means), ops.ptr(v_ls),
-                      ops.ptr(v_q), ops.ptr(v_op), ops.ptr(v_sh), ops.ptr(v_f), ops.stream_ptr(dev))
+                      ops.ptr(v_q), ops.ptr(v_op), ops.ptr(v_sh), ops.ptr(v_f), ops.ptr(v_rgb), ops.stream_ptr(dev))
         if ctx.holder is not None:
             ctx.holder["v_geo"] = v_geo  # [V*n, 8]: columns 0..1 are d loss / d xys (densification statistic)
+            if defer:
+                ctx.holder["v_rgb_views"] = v_rgb
         return (v_means, v_ls, v_q, v_op.reshape(opacity_logit.shape), v_sh, v_f, None, None, None, None, None, None)
 
 
@@ -231,7 +237,9 @@ def render_views(means, log_scales, quats, opacity_logit, sh_coeffs, features, v
     backward, `v_geo` whose first two columns are d loss / d xys, the statistic the model's
     densification reads from `xys.grad` (gaussian_splatting.py:725,377).  If it carries
     `grad_out` (name -> preallocated fp32 tensor, e.g. `GradientBucket.unpack()`), the backward
-    writes the leaf gradients of a single-launch step straight into those buffers.
+    writes the leaf gradients of a single-launch step straight into those buffers.  With
+    `defer_sh_grad` set, the SH-coefficient gradient is not formed: `sh_coeffs.grad` stays None and
+    `holder["v_rgb_views"]` [V,N,3] receives its per-view factor (see distributed.FactoredExchange).
     """
     out, final_T = _RenderViews.apply(means, log_scales, quats, opacity_logit, sh_coeffs, features, views,
                                       int(degrees_to_use), float(depth_background), float(clip_thresh), stats, holder)

@@ -191,7 +191,16 @@ int gg_prepare_views_bwd(int n, int n_views, int feat_dim, int cp, int degree, i
                          const float* fullmats, const float* intrins, const float* positions, int img_h, int img_w,
                          const float* geo, const float* chan, const int32_t* radii, const float* v_geo,
                          const float* v_chan, float* v_means, float* v_log_scales, float* v_quats,
-                         float* v_opacity_logit, float* v_sh_coeffs, float* v_features, void* stream);
+                         float* v_opacity_logit, float* v_sh_coeffs /*nullable iff v_rgb_views*/, float* v_features,
+                         float* v_rgb_views /*nullable*/, void* stream);
+
+/* Factored SH gradient for view-sharded training.  The gradient of the [nb,3] coefficients of a Gaussian is
+ * sum over views of Y(dir_v) (outer) v_rgb_v, so ranks exchange only the clamp-masked colour gradient
+ * v_rgb_views [V*N, 3] (what gg_prepare_views_bwd writes when v_rgb_views != NULL, skipping v_sh_coeffs)
+ * together with the camera centres, and every rank rebuilds the full sum here:
+ * positions [n_views,3], v_rgb_views [n_views*n,3] over ALL views of all ranks -> v_sh_coeffs [n,nb,3]. */
+int gg_sh_grad_from_views(int n, int n_views, int degree, int degrees_to_use, const float* means,
+                          const float* positions, const float* v_rgb_views, float* v_sh_coeffs, void* stream);
 
 /* ---- next rows: the streaming steps directly behind the backward -----------------
  * gg_adam_step: fused torch.optim.Adam (no amsgrad / weight decay) over a flat gradient buffer that

@@ -91,3 +91,81 @@ def test_bucket_layout_single_process():
     assert un["sh_coeffs"].shape == (7, 4, 3) and flat.numel() == b.numel
     with pytest.raises(ValueError):
         ggd.GradientBucket({"bogus": torch.zeros(3)})
+
+
+# ---------------------------------------------------------------------------------------------
+# FactoredExchange: SH gradient exchanged as per-view factors (all-gather) + all-reduce of the rest.
+# The CUDA rebuild kernel is replaced by the oracle's SH basis here (no GPU in this suite).
+# ---------------------------------------------------------------------------------------------
+def _torch_sh_rebuild(degree, degrees_to_use, means, positions, v_rgb_views, out=None):
+    from oracle import torch_oracle
+    vt, n = positions.shape[0], means.shape[0]
+    nb = (degree + 1) ** 2
+    acc = torch.zeros((n, nb, 3))
+    for v in range(vt):
+        dirs = means - positions[v][None]
+        Y = torch_oracle.sh_basis(degrees_to_use, dirs / dirs.norm(dim=-1, keepdim=True))   # [n, nuse]
+        acc[:, :Y.shape[1]] += Y[:, :, None] * v_rgb_views.view(vt, n, 3)[v][:, None, :]
+    out.copy_(acc)
+    return out
+
+
+def _view_factor(n, view):
+    g = torch.Generator().manual_seed(1000 + view)
+    rgb = torch.randn((n, 3), generator=g)
+    rgb[torch.rand(n, generator=g) < 0.3] = 0.0   # Gaussians this view does not see
+    pos = torch.randn(3, generator=g) * 3.0
+    return rgb, pos
+
+
+def _factored_worker(rank, world, port, views_per_rank, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        params = _make_params(n=40, D=4, K=25)
+        ex = ggd.FactoredExchange(params, views_per_rank, reconstruct=_torch_sh_rebuild)
+        holder = ex.holder()
+        assert holder["defer_sh_grad"] and "sh_coeffs" not in holder["grad_out"]
+        # what the backward of this rank's render_views call would write
+        mine = [rank * views_per_rank + j for j in range(views_per_rank)]
+        for k, buf in holder["grad_out"].items():
+            if k != "v_rgb_views":
+                buf.copy_(sum(_per_view_grad(params, v)[k] for v in mine))
+        pos = torch.stack([_view_factor(40, v)[1] for v in mine])
+        holder["grad_out"]["v_rgb_views"].copy_(torch.stack([_view_factor(40, v)[0] for v in mine]))
+        grads = ex.exchange(params["means"], pos, 4, 4, holder)
+        if rank == 0:
+            torch.save({k: g.clone() for k, g in grads.items()}, out)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_factored_exchange_two_ranks(tmp_path):
+    world, vpr = 2, 2
+    out = str(tmp_path / "fgrads.pt")
+    mp.spawn(_factored_worker, args=(world, _free_port(), vpr, out), nprocs=world, join=True)
+    got = torch.load(out)
+    params = _make_params(n=40, D=4, K=25)
+    views = list(range(world * vpr))
+    for k in params:
+        if k == "sh_coeffs":
+            continue
+        want = sum(_per_view_grad(params, v)[k] for v in views)
+        assert torch.allclose(got[k], want, rtol=1e-5, atol=1e-6), k
+    rgb = torch.stack([_view_factor(40, v)[0] for v in views])
+    pos = torch.stack([_view_factor(40, v)[1] for v in views])
+    want_sh = _torch_sh_rebuild(4, 4, params["means"].detach(), pos, rgb, out=torch.zeros(40, 25, 3))
+    assert torch.allclose(got["sh_coeffs"], want_sh, rtol=1e-5, atol=1e-6)
+
+
+def test_factored_exchange_single_process_is_local():
+    params = _make_params(n=9, D=2, K=4)
+    ex = ggd.FactoredExchange(params, 3, reconstruct=_torch_sh_rebuild)
+    h = ex.holder()
+    assert h["grad_out"]["v_rgb_views"].shape == (3, 9, 3) and ex.bucket.numel == 9 * (3 + 3 + 4 + 1 + 2)
+    h["grad_out"]["v_rgb_views"].copy_(torch.ones(3, 9, 3))
+    g = ex.exchange(params["means"], torch.zeros(3, 3) + torch.arange(3.0)[:, None] + 5.0, 1, 1, h)
+    assert g["sh_coeffs"].shape == (9, 4, 3) and torch.isfinite(g["sh_coeffs"]).all()
+    with pytest.raises(ValueError):
+        ex.exchange(params["means"], torch.zeros(2, 3), 1, 1, h)

@@ -537,3 +537,54 @@ def test_config1_full_size_forward_and_backward(dev):
     grad_close(gc.grad.cpu().numpy(), r_con, "v_conics")
     grad_close(gcol.grad.cpu().numpy(), r_col, "v_colors")
     grad_close(gop.grad.cpu().numpy().reshape(-1), r_op, "v_opacity")
+
+
+def test_factored_sh_gradient_equals_fused_backward(dev):
+    """View-sharded exchange (distributed.FactoredExchange): the backward leaves the SH gradient as its
+    per-view factor v_rgb [V,N,3]; rebuilding sum_v Y(dir_v) (x) v_rgb_v from the factors of two separately
+    rendered view batches (two "ranks") gives the gradient of the joint render, and every other leaf gradient
+    is the plain sum."""
+    from gaussiangrasper_b200 import ops
+    from gaussiangrasper_b200.distributed import FactoredExchange
+    from gaussiangrasper_b200.render import ViewBatch, render_views
+    n, W, H, D = 4000, 96, 64, 5
+    sc = scenes.random_scene(n, feature_dim=D, seed=91)
+    sc["log_scales"] = sc["log_scales"] + 0.8
+    names = ("means", "log_scales", "quats", "opacity_logit", "sh_coeffs", "features")
+    cams = scenes.orbit_cameras(4, W, H, total=9)
+    g = torch.Generator().manual_seed(3)
+    v_img = torch.randn((4, H, W, 7 + D), generator=g).to(dev)
+
+    # joint render of the four views: the reference gradients
+    P = {k: sc[k].to(dev).clone().requires_grad_(True) for k in names}
+    out = render_views(*(P[k] for k in names), ViewBatch.from_cameras(cams, dev), degrees_to_use=3)
+    (out["image"] * v_img).sum().backward()
+    want = {k: P[k].grad.clone() for k in names}
+    assert float(want["sh_coeffs"][:, 16:].abs().max()) == 0.0  # bands above degrees_to_use get no gradient
+
+    # two "ranks" with two views each, deferred SH gradient
+    rgb, pos, rest = [], [], None
+    for r in range(2):
+        Q = {k: sc[k].to(dev).clone().requires_grad_(True) for k in names}
+        ex = FactoredExchange(Q, 2)          # no process group: local
+        holder = ex.holder()
+        vb = ViewBatch.from_cameras(cams[2 * r:2 * r + 2], dev)
+        o = render_views(*(Q[k] for k in names), vb, degrees_to_use=3, holder=holder)
+        (o["image"] * v_img[2 * r:2 * r + 2]).sum().backward()
+        assert Q["sh_coeffs"].grad is None and holder["v_rgb_views"].data_ptr() == ex.rgb_send.data_ptr()
+        got = ex.exchange(Q["means"], vb.positions, 4, 3, holder)
+        # single rank: the exchange alone must reproduce that rank's own full gradient
+        Q2 = {k: sc[k].to(dev).clone().requires_grad_(True) for k in names}
+        o2 = render_views(*(Q2[k] for k in names), vb, degrees_to_use=3)
+        (o2["image"] * v_img[2 * r:2 * r + 2]).sum().backward()
+        for k in names:
+            ref = Q2[k].grad.reshape(got[k].shape)
+            assert torch.allclose(got[k], ref, rtol=1e-5, atol=1e-6 * float(ref.abs().max())), (r, k)
+        rgb.append(ex.rgb_send.clone()); pos.append(vb.positions.clone())
+        part = {k: got[k].clone() for k in names if k != "sh_coeffs"}
+        rest = part if rest is None else {k: rest[k] + part[k] for k in part}
+    sh = ops.sh_grad_from_views(4, 3, P["means"].detach(), torch.cat(pos), torch.cat(rgb))
+    assert torch.allclose(sh, want["sh_coeffs"], rtol=1e-4, atol=1e-6 * float(want["sh_coeffs"].abs().max()))
+    for k, gk in rest.items():
+        ref = want[k].reshape(gk.shape)
+        assert torch.allclose(gk, ref, rtol=1e-4, atol=2e-6 * float(ref.abs().max())), k
