@@ -217,8 +217,15 @@ def run_ours(args):
     sh_degree = _ops.sh_degree_from_bases(P["sh_coeffs"].shape[1])
     # gradient exchange of a multi-GPU training step: SH gradient as per-view factors (all-gather) + one
     # all-reduce of the other leaves; --exchange allreduce = one all-reduce of everything
-    factored = world > 1 and cfg["backward"] and len(chunks) == 1 and args.exchange == "factored"
+    # (worth it while the gathered factors, 3 floats per view and Gaussian over ALL views, stay well below the
+    # 3K-float product: at 64 views the all-reduce of the product is the cheaper exchange again)
+    factored = (world > 1 and cfg["backward"] and len(chunks) == 1 and args.exchange == "factored"
+                and world * chunks[0].n_views * 2 <= P["sh_coeffs"].shape[1])
     ex = FactoredExchange(P, chunks[0].n_views) if factored else None
+    # every rank can name every rank's cameras (a shared sampler): no collective for the camera centres
+    all_pos = torch.stack([c.position for r in range(world) for c in
+                           scenes.orbit_cameras(V, W, H, first=r * V, total=max(total_views, 8))]).float().to(dev) \
+        if factored else None
     bucket = GradientBucket(P) if (world > 1 and cfg["backward"] and not factored) else None
 
     def step_dropin():
@@ -251,7 +258,7 @@ def run_ours(args):
             if cfg["backward"]:
                 out["image"].backward(v_img[:vb.n_views])  # leaf gradients accumulate over the chunks
         if ex is not None:
-            return ex.exchange(P["means"], chunks[0].positions, sh_degree, 4, holder)["sh_coeffs"]
+            return ex.exchange(P["means"], chunks[0].positions, sh_degree, 4, holder, all_pos)["sh_coeffs"]
         if bucket is not None:
             if not direct:
                 bucket.pack({k: P[k].grad for k in names})
@@ -369,7 +376,7 @@ def run_ours(args):
                 prefetch_target(q + 1, min(chunk, V - nxt))                 # next chunk (of this or the next step)
             pf["q"] = q + 1
         if ex is not None:
-            ex.exchange(P["means"], vb.positions, sh_degree, 4, holder)
+            ex.exchange(P["means"], vb.positions, sh_degree, 4, holder, all_pos)
         elif bucket is not None:
             bucket.pack({k: P[k].grad for k in names})
             bucket.all_reduce()

@@ -413,35 +413,58 @@ prepare_views_bwd_kernel(const PrepArgs a, const float* __restrict__ geo, const 
 // The gradient of the 3*nb coefficients is an outer product per view, so a data-parallel step only has
 // to exchange the 3 floats per (view, Gaussian) -- all-gathered with the camera centres -- instead of
 // all-reducing 3*nb floats per Gaussian (75 at degree 4); every rank then rebuilds the full sum here.
-__global__ void __launch_bounds__(kPrepThreads)
-sh_grad_views_kernel(int n, int n_views, int nb, int deg_use, const float* __restrict__ means,
+template <int NB>
+__global__ void __launch_bounds__(kPrepThreads, 4)
+sh_grad_views_kernel(int n, int n_views, int deg_use, const float* __restrict__ means,
                      const float* __restrict__ positions, const float* __restrict__ v_rgb, float* __restrict__ v_sh) {
+    // Accumulators live in registers (3*NB per lane, all indices compile-time); shared memory is touched
+    // once, to turn the lane-per-row result into one contiguous span for the bulk store.
     extern __shared__ __align__(16) float sm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row = nb * 3;
+    constexpr int row = NB * 3;
     float* slab = sm + (size_t)warp * 32 * row;
     const long long first = ((long long)blockIdx.x * kPrepWarps + warp) * 32;
     if (first >= n) return;
     const long long i = first + lane;
     const bool active = i < n;
     const int rows_here = (int)min((long long)32, n - first);
-    for (int k = lane; k < 32 * row; k += 32) slab[k] = 0.0f;
-    __syncwarp();
+    float acc[row];
+#pragma unroll
+    for (int k = 0; k < row; ++k) acc[k] = 0.0f;
     if (active) {
         const float px = __ldg(means + 3 * i), py = __ldg(means + 3 * i + 1), pz = __ldg(means + 3 * i + 2);
         const int nuse = sh_num_bases(deg_use);
-        float* sr = slab + lane * row;
-        for (int v = 0; v < n_views; ++v) {
-            const float* g = v_rgb + 3 * ((long long)v * n + i);
-            const float vr = __ldg(g), vg = __ldg(g + 1), vb = __ldg(g + 2);
-            if (vr == 0.0f && vg == 0.0f && vb == 0.0f) continue;  // culled in this view, or clamped / unlit
-            float Y[25];
-            sh_basis(deg_use, px - __ldg(positions + 3 * v), py - __ldg(positions + 3 * v + 1),
-                     pz - __ldg(positions + 3 * v + 2), Y);
-            for (int b = 0; b < nuse; ++b) {
-                sr[3 * b] += Y[b] * vr; sr[3 * b + 1] += Y[b] * vg; sr[3 * b + 2] += Y[b] * vb;
+        constexpr int kPre = 4;  // factors of kPre views are in flight before the first is used
+        for (int v0 = 0; v0 < n_views; v0 += kPre) {
+            float f[kPre][3];
+#pragma unroll
+            for (int u = 0; u < kPre; ++u) {
+                const int v = v0 + u;
+                const float* g = v_rgb + 3 * ((long long)(v < n_views ? v : 0) * n + i);
+                f[u][0] = v < n_views ? __ldg(g) : 0.0f;
+                f[u][1] = v < n_views ? __ldg(g + 1) : 0.0f;
+                f[u][2] = v < n_views ? __ldg(g + 2) : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < kPre; ++u) {
+                if (f[u][0] == 0.0f && f[u][1] == 0.0f && f[u][2] == 0.0f) continue;  // culled / clamped / unlit
+                const int v = v0 + u;
+                float Y[25];
+                sh_basis(deg_use, px - __ldg(positions + 3 * v), py - __ldg(positions + 3 * v + 1),
+                         pz - __ldg(positions + 3 * v + 2), Y);
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    if (b < nuse) {
+                        acc[3 * b] += Y[b] * f[u][0]; acc[3 * b + 1] += Y[b] * f[u][1]; acc[3 * b + 2] += Y[b] * f[u][2];
+                    }
+                }
             }
         }
+    }
+    {
+        float* sr = slab + lane * row;  // odd row stride for NB = 1, 9, 25; 2-way conflicts at most otherwise
+#pragma unroll
+        for (int k = 0; k < row; ++k) sr[k] = acc[k];
     }
     __syncwarp();
     if (rows_here == 32) {
@@ -554,9 +577,18 @@ extern "C" int gg_sh_grad_from_views(int n, int n_views, int degree, int degrees
     GG_REQUIRE(((uintptr_t)v_sh_coeffs & 15) == 0, "gg_sh_grad_from_views: v_sh_coeffs misaligned");
     const int nb = sh_num_bases(degree);
     const size_t smem = sizeof(float) * kPrepWarps * 32 * (size_t)(nb * 3);
-    GG_CUDA(cudaFuncSetAttribute(sh_grad_views_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sh_grad_views_kernel<<<div_up(n, kPrepThreads), kPrepThreads, smem, (cudaStream_t)stream>>>(
-        n, n_views, nb, degrees_to_use, means, positions, v_rgb_views, v_sh_coeffs);
-    count_launch();
-    return check_launch("sh_grad_views_kernel");
+    auto launch = [&](auto kernel) -> int {
+        GG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kernel<<<div_up(n, kPrepThreads), kPrepThreads, smem, (cudaStream_t)stream>>>(
+            n, n_views, degrees_to_use, means, positions, v_rgb_views, v_sh_coeffs);
+        count_launch();
+        return check_launch("sh_grad_views_kernel");
+    };
+    switch (degree) {
+        case 0: return launch(sh_grad_views_kernel<1>);
+        case 1: return launch(sh_grad_views_kernel<4>);
+        case 2: return launch(sh_grad_views_kernel<9>);
+        case 3: return launch(sh_grad_views_kernel<16>);
+        default: return launch(sh_grad_views_kernel<25>);
+    }
 }

@@ -118,3 +118,220 @@ extern "C" int gg_densify_stats(long long n, int n_views, const float* v_geo, co
     count_launch();
     return check_launch("densify_stats_kernel");
 }
+
+// ---------------------------------------------------------------------------------------------
+// Refinement on the device: densify (split / duplicate) + cull, with the Adam-state surgery, as
+// decide -> scan -> map -> gather (GaussianSplattingModel.refinement_after,
+// split_gaussians, dup_gaussians, cull_gaussians, dup_in_optim, remove_from_optim:
+// nerfstudio/models/gaussian_splatting.py:396-546, 333-371).  Output order is the reference's:
+// [kept originals | kept split children, sample-major | kept duplicates].
+// ---------------------------------------------------------------------------------------------
+namespace gg {
+
+constexpr float kSplitShrink = 1.6f;  // size_fac, gaussian_splatting.py:513
+enum : uint8_t { kFlagSplit = 1, kFlagDup = 2, kFlagKeep = 4, kFlagKeepSplit = 8, kFlagKeepDup = 16 };
+
+__device__ __forceinline__ float shrunk_log_scale(float ls) { return logf(expf(ls) / kSplitShrink); }
+
+__global__ void __launch_bounds__(256)
+refine_decide_kernel(int n, const float* __restrict__ xys_grad_norm, const float* __restrict__ vis_counts,
+                     const float* __restrict__ max_2dsize, const float* __restrict__ log_scales,
+                     const float* __restrict__ opacity_logit, const gg_refine_config c, uint8_t* __restrict__ flags,
+                     int32_t* __restrict__ counts) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float ls[3] = {log_scales[3 * i], log_scales[3 * i + 1], log_scales[3 * i + 2]};
+    const float m2d = max_2dsize ? max_2dsize[i] : 0.0f;
+    bool split = false, dup = false;
+    if (c.do_densify) {
+        // :404-418  avg_grad_norm = (xys_grad_norm / vis_counts) * 0.5 * max(W, H)
+        const float avg = (xys_grad_norm[i] / vis_counts[i]) * 0.5f * c.max_dim;
+        const bool high = avg > c.densify_grad_thresh;
+        const float smax = fmaxf(fmaxf(expf(ls[0]), expf(ls[1])), expf(ls[2]));
+        split = smax > c.densify_size_thresh;
+        if (c.split_by_screen) split = split || (m2d > c.split_screen_size);
+        split = split && high;
+        if (split) {  // :513-514 the parent is shrunk in place before the duplicate test reads the scales (:419)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) ls[k] = shrunk_log_scale(ls[k]);
+        }
+        const float smax2 = fmaxf(fmaxf(expf(ls[0]), expf(ls[1])), expf(ls[2]));
+        dup = (smax2 <= c.densify_size_thresh) && high;
+    }
+    bool keep = true, keep_child = true;
+    if (c.do_cull) {  // :466-483 over the concatenated set; children carry the parent's opacity / current scales
+        const float op = 1.0f / (1.0f + expf(-opacity_logit[i]));
+        bool cull = op < c.cull_alpha_thresh;
+        bool cull_child = cull;
+        if (c.cull_by_scale) {
+            const float smax = fmaxf(fmaxf(expf(ls[0]), expf(ls[1])), expf(ls[2]));
+            const bool big = smax > c.cull_scale_thresh;
+            cull = cull || big;
+            cull_child = cull_child || big;
+            if (c.cull_by_screen) cull = cull || (m2d > c.cull_screen_size);  // children start with max_2Dsize 0
+        }
+        keep = !cull;
+        keep_child = !cull_child;
+    }
+    const bool ks = split && keep_child, kd = dup && keep_child;
+    flags[i] = (uint8_t)((split ? kFlagSplit : 0) | (dup ? kFlagDup : 0) | (keep ? kFlagKeep : 0) |
+                         (ks ? kFlagKeepSplit : 0) | (kd ? kFlagKeepDup : 0));
+    counts[i] = keep ? 1 : 0;
+    counts[n + i] = ks ? 1 : 0;
+    counts[2 * n + i] = kd ? 1 : 0;
+    counts[3 * n + i] = split ? 1 : 0;
+}
+
+// source row / role of every output row: role 0 original, 1 split child, 2 duplicate; aux = row of the
+// normal sample the child's position is drawn with
+__global__ void __launch_bounds__(256)
+refine_map_kernel(int n, int samps, const uint8_t* __restrict__ flags, const int32_t* __restrict__ scans,
+                  int n_keep, int n_split_kept, int n_split_all, int32_t* __restrict__ src_row,
+                  uint8_t* __restrict__ role, int32_t* __restrict__ aux) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t f = flags[i];
+    if (f & kFlagKeep) {
+        const int j = scans[i] - 1;
+        src_row[j] = i; role[j] = 0; aux[j] = 0;
+    }
+    if (f & kFlagKeepSplit) {
+        const int r = scans[n + i] - 1, ra = scans[3 * n + i] - 1;
+        for (int s = 0; s < samps; ++s) {
+            const int j = n_keep + s * n_split_kept + r;
+            src_row[j] = i; role[j] = 1; aux[j] = s * n_split_all + ra;
+        }
+    }
+    if (f & kFlagKeepDup) {
+        const int j = n_keep + samps * n_split_kept + scans[2 * n + i] - 1;
+        src_row[j] = i; role[j] = 2; aux[j] = 0;
+    }
+}
+
+struct RefineArrays {
+    int n_arrays;
+    const float* src[GG_REFINE_MAX_ARRAYS];
+    float* dst[GG_REFINE_MAX_ARRAYS];
+    int row[GG_REFINE_MAX_ARRAYS];
+    int kind[GG_REFINE_MAX_ARRAYS];
+};
+
+__global__ void __launch_bounds__(256)
+refine_gather_kernel(long long n_out, const RefineArrays t, const int32_t* __restrict__ src_row,
+                     const uint8_t* __restrict__ role, const int32_t* __restrict__ aux, const uint8_t* __restrict__ flags,
+                     const float* __restrict__ means, const float* __restrict__ log_scales,
+                     const float* __restrict__ quats, const float* __restrict__ samples) {
+    const int a = blockIdx.y;
+    const int row = t.row[a], kind = t.kind[a];
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_out * row) return;
+    const long long j = idx / row;
+    const int e = (int)(idx - j * row);
+    const int i = src_row[j];
+    const int r = role[j];
+    float v = t.src[a][(long long)i * row + e];
+    if (kind == GG_REFINE_MOMENT) {
+        if (r != 0) v = 0.0f;  // dup_in_optim appends zeros (:355-366); survivors keep their moments (:345-346)
+    } else if (kind == GG_REFINE_LOG_SCALES) {
+        if (flags[i] & kFlagSplit) v = shrunk_log_scale(v);  // parent, its children and a duplicate of it (:512-514)
+    } else if (kind == GG_REFINE_MEANS && r == 1) {
+        // :499-507  mean + R(q/|q|) (exp(scale_before_shrink) * z)
+        const float4 q = *reinterpret_cast<const float4*>(quats + 4 * (long long)i);
+        const float inv = 1.0f / sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+        const float w = q.x * inv, x = q.y * inv, y = q.z * inv, z = q.w * inv;
+        const float* smp = samples + 3 * (long long)aux[j];
+        const float s0 = expf(log_scales[3 * (long long)i]) * smp[0];
+        const float s1 = expf(log_scales[3 * (long long)i + 1]) * smp[1];
+        const float s2 = expf(log_scales[3 * (long long)i + 2]) * smp[2];
+        float r0, r1, r2;  // row e of the rotation matrix (same convention as quat_to_rotmat)
+        if (e == 0) { r0 = 1.f - 2.f * (y * y + z * z); r1 = 2.f * (x * y - w * z); r2 = 2.f * (x * z + w * y); }
+        else if (e == 1) { r0 = 2.f * (x * y + w * z); r1 = 1.f - 2.f * (x * x + z * z); r2 = 2.f * (y * z - w * x); }
+        else { r0 = 2.f * (x * z - w * y); r1 = 2.f * (y * z + w * x); r2 = 1.f - 2.f * (x * x + y * y); }
+        v = (r0 * s0 + r1 * s1 + r2 * s2) + v;
+    }
+    t.dst[a][j * row + e] = v;
+}
+
+}  // namespace gg
+
+extern "C" size_t gg_refine_workspace_bytes(int n) {
+    const size_t t = (size_t)(n > 0 ? n : 1);
+    return 256 + ((t + 255) & ~(size_t)255) + 2 * 4 * t * sizeof(int32_t) + 4 * gg_cumsum_workspace_bytes(n) + 1024;
+}
+
+extern "C" int gg_refine_plan(int n, const float* xys_grad_norm, const float* vis_counts, const float* max_2dsize,
+                              const float* log_scales, const float* opacity_logit, const gg_refine_config* cfg,
+                              void* workspace, size_t workspace_bytes, int32_t* totals_host, void* stream) {
+    GG_REQUIRE(n >= 1, "gg_refine_plan: need n >= 1");
+    GG_REQUIRE(cfg && log_scales && opacity_logit && workspace && totals_host, "gg_refine_plan: null pointer");
+    GG_REQUIRE(!cfg->do_densify || (xys_grad_norm && vis_counts), "gg_refine_plan: densify needs the gradient statistics");
+    GG_REQUIRE((!cfg->split_by_screen && !cfg->cull_by_screen) || max_2dsize, "gg_refine_plan: screen-size rules need max_2dsize");
+    GG_REQUIRE(workspace_bytes >= gg_refine_workspace_bytes(n), "gg_refine_plan: workspace too small");
+    GG_REQUIRE(((uintptr_t)workspace & 255) == 0, "gg_refine_plan: workspace must be 256-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char* w = reinterpret_cast<unsigned char*>(workspace);
+    int32_t* totals_dev = reinterpret_cast<int32_t*>(w);
+    uint8_t* flags = w + 256;
+    const size_t t = (size_t)n;
+    int32_t* counts = reinterpret_cast<int32_t*>(w + 256 + ((t + 255) & ~(size_t)255));
+    int32_t* scans = counts + 4 * t;
+    unsigned char* scan_ws = reinterpret_cast<unsigned char*>(scans + 4 * t);
+    scan_ws = reinterpret_cast<unsigned char*>(((uintptr_t)scan_ws + 255) & ~(uintptr_t)255);
+    refine_decide_kernel<<<div_up(n, 256), 256, 0, st>>>(n, xys_grad_norm, vis_counts, max_2dsize, log_scales,
+                                                        opacity_logit, *cfg, flags, counts);
+    count_launch();
+    int rc = check_launch("refine_decide_kernel");
+    if (rc) return rc;
+    const size_t sws = gg_cumsum_workspace_bytes(n);
+    for (int k = 0; k < 4; ++k) {
+        if ((rc = gg_cumsum(n, counts + k * t, scans + k * t, totals_dev + k, scan_ws, sws, stream))) return rc;
+    }
+    GG_CUDA(cudaMemcpyAsync(totals_host, totals_dev, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    return GG_OK;
+}
+
+extern "C" int gg_refine_apply(int n, int n_split_samples, const int32_t* totals, const void* plan_workspace,
+                               int n_arrays, const float* const* src, float* const* dst, const int* row_floats,
+                               const int* kinds, const float* means, const float* log_scales, const float* quats,
+                               const float* samples, void* scratch, size_t scratch_bytes, void* stream) {
+    GG_REQUIRE(n >= 1 && n_split_samples >= 1 && totals && plan_workspace, "gg_refine_apply: bad arguments");
+    GG_REQUIRE(n_arrays >= 1 && n_arrays <= GG_REFINE_MAX_ARRAYS && src && dst && row_floats && kinds,
+               "gg_refine_apply: 1..GG_REFINE_MAX_ARRAYS arrays");
+    GG_REQUIRE(means && log_scales && quats, "gg_refine_apply: null parameter pointer");
+    const long long n_keep = totals[0], n_sk = totals[1], n_dk = totals[2], n_sa = totals[3];
+    GG_REQUIRE(n_keep >= 0 && n_sk >= 0 && n_dk >= 0 && n_sa >= n_sk && n_keep <= n, "gg_refine_apply: inconsistent totals");
+    const long long n_out = n_keep + (long long)n_split_samples * n_sk + n_dk;
+    GG_REQUIRE(n_out < (1ll << 31), "gg_refine_apply: too many Gaussians");
+    GG_REQUIRE(n_sk == 0 || samples, "gg_refine_apply: split children need normal samples");
+    if (n_out == 0) return GG_OK;
+    GG_REQUIRE(scratch && scratch_bytes >= (size_t)n_out * 9 + 512, "gg_refine_apply: scratch too small (9 B per output row + 512)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned char* w = reinterpret_cast<const unsigned char*>(plan_workspace);
+    const uint8_t* flags = w + 256;
+    const size_t t = (size_t)n;
+    const int32_t* scans = reinterpret_cast<const int32_t*>(w + 256 + ((t + 255) & ~(size_t)255)) + 4 * t;
+    unsigned char* s = reinterpret_cast<unsigned char*>(scratch);
+    int32_t* src_row = reinterpret_cast<int32_t*>(s);
+    int32_t* aux = src_row + n_out;
+    uint8_t* role = reinterpret_cast<uint8_t*>(aux + n_out);
+    refine_map_kernel<<<div_up(n, 256), 256, 0, st>>>(n, n_split_samples, flags, scans, (int)n_keep, (int)n_sk, (int)n_sa,
+                                                     src_row, role, aux);
+    count_launch();
+    int rc = check_launch("refine_map_kernel");
+    if (rc) return rc;
+    RefineArrays tab;
+    tab.n_arrays = n_arrays;
+    int max_row = 1;
+    for (int a = 0; a < n_arrays; ++a) {
+        GG_REQUIRE(src[a] && dst[a] && row_floats[a] >= 1, "gg_refine_apply: bad array entry");
+        GG_REQUIRE(kinds[a] >= GG_REFINE_COPY && kinds[a] <= GG_REFINE_LOG_SCALES, "gg_refine_apply: unknown array kind");
+        GG_REQUIRE((kinds[a] != GG_REFINE_MEANS && kinds[a] != GG_REFINE_LOG_SCALES) || row_floats[a] == 3,
+                   "gg_refine_apply: means / log_scales rows are 3 floats");
+        tab.src[a] = src[a]; tab.dst[a] = dst[a]; tab.row[a] = row_floats[a]; tab.kind[a] = kinds[a];
+        if (row_floats[a] > max_row) max_row = row_floats[a];
+    }
+    dim3 grid((unsigned)div_up(n_out * max_row, 256), (unsigned)n_arrays);
+    refine_gather_kernel<<<grid, 256, 0, st>>>(n_out, tab, src_row, role, aux, flags, means, log_scales, quats, samples);
+    count_launch();
+    return check_launch("refine_gather_kernel");
+}

@@ -118,7 +118,10 @@ class FactoredExchange:
         return {"grad_out": go, "defer_sh_grad": True}
 
     def exchange(self, means: torch.Tensor, positions: torch.Tensor, degree: int, degrees_to_use: int,
-                 holder: Optional[dict] = None) -> Dict[str, torch.Tensor]:
+                 holder: Optional[dict] = None, all_positions: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """positions: centres [V,3] of this rank's views.  all_positions: centres [world*V,3] of every
+        rank's views in rank order, when the caller knows them (a shared sampler does) -- saves the small
+        all-gather."""
         if holder is not None and holder.get("v_rgb_views") is not None and \
                 holder["v_rgb_views"].data_ptr() != self.rgb_send.data_ptr():
             self.rgb_send.copy_(holder["v_rgb_views"].view_as(self.rgb_send))
@@ -126,13 +129,20 @@ class FactoredExchange:
         if positions.shape != (self.V, 3):
             raise ValueError(f"expected the centres of {self.V} views, got {tuple(positions.shape)}")
         reduce_work = None
+        if all_positions is not None:
+            if tuple(all_positions.shape) != tuple(self.pos_all.shape):
+                raise ValueError(f"all_positions must be {tuple(self.pos_all.shape)}")
+            self.pos_all.copy_(all_positions)
         if self.on:
-            w_pos = dist.all_gather_into_tensor(self.pos_all, positions, group=self.group, async_op=True)
+            w_pos = None
+            if all_positions is None:
+                w_pos = dist.all_gather_into_tensor(self.pos_all, positions, group=self.group, async_op=True)
             w_rgb = dist.all_gather_into_tensor(self.rgb_all, self.rgb_send, group=self.group, async_op=True)
             reduce_work = self.bucket.all_reduce(async_op=True)
-            w_pos.wait()
+            if w_pos is not None:
+                w_pos.wait()
             w_rgb.wait()
-        else:
+        elif all_positions is None:
             self.pos_all.copy_(positions)
         # rebuilds the SH gradient of ALL views while the all-reduce of the other leaves is in flight
         rec = self._reconstruct

@@ -73,3 +73,103 @@ class DensifyStats:
                       int(img_width), 1 if self.first else 0, self.xys_grad_norm.data_ptr(), self.vis_counts.data_ptr(),
                       self.max_2Dsize.data_ptr(), _lib.stream_ptr(dev))
         self.first = False
+
+
+class RefineConfig(C.Structure):
+    """Mirror of gg_refine_config (include/gg_b200.h)."""
+    _fields_ = [("max_dim", C.c_float), ("densify_grad_thresh", C.c_float), ("densify_size_thresh", C.c_float),
+                ("split_screen_size", C.c_float), ("cull_alpha_thresh", C.c_float), ("cull_scale_thresh", C.c_float),
+                ("cull_screen_size", C.c_float), ("do_densify", C.c_int), ("split_by_screen", C.c_int),
+                ("do_cull", C.c_int), ("cull_by_scale", C.c_int), ("cull_by_screen", C.c_int)]
+
+
+# GaussianSplattingModelConfig defaults (nerfstudio/models/gaussian_splatting.py:113-170)
+REFERENCE_REFINE = dict(warmup_length=500, refine_every=100, cull_alpha_thresh=0.1, cull_scale_thresh=0.5,
+                        reset_alpha_every=30, densify_grad_thresh=0.0002, densify_size_thresh=0.01, n_split_samples=2,
+                        cull_screen_size=0.15, split_screen_size=0.05, stop_screen_size_at=4000, stop_split_at=15000)
+
+
+def refine_schedule(step: int, num_train_data: int, max_dim: int, cfg: Optional[dict] = None) -> Optional[dict]:
+    """Which rules refinement_after applies at `step` (gaussian_splatting.py:396-410, 456, 471-475); None when
+    nothing happens.  The returned dict holds the fields of gg_refine_config plus `reset_opacity`."""
+    c = dict(REFERENCE_REFINE)
+    c.update(cfg or {})
+    if step < c["warmup_length"]:
+        return None
+    reset_interval = c["reset_alpha_every"] * c["refine_every"]
+    past_reset = step % reset_interval > num_train_data + c["refine_every"]
+    return dict(max_dim=float(max_dim), densify_grad_thresh=c["densify_grad_thresh"],
+                densify_size_thresh=c["densify_size_thresh"], split_screen_size=c["split_screen_size"],
+                cull_alpha_thresh=c["cull_alpha_thresh"], cull_scale_thresh=c["cull_scale_thresh"],
+                cull_screen_size=c["cull_screen_size"],
+                do_densify=int(step < c["stop_split_at"] and past_reset),
+                split_by_screen=int(step < c["stop_screen_size_at"]),
+                do_cull=int(past_reset),
+                cull_by_scale=int(step > c["refine_every"] * c["reset_alpha_every"]),
+                cull_by_screen=int(step < c["stop_screen_size_at"]),
+                reset_opacity=bool(step % reset_interval == c["refine_every"]))
+
+
+_ROW_KIND = dict(means=2, log_scales=3)  # GG_REFINE_MEANS / GG_REFINE_LOG_SCALES; everything else copies
+
+
+@torch.no_grad()
+def refine_gaussians(params: Dict[str, torch.Tensor], moments: Optional[Dict[str, tuple]], stats: Optional[DensifyStats],
+                     rules: dict, n_split_samples: int = 2, samples_fn=None):
+    """Densify + cull on the device, in the reference's output order, parameters and Adam moments together.
+
+    params: name -> [N, ...] fp32 CUDA tensors; moments: name -> (exp_avg, exp_avg_sq) like params, or None.
+    rules: fields of gg_refine_config (see refine_schedule).  samples_fn(k) -> [k,3] standard-normal CUDA tensor
+    (default torch.randn); it is called with n_split_samples * (number of split parents), like the reference.
+    Returns (new params, new moments, info).  One host read (the four totals), as the reference has several."""
+    names = [k for k in ("means", "log_scales", "quats", "opacity_logit", "sh_coeffs", "features") if k in params]
+    for k in ("means", "log_scales", "quats", "opacity_logit"):
+        if k not in params:
+            raise _lib.GGError(f"refine_gaussians needs parameter {k}")
+    dev = _lib.require_cuda(*[params[k] for k in names])
+    P = {k: _lib.f32c(params[k].detach()) for k in names}
+    n = P["means"].shape[0]
+    cfg = RefineConfig(**{f: rules[f] for f, _ in RefineConfig._fields_})
+    lib = _lib.load()
+    ws = torch.empty(int(lib.gg_refine_workspace_bytes(n)) + 256, dtype=torch.uint8, device=dev)
+    ws = ws[(-ws.data_ptr()) % 256:]
+    totals = torch.zeros(4, dtype=torch.int32).pin_memory()
+    need_stats = bool(rules["do_densify"])
+    if need_stats and stats is None:
+        raise _lib.GGError("densification needs the DensifyStats of the last refine interval")
+    m2d = stats.max_2Dsize if stats is not None else None
+    with _lib.device_guard(dev):
+        st = _lib.stream_ptr(dev)
+        _lib.call("gg_refine_plan", n, _lib.ptr(stats.xys_grad_norm) if stats is not None else None,
+                  _lib.ptr(stats.vis_counts) if stats is not None else None, _lib.ptr(m2d), _lib.ptr(P["log_scales"]),
+                  _lib.ptr(P["opacity_logit"]), C.byref(cfg), ws.data_ptr(), ws.numel(), totals.data_ptr(), st)
+        torch.cuda.current_stream(dev).synchronize()
+        n_keep, n_sk, n_dk, n_sa = (int(x) for x in totals)
+        n_out = n_keep + n_split_samples * n_sk + n_dk
+        samples = None
+        if n_sa > 0:
+            samples = (samples_fn or (lambda k: torch.randn((k, 3), device=dev)))(n_split_samples * n_sa)
+            samples = _lib.f32c(samples.to(dev))
+        new_p = {k: torch.empty((n_out,) + tuple(P[k].shape[1:]), dtype=torch.float32, device=dev) for k in names}
+        new_m = None
+        src, dst, rows, kinds = [], [], [], []
+        for k in names:
+            src.append(P[k]); dst.append(new_p[k]); rows.append(max(1, P[k][0].numel()) if n else 1)
+            kinds.append(_ROW_KIND.get(k, 0))
+        if moments is not None:
+            new_m = {}
+            for k in names:
+                ea, es = (_lib.f32c(t) for t in moments[k])
+                na, ns = torch.empty_like(new_p[k]), torch.empty_like(new_p[k])
+                new_m[k] = (na, ns)
+                for s_, d_ in ((ea, na), (es, ns)):
+                    src.append(s_); dst.append(d_); rows.append(rows[names.index(k)]); kinds.append(1)
+        if n_out > 0:
+            na_ = len(src)
+            scratch = torch.empty(n_out * 9 + 512, dtype=torch.uint8, device=dev)
+            _lib.call("gg_refine_apply", n, int(n_split_samples), (C.c_int32 * 4)(n_keep, n_sk, n_dk, n_sa), ws.data_ptr(),
+                      na_, (C.c_void_p * na_)(*[t.data_ptr() for t in src]), (C.c_void_p * na_)(*[t.data_ptr() for t in dst]),
+                      (C.c_int * na_)(*rows), (C.c_int * na_)(*kinds), _lib.ptr(P["means"]), _lib.ptr(P["log_scales"]),
+                      _lib.ptr(P["quats"]), _lib.ptr(samples), scratch.data_ptr(), scratch.numel(), st)
+    info = dict(n_in=n, n_out=n_out, n_kept=n_keep, n_split=n_sa, n_split_kept=n_sk, n_dup_kept=n_dk)
+    return new_p, new_m, info

@@ -218,6 +218,45 @@ int gg_densify_stats(long long n, int n_views, const float* v_geo /*[V*n,8]*/, c
                      int img_h, int img_w, int first_call, float* xys_grad_norm, float* vis_counts,
                      float* max_2dsize, void* stream);
 
+/* ---- refinement on the device: densify (split / duplicate) + cull and the Adam-state surgery of
+ * GaussianSplattingModel.refinement_after (nerfstudio/models/gaussian_splatting.py:396-546, 333-371).
+ * gg_refine_plan decides per Gaussian (split, duplicate, and which of {itself, its split children, its duplicate}
+ * survive the cull), scans the counts and copies totals = {kept originals, kept split parents, kept duplicates,
+ * all split parents} to totals_host (pinned; valid once the stream is synchronised).  The output set is
+ * [kept originals | kept split children, sample-major | kept duplicates] -- the reference's order -- with
+ * n_out = totals[0] + n_split_samples * totals[1] + totals[2] rows.  gg_refine_apply gathers every per-Gaussian
+ * array (parameters and Adam moments) into its new [n_out, row] array in one launch; `kinds` says how children
+ * are formed: COPY (parent's row), MOMENT (zeros), MEANS (split children: mean + R(q/|q|)(exp(scale) * z), z =
+ * samples[s * totals[3] + rank among all split parents]), LOG_SCALES (split parents and their children:
+ * log(exp(s) / 1.6)).  means / log_scales / quats are the OLD parameter arrays. */
+typedef struct {
+    float max_dim;              /* max(W, H) of the last rendered image (:415) */
+    float densify_grad_thresh;  /* config.densify_grad_thresh */
+    float densify_size_thresh;  /* config.densify_size_thresh */
+    float split_screen_size;    /* config.split_screen_size (used when split_by_screen) */
+    float cull_alpha_thresh;    /* config.cull_alpha_thresh */
+    float cull_scale_thresh;    /* config.cull_scale_thresh (used when cull_by_scale) */
+    float cull_screen_size;     /* config.cull_screen_size (used when cull_by_screen) */
+    int do_densify;             /* step < stop_split_at and past the post-reset window (:404-408) */
+    int split_by_screen;        /* step < stop_screen_size_at (:421) */
+    int do_cull;                /* :456 */
+    int cull_by_scale;          /* step > refine_every * reset_alpha_every (:471) */
+    int cull_by_screen;         /* ... and step < stop_screen_size_at (:475) */
+} gg_refine_config;
+#define GG_REFINE_MAX_ARRAYS 24
+#define GG_REFINE_COPY 0
+#define GG_REFINE_MOMENT 1
+#define GG_REFINE_MEANS 2
+#define GG_REFINE_LOG_SCALES 3
+size_t gg_refine_workspace_bytes(int n);
+int gg_refine_plan(int n, const float* xys_grad_norm, const float* vis_counts, const float* max_2dsize /*nullable*/,
+                   const float* log_scales, const float* opacity_logit, const gg_refine_config* cfg, void* workspace,
+                   size_t workspace_bytes, int32_t* totals_host /*[4]*/, void* stream);
+int gg_refine_apply(int n, int n_split_samples, const int32_t* totals /*[4] host*/, const void* plan_workspace,
+                    int n_arrays, const float* const* src, float* const* dst, const int* row_floats, const int* kinds,
+                    const float* means, const float* log_scales, const float* quats, const float* samples,
+                    void* scratch /* 9 B per output row + 512 */, size_t scratch_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

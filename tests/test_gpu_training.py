@@ -4,6 +4,8 @@ GaussianSplattingModel.after_train (nerfstudio/models/gaussian_splatting.py:373-
 import pytest
 import torch
 
+from gaussiangrasper_b200 import scenes
+
 pytestmark = pytest.mark.gpu
 
 
@@ -107,3 +109,72 @@ def test_training_step_decreases_loss():
         losses.append(float(loss))
     assert losses[-1] < 0.5 * losses[0], losses
     assert float(stats.vis_counts.max()) >= 12
+
+
+def _refine_inputs(n, D, seed):
+    g = torch.Generator().manual_seed(seed)
+    sc = scenes.random_scene(n, feature_dim=D, seed=seed)
+    P = {k: sc[k].clone() for k in ("means", "log_scales", "quats", "opacity_logit", "sh_coeffs", "features")}
+    P["opacity_logit"] = P["opacity_logit"].reshape(-1)
+    # scales around the 0.01 split threshold, a few huge ones; opacities around the 0.1 cull threshold
+    P["log_scales"] = torch.log(torch.rand((n, 3), generator=g) * 0.03 + 0.002)
+    P["log_scales"][::97] = torch.log(torch.tensor(0.9))
+    P["opacity_logit"] = torch.logit(torch.rand(n, generator=g) * 0.5 + 0.01)
+    M = {k: (torch.randn(v.shape, generator=g), torch.rand(v.shape, generator=g)) for k, v in P.items()}
+    stats = dict(xys_grad_norm=torch.rand(n, generator=g) * 4e-6 * 3, vis_counts=torch.randint(1, 4, (n,), generator=g).float(),
+                 max_2dsize=torch.rand(n, generator=g) * 0.2)
+    return P, M, stats
+
+
+@pytest.mark.parametrize("rules_kw", [dict(), dict(do_densify=0), dict(do_cull=0), dict(split_by_screen=0, cull_by_screen=0),
+                                      dict(cull_by_scale=0)])
+def test_refine_matches_reference_flow(rules_kw):
+    """Densify + cull + Adam-state surgery on the device vs the line-by-line restatement of
+    refinement_after / split_gaussians / dup_gaussians / cull_gaussians (oracle/refine_oracle.py): same
+    survivors in the same order, copied rows bit-identical, new means / shrunk scales within 1e-6."""
+    from gaussiangrasper_b200.training import DensifyStats, refine_gaussians
+    from oracle import refine_oracle
+    dev = torch.device("cuda:0")
+    n, D = 20_000, 5
+    P, M, st = _refine_inputs(n, D, 12)
+    rules = dict(max_dim=640.0, densify_grad_thresh=0.0002, densify_size_thresh=0.01, split_screen_size=0.05,
+                 cull_alpha_thresh=0.1, cull_scale_thresh=0.5, cull_screen_size=0.15, do_densify=1, split_by_screen=1,
+                 do_cull=1, cull_by_scale=1, cull_by_screen=1)
+    rules.update(rules_kw)
+    g = torch.Generator().manual_seed(5)
+    z_all = torch.randn((2 * n, 3), generator=g)
+    want_p, want_m, info = refine_oracle.refine(P, M, st["xys_grad_norm"], st["vis_counts"], st["max_2dsize"], rules,
+                                                lambda k: z_all[:k])
+    assert info["fragile"] == 0, "pick another seed: a decision sits on a threshold"
+    ds = DensifyStats(n, dev)
+    ds.xys_grad_norm, ds.vis_counts, ds.max_2Dsize = (st[k].to(dev) for k in ("xys_grad_norm", "vis_counts", "max_2dsize"))
+    got_p, got_m, ginfo = refine_gaussians({k: v.to(dev) for k, v in P.items()},
+                                           {k: (a.to(dev), b.to(dev)) for k, (a, b) in M.items()}, ds, rules,
+                                           samples_fn=lambda k: z_all[:k].to(dev))
+    assert ginfo["n_out"] == info["n_out"] and ginfo["n_in"] == n
+    if rules["do_densify"] and rules["do_cull"]:
+        assert ginfo["n_split"] > 100 and ginfo["n_dup_kept"] > 100 and info["n_culled"] > 100  # the case is not trivial
+    for k in refine_oracle.PARAMS:
+        a, b = got_p[k].cpu(), want_p[k]
+        assert a.shape == b.shape, k
+        if k in ("means", "log_scales"):
+            assert torch.allclose(a, b, rtol=2e-6, atol=2e-6), k
+            same = (a == b).all(dim=-1)
+            assert int(same.sum()) >= ginfo["n_kept"] - ginfo["n_split"]  # untouched rows are copies
+        else:
+            assert torch.equal(a, b), k
+        for j in range(2):
+            assert torch.equal(got_m[k][j].cpu(), want_m[k][j]), (k, j)
+
+
+def test_refine_everything_culled_and_no_moments():
+    from gaussiangrasper_b200.training import refine_gaussians, refine_schedule
+    dev = torch.device("cuda:0")
+    P, _, _ = _refine_inputs(300, 3, 2)
+    P["opacity_logit"][:] = -10.0
+    rules = refine_schedule(3300, 10, 640)  # past warm-up and the post-reset window: cull is on
+    assert rules["do_cull"] and rules["do_densify"] and not rules["reset_opacity"]
+    rules["do_densify"] = 0
+    newp, newm, info = refine_gaussians({k: v.to(dev) for k, v in P.items()}, None, None, rules)
+    assert info["n_out"] == 0 and newm is None and newp["sh_coeffs"].shape == (0, 25, 3)
+    assert refine_schedule(100, 10, 640) is None and refine_schedule(3100, 10, 640)["reset_opacity"]
