@@ -1,0 +1,79 @@
+"""CPU tests of the host logic behind the refinement step (no GPU): the schedule of
+GaussianSplattingModel.refinement_after (nerfstudio/models/gaussian_splatting.py:396-410, 456, 471-475, 458-464)
+and the layout of the config struct shared with the C ABI."""
+import ctypes
+import os
+import subprocess
+import sys
+
+import torch
+
+from gaussiangrasper_b200 import training
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _reference_conditions(step, num_train_data, c):
+    """The reference's own boolean expressions, spelled out."""
+    if step < c["warmup_length"]:
+        return None
+    reset_interval = c["reset_alpha_every"] * c["refine_every"]
+    densify = step < c["stop_split_at"] and step % reset_interval > num_train_data + c["refine_every"]
+    cull = step % reset_interval > num_train_data + c["refine_every"]
+    return dict(do_densify=int(densify), do_cull=int(cull), split_by_screen=int(step < c["stop_screen_size_at"]),
+                cull_by_scale=int(step > c["refine_every"] * c["reset_alpha_every"]),
+                cull_by_screen=int(step < c["stop_screen_size_at"]),
+                reset_opacity=step % reset_interval == c["refine_every"])
+
+
+def test_refine_schedule_follows_the_reference_conditions():
+    c = training.REFERENCE_REFINE
+    for num_train_data in (10, 150):
+        for step in list(range(0, 20000, 100)) + [499, 500, 3001, 3100, 3111, 14999, 15000]:
+            want = _reference_conditions(step, num_train_data, c)
+            got = training.refine_schedule(step, num_train_data, 640)
+            if want is None:
+                assert got is None, step
+                continue
+            for k, v in want.items():
+                assert got[k] == v, (step, k)
+            assert got["max_dim"] == 640.0 and got["cull_alpha_thresh"] == c["cull_alpha_thresh"]
+    # overrides
+    assert training.refine_schedule(600, 10, 640, dict(warmup_length=1000)) is None
+
+
+def test_refine_config_struct_matches_the_header(tmp_path):
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "gg_b200.h"\n'
+                   'int main(void){printf("%zu %zu %zu", sizeof(gg_refine_config), offsetof(gg_refine_config, do_densify),'
+                   ' offsetof(gg_refine_config, cull_by_screen)); return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    size, off_a, off_b = (int(x) for x in subprocess.check_output([str(exe)]).split())
+    assert ctypes.sizeof(training.RefineConfig) == size
+    assert training.RefineConfig.do_densify.offset == off_a and training.RefineConfig.cull_by_screen.offset == off_b
+    assert [f for f, _ in training.RefineConfig._fields_][:7] == ["max_dim", "densify_grad_thresh", "densify_size_thresh",
+                                                                 "split_screen_size", "cull_alpha_thresh",
+                                                                 "cull_scale_thresh", "cull_screen_size"]
+
+
+def test_refine_oracle_counts_are_consistent():
+    """The restatement itself: sizes add up and the Adam moments follow the parameters."""
+    from oracle import refine_oracle
+    g = torch.Generator().manual_seed(0)
+    n = 500
+    P = dict(means=torch.randn(n, 3, generator=g), log_scales=torch.log(torch.rand(n, 3, generator=g) * 0.03 + 0.002),
+             quats=torch.randn(n, 4, generator=g), opacity_logit=torch.randn(n, generator=g),
+             sh_coeffs=torch.randn(n, 4, 3, generator=g), features=torch.randn(n, 2, generator=g))
+    M = {k: (torch.ones_like(v), torch.ones_like(v) * 2) for k, v in P.items()}
+    rules = dict(max_dim=640.0, densify_grad_thresh=0.0002, densify_size_thresh=0.01, split_screen_size=0.05,
+                 cull_alpha_thresh=0.1, cull_scale_thresh=0.5, cull_screen_size=0.15, do_densify=1, split_by_screen=1,
+                 do_cull=0, cull_by_scale=0, cull_by_screen=0)
+    p, m, info = refine_oracle.refine(P, M, torch.rand(n, generator=g) * 1e-5, torch.ones(n), torch.rand(n, generator=g) * 0.2,
+                                      rules, lambda k: torch.zeros(k, 3))
+    assert info["n_out"] == info["n_cat"] > n and p["means"].shape[0] == info["n_out"]
+    assert torch.equal(p["quats"][:n], P["quats"])                      # originals first, untouched
+    assert float(m["means"][0][:n].min()) == 1.0 and float(m["means"][0][n:].abs().max()) == 0.0   # children: zero moments
+    # zero samples: split children sit on their parent's mean
+    new_means = p["means"][n:]
+    assert all(bool((P["means"] == r).all(dim=-1).any()) for r in new_means[:20])
