@@ -174,7 +174,9 @@ def test_refine_everything_culled_and_no_moments():
     P["opacity_logit"][:] = -10.0
     rules = refine_schedule(3300, 10, 640)  # past warm-up and the post-reset window: cull is on
     assert rules["do_cull"] and rules["do_densify"] and not rules["reset_opacity"]
-    rules["do_densify"] = 0
+    rules.update(do_densify=0, split_by_screen=0, cull_by_screen=0)   # no statistics handed in
+    with pytest.raises(Exception):
+        refine_gaussians({k: v.to(dev) for k, v in P.items()}, None, None, dict(rules, cull_by_screen=1))
     newp, newm, info = refine_gaussians({k: v.to(dev) for k, v in P.items()}, None, None, rules)
     assert info["n_out"] == 0 and newm is None and newp["sh_coeffs"].shape == (0, 25, 3)
     assert refine_schedule(100, 10, 640) is None and refine_schedule(3100, 10, 640)["reset_opacity"]
