@@ -146,6 +146,14 @@ def sample_tiles(ranges, count):
     return pick.tolist(), float(lens.sum() / lens[pick].sum())
 
 
+def cpu_sample_size(sc, cam, D, threads, budget_s):
+    """Number of tiles whose CPU blend takes about `budget_s` seconds (from an 8-tile probe), and the tile total."""
+    cpu_reference_step(sc, cam, D, 8, threads)       # first call pays thread-pool start-up and lazy initialisation
+    tg, tb, scale, ns, nt = cpu_reference_step(sc, cam, D, 8, threads)
+    full = max(tb * scale, 1e-6)                    # estimated blend time of the whole frame
+    return int(min(nt, max(8, round(nt * budget_s / full)))), nt
+
+
 def run_reference(args):
     from gaussiangrasper_b200 import scenes
     rank = int(os.environ.get("RANK", "0"))
@@ -156,8 +164,10 @@ def run_reference(args):
     sc = scenes.random_scene(cfg["n"], feature_dim=cfg["D"], seed=1235)
     cam = scenes.orbit_cameras(1, cfg["W"], cfg["H"])[0]
     times = []
+    # bounded sample per step: the whole run (warm-up + steps) stays within ~3 minutes, one step within ~12 s
+    n_sample, _ = cpu_sample_size(sc, cam, cfg["D"], threads, min(12.0, 170.0 / max(1, args.warmup + args.steps)))
     for s in range(args.warmup + args.steps):
-        tg, tb, scale, ns, nt = cpu_reference_step(sc, cam, cfg["D"], 8, threads)
+        tg, tb, scale, ns, nt = cpu_reference_step(sc, cam, cfg["D"], n_sample, threads)
         if s >= args.warmup:
             times.append(tg + tb * scale)
     t = sum(times) / len(times)
@@ -468,7 +478,8 @@ def run_ours(args):
         threads = os.cpu_count() or 1
         sc_cpu = {k: sc[k] for k in names}
         cam0 = cams[0]
-        tg, tb, scale, ns, nt = cpu_reference_step(sc_cpu, cam0, D, 8, threads)
+        n_sample, _ = cpu_sample_size(sc_cpu, cam0, D, threads, 12.0)   # ~12 s of CPU blend work
+        tg, tb, scale, ns, nt = cpu_reference_step(sc_cpu, cam0, D, n_sample, threads)
         t_full = tg + tb * scale
         cpu = {"value": (W * H / 1e6) / t_full, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": (f"torch-CPU port of the reference maths, 1 step: SH+projection+binning fwd+bwd of all {n} "
