@@ -17,6 +17,7 @@ struct AdamArgs {
     int n_segments;
     float* param[kMaxSegments];
     long long offset[kMaxSegments + 1];  // offsets into the flat buffers; offset[n_segments] = total
+    long long count[kMaxSegments];       // elements of each segment (segments may be padded apart)
     float step_size[kMaxSegments];       // lr / (1 - beta1^t)
     float beta1, beta2, eps, inv_sqrt_bc2;
 };
@@ -33,6 +34,7 @@ adam_kernel(const AdamArgs a, const float* __restrict__ grad, float* __restrict_
 #pragma unroll
         for (int s = 1; s < kMaxSegments; ++s)
             if (s < a.n_segments && i >= a.offset[s]) seg = s;
+        if (i - a.offset[seg] >= a.count[seg]) continue;  // alignment padding between two segments
         const float g = grad[i];
         const float m = a.beta1 * exp_avg[i] + (1.0f - a.beta1) * g;
         const float v = a.beta2 * exp_avg_sq[i] + (1.0f - a.beta2) * g * g;
@@ -90,10 +92,11 @@ extern "C" int gg_adam_step(int n_segments, float* const* params, const long lon
         GG_REQUIRE(params[s] && counts[s] >= 0 && offsets[s] >= end, "gg_adam_step: segments must be ordered, disjoint");
         a.param[s] = params[s];
         a.offset[s] = offsets[s];
+        a.count[s] = counts[s];
         a.step_size[s] = (float)((double)lrs[s] / bc1);
         end = offsets[s] + counts[s];
-        if (s + 1 < n_segments) GG_REQUIRE(offsets[s + 1] == end, "gg_adam_step: segments must tile the flat buffer");
     }
+    for (int s = n_segments; s < kMaxSegments; ++s) a.count[s] = 0;
     a.offset[n_segments] = end;
     for (int s = n_segments + 1; s <= kMaxSegments; ++s) a.offset[s] = end;
     a.beta1 = beta1; a.beta2 = beta2; a.eps = eps;

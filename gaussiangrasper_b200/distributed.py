@@ -36,8 +36,9 @@ def owner_of_view(view: int, world: int) -> int:
 class GradientBucket:
     """One flat fp32 buffer holding every leaf gradient, all-reduced in a single collective.
 
-    Layout: parameters in PARAM_ORDER, each flattened row-major; N x (3+3+4+1+3K+D) floats
-    (408 MB at N = 1M, K = 25, D = 16)."""
+    Layout: parameters in PARAM_ORDER, each flattened row-major and starting on a 16-byte boundary;
+    N x (3+3+4+1+3K+D) floats of payload (408 MB at N = 1M, K = 25, D = 16) plus at most 3 padding
+    floats per segment (they stay zero)."""
 
     def __init__(self, params: Dict[str, torch.Tensor], group: Optional[dist.ProcessGroup] = None):
         self.names = [k for k in PARAM_ORDER if k in params]
@@ -49,9 +50,11 @@ class GradientBucket:
         self.offsets = {}
         off = 0
         for k in self.names:
+            off = (off + 3) // 4 * 4   # every segment starts 16-byte aligned (the backward stores rows in bulk)
             self.offsets[k] = off
             off += self.sizes[k]
         self.numel = off
+        self.payload = sum(self.sizes.values())
         p0 = params[self.names[0]]
         self.flat = torch.zeros(off, dtype=torch.float32, device=p0.device)
         self.group = group

@@ -52,6 +52,38 @@ class FusedAdam:
                       _lib.stream_ptr(dev))
 
 
+    def moments(self) -> Dict[str, tuple]:
+        """name -> (exp_avg, exp_avg_sq) views shaped like the parameters (what refine_gaussians takes)."""
+        b = self.bucket
+        out = {}
+        for k in b.names:
+            o, n = b.offsets[k], b.sizes[k]
+            out[k] = (self.exp_avg[o:o + n].view(b.shapes[k]), self.exp_avg_sq[o:o + n].view(b.shapes[k]))
+        return out
+
+    @torch.no_grad()
+    def rebuild(self, params: Dict[str, torch.Tensor], moments: Optional[Dict[str, tuple]] = None) -> None:
+        """Adopt a refined parameter set (refine_gaussians): new bucket, the given moments (zeros if None).
+        The step count is kept, as the reference's surgery keeps each optimizer's `step`."""
+        self.params = params
+        self.bucket = GradientBucket(params, self.bucket.group)
+        self.exp_avg = torch.zeros_like(self.bucket.flat)
+        self.exp_avg_sq = torch.zeros_like(self.bucket.flat)
+        if moments is not None:
+            for k, (ea, es) in self.moments().items():
+                ea.copy_(moments[k][0].reshape(ea.shape))
+                es.copy_(moments[k][1].reshape(es.shape))
+
+    @torch.no_grad()
+    def reset_opacity(self, cull_alpha_thresh: float = 0.1) -> None:
+        """gaussian_splatting.py:458-464: opacities = logit(0.8 * cull_alpha_thresh), opacity moments cleared."""
+        value = torch.logit(torch.tensor(cull_alpha_thresh * 0.8)).item()
+        self.params["opacity_logit"].fill_(value)
+        ea, es = self.moments()["opacity_logit"]
+        ea.zero_()
+        es.zero_()
+
+
 class DensifyStats:
     """xys_grad_norm / vis_counts / max_2Dsize of gaussian_splatting.py:373-393, fed from the holder of
     render_views after backward (v_geo columns 0..1 are d loss / d xys)."""

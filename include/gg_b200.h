@@ -204,7 +204,8 @@ int gg_sh_grad_from_views(int n, int n_views, int degree, int degrees_to_use, co
 
 /* ---- next rows: the streaming steps directly behind the backward -----------------
  * gg_adam_step: fused torch.optim.Adam (no amsgrad / weight decay) over a flat gradient buffer that
- * is tiled by up to 8 segments, each with its own parameter tensor and learning rate (replaces the
+ * holds up to 8 ordered, disjoint segments (padding between them is skipped), each with its own parameter
+ * tensor and learning rate (replaces the
  * reference's per-group optimizers, method_configs.py:618-664).  params/offsets/counts/lrs are HOST
  * arrays of n_segments entries; `step` is the 1-based update count used for the bias corrections. */
 int gg_adam_step(int n_segments, float* const* params, const long long* offsets, const long long* counts,

@@ -57,7 +57,7 @@ def _worker(rank, world, port, n_views, out):
             for k, g in _per_view_grad(params, v).items():
                 params[k].grad += g
         bucket = ggd.all_reduce_gradients(params)
-        assert bucket.numel == sum(p.numel() for p in params.values())
+        assert bucket.payload == sum(p.numel() for p in params.values()) <= bucket.numel
         # a second step reuses the persistent flat buffer
         ggd.all_reduce_gradients({k: p for k, p in params.items()}, bucket)
         if rank == 0:
@@ -81,7 +81,8 @@ def test_gradient_allreduce_two_ranks_equals_sum_over_views(tmp_path):
 def test_bucket_layout_single_process():
     params = _make_params(n=7, D=3, K=4)
     b = ggd.GradientBucket(params)
-    assert b.numel == 7 * (3 + 3 + 4 + 1 + 12 + 3)
+    assert b.payload == 7 * (3 + 3 + 4 + 1 + 12 + 3) <= b.numel < b.payload + 4 * 6
+    assert all(o % 4 == 0 for o in b.offsets.values())
     grads = {k: torch.full_like(p, i + 1.0) for i, (k, p) in enumerate(params.items())}
     grads["quats"] = None
     flat = b.pack(grads)
@@ -163,7 +164,7 @@ def test_factored_exchange_single_process_is_local():
     params = _make_params(n=9, D=2, K=4)
     ex = ggd.FactoredExchange(params, 3, reconstruct=_torch_sh_rebuild)
     h = ex.holder()
-    assert h["grad_out"]["v_rgb_views"].shape == (3, 9, 3) and ex.bucket.numel == 9 * (3 + 3 + 4 + 1 + 2)
+    assert h["grad_out"]["v_rgb_views"].shape == (3, 9, 3) and ex.bucket.payload == 9 * (3 + 3 + 4 + 1 + 2)
     h["grad_out"]["v_rgb_views"].copy_(torch.ones(3, 9, 3))
     g = ex.exchange(params["means"], torch.zeros(3, 3) + torch.arange(3.0)[:, None] + 5.0, 1, 1, h)
     assert g["sh_coeffs"].shape == (9, 4, 3) and torch.isfinite(g["sh_coeffs"]).all()

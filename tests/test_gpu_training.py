@@ -180,3 +180,57 @@ def test_refine_everything_culled_and_no_moments():
     newp, newm, info = refine_gaussians({k: v.to(dev) for k, v in P.items()}, None, None, rules)
     assert info["n_out"] == 0 and newm is None and newp["sh_coeffs"].shape == (0, 25, 3)
     assert refine_schedule(100, 10, 640) is None and refine_schedule(3100, 10, 640)["reset_opacity"]
+
+
+def test_training_loop_with_refinement():
+    """render -> loss -> backward -> fused Adam -> statistics, a refinement (split / duplicate / cull with the
+    optimizer state carried over) in the middle, then more steps on the refined set."""
+    from gaussiangrasper_b200.render import ViewBatch, render_views
+    from gaussiangrasper_b200.training import DensifyStats, FusedAdam, refine_gaussians
+    dev = torch.device("cuda:0")
+    n, W, H, D = 3000, 96, 64, 4
+    sc = scenes.random_scene(n, feature_dim=D, seed=21)
+    sc["log_scales"] = sc["log_scales"] + 0.8
+    names = ("means", "log_scales", "quats", "opacity_logit", "sh_coeffs", "features")
+    P = {k: sc[k].to(dev).clone().contiguous().requires_grad_(True) for k in names}
+    cams = scenes.orbit_cameras(2, W, H, total=6)
+    vb = ViewBatch.from_cameras(cams, dev)
+    target = torch.rand((2, H, W, 7 + D), generator=torch.Generator().manual_seed(0)).to(dev)
+    opt = FusedAdam(P)
+    stats = DensifyStats(n, dev)
+
+    def run(steps):
+        losses = []
+        for _ in range(steps):
+            holder = {"grad_out": opt.bucket.unpack()}
+            out = render_views(*(P[k] for k in names), vb, holder=holder)
+            loss = ((out["image"][..., :7 + D] - target) ** 2).mean()
+            loss.backward()
+            stats.update(holder["v_geo"], holder["radii"], H, W)
+            opt.step()
+            for p in P.values():
+                p.grad = None
+            losses.append(float(loss.detach()))
+        return losses
+
+    first = run(6)
+    rules = dict(max_dim=float(max(W, H)), densify_grad_thresh=1e-7, densify_size_thresh=0.05, split_screen_size=0.05,
+                 cull_alpha_thresh=0.1, cull_scale_thresh=0.5, cull_screen_size=0.15, do_densify=1, split_by_screen=1,
+                 do_cull=1, cull_by_scale=0, cull_by_screen=0)
+    new_p, new_m, info = refine_gaussians({k: P[k].detach() for k in names}, opt.moments(), stats, rules)
+    assert info["n_split"] > 0 and info["n_dup_kept"] > 0 and info["n_out"] != n
+    n2 = info["n_out"]
+    assert new_p["opacity_logit"].shape == (n2, 1) and new_p["sh_coeffs"].shape == (n2, 25, 3)
+    P = {k: new_p[k].requires_grad_(True) for k in names}
+    opt.rebuild(P, new_m)
+    assert opt.bucket.payload == sum(p.numel() for p in P.values()) <= opt.exp_avg.numel() and opt.t == 6
+    # survivors kept their first moments, children start from zero
+    ea = opt.moments()["means"][0]
+    assert float(ea[:info["n_kept"]].abs().max()) > 0 and float(ea[info["n_kept"]:].abs().max()) == 0.0
+    stats = DensifyStats(n2, dev)
+    second = run(6)
+    assert all(torch.isfinite(torch.tensor(first + second)))
+    assert second[-1] < first[0]
+    opt.reset_opacity(0.1)
+    assert torch.allclose(P["opacity_logit"].detach(), torch.full_like(P["opacity_logit"], float(torch.logit(torch.tensor(0.08)))))
+    assert float(opt.moments()["opacity_logit"][1].abs().max()) == 0.0
