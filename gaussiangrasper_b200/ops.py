@@ -33,7 +33,6 @@ class _Workspace:
         self.ids = None
         self.keys_sorted = None
         self.order_ws = None
-        self.depth = None
         self.begin = None
         self.finish = None
         self.total = torch.zeros(1, dtype=torch.int32, device=device)
@@ -64,14 +63,6 @@ class _Workspace:
         if self.finish is None or self.finish.numel() < need:
             self.finish = torch.zeros(int(need * 1.5) + 4096, dtype=torch.uint8, device=self.device)
         return self.finish
-
-    def depth_buffers(self, total):
-        if self.depth is None or self.depth[0].numel() < total:
-            cap = int(total * 1.25) + 1024
-            i64 = lambda: torch.empty(cap, dtype=torch.int64, device=self.device)
-            i32 = lambda: torch.empty(cap, dtype=torch.int32, device=self.device)
-            self.depth = (i64(), i32(), i64(), i32(), i32())   # keys, rows, keys_sorted, order, counts
-        return self.depth
 
     def key_buffers(self, m):
         if self.keys is None or self.keys.numel() < m:
