@@ -203,22 +203,41 @@ radix_hist_kernel(const uint64_t* __restrict__ keys, long long m, const DigitPla
     const int lane = threadIdx.x & 31;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long rounds = (m + stride - 1) / stride;
-    for (long long r = 0; r < rounds; ++r) {
-        const long long i = r * stride + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-        const bool valid = i < m;
-        const unsigned active = __ballot_sync(0xffffffffu, valid);
-        if (!valid) continue;
-        const uint64_t k = __ldg(keys + i);
-        const int leader = __ffs(active) - 1;
-        const uint32_t pop = (uint32_t)__popc(active);
-        for (int p = 0; p < passes; ++p) {
-            const uint32_t d = (uint32_t)(k >> plan.shift[p]) & plan.mask[p];
-            int same;
-            __match_all_sync(active, d, &same);
-            if (same) {
-                if (lane == leader) atomicAdd(&sh[p * kRadix + d], pop);
-            } else {
-                atomicAdd(&sh[p * kRadix + d], 1u);
+    // kHistBatch independent loads are in flight before the first key is used: the warp votes and the
+    // shared-memory atomics below keep the compiler from overlapping the loads of successive rounds,
+    // and one exposed memory latency per key is what a round would cost otherwise
+    constexpr int kHistBatch = 8;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long long r0 = 0; r0 < rounds; r0 += kHistBatch) {
+        uint64_t kb[kHistBatch];
+        bool vb[kHistBatch];
+#pragma unroll
+        for (int j = 0; j < kHistBatch; ++j) {
+            const long long i = (r0 + j) * stride + tid;
+            vb[j] = (r0 + j < rounds) && i < m;
+            kb[j] = vb[j] ? __ldg(keys + i) : 0ull;
+        }
+#pragma unroll
+        for (int j = 0; j < kHistBatch; ++j) {
+            const bool valid = vb[j];
+            const unsigned active = __ballot_sync(0xffffffffu, valid);
+            if (valid) {
+                const uint64_t k = kb[j];
+                const int leader = __ffs(active) - 1;
+                const uint32_t pop = (uint32_t)__popc(active);
+#pragma unroll
+                for (int p = 0; p < kMaxPasses; ++p) {  // unrolled: the plan is indexed statically
+                    if (p < passes) {
+                        const uint32_t d = (uint32_t)(k >> plan.shift[p]) & plan.mask[p];
+                        int same;
+                        __match_all_sync(active, d, &same);
+                        if (same) {
+                            if (lane == leader) atomicAdd(&sh[p * kRadix + d], pop);
+                        } else {
+                            atomicAdd(&sh[p * kRadix + d], 1u);
+                        }
+                    }
+                }
             }
         }
     }
