@@ -77,3 +77,32 @@ def test_refine_oracle_counts_are_consistent():
     # zero samples: split children sit on their parent's mean
     new_means = p["means"][n:]
     assert all(bool((P["means"] == r).all(dim=-1).any()) for r in new_means[:20])
+
+
+def test_reference_checkpoint_round_trip(tmp_path):
+    """Parameter names / shapes of a reference checkpoint (trainer.py:427-456, gaussian_splatting.py:300-312)."""
+    from gaussiangrasper_b200 import checkpoint
+    g = torch.Generator().manual_seed(0)
+    n = 17
+    model = {"_model.means": torch.randn(n, 3, generator=g), "_model.scales": torch.randn(n, 3, generator=g),
+             "_model.quats": torch.randn(n, 4, generator=g), "_model.opacities": torch.randn(n, 1, generator=g),
+             "_model.colors_all": torch.randn(n, 25, 3, generator=g), "_model.feature": torch.randn(n, 32, generator=g),
+             "_model.camera_optimizer.pose_adjustment": torch.zeros(5, 6), "_model.back_color": torch.zeros(35)}
+    path = str(tmp_path / "step-000000100.ckpt")
+    torch.save({"step": 100, "pipeline": model, "optimizers": {}, "schedulers": {}, "scalers": {}}, path)
+    P = checkpoint.load_reference_checkpoint(path)
+    assert set(P) == {"means", "log_scales", "quats", "opacity_logit", "sh_coeffs", "features"}
+    assert torch.equal(P["log_scales"], model["_model.scales"]) and P["opacity_logit"].shape == (n, 1)
+    assert P["sh_coeffs"].shape == (n, 25, 3) and P["features"].shape == (n, 32)
+    back = checkpoint.reference_state_dict(P)
+    for k in ("means", "scales", "quats", "opacities", "colors_all", "feature"):
+        assert torch.equal(back["_model." + k], model["_model." + k]), k
+    # the bare model state dict works too; a broken one is refused
+    assert torch.equal(checkpoint.params_from_reference({k[7:]: v for k, v in model.items()})["means"], model["_model.means"])
+    bad = dict(model); bad["_model.quats"] = torch.zeros(n, 3)
+    import pytest
+    with pytest.raises(ValueError):
+        checkpoint.params_from_reference(bad)
+    del bad["_model.quats"]
+    with pytest.raises(KeyError):
+        checkpoint.params_from_reference(bad)
