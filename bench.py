@@ -223,6 +223,7 @@ def run_ours(args):
     # views are rendered `chunk` at a time (one projection + one sort + one blend launch per chunk)
     chunks = [ViewBatch.from_cameras(cams[i:i + chunk], dev) for i in range(0, V, chunk)]
     from gaussiangrasper_b200.distributed import FactoredExchange, GradientBucket
+    from gaussiangrasper_b200.training import pixel_loss
     from gaussiangrasper_b200 import ops as _ops
     sh_degree = _ops.sh_degree_from_bases(P["sh_coeffs"].shape[1])
     # gradient exchange of a multi-GPU training step: SH gradient as per-view factors (all-gather) + one
@@ -369,11 +370,10 @@ def run_ours(args):
             if cfg["backward"]:
                 main.wait_event(pf["ready"][q & 1])
                 img = out["image"]
-                diff = img.detach() - target_dev[q & 1][:nv]                # L2 loss against the host-fed targets
-                pf["consumed"][q & 1] = main.record_event()
+                l, grad = pixel_loss(img, target_dev[q & 1][:nv], "l2")    # L2 loss against the host-fed targets:
+                pf["consumed"][q & 1] = main.record_event()                # loss and gradient in one kernel
                 pf["ready"][q & 1] = None
-                l = (diff * diff).mean()
-                img.backward(diff * (2.0 / diff.numel()))
+                img.backward(grad)
             else:
                 l = out["alpha"].mean()
             loss = l if loss is None else loss + l

@@ -338,3 +338,73 @@ extern "C" int gg_refine_apply(int n, int n_split_samples, const int32_t* totals
     count_launch();
     return check_launch("refine_gather_kernel");
 }
+
+// ---------------------------------------------------------------------------------------------
+// Per-pixel L1 / L2 loss with its gradient in one pass (the L1 term of
+// GaussianSplattingModel.get_loss_dict, gaussian_splatting.py:861-866, and the masked variant :853-858 where
+// masked pixels are zeroed in both images but still count in the mean).
+//   loss = weight * mean(|p - t|)  or  weight * mean((p - t)^2)      over all n elements
+//   grad = d loss / d p, written for every element (0 where masked)
+// One read of each image, one write of the gradient; the loss is reduced per block and summed by the last
+// block to finish, in block order (deterministic).
+// ---------------------------------------------------------------------------------------------
+namespace gg {
+
+__global__ void __launch_bounds__(256)
+pixel_loss_kernel(long long n, int channels, const float* __restrict__ pred, const float* __restrict__ target,
+                  const uint8_t* __restrict__ mask, int l2, float scale, float* __restrict__ grad,
+                  float* __restrict__ partial, unsigned int* __restrict__ counter, float* __restrict__ loss) {
+    __shared__ float warp_sum[8];
+    __shared__ bool last;
+    float acc = 0.0f;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const bool on = mask == nullptr || mask[i / channels] != 0;
+        const float d = on ? pred[i] - target[i] : 0.0f;
+        float g;
+        if (l2) { acc += d * d; g = d * (2.0f * scale); }
+        else { acc += fabsf(d); g = d > 0.0f ? scale : (d < 0.0f ? -scale : 0.0f); }
+        grad[i] = g;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.0f;
+        for (int w = 0; w < 8; ++w) s += warp_sum[w];
+        partial[blockIdx.x] = s;
+        __threadfence();
+        last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        double s = 0.0;
+        for (unsigned b = 0; b < gridDim.x; ++b) s += (double)((volatile float*)partial)[b];
+        *loss = (float)(s * (double)scale);
+        *counter = 0u;  // ready for the next call
+    }
+}
+
+}  // namespace gg
+
+extern "C" size_t gg_pixel_loss_workspace_bytes(void) { return sizeof(float) * 2048 + 16; }
+
+extern "C" int gg_pixel_loss(long long n, int channels, const float* pred, const float* target, const uint8_t* mask,
+                             int kind, float weight, float* grad, float* loss, void* workspace, size_t workspace_bytes,
+                             void* stream) {
+    GG_REQUIRE(n >= 1 && channels >= 1 && n % channels == 0, "gg_pixel_loss: n must be a positive multiple of channels");
+    GG_REQUIRE(kind == 1 || kind == 2, "gg_pixel_loss: kind is 1 (L1) or 2 (L2)");
+    GG_REQUIRE(pred && target && grad && loss && workspace, "gg_pixel_loss: null pointer");
+    GG_REQUIRE(workspace_bytes >= gg_pixel_loss_workspace_bytes(), "gg_pixel_loss: workspace too small");
+    int blocks = div_up(n, 256 * 8);
+    if (blocks > 2048) blocks = 2048;
+    float* partial = reinterpret_cast<float*>(workspace);
+    unsigned int* counter = reinterpret_cast<unsigned int*>(partial + 2048);  // zero-initialised by the caller once
+    const float scale = (float)((double)weight / (double)n);
+    pixel_loss_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(n, channels, pred, target, mask, kind == 2 ? 1 : 0, scale,
+                                                               grad, partial, counter, loss);
+    count_launch();
+    return check_launch("pixel_loss_kernel");
+}

@@ -205,3 +205,35 @@ def refine_gaussians(params: Dict[str, torch.Tensor], moments: Optional[Dict[str
                       _lib.ptr(P["quats"]), _lib.ptr(samples), scratch.data_ptr(), scratch.numel(), st)
     info = dict(n_in=n, n_out=n_out, n_kept=n_keep, n_split=n_sa, n_split_kept=n_sk, n_dup_kept=n_dk)
     return new_p, new_m, info
+
+
+_loss_ws = {}
+
+
+@torch.no_grad()
+def pixel_loss(pred: torch.Tensor, target: torch.Tensor, kind: str = "l1", mask: Optional[torch.Tensor] = None,
+               weight: float = 1.0):
+    """weight * mean(|pred - target|) (kind "l1", gaussian_splatting.py:861) or weight * mean((pred - target)^2)
+    ("l2") and its gradient w.r.t. pred, in one kernel.  mask: optional [pixels] bool/uint8, False = ignored pixel
+    (both images zeroed there, :853-858).  Returns (loss [1], grad like pred); continue with `pred.backward(grad)`."""
+    dev = _lib.require_cuda(pred, target, mask)
+    p, t = _lib.f32c(pred.detach()), _lib.f32c(target.detach())
+    if p.shape != t.shape:
+        raise ValueError(f"pred {tuple(p.shape)} and target {tuple(t.shape)} differ")
+    channels = int(p.shape[-1])
+    m = None
+    if mask is not None:
+        m = mask.to(torch.uint8).contiguous()
+        if m.numel() * channels != p.numel():
+            raise ValueError("mask must have one entry per pixel")
+    key = (dev.type, dev.index)
+    ws = _loss_ws.get(key)
+    if ws is None:
+        ws = _loss_ws[key] = torch.zeros(int(_lib.load().gg_pixel_loss_workspace_bytes()), dtype=torch.uint8, device=dev)
+    grad = torch.empty_like(p)
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    with _lib.device_guard(dev):
+        _lib.call("gg_pixel_loss", p.numel(), channels, p.data_ptr(), t.data_ptr(), _lib.ptr(m),
+                  {"l1": 1, "l2": 2}[kind], float(weight), grad.data_ptr(), loss.data_ptr(), ws.data_ptr(), ws.numel(),
+                  _lib.stream_ptr(dev))
+    return loss, grad

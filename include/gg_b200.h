@@ -258,6 +258,16 @@ int gg_refine_apply(int n, int n_split_samples, const int32_t* totals /*[4] host
                     const float* means, const float* log_scales, const float* quats, const float* samples,
                     void* scratch /* 9 B per output row + 512 */, size_t scratch_bytes, void* stream);
 
+/* ---- per-pixel loss with its gradient in one pass (the L1 term and its masked variant,
+ * gaussian_splatting.py:853-866; kind 2 = mean squared error).  pred/target/grad are n contiguous floats
+ * ([..., channels]); mask (nullable) has one byte per pixel (n / channels), 0 = pixel ignored (zero loss and
+ * gradient, still counted in the mean, as the reference zeroes both images).  loss[0] = weight * mean(...),
+ * grad = d loss / d pred.  workspace: gg_pixel_loss_workspace_bytes() bytes, ZERO-FILLED when allocated. */
+size_t gg_pixel_loss_workspace_bytes(void);
+int gg_pixel_loss(long long n, int channels, const float* pred, const float* target, const uint8_t* mask /*nullable*/,
+                  int kind /*1 = L1, 2 = L2*/, float weight, float* grad, float* loss, void* workspace,
+                  size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

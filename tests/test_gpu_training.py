@@ -234,3 +234,30 @@ def test_training_loop_with_refinement():
     opt.reset_opacity(0.1)
     assert torch.allclose(P["opacity_logit"].detach(), torch.full_like(P["opacity_logit"], float(torch.logit(torch.tensor(0.08)))))
     assert float(opt.moments()["opacity_logit"][1].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("kind", ["l1", "l2"])
+@pytest.mark.parametrize("masked", [False, True])
+def test_pixel_loss_matches_torch(kind, masked):
+    """Fused loss + gradient vs the reference's expressions (gaussian_splatting.py:853-866): masked pixels are
+    zeroed in both images and still count in the mean."""
+    from gaussiangrasper_b200.training import pixel_loss
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(4)
+    pred = torch.randn((2, 37, 53, 7), generator=g).to(dev).requires_grad_(True)
+    target = torch.randn((2, 37, 53, 7), generator=g).to(dev)
+    mask = (torch.rand((2, 37, 53), generator=g) > 0.3).to(dev) if masked else None
+    loss, grad = pixel_loss(pred, target, kind, mask, weight=0.8)
+    p, t = pred, target
+    if masked:
+        p = pred * mask[..., None]
+        t = target * mask[..., None]
+    ref = 0.8 * ((p - t).abs().mean() if kind == "l1" else ((p - t) ** 2).mean())
+    ref.backward()
+    assert torch.allclose(loss[0], ref.detach(), rtol=1e-5, atol=1e-8)
+    assert torch.allclose(grad, pred.grad, rtol=1e-6, atol=1e-12)
+    # a second call reuses the workspace (the block counter resets itself)
+    loss2, _ = pixel_loss(pred, target, kind, mask, weight=0.8)
+    assert torch.equal(loss, loss2)
+    with pytest.raises(ValueError):
+        pixel_loss(pred, target[:1], kind)
