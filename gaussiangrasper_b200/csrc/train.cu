@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(256)
 refine_decide_kernel(int n, const float* __restrict__ xys_grad_norm, const float* __restrict__ vis_counts,
                      const float* __restrict__ max_2dsize, const float* __restrict__ log_scales,
                      const float* __restrict__ opacity_logit, const gg_refine_config c, uint8_t* __restrict__ flags,
-                     int32_t* __restrict__ counts) {
+                     int32_t* __restrict__ counts, long long cs /* stride between the four count arrays */) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float ls[3] = {log_scales[3 * i], log_scales[3 * i + 1], log_scales[3 * i + 2]};
@@ -180,15 +180,15 @@ refine_decide_kernel(int n, const float* __restrict__ xys_grad_norm, const float
     flags[i] = (uint8_t)((split ? kFlagSplit : 0) | (dup ? kFlagDup : 0) | (keep ? kFlagKeep : 0) |
                          (ks ? kFlagKeepSplit : 0) | (kd ? kFlagKeepDup : 0));
     counts[i] = keep ? 1 : 0;
-    counts[n + i] = ks ? 1 : 0;
-    counts[2 * n + i] = kd ? 1 : 0;
-    counts[3 * n + i] = split ? 1 : 0;
+    counts[cs + i] = ks ? 1 : 0;
+    counts[2 * cs + i] = kd ? 1 : 0;
+    counts[3 * cs + i] = split ? 1 : 0;
 }
 
 // source row / role of every output row: role 0 original, 1 split child, 2 duplicate; aux = row of the
 // normal sample the child's position is drawn with
 __global__ void __launch_bounds__(256)
-refine_map_kernel(int n, int samps, const uint8_t* __restrict__ flags, const int32_t* __restrict__ scans,
+refine_map_kernel(int n, int samps, const uint8_t* __restrict__ flags, const int32_t* __restrict__ scans, long long cs,
                   int n_keep, int n_split_kept, int n_split_all, int32_t* __restrict__ src_row,
                   uint8_t* __restrict__ role, int32_t* __restrict__ aux) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -199,14 +199,14 @@ refine_map_kernel(int n, int samps, const uint8_t* __restrict__ flags, const int
         src_row[j] = i; role[j] = 0; aux[j] = 0;
     }
     if (f & kFlagKeepSplit) {
-        const int r = scans[n + i] - 1, ra = scans[3 * n + i] - 1;
+        const int r = scans[cs + i] - 1, ra = scans[3 * cs + i] - 1;
         for (int s = 0; s < samps; ++s) {
             const int j = n_keep + s * n_split_kept + r;
             src_row[j] = i; role[j] = 1; aux[j] = s * n_split_all + ra;
         }
     }
     if (f & kFlagKeepDup) {
-        const int j = n_keep + samps * n_split_kept + scans[2 * n + i] - 1;
+        const int j = n_keep + samps * n_split_kept + scans[2 * cs + i] - 1;
         src_row[j] = i; role[j] = 2; aux[j] = 0;
     }
 }
@@ -257,8 +257,11 @@ refine_gather_kernel(long long n_out, const RefineArrays t, const int32_t* __res
 
 }  // namespace gg
 
+// the four count / scan arrays are `refine_stride(n)` entries apart so that each starts 16-byte aligned
+static size_t refine_stride(int n) { return ((size_t)(n > 0 ? n : 1) + 3) & ~(size_t)3; }
+
 extern "C" size_t gg_refine_workspace_bytes(int n) {
-    const size_t t = (size_t)(n > 0 ? n : 1);
+    const size_t t = refine_stride(n);
     return 256 + ((t + 255) & ~(size_t)255) + 2 * 4 * t * sizeof(int32_t) + 4 * gg_cumsum_workspace_bytes(n) + 1024;
 }
 
@@ -275,13 +278,13 @@ extern "C" int gg_refine_plan(int n, const float* xys_grad_norm, const float* vi
     unsigned char* w = reinterpret_cast<unsigned char*>(workspace);
     int32_t* totals_dev = reinterpret_cast<int32_t*>(w);
     uint8_t* flags = w + 256;
-    const size_t t = (size_t)n;
+    const size_t t = refine_stride(n);
     int32_t* counts = reinterpret_cast<int32_t*>(w + 256 + ((t + 255) & ~(size_t)255));
     int32_t* scans = counts + 4 * t;
     unsigned char* scan_ws = reinterpret_cast<unsigned char*>(scans + 4 * t);
     scan_ws = reinterpret_cast<unsigned char*>(((uintptr_t)scan_ws + 255) & ~(uintptr_t)255);
     refine_decide_kernel<<<div_up(n, 256), 256, 0, st>>>(n, xys_grad_norm, vis_counts, max_2dsize, log_scales,
-                                                        opacity_logit, *cfg, flags, counts);
+                                                        opacity_logit, *cfg, flags, counts, (long long)t);
     count_launch();
     int rc = check_launch("refine_decide_kernel");
     if (rc) return rc;
@@ -311,13 +314,13 @@ extern "C" int gg_refine_apply(int n, int n_split_samples, const int32_t* totals
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned char* w = reinterpret_cast<const unsigned char*>(plan_workspace);
     const uint8_t* flags = w + 256;
-    const size_t t = (size_t)n;
+    const size_t t = refine_stride(n);
     const int32_t* scans = reinterpret_cast<const int32_t*>(w + 256 + ((t + 255) & ~(size_t)255)) + 4 * t;
     unsigned char* s = reinterpret_cast<unsigned char*>(scratch);
     int32_t* src_row = reinterpret_cast<int32_t*>(s);
     int32_t* aux = src_row + n_out;
     uint8_t* role = reinterpret_cast<uint8_t*>(aux + n_out);
-    refine_map_kernel<<<div_up(n, 256), 256, 0, st>>>(n, n_split_samples, flags, scans, (int)n_keep, (int)n_sk, (int)n_sa,
+    refine_map_kernel<<<div_up(n, 256), 256, 0, st>>>(n, n_split_samples, flags, scans, (long long)t, (int)n_keep, (int)n_sk, (int)n_sa,
                                                      src_row, role, aux);
     count_launch();
     int rc = check_launch("refine_map_kernel");

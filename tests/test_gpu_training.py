@@ -135,7 +135,7 @@ def test_refine_matches_reference_flow(rules_kw):
     from gaussiangrasper_b200.training import DensifyStats, refine_gaussians
     from oracle import refine_oracle
     dev = torch.device("cuda:0")
-    n, D = 20_000, 5
+    n, D = 20_003, 5   # not a multiple of 4: the scan arrays of the plan are padded apart
     P, M, st = _refine_inputs(n, D, 12)
     rules = dict(max_dim=640.0, densify_grad_thresh=0.0002, densify_size_thresh=0.01, split_screen_size=0.05,
                  cull_alpha_thresh=0.1, cull_scale_thresh=0.5, cull_screen_size=0.15, do_densify=1, split_by_screen=1,
