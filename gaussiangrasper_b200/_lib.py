@@ -59,7 +59,9 @@ _SIGNATURES = {
     "gg_refine_plan": (C.c_int, [_i, _p, _p, _p, _p, _p, _p, _p, _sz, _p, _p]),
     "gg_refine_apply": (C.c_int, [_i, _i, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "gg_pixel_loss_workspace_bytes": (C.c_size_t, []),
-    "gg_pixel_loss": (C.c_int, [_ll, _i, _p, _p, _p, _i, _f, _p, _p, _p, _sz, _p]),
+    "gg_pixel_loss": (C.c_int, [_ll, _i, _p, _p, _p, _p, _i, _f, _p, _p, _p, _sz, _p]),
+    "gg_ssim_workspace_bytes": (C.c_size_t, [_i, _i, _i, _i]),
+    "gg_ssim_loss": (C.c_int, [_i, _i, _i, _i, _p, _i, _p, _i, _f, _p, _i, _i, _p, _p, _sz, _p]),
     "gg_densify_stats": (C.c_int, [_ll, _i, _p, _p, _i, _i, _i, _p, _p, _p, _p]),
     "gg_prepare_views": (C.c_int, [_i] * 6 + [_p] * 10 + [_i] * 4 + [_f] + [_p] * 7 + [_i, _p]),
     "gg_prepare_views_bwd": (C.c_int, [_i] * 6 + [_p] * 9 + [_i] * 2 + [_p] * 13),

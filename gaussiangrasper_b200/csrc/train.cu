@@ -346,8 +346,10 @@ extern "C" int gg_refine_apply(int n, int n_split_samples, const int32_t* totals
 // Per-pixel L1 / L2 loss with its gradient in one pass (the L1 term of
 // GaussianSplattingModel.get_loss_dict, gaussian_splatting.py:861-866, and the masked variant :853-858 where
 // masked pixels are zeroed in both images but still count in the mean).
-//   loss = weight * mean(|p - t|)  or  weight * mean((p - t)^2)      over all n elements
+//   loss = weight * mean(|p - t|)  or  weight * mean((p - t)^2)
 //   grad = d loss / d p, written for every element (0 where masked)
+// The mean runs over all n elements, or -- with valid_pixels, a device int32 holding the number of unmasked
+// pixels -- over the valid ones only, which is what :882 computes.
 // One read of each image, one write of the gradient; the loss is reduced per block and summed by the last
 // block to finish, in block order (deterministic).
 // ---------------------------------------------------------------------------------------------
@@ -355,10 +357,14 @@ namespace gg {
 
 __global__ void __launch_bounds__(256)
 pixel_loss_kernel(long long n, int channels, const float* __restrict__ pred, const float* __restrict__ target,
-                  const uint8_t* __restrict__ mask, int l2, float scale, float* __restrict__ grad,
-                  float* __restrict__ partial, unsigned int* __restrict__ counter, float* __restrict__ loss) {
+                  const uint8_t* __restrict__ mask, const int32_t* __restrict__ valid_pixels, int l2, float weight,
+                  float* __restrict__ grad, float* __restrict__ partial, unsigned int* __restrict__ counter,
+                  float* __restrict__ loss) {
     __shared__ float warp_sum[8];
     __shared__ bool last;
+    // mean over every element, or over the elements of the valid pixels only (gaussian_splatting.py:882)
+    const double denom = valid_pixels ? (double)max(*valid_pixels, 1) * (double)channels : (double)n;
+    const float scale = (float)((double)weight / denom);
     float acc = 0.0f;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -395,8 +401,8 @@ pixel_loss_kernel(long long n, int channels, const float* __restrict__ pred, con
 extern "C" size_t gg_pixel_loss_workspace_bytes(void) { return sizeof(float) * 2048 + 16; }
 
 extern "C" int gg_pixel_loss(long long n, int channels, const float* pred, const float* target, const uint8_t* mask,
-                             int kind, float weight, float* grad, float* loss, void* workspace, size_t workspace_bytes,
-                             void* stream) {
+                             const int32_t* valid_pixels, int kind, float weight, float* grad, float* loss,
+                             void* workspace, size_t workspace_bytes, void* stream) {
     GG_REQUIRE(n >= 1 && channels >= 1 && n % channels == 0, "gg_pixel_loss: n must be a positive multiple of channels");
     GG_REQUIRE(kind == 1 || kind == 2, "gg_pixel_loss: kind is 1 (L1) or 2 (L2)");
     GG_REQUIRE(pred && target && grad && loss && workspace, "gg_pixel_loss: null pointer");
@@ -405,9 +411,202 @@ extern "C" int gg_pixel_loss(long long n, int channels, const float* pred, const
     if (blocks > 2048) blocks = 2048;
     float* partial = reinterpret_cast<float*>(workspace);
     unsigned int* counter = reinterpret_cast<unsigned int*>(partial + 2048);  // zero-initialised by the caller once
-    const float scale = (float)((double)weight / (double)n);
-    pixel_loss_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(n, channels, pred, target, mask, kind == 2 ? 1 : 0, scale,
-                                                               grad, partial, counter, loss);
+    pixel_loss_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(n, channels, pred, target, mask, valid_pixels,
+                                                               kind == 2 ? 1 : 0, weight, grad, partial, counter, loss);
     count_launch();
     return check_launch("pixel_loss_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------
+// SSIM loss with its gradient: weight * (1 - SSIM(pred, target)) as the reference uses it
+// (pytorch_msssim.SSIM(data_range=1, size_average=True, channel=3): 11x11 Gaussian window, sigma 1.5, no
+// padding, K = (0.01, 0.03); gaussian_splatting.py:284, :885).  Images are channel-last [n_img, H, W, stride];
+// the first `channels` channels are compared.
+//   ssim_stats_kernel : per output position, the five windowed moments -> SSIM value (summed per block) and the
+//                       partial derivatives w.r.t. E[x], E[x^2], E[xy], written as three maps
+//   ssim_grad_kernel  : d loss / d x[q] = -scale * sum_p w(q - p) (dmu[p] + 2 x[q] ds11[p] + y[q] ds12[p])
+// Both stage a 26x26 patch per 16x16 tile in shared memory and apply the window directly in 2-D.
+// ---------------------------------------------------------------------------------------------
+namespace gg {
+
+constexpr int kSsimWin = 11, kSsimTile = 16, kSsimPatch = kSsimTile + kSsimWin - 1;
+
+struct SsimArgs {
+    int n_img, H, W, channels, oh, ow;
+    int ps, ts, gs;  // floats per pixel of pred, target, grad
+    float g[kSsimWin];
+    float c1, c2;
+};
+
+__global__ void __launch_bounds__(kSsimTile * kSsimTile)
+ssim_stats_kernel(const SsimArgs a, const float* __restrict__ pred, const float* __restrict__ target,
+                  float* __restrict__ maps, float* __restrict__ partial) {
+    __shared__ float xs[kSsimPatch][kSsimPatch + 1], ys[kSsimPatch][kSsimPatch + 1];
+    __shared__ float warp_sum[8];
+    const int img = blockIdx.z / a.channels, c = blockIdx.z - img * a.channels;
+    const int ox0 = blockIdx.x * kSsimTile, oy0 = blockIdx.y * kSsimTile;
+    const int tid = threadIdx.y * kSsimTile + threadIdx.x;
+    for (int k = tid; k < kSsimPatch * kSsimPatch; k += kSsimTile * kSsimTile) {
+        const int py = k / kSsimPatch, px = k - py * kSsimPatch;
+        const int y = oy0 + py, x = ox0 + px;
+        float vx = 0.0f, vy = 0.0f;
+        if (y < a.H && x < a.W) {
+            const long long pix = ((long long)img * a.H + y) * a.W + x;
+            vx = pred[pix * a.ps + c];
+            vy = target[pix * a.ts + c];
+        }
+        xs[py][px] = vx;
+        ys[py][px] = vy;
+    }
+    __syncthreads();
+    const int ox = ox0 + threadIdx.x, oy = oy0 + threadIdx.y;
+    float val = 0.0f;
+    if (ox < a.ow && oy < a.oh) {
+        float mu1 = 0.f, mu2 = 0.f, s11 = 0.f, s22 = 0.f, s12 = 0.f;
+#pragma unroll
+        for (int dy = 0; dy < kSsimWin; ++dy) {
+            float r1 = 0.f, r2 = 0.f, r11 = 0.f, r22 = 0.f, r12 = 0.f;  // the window is applied row by row
+#pragma unroll
+            for (int dx = 0; dx < kSsimWin; ++dx) {
+                const float x = xs[threadIdx.y + dy][threadIdx.x + dx], y = ys[threadIdx.y + dy][threadIdx.x + dx];
+                const float w = a.g[dx];
+                r1 = fmaf(w, x, r1); r2 = fmaf(w, y, r2);
+                r11 = fmaf(w, x * x, r11); r22 = fmaf(w, y * y, r22); r12 = fmaf(w, x * y, r12);
+            }
+            const float w = a.g[dy];
+            mu1 = fmaf(w, r1, mu1); mu2 = fmaf(w, r2, mu2);
+            s11 = fmaf(w, r11, s11); s22 = fmaf(w, r22, s22); s12 = fmaf(w, r12, s12);
+        }
+        const float v1 = s11 - mu1 * mu1, v2 = s22 - mu2 * mu2, cov = s12 - mu1 * mu2;
+        const float A1 = 2.0f * mu1 * mu2 + a.c1, A2 = 2.0f * cov + a.c2;
+        const float B1 = mu1 * mu1 + mu2 * mu2 + a.c1, B2 = v1 + v2 + a.c2;
+        const float inv = 1.0f / (B1 * B2);
+        val = A1 * A2 * inv;
+        const float dA1 = A2 * inv, dA2 = A1 * inv, dB1 = -val / B1, dB2 = -val / B2;
+        // x enters through mu1 (A1, B1, and the covariance / variance terms) and through E[x^2], E[xy]
+        const float dmu = 2.0f * mu2 * dA1 + 2.0f * mu1 * dB1 - 2.0f * mu2 * dA2 - 2.0f * mu1 * dB2;
+        const long long plane = (long long)a.oh * a.ow;
+        const long long o = ((long long)blockIdx.z * 3) * plane + (long long)oy * a.ow + ox;
+        maps[o] = dmu;
+        maps[o + plane] = dB2;          // d / d E[x^2]
+        maps[o + 2 * plane] = 2.0f * dA2;  // d / d E[xy]
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+    if ((tid & 31) == 0) warp_sum[tid >> 5] = val;
+    __syncthreads();
+    if (tid == 0) {
+        float s = 0.0f;
+        for (int w = 0; w < 8; ++w) s += warp_sum[w];
+        partial[((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = s;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+ssim_sum_kernel(long long n_partial, const float* __restrict__ partial, double inv_count, float weight,
+                float* __restrict__ loss, int accumulate) {
+    __shared__ double sh[256];
+    double s = 0.0;
+    for (long long i = threadIdx.x; i < n_partial; i += 256) s += (double)partial[i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const float l = (float)((double)weight * (1.0 - sh[0] * inv_count));
+        *loss = accumulate ? *loss + l : l;
+    }
+}
+
+__global__ void __launch_bounds__(kSsimTile * kSsimTile)
+ssim_grad_kernel(const SsimArgs a, const float* __restrict__ pred, const float* __restrict__ target,
+                 const float* __restrict__ maps, float scale, float* __restrict__ grad, int accumulate) {
+    __shared__ float m0[kSsimPatch][kSsimPatch + 1], m1[kSsimPatch][kSsimPatch + 1], m2[kSsimPatch][kSsimPatch + 1];
+    const int img = blockIdx.z / a.channels, c = blockIdx.z - img * a.channels;
+    const int qx0 = blockIdx.x * kSsimTile, qy0 = blockIdx.y * kSsimTile;
+    const int tid = threadIdx.y * kSsimTile + threadIdx.x;
+    const long long plane = (long long)a.oh * a.ow;
+    const float* mp = maps + ((long long)blockIdx.z * 3) * plane;
+    // output positions p in [q - 10, q] cover input pixel q: patch origin is (qy0 - 10, qx0 - 10)
+    for (int k = tid; k < kSsimPatch * kSsimPatch; k += kSsimTile * kSsimTile) {
+        const int py = k / kSsimPatch, px = k - py * kSsimPatch;
+        const int oy = qy0 - (kSsimWin - 1) + py, ox = qx0 - (kSsimWin - 1) + px;
+        float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+        if (oy >= 0 && ox >= 0 && oy < a.oh && ox < a.ow) {
+            const long long o = (long long)oy * a.ow + ox;
+            v0 = mp[o]; v1 = mp[o + plane]; v2 = mp[o + 2 * plane];
+        }
+        m0[py][px] = v0; m1[py][px] = v1; m2[py][px] = v2;
+    }
+    __syncthreads();
+    const int qx = qx0 + threadIdx.x, qy = qy0 + threadIdx.y;
+    if (qx >= a.W || qy >= a.H) return;
+    float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < kSsimWin; ++dy) {
+        float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+#pragma unroll
+        for (int dx = 0; dx < kSsimWin; ++dx) {
+            // position p = q - d sits at patch (ty + 10 - dy, tx + 10 - dx)
+            const int py = threadIdx.y + (kSsimWin - 1) - dy, px = threadIdx.x + (kSsimWin - 1) - dx;
+            const float w = a.g[dx];
+            r0 = fmaf(w, m0[py][px], r0); r1 = fmaf(w, m1[py][px], r1); r2 = fmaf(w, m2[py][px], r2);
+        }
+        const float w = a.g[dy];
+        g0 = fmaf(w, r0, g0); g1 = fmaf(w, r1, g1); g2 = fmaf(w, r2, g2);
+    }
+    const long long pix = ((long long)img * a.H + qy) * a.W + qx;
+    const float x = pred[pix * a.ps + c], y = target[pix * a.ts + c];
+    const float v = -scale * (g0 + 2.0f * x * g1 + y * g2);
+    float* gp = grad + pix * a.gs + c;
+    *gp = accumulate ? *gp + v : v;
+}
+
+}  // namespace gg
+
+extern "C" size_t gg_ssim_workspace_bytes(int n_img, int img_h, int img_w, int channels) {
+    if (n_img < 1 || channels < 1 || img_h < 11 || img_w < 11) return 0;
+    const size_t oh = (size_t)img_h - 10, ow = (size_t)img_w - 10;
+    const size_t blocks = (size_t)div_up((long long)ow, 16) * (size_t)div_up((long long)oh, 16) * (size_t)n_img * channels;
+    return sizeof(float) * (3 * oh * ow * (size_t)n_img * channels + blocks) + 256;
+}
+
+extern "C" int gg_ssim_loss(int n_img, int img_h, int img_w, int channels, const float* pred, int pred_stride,
+                            const float* target, int target_stride, float weight, float* grad, int grad_stride,
+                            int accumulate, float* loss, void* workspace, size_t workspace_bytes, void* stream) {
+    GG_REQUIRE(n_img >= 1 && channels >= 1 && img_h >= 11 && img_w >= 11, "gg_ssim_loss: images must be at least 11x11");
+    GG_REQUIRE(pred && target && grad && loss && workspace, "gg_ssim_loss: null pointer");
+    GG_REQUIRE(pred_stride >= channels && target_stride >= channels && grad_stride >= channels,
+               "gg_ssim_loss: strides must cover the compared channels");
+    GG_REQUIRE((long long)n_img * channels <= 65535, "gg_ssim_loss: too many image planes");
+    GG_REQUIRE(workspace_bytes >= gg_ssim_workspace_bytes(n_img, img_h, img_w, channels), "gg_ssim_loss: workspace too small");
+    SsimArgs a;
+    a.n_img = n_img; a.H = img_h; a.W = img_w; a.channels = channels; a.oh = img_h - 10; a.ow = img_w - 10;
+    a.ps = pred_stride; a.ts = target_stride; a.gs = grad_stride;
+    // pytorch_msssim._fspecial_gauss_1d(11, 1.5) in fp32
+    float sum = 0.0f;
+    for (int i = 0; i < kSsimWin; ++i) {
+        const float d = (float)(i - kSsimWin / 2);
+        a.g[i] = expf(-(d * d) / (2.0f * 1.5f * 1.5f));
+        sum += a.g[i];
+    }
+    for (int i = 0; i < kSsimWin; ++i) a.g[i] /= sum;
+    a.c1 = 0.01f * 0.01f;
+    a.c2 = 0.03f * 0.03f;
+    cudaStream_t st = (cudaStream_t)stream;
+    float* maps = reinterpret_cast<float*>(workspace);
+    const long long plane = (long long)a.oh * a.ow;
+    float* partial = maps + 3 * plane * n_img * channels;
+    dim3 block(kSsimTile, kSsimTile);
+    dim3 ogrid(div_up(a.ow, kSsimTile), div_up(a.oh, kSsimTile), n_img * channels);
+    ssim_stats_kernel<<<ogrid, block, 0, st>>>(a, pred, target, maps, partial);
+    const long long n_partial = (long long)ogrid.x * ogrid.y * ogrid.z;
+    const double count = (double)plane * n_img * channels;
+    ssim_sum_kernel<<<1, 256, 0, st>>>(n_partial, partial, 1.0 / count, weight, loss, accumulate);
+    dim3 igrid(div_up(img_w, kSsimTile), div_up(img_h, kSsimTile), n_img * channels);
+    ssim_grad_kernel<<<igrid, block, 0, st>>>(a, pred, target, maps, (float)((double)weight / count), grad, accumulate);
+    count_launch(3);
+    return check_launch("gg_ssim_loss");
 }

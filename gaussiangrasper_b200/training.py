@@ -212,10 +212,12 @@ _loss_ws = {}
 
 @torch.no_grad()
 def pixel_loss(pred: torch.Tensor, target: torch.Tensor, kind: str = "l1", mask: Optional[torch.Tensor] = None,
-               weight: float = 1.0):
-    """weight * mean(|pred - target|) (kind "l1", gaussian_splatting.py:861) or weight * mean((pred - target)^2)
-    ("l2") and its gradient w.r.t. pred, in one kernel.  mask: optional [pixels] bool/uint8, False = ignored pixel
-    (both images zeroed there, :853-858).  Returns (loss [1], grad like pred); continue with `pred.backward(grad)`."""
+               weight: float = 1.0, mean_over: str = "valid"):
+    """weight * mean(|pred - target|) (kind "l1") or weight * mean((pred - target)^2) ("l2") and its gradient
+    w.r.t. pred, in one kernel.  mask: optional [pixels] bool/uint8, False = ignored pixel; the mean then runs
+    over the valid pixels (mean_over="valid": `abs(gt[valid] - rgb[valid]).mean()`, gaussian_splatting.py:882)
+    or over all pixels with the ignored ones contributing zero (mean_over="all").
+    Returns (loss [1], grad like pred); continue with `pred.backward(grad)`."""
     dev = _lib.require_cuda(pred, target, mask)
     p, t = _lib.f32c(pred.detach()), _lib.f32c(target.detach())
     if p.shape != t.shape:
@@ -232,8 +234,52 @@ def pixel_loss(pred: torch.Tensor, target: torch.Tensor, kind: str = "l1", mask:
         ws = _loss_ws[key] = torch.zeros(int(_lib.load().gg_pixel_loss_workspace_bytes()), dtype=torch.uint8, device=dev)
     grad = torch.empty_like(p)
     loss = torch.empty(1, dtype=torch.float32, device=dev)
+    if mean_over not in ("valid", "all"):
+        raise ValueError("mean_over is 'valid' or 'all'")
+    count = m.sum(dtype=torch.int32).reshape(1) if (m is not None and mean_over == "valid") else None
     with _lib.device_guard(dev):
-        _lib.call("gg_pixel_loss", p.numel(), channels, p.data_ptr(), t.data_ptr(), _lib.ptr(m),
+        _lib.call("gg_pixel_loss", p.numel(), channels, p.data_ptr(), t.data_ptr(), _lib.ptr(m), _lib.ptr(count),
                   {"l1": 1, "l2": 2}[kind], float(weight), grad.data_ptr(), loss.data_ptr(), ws.data_ptr(), ws.numel(),
                   _lib.stream_ptr(dev))
     return loss, grad
+
+
+_ssim_ws = {}
+
+
+@torch.no_grad()
+def ssim_loss(pred: torch.Tensor, target: torch.Tensor, channels: int = 3, weight: float = 1.0,
+              grad: Optional[torch.Tensor] = None, loss: Optional[torch.Tensor] = None):
+    """weight * (1 - SSIM(pred[..., :channels], target[..., :channels])) with the reference's SSIM settings
+    (gaussian_splatting.py:284, :885) and its gradient w.r.t. pred.  pred [V,H,W,Cp] or [H,W,Cp], target
+    [...,Ct] (channel-last, contiguous).  If `grad` (like pred) / `loss` ([1]) are given, the results are ADDED
+    to them -- e.g. the outputs of pixel_loss, to form main_loss = (1-l) L1 + l (1-SSIM) (:931).
+    Returns (loss [1], grad like pred)."""
+    dev = _lib.require_cuda(pred, target, grad, loss)
+    p, t = _lib.f32c(pred.detach()), _lib.f32c(target.detach())
+    if p.dim() == 3:
+        p, t = p[None], t[None]
+    if p.dim() != 4 or t.dim() != 4 or p.shape[:3] != t.shape[:3] or min(p.shape[3], t.shape[3]) < channels:
+        raise ValueError(f"pred {tuple(pred.shape)} / target {tuple(target.shape)} must be [V,H,W,C>=channels]")
+    V, H, W, ps = p.shape
+    if H < 11 or W < 11:
+        raise ValueError("SSIM needs images of at least 11x11 pixels")
+    accumulate = grad is not None
+    if (grad is None) != (loss is None):
+        raise ValueError("pass both grad and loss to accumulate, or neither")
+    if accumulate:
+        if grad.numel() != p.numel() or not grad.is_contiguous() or grad.dtype != torch.float32:
+            raise ValueError("grad must be a contiguous fp32 tensor shaped like pred")
+    else:
+        grad = torch.zeros_like(p)   # channels beyond `channels` get no SSIM gradient
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+    need = int(_lib.load().gg_ssim_workspace_bytes(V, H, W, channels))
+    key = (dev.type, dev.index)
+    ws = _ssim_ws.get(key)
+    if ws is None or ws.numel() < need:
+        ws = _ssim_ws[key] = torch.empty(need, dtype=torch.uint8, device=dev)
+    with _lib.device_guard(dev):
+        _lib.call("gg_ssim_loss", V, H, W, int(channels), p.data_ptr(), int(ps), t.data_ptr(), int(t.shape[3]),
+                  float(weight), grad.data_ptr(), int(ps), 1 if accumulate else 0, loss.data_ptr(), ws.data_ptr(),
+                  ws.numel(), _lib.stream_ptr(dev))
+    return loss, grad.view(pred.shape)

@@ -261,12 +261,23 @@ int gg_refine_apply(int n, int n_split_samples, const int32_t* totals /*[4] host
 /* ---- per-pixel loss with its gradient in one pass (the L1 term and its masked variant,
  * gaussian_splatting.py:853-866; kind 2 = mean squared error).  pred/target/grad are n contiguous floats
  * ([..., channels]); mask (nullable) has one byte per pixel (n / channels), 0 = pixel ignored (zero loss and
- * gradient, still counted in the mean, as the reference zeroes both images).  loss[0] = weight * mean(...),
+ * gradient).  The mean runs over all n elements, or, when valid_pixels (device int32: number of unmasked
+ * pixels) is given, over the valid pixels' elements only (:882).  loss[0] = weight * mean(...),
  * grad = d loss / d pred.  workspace: gg_pixel_loss_workspace_bytes() bytes, ZERO-FILLED when allocated. */
 size_t gg_pixel_loss_workspace_bytes(void);
 int gg_pixel_loss(long long n, int channels, const float* pred, const float* target, const uint8_t* mask /*nullable*/,
-                  int kind /*1 = L1, 2 = L2*/, float weight, float* grad, float* loss, void* workspace,
-                  size_t workspace_bytes, void* stream);
+                  const int32_t* valid_pixels /*nullable, device*/, int kind /*1 = L1, 2 = L2*/, float weight, float* grad,
+                  float* loss, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- SSIM loss with its gradient: weight * (1 - SSIM) with pytorch_msssim's defaults as the
+ * reference configures them (gaussian_splatting.py:284, :885: 11x11 Gaussian window, sigma 1.5, data_range 1, no
+ * padding, mean over batch, channels and positions).  pred / target / grad are channel-last [n_img, H, W, stride]
+ * (strides in floats per pixel); the first `channels` channels are compared.  accumulate != 0 adds to *loss and to
+ * grad instead of overwriting them (main_loss = (1-l) * L1 + l * (1 - SSIM), :931). */
+size_t gg_ssim_workspace_bytes(int n_img, int img_h, int img_w, int channels);
+int gg_ssim_loss(int n_img, int img_h, int img_w, int channels, const float* pred, int pred_stride, const float* target,
+                 int target_stride, float weight, float* grad, int grad_stride, int accumulate, float* loss,
+                 void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

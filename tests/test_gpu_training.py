@@ -248,16 +248,56 @@ def test_pixel_loss_matches_torch(kind, masked):
     target = torch.randn((2, 37, 53, 7), generator=g).to(dev)
     mask = (torch.rand((2, 37, 53), generator=g) > 0.3).to(dev) if masked else None
     loss, grad = pixel_loss(pred, target, kind, mask, weight=0.8)
-    p, t = pred, target
-    if masked:
-        p = pred * mask[..., None]
-        t = target * mask[..., None]
-    ref = 0.8 * ((p - t).abs().mean() if kind == "l1" else ((p - t) ** 2).mean())
+    d = (pred[mask] - target[mask]) if masked else (pred - target)        # :882 averages over the valid pixels
+    ref = 0.8 * (d.abs().mean() if kind == "l1" else (d ** 2).mean())
     ref.backward()
     assert torch.allclose(loss[0], ref.detach(), rtol=1e-5, atol=1e-8)
     assert torch.allclose(grad, pred.grad, rtol=1e-6, atol=1e-12)
+    if masked:  # mean over all pixels, ignored ones contributing zero
+        loss_all, grad_all = pixel_loss(pred, target, kind, mask, weight=0.8, mean_over="all")
+        frac = float(mask.float().mean())
+        assert torch.allclose(loss_all, loss * frac, rtol=1e-5) and torch.allclose(grad_all, grad * frac, rtol=1e-5, atol=1e-12)
     # a second call reuses the workspace (the block counter resets itself)
     loss2, _ = pixel_loss(pred, target, kind, mask, weight=0.8)
     assert torch.equal(loss, loss2)
     with pytest.raises(ValueError):
         pixel_loss(pred, target[:1], kind)
+
+
+def test_ssim_loss_and_main_loss_match_the_restatement():
+    """SSIM loss + gradient vs oracle/loss_oracle.py (pytorch_msssim's algorithm, autograd gradient), alone and
+    accumulated onto the L1 term as the reference's main_loss (gaussian_splatting.py:882-885, :931)."""
+    from gaussiangrasper_b200.training import pixel_loss, ssim_loss
+    from oracle import loss_oracle
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(8)
+    H, W = 45, 70   # partial tiles in both directions
+    base = torch.rand((H, W, 3), generator=g)
+    gt = (base + 0.1 * torch.randn((H, W, 3), generator=g)).clamp(0, 1)
+    pred_full = torch.rand((H, W, 8), generator=g)          # rgb + 5 more channels, like the blended image
+    pred_full[..., :3] = (base + 0.2 * torch.randn((H, W, 3), generator=g)).clamp(0, 1)
+    x = pred_full[..., :3].clone().double().requires_grad_(True)
+    ref = 1 - loss_oracle.ssim(gt.double().permute(2, 0, 1)[None], x.permute(2, 0, 1)[None])
+    ref.backward()
+    loss, grad = ssim_loss(pred_full.to(dev), gt.to(dev))
+    assert abs(float(loss) - float(ref)) < 2e-6
+    gmax = float(x.grad.abs().max())
+    assert float((grad[..., :3].cpu().double() - x.grad).abs().max()) < 2e-5 * gmax + 1e-10
+    assert float(grad[..., 3:].abs().max()) == 0.0
+    # main loss: L1 (rgb only) then SSIM accumulated on top
+    lam = 0.2
+    x2 = pred_full[..., :3].clone().double().requires_grad_(True)
+    ref2 = loss_oracle.main_loss(x2, gt.double(), lam)
+    ref2.backward()
+    p3 = pred_full[..., :3].contiguous().to(dev)
+    l1, g1 = pixel_loss(p3, gt.to(dev), "l1", weight=1 - lam)
+    tot, gtot = ssim_loss(p3, gt.to(dev), weight=lam, grad=g1, loss=l1)
+    assert abs(float(tot) - float(ref2)) < 2e-6
+    assert float((gtot.cpu().double() - x2.grad).abs().max()) < 2e-5 * float(x2.grad.abs().max()) + 1e-10
+    # a batch of two images equals the mean of the two single-image values
+    two = torch.stack([pred_full, pred_full.flip(0)]).to(dev)
+    gt2 = torch.stack([gt, gt.flip(0)]).to(dev)
+    lb, _ = ssim_loss(two, gt2)
+    assert abs(float(lb) - float(loss)) < 2e-6
+    with pytest.raises(ValueError):
+        ssim_loss(torch.zeros((5, 70, 3), device=dev), torch.zeros((5, 70, 3), device=dev))

@@ -106,3 +106,19 @@ def test_reference_checkpoint_round_trip(tmp_path):
     del bad["_model.quats"]
     with pytest.raises(KeyError):
         checkpoint.params_from_reference(bad)
+
+
+def test_ssim_restatement_properties():
+    """oracle/loss_oracle.ssim: 1 for identical images, symmetric, below 1 otherwise, window sums to 1."""
+    from oracle import loss_oracle
+    g = torch.Generator().manual_seed(0)
+    a = torch.rand((1, 3, 40, 33), generator=g, dtype=torch.float64)
+    b = (a + 0.1 * torch.randn(a.shape, generator=g, dtype=torch.float64)).clamp(0, 1)
+    assert abs(float(loss_oracle.ssim(a, a)) - 1.0) < 1e-9
+    assert abs(float(loss_oracle.ssim(a, b)) - float(loss_oracle.ssim(b, a))) < 1e-12
+    assert 0.0 < float(loss_oracle.ssim(a, b)) < 1.0
+    assert abs(float(loss_oracle._gauss_1d().sum()) - 1.0) < 1e-6 and loss_oracle._gauss_1d().shape == (11,)
+    # constant images: mu terms only -> (2ab + c1) / (a^2 + b^2 + c1)
+    ca, cb = torch.full((1, 1, 20, 20), 0.3, dtype=torch.float64), torch.full((1, 1, 20, 20), 0.6, dtype=torch.float64)
+    want = (2 * 0.3 * 0.6 + 1e-4) / (0.09 + 0.36 + 1e-4)
+    assert abs(float(loss_oracle.ssim(ca, cb)) - want) < 1e-5   # the fp32 window sums to 1 only to ~1e-7
