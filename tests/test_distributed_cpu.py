@@ -170,3 +170,24 @@ def test_factored_exchange_single_process_is_local():
     assert g["sh_coeffs"].shape == (9, 4, 3) and torch.isfinite(g["sh_coeffs"]).all()
     with pytest.raises(ValueError):
         ex.exchange(params["means"], torch.zeros(2, 3), 1, 1, h)
+
+
+def test_factorisation_equals_the_oracle_sh_backward():
+    """The identity FactoredExchange relies on: the SH backward of the C oracle (gsplat's compute_sh_backward
+    restated) for one view is the outer product Y(dir) (x) v_rgb, and gradients of several views add."""
+    import numpy as np
+    from oracle import c_oracle
+    g = torch.Generator().manual_seed(3)
+    n = 64
+    means = torch.randn(n, 3, generator=g)
+    pos = torch.randn(3, 3, generator=g) * 4
+    rgb = torch.randn(3, n, 3, generator=g)
+    rgb[1, ::5] = 0.0
+    for deg_use in (4, 2, 0):
+        want = np.zeros((n, 25, 3), np.float64)
+        for v in range(3):
+            dirs = (means - pos[v]).numpy()
+            want += c_oracle.sh_bwd(4, deg_use, dirs, rgb[v].numpy())
+        got = _torch_sh_rebuild(4, deg_use, means, pos, rgb, out=torch.zeros(n, 25, 3))
+        np.testing.assert_allclose(got.numpy(), want, rtol=2e-5, atol=2e-6)
+        assert not got[:, (deg_use + 1) ** 2:].any()
