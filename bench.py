@@ -361,7 +361,11 @@ def run_ours(args):
             q = pf["q"]
             if cfg["backward"] and pf["ready"][q & 1] is None:
                 prefetch_target(q, nv)                                      # very first chunk only
-            vb = ViewBatch.from_cameras(cc, dev)                            # H2D: cameras (pinned)
+            # H2D: cameras (pinned).  Like the images, the next chunk's cameras are staged once this chunk's
+            # kernels are enqueued (below), so the copy is not on the launch-bound front of the step.
+            vb = pf.pop("vb", None)
+            if vb is None:
+                vb = ViewBatch.from_cameras(cc, dev)                        # very first chunk only
             holder = ex.holder() if ex is not None else None
             with torch.set_grad_enabled(cfg["backward"]):
                 out = render_views(P["means"], P["log_scales"], P["quats"], P["opacity_logit"], P["sh_coeffs"],
@@ -383,9 +387,10 @@ def run_ours(args):
                 rgb_host[:nv].copy_(out["rgb"].detach(), non_blocking=True)  # D2H: rendered rgb
                 out["rgb"].record_stream(d2h_stream)
                 rgb_done = d2h_stream.record_event()
+            nxt = ci + chunk if ci + chunk < V else 0
             if cfg["backward"]:
-                nxt = ci + chunk if ci + chunk < V else 0
                 prefetch_target(q + 1, min(chunk, V - nxt))                 # next chunk (of this or the next step)
+            pf["vb"] = ViewBatch.from_cameras(cams[nxt:nxt + chunk], dev)   # next chunk's cameras
             pf["q"] = q + 1
         if ex is not None:
             ex.exchange(P["means"], vb.positions, sh_degree, 4, holder, all_pos)
