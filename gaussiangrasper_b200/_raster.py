@@ -27,7 +27,10 @@ def binning_for(xys, depths, radii, num_tiles_hit, img_height, img_width) -> ops
     if hit is not None and hit[0] == key:
         return hit[1]
     tile_bounds = ops.tile_bounds_for(img_height, img_width)
-    binning = ops.bin_views(xys.shape[0], 1, xys.detach(), depths.detach(), radii, num_tiles_hit, tile_bounds)
+    # the drop-in signatures hand the image back to code that expects it to be valid at once: exact sizing
+    # (one host wait for the intersection count, where the reference has one per rasterize call)
+    binning = ops.bin_views(xys.shape[0], 1, xys.detach(), depths.detach(), radii, num_tiles_hit, tile_bounds,
+                            sync_free=False)
     # the cache entry keeps the keyed tensors alive so their addresses cannot be recycled under it
     _bin_cache[slot] = (key, binning, (xys.detach(), depths.detach(), radii, num_tiles_hit))
     return binning

@@ -22,6 +22,7 @@ UNITS = [
     ("capi.cu", []),
     ("project.cu", ["-fmad=false"]),
     ("binning.cu", ["-fmad=false"]),
+    ("binning2.cu", ["-fmad=false"]),
     ("blend.cu", []),
     ("fused.cu", ["-fmad=false"]),
     ("train.cu", ["-fmad=false"]),

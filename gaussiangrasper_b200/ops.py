@@ -6,7 +6,6 @@ that gsplat 0.1.0's Python layer calls (see include/gg_b200.h for the mapping).
 """
 from __future__ import annotations
 
-from dataclasses import dataclass
 from typing import Optional, Tuple
 
 import torch
@@ -15,6 +14,7 @@ from . import _lib
 from ._lib import check, f32c, ptr, require_cuda, stream_ptr
 
 TILE = 16
+_INFO_SLOTS = 64
 
 
 def tile_bounds_for(img_height: int, img_width: int) -> Tuple[int, int, int]:
@@ -38,6 +38,13 @@ class _Workspace:
         self.total = torch.zeros(1, dtype=torch.int32, device=device)
         self.total_host = torch.zeros(1, dtype=torch.int32).pin_memory()
         self.total_event = torch.cuda.Event()
+        # tile-first binning: scratch, capacity per problem signature, ring of pinned info records
+        self.tiles_scratch = None
+        self.capacity = {}
+        self.info_host = torch.zeros((_INFO_SLOTS, 4), dtype=torch.int32).pin_memory()
+        self.info_next = 0
+        self.info_pending = []   # BinInfo records whose read-back has not been looked at yet
+        self.overflow_note = None
 
     def scan_ws(self, n):
         need = int(_lib.load().gg_cumsum_workspace_bytes(n))
@@ -63,6 +70,38 @@ class _Workspace:
         if self.finish is None or self.finish.numel() < need:
             self.finish = torch.zeros(int(need * 1.5) + 4096, dtype=torch.uint8, device=self.device)
         return self.finish
+
+    def note(self, info):
+        """Book-keeping of one finished read-back: remember the largest count per signature, raise the
+        capacity past an overflow."""
+        m, overflow = info.values[0], info.values[1]
+        cap = self.capacity.get(info.key)
+        if cap is not None and (overflow or m > 0.85 * cap):
+            self.capacity[info.key] = max(cap, _capacity_for(m))
+        if overflow and info.capacity > 0:
+            self.overflow_note = (m, info.capacity)
+
+    def poll(self):
+        """Look at the read-backs that have arrived (never blocks); report an overflow of an earlier call."""
+        keep = []
+        for info in self.info_pending:
+            if info.values is None and info.ready():
+                info.wait()
+            if info.values is None:
+                keep.append(info)
+        self.info_pending = keep[-(_INFO_SLOTS - 8):]
+        if self.overflow_note is not None:
+            m, cap = self.overflow_note
+            self.overflow_note = None
+            raise _lib.GGError(
+                f"tile binning overflow in an earlier call: {m} intersections > capacity {cap}; that call drew the "
+                "background only. The capacity has been raised: repeat the step")
+
+    def tiles_scratch_for(self, num_tiles, capacity):
+        need = int(_lib.load().gg_bin_tiles_scratch_bytes(num_tiles, capacity))
+        if self.tiles_scratch is None or self.tiles_scratch.numel() < need:
+            self.tiles_scratch = torch.empty(int(need * 1.25) + 4096, dtype=torch.uint8, device=self.device)
+        return self.tiles_scratch
 
     def key_buffers(self, m):
         if self.keys is None or self.keys.numel() < m:
@@ -232,28 +271,160 @@ def tile_order(ranges: torch.Tensor) -> torch.Tensor:
     return order
 
 
-@dataclass
+class BinInfo:
+    """{M, overflow, longest tile list} of one gg_bin_tiles call, read back without blocking the stream:
+    the record lands in a pinned ring slot; `wait()` blocks the host only when somebody asks."""
+
+    def __init__(self, ws, slot, event, key, capacity):
+        self.ws, self.slot, self.event, self.key, self.capacity = ws, slot, event, key, capacity
+        self.values = None
+
+    def ready(self) -> bool:
+        return self.values is not None or self.event is None or self.event.query()
+
+    def wait(self):
+        if self.values is None:
+            if self.event is not None:
+                self.event.synchronize()
+            else:  # recorded inside a stream capture: the caller synchronises after the replay
+                torch.cuda.current_stream(self.ws.device).synchronize()
+            self.values = tuple(int(x) for x in self.ws.info_host[self.slot])
+            self.ws.note(self)
+        return self.values
+
+
 class Binning:
-    """Sorted intersection list of one batch of views (what the blend kernels consume)."""
-    n: int
-    n_views: int
-    num_intersects: int
-    ids_sorted: torch.Tensor    # [M] int32
-    tile_ranges: torch.Tensor   # [V*T, 2] int32
-    tile_bounds: Tuple[int, int, int]
-    tile_order: Optional[torch.Tensor] = None  # [V*T] int32, tiles by descending list length
+    """Sorted intersection list of one batch of views (what the blend kernels consume).
+
+    ids_buffer holds `capacity` >= M entries; M itself (`num_intersects`) is known on the host only after a
+    read-back, which the tile-first path never waits for: `ids_sorted` / `num_intersects` / `check()` block
+    on it when they are asked."""
+
+    def __init__(self, n, n_views, ids_buffer, tile_ranges, tile_bounds, tile_order=None, num_intersects=None,
+                 info: Optional["BinInfo"] = None):
+        self.n, self.n_views = n, n_views
+        self.ids_buffer = ids_buffer          # [capacity] int32
+        self.tile_ranges = tile_ranges        # [V*T, 2] int32
+        self.tile_bounds = tile_bounds
+        self.tile_order = tile_order          # [V*T] int32, tiles by descending list length
+        self._m = num_intersects
+        self.info = info
+
+    @property
+    def capacity(self) -> int:
+        return int(self.ids_buffer.numel())
+
+    @property
+    def num_intersects(self) -> int:
+        if self._m is None:
+            self.check()
+        return self._m
+
+    @property
+    def ids_sorted(self) -> torch.Tensor:
+        return self.ids_buffer[:self.num_intersects]
+
+    def check(self) -> "Binning":
+        """Block until the device's intersection count is on the host; raise if it exceeded the capacity
+        (the render that used this binning then drew the background only)."""
+        if self._m is None:
+            m, overflow, _longest, _ = self.info.wait()
+            if overflow:
+                self.info.ws.overflow_note = None   # reported here, not again by the next call
+                raise _lib.GGError(
+                    f"tile binning overflow: {m} intersections > capacity {self.info.capacity}; the images of "
+                    "this call are invalid (background only). The capacity has been raised: repeat the call")
+            self._m = m
+        return self
+
+
+def _capacity_for(m: int) -> int:
+    return int(m * 1.3) + 65536
+
+
+def bin_views_tiles(n, n_views, xys, depths, radii, tile_bounds, xy_from_geo=False, sync_free=True) -> Binning:
+    """Tile-first binning (gg_bin_tiles): count -> scan -> scatter -> per-tile sort, no host read.
+
+    The buffers are sized by a capacity remembered per problem signature (rows, tiles): the first call of a
+    signature measures M (one synchronous counting pass), later calls reuse 1.3 x the largest M seen and never
+    wait.  An overflow (M jumped past the capacity between two calls) leaves every tile range empty, is
+    reported by `Binning.check()` / the next call, and raises the capacity.  sync_free=False waits for the
+    count after every call and repeats the binning itself on overflow (always exact, one host wait)."""
+    dev = require_cuda(xys, depths, radii)
+    ws = workspace(dev)
+    xys, depths = f32c(xys), f32c(depths)
+    radii = radii.contiguous().reshape(-1)
+    tiles_x, tiles_y = int(tile_bounds[0]), int(tile_bounds[1])
+    num_tiles = tiles_x * tiles_y * n_views
+    key = (int(n) * int(n_views), num_tiles)
+    capturing = torch.cuda.is_current_stream_capturing()
+    if not capturing:
+        ws.poll()
+    if _FORCE_SYNC:
+        sync_free = False
+
+    def run(capacity):
+        scratch = ws.tiles_scratch_for(num_tiles, capacity)
+        ids = torch.empty((max(capacity, 1),), dtype=torch.int32, device=dev)
+        ranges = torch.empty((num_tiles, 2), dtype=torch.int32, device=dev)
+        order_t = torch.empty((num_tiles,), dtype=torch.int32, device=dev)
+        slot = ws.info_next
+        ws.info_next = (slot + 1) % _INFO_SLOTS
+        with _lib.device_guard(dev):
+            _lib.call("gg_bin_tiles", int(n), int(n_views), ptr(xys), 8 if xy_from_geo else 2, ptr(depths), ptr(radii),
+                      tiles_x, tiles_y, int(capacity), ptr(scratch), scratch.numel(), ptr(ids), ptr(ranges), ptr(order_t),
+                      None, ws.info_host[slot].data_ptr(), stream_ptr(dev))
+        ev = None
+        if not capturing:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+        info = BinInfo(ws, slot, ev, key, capacity)
+        if not capturing:
+            ws.info_pending.append(info)
+        return Binning(n, n_views, ids, ranges, tuple(tile_bounds), order_t, None, info)
+
+    cap = ws.capacity.get(key)
+    if cap is None:
+        if capturing:
+            raise _lib.GGError("bin_views_tiles: the first call of a problem size measures the intersection count "
+                               "on the host; run one step before capturing a CUDA graph")
+        m, _, _, _ = run(0).info.wait()       # counting pass only
+        cap = ws.capacity[key] = _capacity_for(m)
+    b = run(cap)
+    if not sync_free and not capturing:
+        m, overflow, _, _ = b.info.wait()
+        if overflow:
+            ws.overflow_note = None
+            b = run(ws.capacity[key])         # note() has raised it past m
+            b.check()
+        else:
+            b._m = m
+    return b
+
+
+import os as _os
+_FORCE_SYNC = _os.environ.get("GG_BIN_SYNC", "0") not in ("", "0")
 
 
 def bin_views(n, n_views, xys, depths, radii, num_tiles_hit, tile_bounds, xy_from_geo=False,
-              while_waiting=None, depth_first=True) -> Binning:
+              while_waiting=None, mode="tiles", sync_free=True) -> Binning:
     """Sorted (tile, depth, id) intersection list of a batch of views.
 
-    depth_first (default): sort the V*n Gaussians by (view, depth), emit their tile entries in that
-    order, stable-sort the M entries by tile id -- 4-5 small passes + 2-3 M-sized passes.  Otherwise the
-    reference's formulation: emit 64-bit tile|depth keys in id order and sort all M of them (6-7
-    M-sized passes).  Both give bit-identical ids_sorted / tile_ranges.
+    mode "tiles" (default): tile-first, no host read -- see bin_views_tiles.
+    mode "depth": sort the V*n Gaussians by (view, depth), emit their tile entries in that order, stable-sort
+    the M entries by tile id -- 4-5 small passes + 2-3 M-sized passes, one host read of M.
+    mode "reference": the reference's formulation: emit 64-bit tile|depth keys in id order and sort all M of
+    them (6-7 M-sized passes).  All three give bit-identical ids_sorted / tile_ranges.
     xy_from_geo: `xys` is the packed [V*n, 8] geo table (pixel centres in columns 0..1).
     while_waiting: callable run after the M read-back is enqueued and before the host waits for it."""
+    if mode not in ("tiles", "depth", "reference"):
+        raise ValueError(f"bin_views: unknown mode {mode!r}")
+    if mode == "tiles":
+        b = bin_views_tiles(n, n_views, xys, depths, radii, tile_bounds, xy_from_geo, sync_free=sync_free)
+        if while_waiting is not None:
+            while_waiting()
+        return b
+    depth_first = mode == "depth"
     dev = require_cuda(xys, depths, radii, num_tiles_hit)
     ws = workspace(dev)
     lib_call = _lib.call
@@ -264,7 +435,7 @@ def bin_views(n, n_views, xys, depths, radii, num_tiles_hit, tile_bounds, xy_fro
     num_tiles = tiles_x * tiles_y * n_views
     with _lib.device_guard(dev):
         st = stream_ptr(dev)
-        # the one device->host read of the path (the reference has five per view): M sizes the sort.
+        # the one device->host read of these two paths (the reference has five per view): M sizes the sort.
         # Work passed as `while_waiting` is enqueued behind the copy so the GPU stays busy meanwhile.
         if depth_first:
             begin = ws.begin_scratch(total)
@@ -285,7 +456,7 @@ def bin_views(n, n_views, xys, depths, radii, num_tiles_hit, tile_bounds, xy_fro
             raise _lib.GGError("number of tile intersections overflows int32")
         if m == 0:
             ranges = torch.zeros((num_tiles, 2), dtype=torch.int32, device=dev)
-            return Binning(n, n_views, 0, torch.empty((0,), dtype=torch.int32, device=dev), ranges, tuple(tile_bounds), None)
+            return Binning(n, n_views, torch.empty((0,), dtype=torch.int32, device=dev), ranges, tuple(tile_bounds), None, 0)
         ids_sorted = torch.empty((m,), dtype=torch.int32, device=dev)
         if depth_first:
             ranges = torch.empty((num_tiles, 2), dtype=torch.int32, device=dev)
@@ -299,7 +470,7 @@ def bin_views(n, n_views, xys, depths, radii, num_tiles_hit, tile_bounds, xy_fro
             sort_pairs(m, key_bits_for(num_tiles), keys, ids, keys_sorted, ids_sorted)
             ranges = tile_ranges(m, keys_sorted, num_tiles)
             order_t = tile_order(ranges)
-    return Binning(n, n_views, m, ids_sorted, ranges, tuple(tile_bounds), order_t)
+    return Binning(n, n_views, ids_sorted, ranges, tuple(tile_bounds), order_t, m)
 
 
 # ------------------------------------------------------------------------------------------
@@ -318,8 +489,8 @@ def pack_geo(n, n_views, xys, conics, opacity, opac_per_view=False):
 def _ids_ptr(binning: "Binning"):
     """Pointer of the sorted id list; an empty list (nothing visible) still needs a valid address
     for the C ABI's null checks -- no kernel dereferences it, every tile range is (0,0)."""
-    if binning.ids_sorted.numel() > 0:
-        return ptr(binning.ids_sorted)
+    if binning.ids_buffer.numel() > 0:
+        return ptr(binning.ids_buffer)
     return ptr(workspace(binning.tile_ranges.device).total)
 
 
@@ -344,8 +515,8 @@ def blend_fwd(binning: Binning, geo, colors, background, img_height, img_width, 
     tb = binning.tile_bounds
     step = max_channels()
     hit_words = None
-    if record_hits and C <= step and binning.num_intersects > 0:
-        nwords = int(_lib.load().gg_blend_hit_words(binning.num_intersects, binning.tile_ranges.shape[0], C))
+    if record_hits and C <= step and binning.capacity > 0:
+        nwords = int(_lib.load().gg_blend_hit_words(binning.capacity, binning.tile_ranges.shape[0], C))
         hit_words = torch.zeros(nwords, dtype=torch.int32, device=dev)
     with _lib.device_guard(dev):
         for c0 in range(0, C, step):

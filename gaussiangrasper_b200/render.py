@@ -163,10 +163,17 @@ class _RenderViews(Function):
                           ops.ptr(chan), ops.ptr(depths), ops.ptr(radii), ops.ptr(nth), ops.ptr(s_out), ops.ptr(q_out),
                           phase, ops.stream_ptr(dev))
 
-        # geometry first; the channel rows (SH, normals, features) are produced while the host waits
-        # for the intersection count that sizes the sort
-        prepare(1)
-        binning = ops.bin_views(n, V, geo, depths, radii, nth, tb, xy_from_geo=True, while_waiting=lambda: prepare(2))
+        # one view: geometry and channel rows in one launch.  Several views: geometry per (view, Gaussian),
+        # then the channel rows of all views from one read of the SH / feature rows (prepare_chan_kernel).
+        # The binning never waits for the host (ops.bin_views_tiles).
+        if V == 1:
+            prepare(0)
+        else:
+            prepare(1)
+        binning = ops.bin_views(n, V, geo, depths, radii, nth, tb, xy_from_geo=True,
+                                sync_free=not (holder or {}).get("exact_binning", False))
+        if V > 1:
+            prepare(2)
         bg = _background(CP, float(depth_background), dev)
         out, final_T, final_idx, hit_words = ops.blend_fwd(binning, geo, chan, bg, H, W, colors_per_view=True,
                                                            pair_counter=stats,

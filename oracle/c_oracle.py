@@ -86,6 +86,15 @@ def sh_bwd(degree, degrees_to_use, dirs, v_colors):
     return out
 
 
+def tile_counts(xys, radii, tile_bounds):
+    """num_tiles_hit of made-up projection outputs (A6 only)."""
+    xys, radii = _f32(xys), _i32(radii)
+    out = np.empty((xys.shape[0],), np.int32)
+    lib().gg_oracle_tile_counts(C.c_int(xys.shape[0]), _p(xys), _p(radii), C.c_int(int(tile_bounds[0])),
+                                C.c_int(int(tile_bounds[1])), _p(out))
+    return out
+
+
 def bin_and_sort(xys, depths, radii, num_tiles_hit, tile_bounds):
     """Returns (cum, keys_unsorted, ids_unsorted, keys_sorted, ids_sorted, tile_ranges[T,2])."""
     xys, depths, radii, nth = _f32(xys), _f32(depths), _i32(radii), _i32(num_tiles_hit)

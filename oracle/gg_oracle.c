@@ -230,6 +230,20 @@ void gg_oracle_cumsum(int n, const int32_t *num_tiles_hit, int32_t *cum) {
     for (int i = 0; i < n; ++i) { acc += num_tiles_hit[i]; cum[i] = acc; }
 }
 
+/* A6 alone: tiles touched by (centre, integer radius) -- what the projection reports as num_tiles_hit; lets the
+ * binning tests make up projection outputs directly (0 for radius <= 0 or an empty box). */
+void gg_oracle_tile_counts(int n, const float *xys, const int32_t *radii, int tiles_x, int tiles_y,
+                           int32_t *num_tiles_hit) {
+    for (int i = 0; i < n; ++i) {
+        num_tiles_hit[i] = 0;
+        if (radii[i] <= 0) continue;
+        int minx, miny, maxx, maxy;
+        tile_bbox(xys[2 * i], xys[2 * i + 1], (float)radii[i], tiles_x, tiles_y, &minx, &miny, &maxx, &maxy);
+        const int area = (maxx - minx) * (maxy - miny);
+        num_tiles_hit[i] = area > 0 ? area : 0;
+    }
+}
+
 /* keys/ids must hold cum[n-1] entries */
 void gg_oracle_map_to_intersects(int n, const float *xys, const float *depths, const int32_t *radii,
                                  const int32_t *cum, int tiles_x, int tiles_y, int64_t *keys,

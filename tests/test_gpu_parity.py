@@ -207,10 +207,17 @@ def test_depth_first_binning_equals_reference_formulation(dev, n, W, H, seed, bi
     cat = lambda k: torch.from_numpy(np.concatenate([o[k] for o in outs])).to(dev)
     xys, depths, radii, nth = cat(0), cat(1), cat(2), cat(4)
     tb = cams[0].tile_bounds
-    a = ops.bin_views(n, views, xys, depths, radii, nth, tb, depth_first=True)
-    b = ops.bin_views(n, views, xys, depths, radii, nth, tb, depth_first=False)
-    assert a.num_intersects == b.num_intersects > 0
+    a = ops.bin_views(n, views, xys, depths, radii, nth, tb, mode="depth")
+    b = ops.bin_views(n, views, xys, depths, radii, nth, tb, mode="reference")
+    c = ops.bin_views(n, views, xys, depths, radii, nth, tb, mode="tiles")
+    assert a.num_intersects == b.num_intersects == c.num_intersects > 0
     assert torch.equal(a.ids_sorted, b.ids_sorted) and torch.equal(a.tile_ranges, b.tile_ranges)
+    assert torch.equal(c.ids_sorted, b.ids_sorted) and torch.equal(c.tile_ranges, b.tile_ranges)
+    for bn in (a, c):
+        order = bn.tile_order.cpu().numpy()
+        assert sorted(order.tolist()) == list(range(tb[0] * tb[1] * views))
+        lens = (bn.tile_ranges[:, 1] - bn.tile_ranges[:, 0]).cpu().numpy()[order] >> 3
+        assert (np.diff(np.minimum(lens, 1023)) <= 0).all()
     # against the oracle, view by view
     T = tb[0] * tb[1]
     off = 0
@@ -228,7 +235,8 @@ def test_depth_first_binning_equals_reference_formulation(dev, n, W, H, seed, bi
     assert (np.diff(np.minimum(lens, 1023)) <= 0).all()
 
 
-def test_binning_scratch_reuse_across_sizes(dev):
+@pytest.mark.parametrize("mode", ["tiles", "depth"])
+def test_binning_scratch_reuse_across_sizes(dev, mode):
     """The binning scratch is laid out per call inside grow-only buffers: a sequence of larger and smaller
     problems (the layout shifts under stale data of the previous call) must keep matching the oracle."""
     from gaussiangrasper_b200 import ops
@@ -238,19 +246,112 @@ def test_binning_scratch_reuse_across_sizes(dev):
         xys, depths, radii, conics, nth, _ = oracle_project(sc, cam, scales, quats)
         _, _, _, _, ids_s, ranges = c_oracle.bin_and_sort(xys, depths, radii, nth, cam.tile_bounds)
         t = lambda a: torch.from_numpy(a).to(dev)
-        b = ops.bin_views(n, 1, t(xys), t(depths), t(radii), t(nth), cam.tile_bounds)
+        b = ops.bin_views(n, 1, t(xys), t(depths), t(radii), t(nth), cam.tile_bounds, mode=mode)
         assert np.array_equal(b.ids_sorted.cpu().numpy(), ids_s)
         got = b.tile_ranges.cpu().numpy()
         ne = ranges[:, 1] > ranges[:, 0]
         assert np.array_equal(got[ne], ranges[ne]) and not got[~ne].any()
 
 
-def test_binning_empty(dev):
+@pytest.mark.parametrize("mode", ["tiles", "depth", "reference"])
+def test_binning_empty(dev, mode):
     from gaussiangrasper_b200 import ops
     n = 100
     z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=dev)
-    b = ops.bin_views(n, 1, z(n, 2), z(n), z(n, dt=torch.int32), z(n, dt=torch.int32), (4, 3, 1))
+    b = ops.bin_views(n, 1, z(n, 2), z(n), z(n, dt=torch.int32), z(n, dt=torch.int32), (4, 3, 1), mode=mode)
     assert b.num_intersects == 0 and b.ids_sorted.numel() == 0 and not b.tile_ranges.any()
+
+
+def _synthetic_projection(n, W, H, seed, depth_values=None, radius_hi=40, centre=None, spread=None):
+    """Projection outputs made up directly (pixel centres, integer radii, depths) -- what the binning consumes --
+    with the tile counts the projection kernel would report for them (C oracle's tile bbox)."""
+    rng = np.random.default_rng(seed)
+    if centre is None:
+        xys = np.stack([rng.uniform(-20, W + 20, n), rng.uniform(-20, H + 20, n)], 1).astype(np.float32)
+    else:
+        xys = (np.asarray(centre, np.float32)[None] + rng.normal(0, spread, (n, 2))).astype(np.float32)
+    radii = rng.integers(0, radius_hi, n).astype(np.int32)
+    if depth_values is None:
+        depths = rng.uniform(0.5, 9.0, n).astype(np.float32)
+    else:
+        depths = rng.choice(np.asarray(depth_values, np.float32), n).astype(np.float32)
+    tb = ((W + 15) // 16, (H + 15) // 16, 1)
+    nth = c_oracle.tile_counts(xys, radii, tb)
+    radii = np.where(nth > 0, radii, 0).astype(np.int32)
+    return xys, depths, radii, nth, tb
+
+
+@pytest.mark.parametrize("case", ["ties", "all_equal", "one_huge_tile", "screen_filling", "mid_tiles"])
+def test_tile_binning_hard_cases(dev, case):
+    """Tile-first binning against the C oracle where its per-tile sort has to work for its result: equal depths
+    (order by id, whatever the scatter order was), a tile list beyond the shared-memory classes (> 16384), tile
+    lists in the 1024-thread class, and footprints of hundreds of tiles (warp-shared emission)."""
+    from gaussiangrasper_b200 import ops
+    if case == "ties":        # 40 distinct depths over 30k Gaussians: every tile is full of ties
+        args = _synthetic_projection(30_000, 320, 240, 1, depth_values=np.linspace(1.0, 5.0, 40))
+    elif case == "all_equal":  # no depth bit varies at all
+        args = _synthetic_projection(20_000, 160, 128, 2, depth_values=[2.5])
+    elif case == "one_huge_tile":  # ~40k entries in the centre tiles
+        args = _synthetic_projection(40_000, 160, 128, 3, radius_hi=6, centre=(80.0, 64.0), spread=3.0)
+    elif case == "screen_filling":  # radii up to 600 px: 300-tile footprints
+        args = _synthetic_projection(3_000, 640, 480, 4, radius_hi=600)
+    else:                      # 5-15k entries per tile
+        args = _synthetic_projection(60_000, 96, 64, 5, radius_hi=30)
+    xys, depths, radii, nth, tb = args
+    n = len(radii)
+    _, _, _, _, ids_s, ranges = c_oracle.bin_and_sort(xys, depths, radii, nth, tb)
+    t = lambda a: torch.from_numpy(a).to(dev)
+    for rep in range(2):   # twice: the second call runs without the counting pass
+        b = ops.bin_views(n, 1, t(xys), t(depths), t(radii), t(nth), tb, mode="tiles")
+        assert b.num_intersects == len(ids_s)
+        assert np.array_equal(b.ids_sorted.cpu().numpy(), ids_s), case
+        got = b.tile_ranges.cpu().numpy()
+        ne = ranges[:, 1] > ranges[:, 0]
+        assert np.array_equal(got[ne], ranges[ne]) and not got[~ne].any()
+    lens = ranges[:, 1] - ranges[:, 0]
+    if case == "one_huge_tile":
+        assert lens.max() > 16384
+    if case == "mid_tiles":
+        assert 4096 < lens.max() <= 16384
+
+
+def test_tile_binning_overflow_is_reported_and_recovered(dev):
+    """M jumping past the remembered capacity: the call must not write out of bounds, must flag the overflow
+    (every tile range empty), and the next call must work with the raised capacity."""
+    from gaussiangrasper_b200 import ops
+    from gaussiangrasper_b200._lib import GGError
+    W, H = 320, 240
+    small = _synthetic_projection(5_000, W, H, 11, radius_hi=8)
+    large = _synthetic_projection(5_000, W, H, 12, radius_hi=200)   # same signature (rows, tiles), ~100x the entries
+    t = lambda a: torch.from_numpy(a).to(dev)
+
+    def run(args, **kw):
+        xys, depths, radii, nth, tb = args
+        return ops.bin_views(len(radii), 1, t(xys), t(depths), t(radii), t(nth), tb, mode="tiles", **kw)
+
+    ops.workspace(torch.device(dev)).capacity.clear()
+    b0 = run(small)
+    assert b0.num_intersects == int(small[3].sum())
+    b1 = run(large)                       # sized for `small`: overflows
+    assert not b1.tile_ranges.any()
+    with pytest.raises(GGError, match="overflow"):
+        b1.check()
+    b2 = run(large)                       # capacity raised by the read-back of b1
+    _, _, _, _, ids_s, ranges = c_oracle.bin_and_sort(large[0], large[1], large[2], large[3], large[4])
+    assert b2.num_intersects == len(ids_s) and np.array_equal(b2.ids_sorted.cpu().numpy(), ids_s)
+    # the exact mode repairs an overflow by itself
+    ops.workspace(torch.device(dev)).capacity.clear()
+    run(small)
+    b3 = run(large, sync_free=False)
+    assert np.array_equal(b3.ids_sorted.cpu().numpy(), ids_s)
+    # an overflow nobody checked is reported by the next call
+    ops.workspace(torch.device(dev)).capacity.clear()
+    run(small)
+    run(large)
+    torch.cuda.synchronize()
+    with pytest.raises(GGError, match="earlier call"):
+        run(small)
+    run(small)
 
 
 # ---------------------------------------------------------------------------------------------
