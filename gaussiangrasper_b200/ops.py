@@ -97,8 +97,8 @@ class _Workspace:
                 f"tile binning overflow in an earlier call: {m} intersections > capacity {cap}; that call drew the "
                 "background only. The capacity has been raised: repeat the step")
 
-    def tiles_scratch_for(self, num_tiles, capacity):
-        need = int(_lib.load().gg_bin_tiles_scratch_bytes(num_tiles, capacity))
+    def tiles_scratch_for(self, n_views, tiles_per_view, capacity):
+        need = int(_lib.load().gg_bin_tiles_scratch_bytes(n_views, tiles_per_view, capacity))
         if self.tiles_scratch is None or self.tiles_scratch.numel() < need:
             self.tiles_scratch = torch.empty(int(need * 1.25) + 4096, dtype=torch.uint8, device=self.device)
         return self.tiles_scratch
@@ -364,7 +364,7 @@ def bin_views_tiles(n, n_views, xys, depths, radii, tile_bounds, xy_from_geo=Fal
         sync_free = False
 
     def run(capacity):
-        scratch = ws.tiles_scratch_for(num_tiles, capacity)
+        scratch = ws.tiles_scratch_for(int(n_views), tiles_x * tiles_y, capacity)
         ids = torch.empty((max(capacity, 1),), dtype=torch.int32, device=dev)
         ranges = torch.empty((num_tiles, 2), dtype=torch.int32, device=dev)
         order_t = torch.empty((num_tiles,), dtype=torch.int32, device=dev)

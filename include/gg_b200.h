@@ -139,7 +139,7 @@ int gg_bin_finish(int n, int n_views, long long m, const float* xys, int xy_stri
  * passed this call) receive {M, overflow, longest tile list, 0}.  If M > capacity nothing is binned: overflow = 1,
  * every tile range is (0,0) (the blend kernels then render the background only) and the caller repeats the call
  * with capacity >= M.  capacity = 0 only counts.  The scratch needs no initialisation. */
-size_t gg_bin_tiles_scratch_bytes(long long num_tiles /* V * tiles */, long long capacity);
+size_t gg_bin_tiles_scratch_bytes(int n_views, long long tiles_per_view, long long capacity);
 int gg_bin_tiles(int n, int n_views, const float* xys, int xy_stride /*2 or 8*/, const float* depths /*[V*n]*/,
                  const int32_t* radii /*[V*n]*/, int tiles_x, int tiles_y, long long capacity, void* scratch,
                  size_t scratch_bytes, int32_t* ids_sorted /*[capacity]*/, int32_t* tile_ranges /*[V*tiles, 2]*/,

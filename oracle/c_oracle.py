@@ -146,3 +146,23 @@ def blend_bwd(H, W, tile_bounds, ids_sorted, tile_ranges, xys, conics, opac, col
         _p(ids_sorted), _p(tile_ranges), _p(xys), _p(conics), _p(opac), _p(colors), _p(bg), _p(v_out),
         _p(v_xy), _p(v_conic), _p(v_colors), _p(v_opac))
     return v_xy, v_conic, v_colors, v_opac
+
+
+def blend_bwd_ex(H, W, tile_bounds, ids_sorted, tile_ranges, xys, conics, opac, colors, bg, v_out, eps=2e-5):
+    """blend_bwd plus the two element-wise error scales of gg_oracle_blend_bwd_ex:
+    returns dict(v_xy, v_conic, v_colors, v_opac, abs_geo[N,6], abs_colors[N,C], taint_geo[N,6], taint_colors[N,C])
+    with the geo columns ordered (x, y, A, B, C, opacity)."""
+    ids_sorted, tile_ranges = _i32(ids_sorted), _i32(tile_ranges)
+    xys, conics, opac, colors, bg = _f32(xys), _f32(conics), _f32(opac).reshape(-1), _f32(colors), _f32(bg)
+    v_out = _f32(v_out)
+    n, ch = colors.shape
+    r = dict(v_xy=np.empty((n, 2), np.float64), v_conic=np.empty((n, 3), np.float64),
+             v_colors=np.empty((n, ch), np.float64), v_opac=np.empty((n,), np.float64),
+             abs_geo=np.empty((n, 6), np.float64), abs_colors=np.empty((n, ch), np.float64),
+             taint_geo=np.empty((n, 6), np.float64), taint_colors=np.empty((n, ch), np.float64))
+    lib().gg_oracle_blend_bwd_ex(
+        C.c_int(n), C.c_int(ch), C.c_int(H), C.c_int(W), C.c_int(tile_bounds[0]),
+        _p(ids_sorted), _p(tile_ranges), _p(xys), _p(conics), _p(opac), _p(colors), _p(bg), _p(v_out),
+        _p(r["v_xy"]), _p(r["v_conic"]), _p(r["v_colors"]), _p(r["v_opac"]), C.c_float(eps),
+        _p(r["abs_geo"]), _p(r["abs_colors"]), _p(r["taint_geo"]), _p(r["taint_colors"]))
+    return r

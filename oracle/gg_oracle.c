@@ -356,15 +356,28 @@ int64_t gg_oracle_blend_fwd(int channels, int img_h, int img_w, int tiles_x, int
 /* 0.999 passes no gradient to sigma/opacity.                                  */
 /* v_xy[N,2], v_conic[N,3], v_colors[N,C], v_opac[N] are doubles.              */
 /* ------------------------------------------------------------------------- */
-void gg_oracle_blend_bwd(int n, int channels, int img_h, int img_w, int tiles_x,
-                         const int32_t *ids_sorted, const int32_t *tile_ranges, const float *xys,
-                         const float *conics, const float *opac, const float *colors,
-                         const float *bg, const float *v_out, double *v_xy, double *v_conic,
-                         double *v_colors, double *v_opac) {
+/* Extended form.  Besides the gradients it can return, per gradient component,                                 */
+/*   abs_*  : the sum of the ABSOLUTE values of the per-pixel contributions (the scale fp32 accumulation error   */
+/*            is proportional to: a sum that cancels has |sum| << abs sum), and                                  */
+/*   taint_*: the same sum restricted to pixels the forward flags fragile (a pair within `eps` relative of a     */
+/*            branch threshold): a flip there changes that pixel's contributions by about alpha_min = 1/255.     */
+/* The parity tests bound |got - ref| <= rtol |ref| + k eps_fp32 abs + 0.01 taint element by element.            */
+/* abs / taint pointers may be NULL (all or none of each group).                                                 */
+void gg_oracle_blend_bwd_ex(int n, int channels, int img_h, int img_w, int tiles_x,
+                            const int32_t *ids_sorted, const int32_t *tile_ranges, const float *xys,
+                            const float *conics, const float *opac, const float *colors,
+                            const float *bg, const float *v_out, double *v_xy, double *v_conic,
+                            double *v_colors, double *v_opac, float eps, double *abs_geo /*[n,6]*/,
+                            double *abs_colors /*[n,C]*/, double *taint_geo /*[n,6]*/,
+                            double *taint_colors /*[n,C]*/) {
     memset(v_xy, 0, sizeof(double) * 2 * (size_t)n);
     memset(v_conic, 0, sizeof(double) * 3 * (size_t)n);
     memset(v_colors, 0, sizeof(double) * (size_t)channels * (size_t)n);
     memset(v_opac, 0, sizeof(double) * (size_t)n);
+    if (abs_geo) memset(abs_geo, 0, sizeof(double) * 6 * (size_t)n);
+    if (abs_colors) memset(abs_colors, 0, sizeof(double) * (size_t)channels * (size_t)n);
+    if (taint_geo) memset(taint_geo, 0, sizeof(double) * 6 * (size_t)n);
+    if (taint_colors) memset(taint_colors, 0, sizeof(double) * (size_t)channels * (size_t)n);
     double *S = (double *)malloc(sizeof(double) * (size_t)channels);
     for (int py = 0; py < img_h; ++py) {
         for (int pxi = 0; pxi < img_w; ++pxi) {
@@ -376,15 +389,19 @@ void gg_oracle_blend_bwd(int n, int channels, int img_h, int img_w, int tiles_x,
             /* forward replay in fp32 to find the contributing set exactly as A9 does */
             float T = 1.0f;
             int last = start;
+            int frag = 0;
             for (int k = start; k < end; ++k) {
                 const int g = ids_sorted[k];
                 const float dx = xys[2 * g] - fx, dy = xys[2 * g + 1] - fy;
                 const float A = conics[3 * g], B = conics[3 * g + 1], C = conics[3 * g + 2];
                 const float sigma = 0.5f * (A * dx * dx + C * dy * dy) + B * dx * dy;
+                if (fabsf(sigma) <= 1e-6f) frag = 1;
                 if (sigma < 0.0f) continue;
                 const float alpha = fminf(0.999f, opac[g] * expf(-sigma));
+                if (fabsf(alpha - (1.0f / 255.0f)) <= eps * (1.0f / 255.0f)) frag = 1;
                 if (alpha < 1.0f / 255.0f) continue;
                 const float next_T = T * (1.0f - alpha);
+                if (fabsf(next_T - 1e-4f) <= eps * 1e-4f) frag = 1;
                 if (next_T <= 1e-4f) break;
                 T = next_T;
                 last = k + 1;
@@ -429,7 +446,10 @@ void gg_oracle_blend_bwd(int n, int channels, int img_h, int img_w, int tiles_x,
                 const float *col = colors + (size_t)g * channels;
                 double v_alpha = 0.0;
                 for (int c = 0; c < channels; ++c) {
-                    v_colors[(size_t)g * channels + c] += fac * vo[c];
+                    const double t = fac * vo[c];
+                    v_colors[(size_t)g * channels + c] += t;
+                    if (abs_colors) abs_colors[(size_t)g * channels + c] += fabs(t);
+                    if (taint_colors && frag) taint_colors[(size_t)g * channels + c] += fabs(t);
                     v_alpha += ((double)col[c] * Tb - S[c] * ra) * vo[c];
                     S[c] += (double)col[c] * fac;
                 }
@@ -437,16 +457,29 @@ void gg_oracle_blend_bwd(int n, int channels, int img_h, int img_w, int tiles_x,
                 Tcur = Tb;
                 if (clamped) continue;
                 const double v_sigma = -al * v_alpha; /* d alpha / d sigma = -o e^-s */
-                v_opac[g] += vis * v_alpha;
-                v_conic[3 * g] += 0.5 * v_sigma * dx * dx;
-                v_conic[3 * g + 1] += v_sigma * dx * dy;
-                v_conic[3 * g + 2] += 0.5 * v_sigma * dy * dy;
-                v_xy[2 * g] += v_sigma * ((double)A * dx + (double)B * dy);
-                v_xy[2 * g + 1] += v_sigma * ((double)B * dx + (double)C * dy);
+                const double t6[6] = {v_sigma * ((double)A * dx + (double)B * dy), v_sigma * ((double)B * dx + (double)C * dy),
+                                      0.5 * v_sigma * dx * dx, v_sigma * dx * dy, 0.5 * v_sigma * dy * dy, vis * v_alpha};
+                v_xy[2 * g] += t6[0];
+                v_xy[2 * g + 1] += t6[1];
+                v_conic[3 * g] += t6[2];
+                v_conic[3 * g + 1] += t6[3];
+                v_conic[3 * g + 2] += t6[4];
+                v_opac[g] += t6[5];
+                if (abs_geo) for (int q = 0; q < 6; ++q) abs_geo[6 * (size_t)g + q] += fabs(t6[q]);
+                if (taint_geo && frag) for (int q = 0; q < 6; ++q) taint_geo[6 * (size_t)g + q] += fabs(t6[q]);
             }
         }
     }
     free(S);
+}
+
+void gg_oracle_blend_bwd(int n, int channels, int img_h, int img_w, int tiles_x,
+                         const int32_t *ids_sorted, const int32_t *tile_ranges, const float *xys,
+                         const float *conics, const float *opac, const float *colors,
+                         const float *bg, const float *v_out, double *v_xy, double *v_conic,
+                         double *v_colors, double *v_opac) {
+    gg_oracle_blend_bwd_ex(n, channels, img_h, img_w, tiles_x, ids_sorted, tile_ranges, xys, conics, opac, colors, bg,
+                           v_out, v_xy, v_conic, v_colors, v_opac, 0.0f, NULL, NULL, NULL, NULL);
 }
 
 /* ------------------------------------------------------------------------- */

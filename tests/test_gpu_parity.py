@@ -281,7 +281,8 @@ def _synthetic_projection(n, W, H, seed, depth_values=None, radius_hi=40, centre
     return xys, depths, radii, nth, tb
 
 
-@pytest.mark.parametrize("case", ["ties", "all_equal", "one_huge_tile", "screen_filling", "mid_tiles"])
+@pytest.mark.parametrize("case", ["ties", "all_equal", "one_huge_tile", "screen_filling", "mid_tiles", "clustered",
+                                  "huge_tile_ties", "very_long_tile"])
 def test_tile_binning_hard_cases(dev, case):
     """Tile-first binning against the C oracle where its per-tile sort has to work for its result: equal depths
     (order by id, whatever the scatter order was), a tile list beyond the shared-memory classes (> 16384), tile
@@ -295,6 +296,15 @@ def test_tile_binning_hard_cases(dev, case):
         args = _synthetic_projection(40_000, 160, 128, 3, radius_hi=6, centre=(80.0, 64.0), spread=3.0)
     elif case == "screen_filling":  # radii up to 600 px: 300-tile footprints
         args = _synthetic_projection(3_000, 640, 480, 4, radius_hi=600)
+    elif case == "clustered":   # two thin depth layers: the bucket sort hands the tiles to the radix kernel
+        rng = np.random.default_rng(6)
+        dv = np.concatenate([rng.normal(1.0, 1e-4, 500), rng.normal(6.0, 1e-4, 500)])
+        args = _synthetic_projection(50_000, 320, 240, 6, depth_values=dv)
+    elif case == "huge_tile_ties":   # > 16384 entries AND piled-up depths: bucket sort -> bitonic list
+        args = _synthetic_projection(40_000, 160, 128, 7, radius_hi=6, centre=(80.0, 64.0), spread=3.0,
+                                     depth_values=np.linspace(1.0, 2.0, 25))
+    elif case == "very_long_tile":   # > 24576 entries: listed for the bitonic kernel by the scan
+        args = _synthetic_projection(70_000, 160, 128, 8, radius_hi=5, centre=(80.0, 64.0), spread=2.0)
     else:                      # 5-15k entries per tile
         args = _synthetic_projection(60_000, 96, 64, 5, radius_hi=30)
     xys, depths, radii, nth, tb = args
@@ -309,8 +319,10 @@ def test_tile_binning_hard_cases(dev, case):
         ne = ranges[:, 1] > ranges[:, 0]
         assert np.array_equal(got[ne], ranges[ne]) and not got[~ne].any()
     lens = ranges[:, 1] - ranges[:, 0]
-    if case == "one_huge_tile":
-        assert lens.max() > 16384
+    if case in ("one_huge_tile", "huge_tile_ties"):
+        assert 16384 < lens.max() <= 24576
+    if case == "very_long_tile":
+        assert lens.max() > 24576
     if case == "mid_tiles":
         assert 4096 < lens.max() <= 16384
 
