@@ -52,7 +52,7 @@ _SIGNATURES = {
     "gg_bin_wait": (C.c_int, []),
     "gg_bin_finish": (C.c_int, [_i, _i, _ll, _p, _i, _p, _i, _i, _p, _p, _sz, _p, _p, _p, _p]),
     "gg_bin_tiles_scratch_bytes": (C.c_size_t, [_i, _ll, _ll]),
-    "gg_bin_tiles": (C.c_int, [_i, _i, _p, _i, _p, _p, _i, _i, _ll, _p, _sz, _p, _p, _p, _p, _p, _p]),
+    "gg_bin_tiles": (C.c_int, [_i, _i, _p, _i, _p, _p, _i, _i, _ll, _p, _sz, _p, _p, _p, _p, _p, _i, _p]),
     "gg_tile_order_workspace_bytes": (C.c_size_t, []),
     "gg_tile_order": (C.c_int, [_ll, _p, _p, _p, _sz, _p]),
     "gg_unpack_vgeo": (C.c_int, [_ll, _i, _p, _p, _p, _p, _i, _p]),

@@ -100,6 +100,8 @@ tile_count_kernel(long long total, int n, const float* __restrict__ xys, int xy_
 // Gaussians [b * per, (b+1) * per) of that view (per is a multiple of 32, identical in both kernels).
 // ---------------------------------------------------------------------------------------------
 constexpr int kHistThreads = 1024;
+constexpr int kHistBlocksTotal = 296;            // 2 CTAs of 1024 threads per SM
+constexpr int kHistMaxTiles = 40960;             // tiles per view whose counters fit a shared-memory histogram
 
 // Every tile of every lane's box: GG_FOR_TILES(b, rec) { ... uses `tile` and `r` (the owner's record) ... }
 // Small boxes are walked by their own lane; boxes of more than kBigBox tiles by the whole warp, 32 tiles per
@@ -187,7 +189,7 @@ __device__ __forceinline__ int warp_incl_scan_i(int v, int lane) {
 // base), tile_order (tiles by descending length bucket), info = {M, overflow, longest, 0}, redo[t] <- 0.
 __device__ __forceinline__ void scan_order_body(int num_tiles, long long capacity, int* counts, int32_t* tile_ranges,
                                                 int32_t* tile_order, int32_t* info, int32_t* lists,
-                                                int32_t* list_counts) {
+                                                int32_t* list_counts, int class_limit) {
     __shared__ long long s_sum[32];
     __shared__ int s_max[32];
     __shared__ int s_wsum[32];
@@ -249,7 +251,10 @@ __device__ __forceinline__ void scan_order_body(int num_tiles, long long capacit
             tile_ranges[2 * t + 1] = c ? start + c : 0;
             counts[t] = start;
             atomicAdd(&bins[len_bucket(c)], 1);
-            if (c > kBucketMax) lists[num_tiles + atomicAdd(list_counts + 1, 1)] = t;  // beyond shared memory
+            if (c > class_limit) {  // longer than the bucket-sort classes launched by this call
+                const int which = c <= kSortMaxSmem ? 0 : 1;
+                lists[which * num_tiles + atomicAdd(list_counts + which, 1)] = t;
+            }
         }
         carry += btot;
         __syncthreads();
@@ -275,34 +280,49 @@ __device__ __forceinline__ void scan_order_body(int num_tiles, long long capacit
 
 __global__ void __launch_bounds__(1024)
 tile_scan_order_kernel(int num_tiles, long long capacity, int* counts, int32_t* tile_ranges, int32_t* tile_order,
-                       int32_t* info, int32_t* lists, int32_t* list_counts) {
-    scan_order_body(num_tiles, capacity, counts, tile_ranges, tile_order, info, lists, list_counts);
+                       int32_t* info, int32_t* lists, int32_t* list_counts, int class_limit) {
+    scan_order_body(num_tiles, capacity, counts, tile_ranges, tile_order, info, lists, list_counts, class_limit);
 }
 
-// Per tile (one thread each): exclusive prefix over the rows of its view's CTAs, total -> counts.  The CTA that
-// finishes last runs the scan over the tiles (the rows and counts of the others are complete by then).
+// Exclusive prefix over the rows of a view's counting CTAs, per tile: CTA = 32 tiles x 32 row groups (thread
+// (x, y) sums rows y*rpg .. of tile x, the groups are scanned through shared memory, then every thread rewrites
+// its rows as running offsets); total -> counts.  The CTA that finishes last runs the scan over the tiles (the
+// rows and counts of the others are complete by then).
 __global__ void __launch_bounds__(1024)
 tile_prefix_scan_kernel(int num_tiles, int tiles_per_view, int blocks_per_view, long long capacity, int* blockhist,
                         int* counts, int32_t* tile_ranges, int32_t* tile_order, int32_t* info, int32_t* lists,
-                        int32_t* list_counts, unsigned* done) {
+                        int32_t* list_counts, int class_limit, unsigned* done) {
     __shared__ bool s_last;
-    const int gt = blockIdx.x * 1024 + threadIdx.x;
-    if (gt < num_tiles) {
-        const int view = gt / tiles_per_view, t = gt - view * tiles_per_view;
-        int* p = blockhist + (size_t)view * blocks_per_view * tiles_per_view + t;
-        int run = 0;
-        for (int b0 = 0; b0 < blocks_per_view; b0 += 8) {  // 8 independent loads in flight, then the stores
-            int c[8];
+    __shared__ int s_grp[32][33];
+    constexpr int kMaxRows = 10;                      // rows per thread: 32 * 10 >= kHistBlocksTotal
+    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    const int gt = blockIdx.x * 32 + x;
+    const int rpg = (blocks_per_view + 31) >> 5;      // rows per group (<= kMaxRows)
+    const bool live = gt < num_tiles;
+    const int view = live ? gt / tiles_per_view : 0, t = live ? gt - view * tiles_per_view : 0;
+    int* p = blockhist + ((size_t)view * blocks_per_view + (size_t)y * rpg) * tiles_per_view + t;
+    int c[kMaxRows];
+    int sum = 0;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) c[u] = b0 + u < blocks_per_view ? p[(size_t)(b0 + u) * tiles_per_view] : 0;
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                if (b0 + u < blocks_per_view) p[(size_t)(b0 + u) * tiles_per_view] = run;
-                run += c[u];
-            }
-        }
-        counts[gt] = run;
+    for (int u = 0; u < kMaxRows; ++u) {
+        c[u] = (live && u < rpg && y * rpg + u < blocks_per_view) ? p[(size_t)u * tiles_per_view] : 0;
+        sum += c[u];
     }
+    s_grp[y][x] = sum;
+    __syncthreads();
+    int run = 0, total = 0;
+#pragma unroll
+    for (int g = 0; g < 32; ++g) {
+        const int v = s_grp[g][x];
+        if (g < y) run += v;
+        total += v;
+    }
+#pragma unroll
+    for (int u = 0; u < kMaxRows; ++u) {
+        if (live && u < rpg && y * rpg + u < blocks_per_view) p[(size_t)u * tiles_per_view] = run;
+        run += c[u];
+    }
+    if (live && y == 0) counts[gt] = total;
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) s_last = atomicAdd(done, 1u) == gridDim.x - 1;
@@ -310,7 +330,7 @@ tile_prefix_scan_kernel(int num_tiles, int tiles_per_view, int blocks_per_view, 
     if (!s_last) return;
     if (threadIdx.x == 0) *done = 0u;  // armed for the next call
     __threadfence();
-    scan_order_body(num_tiles, capacity, counts, tile_ranges, tile_order, info, lists, list_counts);
+    scan_order_body(num_tiles, capacity, counts, tile_ranges, tile_order, info, lists, list_counts, class_limit);
 }
 
 __global__ void __launch_bounds__(256)
@@ -478,8 +498,7 @@ constexpr size_t tile_sort_smem() {
 }
 
 template <int THREADS, int IPT>
-__global__ void __launch_bounds__(THREADS, (THREADS >= 1024) ? 1 : ((THREADS >= 256) ? 3 : 8))
-tile_sort_kernel(const SortArgs a) {
+__device__ __forceinline__ void radix_sort_tiles(const SortArgs& a) {
     constexpr int CAP = THREADS * IPT;
     constexpr int NW = THREADS / 32;
     static_assert(IPT % 2 == 0 && 32 * IPT < 65536, "ranks are packed in 16 bits");
@@ -647,8 +666,7 @@ tile_sort_kernel(const SortArgs a) {
 // Segments longer than the shared-memory classes: bitonic network over the 64-bit records (depth << 32 | id
 // order = the wanted order) in global memory, all comparators ascending (the "flip" form), so that virtual
 // +inf padding beyond the segment never moves and the length need not be a power of two.
-__global__ void __launch_bounds__(1024)
-tile_sort_big_kernel(const SortArgs a) {
+__device__ __forceinline__ void bitonic_sort_tiles(const SortArgs& a) {
     const int n_todo = __ldcg(a.list_counts + 1);
   for (int it = blockIdx.x; it < n_todo; it += gridDim.x) {
     const int tile = __ldcg(a.lists + a.num_tiles + it);
@@ -685,12 +703,17 @@ tile_sort_big_kernel(const SortArgs a) {
   }
 }
 
+// The tiles the bucket sort left behind (normally none): radix list, then bitonic list, persistent CTAs.
+__global__ void __launch_bounds__(1024, 1)
+tile_sort_fallback_kernel(const SortArgs a) {
+    radix_sort_tiles<1024, 16>(a);
+    __syncthreads();
+    bitonic_sort_tiles(a);
+}
+
 struct Bin2Layout {
     size_t info, done, list_counts, counts, lists, blockhist, pairs, bytes;
 };
-
-constexpr int kHistBlocksTotal = 296;            // 2 CTAs of 1024 threads per SM
-constexpr int kHistMaxTiles = 40960;             // tiles per view whose counters fit a shared-memory histogram
 
 // CTAs per view and Gaussians per CTA of the shared-memory counting / placement kernels
 static void hist_blocks(int n, int n_views, int& blocks, int& per) {
@@ -731,7 +754,7 @@ extern "C" size_t gg_bin_tiles_scratch_bytes(int n_views, long long tiles_per_vi
 extern "C" int gg_bin_tiles(int n, int n_views, const float* xys, int xy_stride, const float* depths,
                             const int32_t* radii, int tiles_x, int tiles_y, long long capacity, void* scratch,
                             size_t scratch_bytes, int32_t* ids_sorted, int32_t* tile_ranges, int32_t* tile_order,
-                            int32_t* info_dev, int32_t* info_host, void* stream) {
+                            int32_t* info_dev, int32_t* info_host, int longest_hint, void* stream) {
     GG_REQUIRE(n >= 1 && n_views >= 1 && (long long)n * n_views < (1ll << 31), "gg_bin_tiles: bad sizes");
     GG_REQUIRE(tiles_x >= 1 && tiles_y >= 1 && (long long)n_views * tiles_x * tiles_y < (1ll << 30),
                "gg_bin_tiles: too many tiles");
@@ -759,19 +782,23 @@ extern "C" int gg_bin_tiles(int n, int n_views, const float* xys, int xy_stride,
     hist_blocks(n, n_views, blocks, per);
     const size_t hist_smem = sizeof(int) * (size_t)T;
     int launches = 0;
+    // the 1024-thread bucket class (8193 .. 24576 entries) is launched only when such tiles are expected; a tile
+    // beyond the launched classes is listed for the fallback kernel by the scan, so the hint never costs exactness
+    const bool long_class = longest_hint <= 0 || longest_hint > 6144;
+    const int class_limit = long_class ? kBucketMax : 8192;
     if (smem_path) {
         GG_CUDA(cudaFuncSetAttribute(tile_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
         tile_hist_kernel<<<dim3(blocks, n_views), kHistThreads, hist_smem, st>>>(n, per, xys, xy_stride, radii, tiles_x,
                                                                                  tiles_y, blockhist, done);
-        tile_prefix_scan_kernel<<<div_up(num_tiles, 1024), 1024, 0, st>>>(num_tiles, T, blocks, capacity, blockhist,
+        tile_prefix_scan_kernel<<<div_up(num_tiles, 32), 1024, 0, st>>>(num_tiles, T, blocks, capacity, blockhist,
                                                                           counts, tile_ranges, tile_order, info, lists,
-                                                                          list_counts, done);
+                                                                          list_counts, class_limit, done);
         launches += 2;
     } else {
         GG_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)num_tiles, st));
         tile_count_kernel<<<div_up(total, 256), 256, 0, st>>>(total, n, xys, xy_stride, radii, tiles_x, tiles_y, counts);
         tile_scan_order_kernel<<<1, 1024, 0, st>>>(num_tiles, capacity, counts, tile_ranges, tile_order, info, lists,
-                                                   list_counts);
+                                                   list_counts, class_limit);
         launches += 2;
     }
     if (capacity > 0) {
@@ -798,19 +825,19 @@ extern "C" int gg_bin_tiles(int n, int n_views, const float* xys, int xy_stride,
             tile_bucket_sort_kernel<256><<<(unsigned)num_tiles, 256, sm, st>>>(a, 0, 2048);
             tile_bucket_sort_kernel<256><<<grid_for(2048), 256, bucket_smem(256, 8192), st>>>(a, 2048, 8192);
         }
-        {
+        if (long_class) {
             const size_t sm = bucket_smem(1024, kBucketMax);
             GG_CUDA(cudaFuncSetAttribute(tile_bucket_sort_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
             tile_bucket_sort_kernel<1024><<<grid_for(8184), 1024, sm, st>>>(a, 8192, kBucketMax);
+            ++launches;
         }
         {
             constexpr size_t sm = tile_sort_smem<1024, 16>();
-            GG_CUDA(cudaFuncSetAttribute(tile_sort_kernel<1024, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            GG_CUDA(cudaFuncSetAttribute(tile_sort_fallback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
             const unsigned g = (unsigned)(num_tiles < 148 ? num_tiles : 148);
-            tile_sort_kernel<1024, 16><<<g, 1024, sm, st>>>(a);
-            tile_sort_big_kernel<<<g, 1024, 0, st>>>(a);
+            tile_sort_fallback_kernel<<<g, 1024, sm, st>>>(a);
         }
-        launches += 6;
+        launches += 4;
     }
     count_launch(launches);
     if (info_host) GG_CUDA(cudaMemcpyAsync(info_host, info, sizeof(int32_t) * 4, cudaMemcpyDeviceToHost, st));

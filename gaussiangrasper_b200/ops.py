@@ -41,6 +41,7 @@ class _Workspace:
         # tile-first binning: scratch, capacity per problem signature, ring of pinned info records
         self.tiles_scratch = None
         self.capacity = {}
+        self.longest = {}        # longest tile list seen per signature (hint for the sort classes to launch)
         self.info_host = torch.zeros((_INFO_SLOTS, 4), dtype=torch.int32).pin_memory()
         self.info_next = 0
         self.info_pending = []   # BinInfo records whose read-back has not been looked at yet
@@ -75,6 +76,7 @@ class _Workspace:
         """Book-keeping of one finished read-back: remember the largest count per signature, raise the
         capacity past an overflow."""
         m, overflow = info.values[0], info.values[1]
+        self.longest[info.key] = max(self.longest.get(info.key, 0), info.values[2])
         cap = self.capacity.get(info.key)
         if cap is not None and (overflow or m > 0.85 * cap):
             self.capacity[info.key] = max(cap, _capacity_for(m))
@@ -373,7 +375,7 @@ def bin_views_tiles(n, n_views, xys, depths, radii, tile_bounds, xy_from_geo=Fal
         with _lib.device_guard(dev):
             _lib.call("gg_bin_tiles", int(n), int(n_views), ptr(xys), 8 if xy_from_geo else 2, ptr(depths), ptr(radii),
                       tiles_x, tiles_y, int(capacity), ptr(scratch), scratch.numel(), ptr(ids), ptr(ranges), ptr(order_t),
-                      None, ws.info_host[slot].data_ptr(), stream_ptr(dev))
+                      None, ws.info_host[slot].data_ptr(), int(ws.longest.get(key, 0) * 1.25), stream_ptr(dev))
         ev = None
         if not capturing:
             ev = torch.cuda.Event()

@@ -138,13 +138,15 @@ int gg_bin_finish(int n, int n_views, long long m, const float* xys, int xy_stri
  * (device, nullable: kept in the scratch) / info_host (pinned host, nullable; valid once the stream has
  * passed this call) receive {M, overflow, longest tile list, 0}.  If M > capacity nothing is binned: overflow = 1,
  * every tile range is (0,0) (the blend kernels then render the background only) and the caller repeats the call
- * with capacity >= M.  capacity = 0 only counts.  The scratch needs no initialisation. */
+ * with capacity >= M.  capacity = 0 only counts.  The scratch needs no initialisation.
+ * longest_hint: the longest tile list an earlier call reported (info[2]) or 0 if unknown; it only decides
+ * which sort kernels are worth launching (lists beyond the launched classes take the slower general kernel). */
 size_t gg_bin_tiles_scratch_bytes(int n_views, long long tiles_per_view, long long capacity);
 int gg_bin_tiles(int n, int n_views, const float* xys, int xy_stride /*2 or 8*/, const float* depths /*[V*n]*/,
                  const int32_t* radii /*[V*n]*/, int tiles_x, int tiles_y, long long capacity, void* scratch,
                  size_t scratch_bytes, int32_t* ids_sorted /*[capacity]*/, int32_t* tile_ranges /*[V*tiles, 2]*/,
                  int32_t* tile_order /*[V*tiles]*/, int32_t* info /*[4] device, nullable*/,
-                 int32_t* info_host /*[4] pinned, nullable*/, void* stream);
+                 int32_t* info_host /*[4] pinned, nullable*/, int longest_hint, void* stream);
 
 /* visiting order of the tiles for the blend kernels: tile ids by descending list length (only
  * scheduling depends on it, never results); tile_order [num_tiles] int32 */

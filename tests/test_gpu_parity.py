@@ -311,7 +311,11 @@ def test_tile_binning_hard_cases(dev, case):
     n = len(radii)
     _, _, _, _, ids_s, ranges = c_oracle.bin_and_sort(xys, depths, radii, nth, tb)
     t = lambda a: torch.from_numpy(a).to(dev)
-    for rep in range(2):   # twice: the second call runs without the counting pass
+    ws = ops.workspace(torch.device(dev))
+    for rep in range(3):   # the second call runs without the counting pass and with the first call's length hint;
+        if rep == 2:       # the third with a hint that is far too small: long lists must still come out sorted
+            for k in ws.longest:
+                ws.longest[k] = 64
         b = ops.bin_views(n, 1, t(xys), t(depths), t(radii), t(nth), tb, mode="tiles")
         assert b.num_intersects == len(ids_s)
         assert np.array_equal(b.ids_sorted.cpu().numpy(), ids_s), case
