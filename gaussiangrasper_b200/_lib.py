@@ -15,6 +15,7 @@ from . import build as _build
 
 _lock = threading.Lock()
 _lib = None
+ABI_VERSION = 200   # == GG_ABI_VERSION in include/gg_b200.h; bumped whenever a signature changes
 
 _i, _ll, _f, _p, _sz = C.c_int, C.c_longlong, C.c_float, C.c_void_p, C.c_size_t
 
@@ -93,12 +94,19 @@ def load():
         if _build.needs_build():
             try:
                 _build.build()
-            except Exception as e:  # no nvcc on this box and no prebuilt library
-                if not os.path.exists(_build.LIB):
-                    raise ImportError(
-                        "gaussiangrasper_b200: libgg_b200.so is missing and could not be built "
-                        f"({e}); there is no CPU fallback") from e
+            except Exception as e:
+                # A library older than its sources must not be bound to these (newer) signatures: argument
+                # drift would corrupt memory instead of raising.  Missing or stale, the answer is the same.
+                state = "stale (older than csrc/ or the header)" if os.path.exists(_build.LIB) else "missing"
+                raise ImportError(
+                    f"gaussiangrasper_b200: libgg_b200.so is {state} and could not be rebuilt ({e}); "
+                    "there is no CPU fallback") from e
         lib = C.CDLL(_build.LIB)
+        lib.gg_version.restype = C.c_int
+        if int(lib.gg_version()) != ABI_VERSION:
+            raise ImportError(f"gaussiangrasper_b200: libgg_b200.so reports ABI version {int(lib.gg_version())}, the "
+                              f"bindings expect {ABI_VERSION} (include/gg_b200.h GG_ABI_VERSION); rebuild with "
+                              "python -m gaussiangrasper_b200.build --force")
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(lib, name)  # AttributeError if the library does not export the header's symbol
             fn.restype = res

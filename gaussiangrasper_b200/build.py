@@ -53,10 +53,26 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile and link under an exclusive file lock (N ranks started by torchrun may all find the library stale
+    at once); objects go to a per-process directory and the library is linked under a temporary name and moved
+    into place atomically, so no process can ever load a half-written file."""
     if not force and not needs_build():
         return LIB
+    import fcntl
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    with open(os.path.join(HERE, "build", ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():   # another process built it while we waited
+                return LIB
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool) -> str:
     nvcc = _nvcc()
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build", f"obj.{os.getpid()}")
     os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []
@@ -80,10 +96,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(f"--- {src} ---\n{out}\n")
     if failed:
         raise RuntimeError("nvcc compilation failed")
-    link = [nvcc, *ARCH, *_host_cxx_flags(), "-shared", "-o", LIB, *objs, "-lcudart"]
+    tmp = f"{LIB}.tmp.{os.getpid()}"
+    link = [nvcc, *ARCH, *_host_cxx_flags(), "-shared", "-o", tmp, *objs, "-lcudart"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout)
+    os.replace(tmp, LIB)
+    shutil.rmtree(objdir, ignore_errors=True)
     return LIB
 
 

@@ -24,7 +24,7 @@ void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memo
 
 }  // namespace gg
 
-extern "C" int gg_version(void) { return 100; }
+extern "C" int gg_version(void) { return GG_ABI_VERSION; }
 
 extern "C" const char* gg_last_error_string(void) { return gg::g_err; }
 

@@ -51,32 +51,48 @@ class ViewBatch:
     @staticmethod
     def from_cameras(cams: Sequence, device) -> "ViewBatch":
         # one packed row of 35 floats per camera, built once and kept on the camera object
+        # The row is cached on the camera together with the identity and version counters of the tensors it
+        # was built from: a camera optimiser that updates the pose in place, or assigns a new one, invalidates it.
         rows = []
         for c in cams:
-            r = getattr(c, "_gg_row", None)
-            if r is None:
-                r = torch.cat([c.viewmat[:3].reshape(-1).float(), c.fullmat.reshape(-1).float(),
-                               torch.tensor([c.fx, c.fy, c.cx, c.cy], dtype=torch.float32), c.position.reshape(-1).float()])
+            stamp = (id(c.viewmat), c.viewmat._version, id(c.fullmat), c.fullmat._version, id(c.position),
+                     c.position._version, float(c.fx), float(c.fy), float(c.cx), float(c.cy))
+            cached = getattr(c, "_gg_row", None)
+            if cached is not None and cached[0] == stamp:
+                r = cached[1]
+            else:
+                r = torch.cat([c.viewmat[:3].reshape(-1).float().cpu(), c.fullmat.reshape(-1).float().cpu(),
+                               torch.tensor([c.fx, c.fy, c.cx, c.cy], dtype=torch.float32),
+                               c.position.reshape(-1).float().cpu()])
                 try:
-                    c._gg_row = r
+                    c._gg_row = (stamp, r)
                 except AttributeError:
                     pass
             rows.append(r)
         V = len(rows)
         if device.type == "cuda":
-            # a small ring of reusable pinned staging buffers per batch size (pinning memory per call
-            # costs more than the render's whole prepare stage; the ring keeps a buffer untouched
-            # until the asynchronous copy that reads it has long completed); one H2D copy per batch
-            ring = _pinned_ring.get(V)
+            # a small ring of reusable pinned staging buffers per (device, batch size): pinning memory per call
+            # costs more than the render's whole prepare stage.  Every slot carries the event recorded behind
+            # the asynchronous copy that last read it; a slot is rewritten only after that event has completed
+            # (normally long ago -- the wait is free unless a caller stages many batches without rendering).
+            dev_index = device.index if device.index is not None else torch.cuda.current_device()
+            key = (dev_index, V)
+            ring = _pinned_ring.get(key)
             if ring is None:
-                ring = _pinned_ring[V] = [0, [torch.empty((V, 35)).pin_memory() for _ in range(8)]]
+                ring = _pinned_ring[key] = [0, [torch.empty((V, 35)).pin_memory() for _ in range(8)], [None] * 8]
             ring[0] = (ring[0] + 1) % len(ring[1])
             stage = ring[1][ring[0]]
+            pending = ring[2][ring[0]]
+            if pending is not None:
+                pending.synchronize()
             if V == 1:
                 stage[0].copy_(rows[0])
             else:
                 torch.stack(rows, out=stage)
             packed = stage.to(device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(device))
+            ring[2][ring[0]] = ev
         else:
             packed = torch.stack(rows)
         if V == 1:  # slices of a single row are contiguous already
@@ -201,9 +217,18 @@ class _RenderViews(Function):
 
         def buf(name, shape):
             t = go.get(name) if go else None
-            if t is not None and t.numel() == int(torch.Size(shape).numel()) and t.is_contiguous() and t.dtype == torch.float32:
-                return t.view(shape)
-            return torch.empty(shape, dtype=torch.float32, device=dev)
+            if t is None:
+                return torch.empty(shape, dtype=torch.float32, device=dev)
+            # a caller-owned gradient buffer that does not fit (e.g. a bucket built before a densification
+            # changed N) must not be bypassed silently: the optimizer would then consume stale contents
+            if (t.numel() != int(torch.Size(shape).numel()) or not t.is_contiguous() or t.dtype != torch.float32
+                    or t.device != dev):
+                raise _lib.GGError(
+                    f"render_views backward: grad_out[{name!r}] is {tuple(t.shape)} {t.dtype} on {t.device}"
+                    f"{'' if t.is_contiguous() else ' (non-contiguous)'}, expected a contiguous fp32 buffer of "
+                    f"{tuple(shape)} on {dev}; rebuild the GradientBucket / FactoredExchange after the Gaussian "
+                    "count changes")
+            return t.view(shape)
 
         v_means, v_ls, v_q = buf("means", (n, 3)), buf("log_scales", (n, 3)), buf("quats", (n, 4))
         v_op, v_f = buf("opacity_logit", (n,)), buf("features", (n, D))

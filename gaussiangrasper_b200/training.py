@@ -37,9 +37,13 @@ class FusedAdam:
         """Apply one update from the gradients currently in the bucket (already summed over ranks)."""
         if lrs:
             self.lrs.update(lrs)
-        self.t += 1
         b = self.bucket
         names = b.names
+        for k in names:   # a bucket left over from before a refinement must not be applied to the new parameters
+            if tuple(self.params[k].shape) != b.shapes[k]:
+                raise _lib.GGError(f"FusedAdam.step: parameter {k} is {tuple(self.params[k].shape)} but the gradient "
+                                   f"bucket was built for {b.shapes[k]}; call rebuild() after refine_gaussians")
+        self.t += 1
         n = len(names)
         ptrs = (C.c_void_p * n)(*[self.params[k].data_ptr() for k in names])
         offs = (C.c_longlong * n)(*[b.offsets[k] for k in names])

@@ -29,7 +29,8 @@ extern "C" {
 #endif
 
 /* ---- library state ---------------------------------------------------------------------- */
-int gg_version(void);
+#define GG_ABI_VERSION 200 /* bumped whenever a signature below changes; the bindings refuse another value */
+int gg_version(void); /* returns GG_ABI_VERSION of the build */
 const char* gg_last_error_string(void);
 /* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
 unsigned long long gg_launch_count(void);

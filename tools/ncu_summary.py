@@ -8,7 +8,14 @@ KEYS = ['gpu__time_duration.sum', 'launch__registers_per_thread', 'launch__occup
         'smsp__thread_inst_executed_per_inst_executed.ratio', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
         'sm__cycles_active.avg', 'sm__cycles_elapsed.max', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum',
         'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'lts__t_sectors_op_red.sum',
-        'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed']
+        'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+        'smsp__sass_thread_inst_executed_op_ffma_pred_on.sum', 'smsp__sass_thread_inst_executed_op_fadd_pred_on.sum',
+        'smsp__sass_thread_inst_executed_op_fmul_pred_on.sum', 'smsp__thread_inst_executed.sum',
+        'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active',
+        'sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active',
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared.avg.pct_of_peak_sustained_elapsed']
 
 def main(path):
     out = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
