@@ -96,62 +96,98 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------
+# what both arms print as `config` (same keys, same values: the reference arm runs our arm's workload)
+# ---------------------------------------------------------------------------------------------
+SETUP_STEPS = 3   # untimed initialisation before the warm-up: first-call capacity measurement of the binning,
+                  # allocator growth, NCCL communicator set-up.  Not counted as warm-up, never timed.
+
+
+def bench_config(args, world):
+    from gaussiangrasper_b200 import scenes
+    cfg = scenes.CONFIGS[args.config]
+    D = cfg["D"] if args.feat < 0 else args.feat
+    strong = args.config == 2
+    V = args.views if args.views else (1 if args.config == 1 else (max(1, cfg["views"] // world) if strong else cfg["views"]))
+    chunk = min(V, args.chunk)
+    n = cfg["n"]
+    n_chunks = (V + chunk - 1) // chunk
+    factored = (world > 1 and cfg["backward"] and n_chunks == 1 and args.exchange == "factored" and world * chunk * 2 <= 25)
+    exchange = ("sh factors all-gather + all-reduce of the other leaves" if factored else
+                "all-reduce" if (world > 1 and cfg["backward"]) else "none")
+    return cfg, D, V, chunk, strong, {
+        "workload": cfg["name"], "gaussians": n, "image": [cfg["W"], cfg["H"]], "views_per_gpu": V,
+        "views_per_launch": chunk, "channels": 7 + D, "backward": cfg["backward"],
+        "parallelism": f"view-sharded x{world}", "path": args.path, "gradient_exchange": exchange,
+        "l2": "inputs larger than L2 (parameters+gradients 2x%.0f MB per step)" % (n * (86 + D) * 4 / 1e6),
+        "setup_steps": SETUP_STEPS}
+
+
+# ---------------------------------------------------------------------------------------------
 # the reference's CPU maths (oracle/torch_oracle.py is the port of gsplat's _torch_impl)
 # ---------------------------------------------------------------------------------------------
-def cpu_reference_step(sc, cam, D, n_tiles, threads):
-    """One fwd+bwd of the reference maths on the host: full SH + projection + binning for all
-    Gaussians (timed), blend fwd+bwd on `n_tiles` sampled tiles (timed); returns
-    (t_geom, t_blend_sample, scale, n_sampled, n_total) with scale = frame pairs / sample pairs."""
+def cpu_reference_step(sc, cam, D, tiles, threads, backward=True):
+    """One step of the reference maths on the host: SH + projection + binning of ALL Gaussians, blend of the
+    tiles in `tiles` (None = the whole frame), backward to the leaves when `backward`.
+    Returns (seconds, pixels blended, tiles blended, tiles of the frame)."""
     from oracle import torch_oracle as to
     torch.set_num_threads(threads)
-    P = {k: v.clone().requires_grad_(True) for k, v in sc.items()}
+    P = {k: v.clone().requires_grad_(backward) for k, v in sc.items()}
     t0 = time.perf_counter()
-    scales = torch.exp(P["log_scales"])
-    q = P["quats"] / P["quats"].norm(dim=-1, keepdim=True)
-    xys, depths, radii, conics, nth, _ = to.project_gaussians(P["means"], scales, 1.0, q, cam.viewmat, cam.fullmat,
-                                                              cam.fx, cam.fy, cam.cx, cam.cy, cam.H, cam.W,
-                                                              cam.tile_bounds)
-    dirs = P["means"].detach() - cam.position
-    rgbs = torch.clamp(to.spherical_harmonics(4, dirs, P["sh_coeffs"]) + 0.5, 0.0, 1.0)
-    op = torch.sigmoid(P["opacity_logit"]).reshape(-1)
-    R = to.quat_to_rotmat(P["quats"])
-    idx = P["log_scales"].min(dim=-1)[1][..., None, None].expand(-1, 3, -1)
-    normals = R.gather(2, idx).squeeze(dim=2)
-    cols = torch.cat([rgbs, depths[:, None], normals, P["features"]], dim=1)
-    _, _, ids_s, ranges = to.bin_and_sort(xys, depths, radii, nth, cam.tile_bounds)
-    t1 = time.perf_counter()
-    tiles, scale = sample_tiles(ranges, n_tiles)
-    t1b = time.perf_counter()
+    with torch.set_grad_enabled(backward):
+        scales = torch.exp(P["log_scales"])
+        q = P["quats"] / P["quats"].norm(dim=-1, keepdim=True)
+        xys, depths, radii, conics, nth, _ = to.project_gaussians(P["means"], scales, 1.0, q, cam.viewmat, cam.fullmat,
+                                                                  cam.fx, cam.fy, cam.cx, cam.cy, cam.H, cam.W,
+                                                                  cam.tile_bounds)
+        dirs = P["means"].detach() - cam.position
+        rgbs = torch.clamp(to.spherical_harmonics(4, dirs, P["sh_coeffs"]) + 0.5, 0.0, 1.0)
+        op = torch.sigmoid(P["opacity_logit"]).reshape(-1)
+        parts = [rgbs, depths[:, None]]
+        if D > 0 or backward:
+            R = to.quat_to_rotmat(P["quats"])
+            idx = P["log_scales"].min(dim=-1)[1][..., None, None].expand(-1, 3, -1)
+            parts += [R.gather(2, idx).squeeze(dim=2), P["features"]]
+        cols = torch.cat(parts, dim=1)
+        _, _, ids_s, ranges = to.bin_and_sort(xys, depths, radii, nth, cam.tile_bounds)
+    n_tiles = int(ranges.shape[0])
+    tile_list = list(range(n_tiles)) if tiles is None else list(tiles)
     bg = torch.zeros(cols.shape[1]); bg[3] = 10.0
-    g = torch.Generator().manual_seed(0)
-    v_out = torch.randn((cam.H, cam.W, cols.shape[1]), generator=g)
-    out, v_xys, v_con, v_op, v_col = to.rasterize_grads(xys.detach(), conics.detach(), op.detach(), cols.detach(),
-                                                        ids_s, ranges, cam.H, cam.W, bg, v_out, tiles=tiles)
-    t2 = time.perf_counter()
-    torch.autograd.backward([xys, conics, op, cols], [v_xys, v_con, v_op, v_col])
-    t3 = time.perf_counter()
-    return (t1 - t0) + (t3 - t2), (t2 - t1b), scale, len(tiles), int(ranges.shape[0])
+    if backward:
+        v_out = torch.randn((cam.H, cam.W, cols.shape[1]), generator=torch.Generator().manual_seed(0))
+        out, v_xys, v_con, v_op, v_col = to.rasterize_grads(xys.detach(), conics.detach(), op.detach(), cols.detach(),
+                                                            ids_s, ranges, cam.H, cam.W, bg, v_out, tiles=tile_list)
+        torch.autograd.backward([xys, conics, op, cols], [v_xys, v_con, v_op, v_col])
+    else:
+        with torch.no_grad():
+            to.rasterize(xys, conics, op, cols, ids_s, ranges, cam.H, cam.W, bg, tiles=tile_list)
+    dt = time.perf_counter() - t0
+    tx = cam.tile_bounds[0]
+    pixels = sum((min(16, cam.W - 16 * (t % tx))) * (min(16, cam.H - 16 * (t // tx))) for t in tile_list)
+    return dt, pixels, len(tile_list), n_tiles
 
 
-def sample_tiles(ranges, count):
-    """Tiles at evenly spaced quantiles of the tile-list length; returns (tile ids, scale) where
-    scale = total pixel-Gaussian pairs of the frame / pairs of the sample (the vectorised CPU blend
-    costs time proportional to the list length of a tile)."""
-    lens = (ranges[:, 1] - ranges[:, 0]).to(torch.float64)
-    order = torch.argsort(lens)
-    nz = order[lens[order] > 0]
-    if nz.numel() == 0:
-        return [0], 1.0
-    pick = nz[torch.linspace(0, nz.numel() - 1, min(count, nz.numel())).round().long()]
-    return pick.tolist(), float(lens.sum() / lens[pick].sum())
+def spread_tiles(n_tiles, count):
+    """`count` tile ids spread evenly over the frame (deterministic)."""
+    if count >= n_tiles:
+        return None
+    step = n_tiles / count
+    return sorted({int(i * step) for i in range(count)})
 
 
-def cpu_sample_size(sc, cam, D, threads, budget_s):
-    """Number of tiles whose CPU blend takes about `budget_s` seconds (from an 8-tile probe), and the tile total."""
-    cpu_reference_step(sc, cam, D, 8, threads)       # first call pays thread-pool start-up and lazy initialisation
-    tg, tb, scale, ns, nt = cpu_reference_step(sc, cam, D, 8, threads)
-    full = max(tb * scale, 1e-6)                    # estimated blend time of the whole frame
-    return int(min(nt, max(8, round(nt * budget_s / full)))), nt
+def cpu_plan(sc, cam, D, threads, budget_s, backward=True):
+    """Tiles one CPU step blends so that it takes about `budget_s` seconds: the whole frame when that fits, else an
+    evenly spread subset.  Sized from a warm 16-tile probe (its first call pays thread-pool start-up).  The
+    throughput of a step is ALWAYS (pixels it blended) / (seconds it took): nothing is extrapolated."""
+    nt = cam.tile_bounds[0] * cam.tile_bounds[1]
+    cpu_reference_step(sc, cam, D, spread_tiles(nt, 16), threads, backward)
+    dt16, _, _, n_tiles = cpu_reference_step(sc, cam, D, spread_tiles(nt, 16), threads, backward)
+    dt32, _, _, _ = cpu_reference_step(sc, cam, D, spread_tiles(nt, 48), threads, backward)
+    per_tile = max((dt32 - dt16) / 32.0, 1e-6)
+    fixed = max(dt16 - 16 * per_tile, 0.0)
+    full = fixed + per_tile * n_tiles
+    if full <= budget_s:
+        return None, n_tiles, full
+    return spread_tiles(n_tiles, max(16, int((budget_s - fixed) / per_tile))), n_tiles, full
 
 
 def run_reference(args):
@@ -159,32 +195,76 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cfg = scenes.CONFIGS[1]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cfg, D, V, chunk, strong, config = bench_config(args, world)
     threads = os.cpu_count() or 1
-    sc = scenes.random_scene(cfg["n"], feature_dim=cfg["D"], seed=1235)
-    cam = scenes.orbit_cameras(1, cfg["W"], cfg["H"])[0]
-    times = []
-    # bounded sample per step: the whole run (warm-up + steps) stays within ~3 minutes, one step within ~12 s
-    n_sample, _ = cpu_sample_size(sc, cam, cfg["D"], threads, min(12.0, 170.0 / max(1, args.warmup + args.steps)))
-    for s in range(args.warmup + args.steps):
-        tg, tb, scale, ns, nt = cpu_reference_step(sc, cam, cfg["D"], n_sample, threads)
-        if s >= args.warmup:
-            times.append(tg + tb * scale)
+    sc = scenes.random_scene(cfg["n"], feature_dim=D, seed=1234 + args.config)
+    cam = scenes.orbit_cameras(1, cfg["W"], cfg["H"], total=8)[0]
+    # the whole run (warm-up + steps) stays within ~5 minutes; one step blends the full frame when that fits
+    budget = min(14.0, 300.0 / max(1, args.warmup + args.steps))
+    tiles, n_tiles, est_full = cpu_plan(sc, cam, D, threads, budget, cfg["backward"])
+    times, pix = [], 0
+    for s_i in range(args.warmup + args.steps):
+        dt, pixels, nt, _ = cpu_reference_step(sc, cam, D, tiles, threads, cfg["backward"])
+        if s_i >= args.warmup:
+            times.append(dt)
+            pix = pixels
     t = sum(times) / len(times)
-    mpix = cfg["W"] * cfg["H"] / 1e6
-    val = mpix / t
-    sample = (f"each step: SH+projection+binning of all {cfg['n']} Gaussians fwd+bwd (timed in full) + blend "
-              f"fwd+bwd of {ns} of {nt} tiles (length quantiles), blend time scaled by frame pairs / sample pairs "
-              f"= {scale:.1f}")
+    val = pix / 1e6 / t
+    sample = (f"each step: SH+projection+binning of all {cfg['n']} Gaussians + blend of "
+              f"{'the whole frame' if tiles is None else f'{len(tiles)} of {n_tiles} tiles spread over the frame'} "
+              f"({pix} pixels){', forward and backward' if cfg['backward'] else ''}; value = pixels blended / seconds "
+              f"taken, nothing extrapolated{'' if tiles is None else '; the per-Gaussian stage is not sampled, so a partial frame understates the CPU rate'}"
+              " (one view; the CPU port has no multi-view path)")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": cfg["name"], "gaussians": cfg["n"], "image": [cfg["W"], cfg["H"]], "views": 1,
-                       "channels": 7 + cfg["D"]},
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config,
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_leg(sc, cam, D, n, W, H, backward):
+    """The `cpu_baseline` object of our arm's line (rank 0, N=1): ~10-30 s of CPU work in total.
+    (ii) of SURVEY 8d on the benchmarked workload, plus (i) the literal-loop crop and config 0's plumbing case."""
+    from gaussiangrasper_b200 import scenes
+    from oracle import torch_oracle as to
+    threads = os.cpu_count() or 1
+    tiles, n_tiles, _ = cpu_plan(sc, cam, D, threads, 14.0, backward)
+    dt, pixels, nt, _ = cpu_reference_step(sc, cam, D, tiles, threads, backward)
+    cpu = {"value": pixels / 1e6 / dt, "unit": UNIT, "cores": threads, "kind": "port",
+           "sample": (f"torch-CPU port of the reference maths (oracle/torch_oracle.py), 1 step of {dt:.1f} s: SH+projection+"
+                      f"binning of all {n} Gaussians + blend of "
+                      f"{'the whole frame' if tiles is None else f'{nt} of {n_tiles} tiles spread over the frame'} "
+                      f"({pixels} pixels){', forward and backward' if backward else ''}; pixels blended / seconds, "
+                      "nothing extrapolated")}
+    # BASELINE configs[0]: 50k Gaussians, 640x480, RGB+depth forward on the CPU (plumbing case)
+    c0 = scenes.CONFIGS[0]
+    sc0 = scenes.random_scene(c0["n"], feature_dim=0, seed=1234)
+    cam0 = scenes.orbit_cameras(1, c0["W"], c0["H"], total=8)[0]
+    dt0, pix0, _, _ = cpu_reference_step(sc0, cam0, 0, None, threads, backward=False)
+    cpu["config0"] = {"workload": c0["name"], "value": pix0 / 1e6 / dt0, "unit": UNIT, "seconds": dt0,
+                      "what": "vectorised torch-CPU forward, RGB+depth, whole frame"}
+    # SURVEY 8d (i): the literal per-pixel / per-entry Python loop on a fixed 64x48 crop of config 0
+    with torch.no_grad():
+        q = sc0["quats"] / sc0["quats"].norm(dim=-1, keepdim=True)
+        xys, depths, radii, conics, nth, _ = to.project_gaussians(sc0["means"], sc0["log_scales"].exp(), 1.0, q,
+                                                                  cam0.viewmat, cam0.fullmat, cam0.fx, cam0.fy, cam0.cx,
+                                                                  cam0.cy, cam0.H, cam0.W, cam0.tile_bounds)
+        _, _, ids_s, ranges = to.bin_and_sort(xys, depths, radii, nth, cam0.tile_bounds)
+        rgbs = torch.clamp(to.spherical_harmonics(4, sc0["means"] - cam0.position, sc0["sh_coeffs"]) + 0.5, 0.0, 1.0)
+        cols = torch.cat([rgbs, depths[:, None]], dim=1)
+        bg = torch.tensor([0.0, 0.0, 0.0, 10.0])
+        t0 = time.perf_counter()
+        _, pairs = to.rasterize_literal(xys, conics, torch.sigmoid(sc0["opacity_logit"]), cols, ids_s, ranges, cam0.H,
+                                        cam0.W, bg, crop=(288, 216, 64, 48))
+        dtl = time.perf_counter() - t0
+    cpu["literal_loop_crop"] = {"crop": [288, 216, 64, 48], "pairs": pairs, "seconds": dtl, "pairs_per_s": pairs / dtl,
+                                "Mpixels/s": 64 * 48 / 1e6 / dtl, "cores": 1,
+                                "what": "per-pixel, per-entry Python loop (the shape of gsplat's _torch_impl rasterizer)"}
+    return cpu
 
 
 # ---------------------------------------------------------------------------------------------
@@ -204,12 +284,9 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     _lib.check(_lib.load().gg_check_device(), "gg_check_device")
 
-    cfg = scenes.CONFIGS[args.config]
-    n, W, H, D = cfg["n"], cfg["W"], cfg["H"], (cfg["D"] if args.feat < 0 else args.feat)
     # config 2 is a fixed 64-view batch split over the ranks (strong scaling); the others fix the work per GPU
-    strong = args.config == 2
-    V = args.views if args.views else (1 if args.config == 1 else (max(1, cfg["views"] // world) if strong else cfg["views"]))
-    chunk = min(V, args.chunk)
+    cfg, D, V, chunk, strong, config = bench_config(args, world)
+    n, W, H = cfg["n"], cfg["W"], cfg["H"]
     C = 7 + D
     CP = (C + 3) // 4 * 4
     sc = scenes.random_scene(n, feature_dim=D, seed=1234 + args.config)
@@ -232,7 +309,20 @@ def run_ours(args):
     # 3K-float product: at 64 views the all-reduce of the product is the cheaper exchange again)
     factored = (world > 1 and cfg["backward"] and len(chunks) == 1 and args.exchange == "factored"
                 and world * chunks[0].n_views * 2 <= P["sh_coeffs"].shape[1])
-    ex = FactoredExchange(P, chunks[0].n_views) if factored else None
+    ex, transport = None, ("nccl" if world > 1 and cfg["backward"] else "none")
+    if factored:
+        if args.transport in ("auto", "nvls"):
+            try:   # one kernel of this library over symmetric memory (multimem through the NVSwitch)
+                from gaussiangrasper_b200.distributed import NvlsExchange
+                ex = NvlsExchange(P, chunks[0].n_views)
+                transport = "gg_nvls_exchange kernel over symmetric memory (%s)" % (
+                    "NVLS multimem.ld_reduce / multimem.st" if ex.multicast else "peer ld/st, no multicast mapping")
+            except Exception as e:   # no symmetric memory on this box: NCCL collectives
+                if args.transport == "nvls":
+                    raise
+                ex, transport = None, f"nccl (symmetric memory unavailable: {type(e).__name__}: {str(e)[:120]})"
+        if ex is None:
+            ex = FactoredExchange(P, chunks[0].n_views)
     # every rank can name every rank's cameras (a shared sampler): no collective for the camera centres
     all_pos = torch.stack([c.position for r in range(world) for c in
                            scenes.orbit_cameras(V, W, H, first=r * V, total=max(total_views, 8))]).float().to(dev) \
@@ -277,8 +367,14 @@ def run_ours(args):
             return bucket.flat
         return out["image"]
 
-    # at least 10 untimed steps: the first collectives / allocations of a fresh process settle here
-    n_warm = max(args.warmup, 10 if args.path == "fused" else 3)
+    # SETUP_STEPS of initialisation (first-call capacity measurement, allocator growth, communicator set-up), then
+    # exactly --warmup untimed warm-up steps
+    if args.warmup < 3:
+        raise SystemExit("bench.py: --warmup must be >= 3")
+    for _ in range(SETUP_STEPS):
+        step()
+    torch.cuda.synchronize()
+    n_warm = args.warmup
     for _ in range(n_warm):
         step()
     torch.cuda.synchronize()
@@ -427,14 +523,18 @@ def run_ours(args):
 
     # --- roofline of the dominant kernel ------------------------------------------------------
     hbm_peak, peak_src = load_peaks()
+    hbm_nominal = 8000.0   # B200 HBM3e nominal GB/s (the north star's "~8 TB/s"); the measured copy peak is the bar
     avg = {k: sum(v) / len(v) for k, v in per_call.items() if v}
     share = {k: sum(v) / (args.steps if k in blend_calls else prof_steps) for k, v in per_call.items()}
-    stats = torch.zeros(1, dtype=torch.int64, device=dev)
+    # workload counters of the first chunk: pairs visited (K of SURVEY 8d) and pairs blended, intersections M
+    hold = {}
     with torch.no_grad():
-        o = render_views(*(P[k].detach() for k in names), views, stats=stats)  # first chunk only
-    torch.cuda.synchronize()
-    pairs = int(stats.item())
-    binning_m = None
+        render_views(*(P[k].detach() for k in names), views, holder=hold)
+    pairs, pairs_contrib = _ops.blend_pair_stats(hold["binning"], hold["geo"], H, W)
+    m_intersects = int(hold["binning"].num_intersects)
+    n_tiles_total = int(hold["binning"].tile_ranges.shape[0])
+    n_launch_groups = len(chunks)
+    del hold
     # measured FP32 FMA roof (same process, same clocks)
     lib = _lib.load()
     probe = torch.zeros(1, device=dev)
@@ -448,64 +548,94 @@ def run_ours(args):
     torch.cuda.synchronize()
     fma_tflops = fl.value / (a.elapsed_time(b) * 1e-3) / 1e12
     dom = max(avg, key=lambda k: share[k]) if avg else None
-    flops_fwd = pairs * (12 + 2 * C)
-    flops_bwd = pairs * (30 + 8 * C)
-    roof = None
-    traffic = None
+    # per launch (one launch group = `chunk` views; `pairs` was counted on the first chunk)
+    flops_model = {"gg_blend_fwd": (12 + 2 * C), "gg_blend_bwd": (30 + 8 * C)}
+    # static ncu evidence of the same kernels on config 1 (profiles/traffic.json, with its provenance)
+    ncu = {}
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath) and args.config == 1 and V == 1:
+    if os.path.exists(tpath) and args.config == 1 and V == 1 and args.feat < 0:
         with open(tpath) as f:
-            traffic = json.load(f).get(dom, {}).get("dram_bytes_per_launch")
-    if dom in ("gg_blend_bwd", "gg_blend_fwd"):
-        fl_k = flops_bwd if dom == "gg_blend_bwd" else flops_fwd
-        ach = fl_k / (avg[dom] * 1e-3) / 1e12
-        roof = {"kernel": dom, "bound": "fp32", "achieved": ach, "peak": fma_tflops, "unit": "TFLOP/s",
-                "frac": ach / fma_tflops, "traffic": traffic, "traffic_source": "ncu --set full capture, profiles/traffic.json",
-                "peak_source": "FMA probe kernel timed in this run",
-                "algorithmic_flops": fl_k, "pairs": pairs, "avg_launch_ms": avg[dom]}
-    elif dom is not None:
+            ncu = json.load(f)
+
+    def fp32_roof(kernel):
+        """SURVEY 8d's fraction (every VISITED pair charged the full per-pair flops) next to what is executed:
+        the same model over the pairs that are actually blended, and ncu's executed-instruction count."""
+        if kernel not in avg:
+            return None
+        t = avg[kernel] * 1e-3
+        fl_k = pairs * flops_model[kernel]
+        ach = fl_k / t / 1e12
+        r = {"kernel": kernel, "bound": "fp32", "achieved": ach, "peak": fma_tflops, "unit": "TFLOP/s",
+             "frac": ach / fma_tflops, "peak_source": "FMA probe kernel timed in this run (nominal 74.4)",
+             "algorithmic_flops": fl_k, "pairs": pairs, "pairs_contributing": pairs_contrib,
+             "frac_contributing_pairs": pairs_contrib * flops_model[kernel] / t / 1e12 / fma_tflops,
+             "avg_launch_ms": avg[kernel]}
+        e = ncu.get(kernel, {})
+        r["traffic"] = e.get("dram_bytes_per_launch")
+        if e:
+            r["traffic_source"] = "ncu capture of this kernel on this workload: " + e.get("source", "profiles/traffic.json")
+            if e.get("executed_fp32_flops_per_launch"):
+                r["executed_frac"] = e["executed_fp32_flops_per_launch"] / t / 1e12 / fma_tflops
+                r["executed_frac_source"] = ("(2 x FFMA + FADD + FMUL thread instructions, ncu smsp__sass_thread_inst_executed_"
+                                             "op_*_pred_on.sum) / this run's launch time / FMA probe")
+            if e.get("pipe_fma_cycles_active_pct") is not None:
+                r["ncu_pipe_fma_cycles_active_pct"] = e["pipe_fma_cycles_active_pct"]
+        return r
+
+    roof = fp32_roof(dom) if dom in flops_model else None
+    if roof is None and dom is not None:
         roof = {"kernel": dom, "bound": "hbm", "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None,
                 "traffic": None, "peak_source": peak_src, "avg_launch_ms": avg[dom]}
-    # HBM-bound stages against the measured copy bandwidth
-    # algorithmic bytes per (view, Gaussian) of the HBM-bound stages
-    prep_b = (12 + 12 + 16 + 4 + 300 + 4 * D) + (32 + 4 * CP + 12) + 44      # in + out + phase-2 re-read
-    prep_bwd_b = (44 + 32 + 12 + 4 + 32 + 4 * CP) + (12 + 12 + 16 + 4 + 300 + 4 * D)
-    bytes_model = {"gg_prepare_views": n * V * prep_b, "gg_prepare_views_bwd": n * V * prep_bwd_b}
+    roofline_other = {k: fp32_roof(k) for k in flops_model if k != dom and k in avg}
+    # HBM-bound stages: algorithmic bytes per STEP (DESIGN.md section 4) against the measured copy bandwidth and
+    # the nominal 8 TB/s.  Per launch group of v views over n Gaussians:
+    #   prepare fwd : parameters once (44 geometry + 300 SH + 4D features; +40 re-read by the channel kernel when
+    #                 v > 1) + per view geo 32 + depth/radius/count 12 + channel row 4CP (+8 re-read when v > 1)
+    #   prepare bwd : per view geo 32 + chan 4CP + radius 4 + v_geo 32 + v_chan 4CP, parameters 44 once, gradients
+    #                 44 + 4D + (300, or 12 per view when the SH gradient is left as its factor)
+    #   binning     : SURVEY 8d: scan 8 + key emission 20 per (view, Gaussian); 12 + 24 (sort, compulsory) + 8
+    #                 (ranges) per intersection; 8 per tile
+    def prep_bytes(v):
+        return n * (344 + 4 * D + (40 if v > 1 else 0)) + v * n * (44 + 4 * CP + (8 if v > 1 else 0))
+
+    def prep_bwd_bytes(v):
+        sh_out = 12 * v if ex is not None else 300
+        return v * n * (68 + 8 * CP) + n * 44 + n * (44 + 4 * D + sh_out)
+
+    groups = [c.n_views for c in chunks]
+    m_per_view = m_intersects / max(1, chunks[0].n_views)
+    bytes_model = {"gg_prepare_views": sum(prep_bytes(v) for v in groups),
+                   "gg_prepare_views_bwd": sum(prep_bwd_bytes(v) for v in groups),
+                   "gg_bin_tiles": sum(28 * n * v + 44 * m_per_view * v + 8 * (n_tiles_total / chunks[0].n_views) * v
+                                       for v in groups)}
     hbm_stages = {}
     for k, bts in bytes_model.items():
-        if k in share:
+        if k in share and share[k] > 0:
             gbs = bts / (share[k] * 1e-3) / 1e9   # all launches of the stage in one step
-            hbm_stages[k] = {"GB/s": gbs, "frac": gbs / hbm_peak, "ms_per_step": share[k], "bytes_per_step": bts}
+            hbm_stages[k] = {"GB/s": gbs, "frac": gbs / hbm_peak, "frac_of_nominal_8000": gbs / hbm_nominal,
+                             "ms_per_step": share[k], "bytes_per_step": int(bts)}
+    if "gg_bin_tiles" in hbm_stages:
+        hbm_stages["gg_bin_tiles"]["intersections_first_group"] = m_intersects
 
     # --- CPU baseline (rank 0, N=1 only): the reference maths on the host cores ---------------
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        sc_cpu = {k: sc[k] for k in names}
-        cam0 = cams[0]
-        n_sample, _ = cpu_sample_size(sc_cpu, cam0, D, threads, 12.0)   # ~12 s of CPU blend work
-        tg, tb, scale, ns, nt = cpu_reference_step(sc_cpu, cam0, D, n_sample, threads)
-        t_full = tg + tb * scale
-        cpu = {"value": (W * H / 1e6) / t_full, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": (f"torch-CPU port of the reference maths, 1 step: SH+projection+binning fwd+bwd of all {n} "
-                          f"Gaussians ({tg:.2f} s) + blend fwd+bwd of {ns}/{nt} tiles at length quantiles ({tb:.2f} s, "
-                          f"scaled by frame pairs / sample pairs = {scale:.1f})")}
+        cpu = cpu_baseline_leg({k: sc[k] for k in names}, cams[0], D, n, W, H, cfg["backward"])
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": n_warm,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": cfg["name"], "gaussians": n, "image": [W, H], "views_per_gpu": V, "views_per_launch": chunk,
-                   "channels": C, "backward": cfg["backward"], "parallelism": f"view-sharded x{world}", "path": args.path,
-                   "gradient_exchange": ("sh factors all-gather + all-reduce of the other leaves" if ex is not None else
-                                         "all-reduce" if bucket is not None else "none"),
-                   "l2": "inputs larger than L2 (parameters+gradients 2x%.0f MB per step)" % (n * (86 + D) * 4 / 1e6)},
+        "config": config,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roof,
+        "roofline_other_kernels": roofline_other,
         "hbm_stages": hbm_stages,
+        "hbm_peak_GBs": {"measured": hbm_peak, "source": peak_src, "nominal": hbm_nominal},
         "stage_ms_per_step": share,
+        "exchange_transport": transport,
         "fma_probe_tflops": fma_tflops,
         "cpu_baseline": cpu,
     }
@@ -556,6 +686,8 @@ def main():
     ap.add_argument("--exchange", default="factored", choices=["factored", "allreduce"],
                     help="N>1 training steps: SH gradient exchanged as per-view factors (default) or one all-reduce of "
                          "every leaf gradient")
+    ap.add_argument("--transport", default="auto", choices=["auto", "nvls", "nccl"],
+                    help="factored exchange: this library's symmetric-memory kernel (nvls; auto = when available) or NCCL")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--trace", default="", help="diagnostic: write a GPU timeline (kernels + idle gaps) of one e2e and one "
                                                 "device-timed step to this file (torch.profiler; not part of the measurement)")

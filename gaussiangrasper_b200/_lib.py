@@ -43,6 +43,7 @@ _SIGNATURES = {
     "gg_blend_fwd": (C.c_int, [_i, _ll, _i, _i, _i, _i, _i, _i, _i, _i] + [_p] * 12),
     "gg_blend_bwd": (C.c_int, [_i, _ll, _i, _i, _i, _i, _i, _i, _i, _i] + [_p] * 13),
     "gg_blend_hit_words": (C.c_size_t, [_ll, _ll, _i]),
+    "gg_blend_pair_stats": (C.c_int, [_i, _ll, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "gg_depth_keys": (C.c_int, [_ll, _i, _p, _p, _p, _p]),
     "gg_gather_counts": (C.c_int, [_ll, _p, _p, _p, _p]),
     "gg_emit_tiles_sorted": (C.c_int, [_i, _i, _p, _p, _i, _p, _p, _i, _i, _p, _p, _p]),
@@ -57,18 +58,25 @@ _SIGNATURES = {
     "gg_tile_order_workspace_bytes": (C.c_size_t, []),
     "gg_tile_order": (C.c_int, [_ll, _p, _p, _p, _sz, _p]),
     "gg_unpack_vgeo": (C.c_int, [_ll, _i, _p, _p, _p, _p, _i, _p]),
-    "gg_adam_step": (C.c_int, [_i, _p, _p, _p, _p, _p, _p, _p, _f, _f, _f, _i, _p]),
+    "gg_adam_step": (C.c_int, [_i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _f, _f, _f, _p]),
     "gg_refine_workspace_bytes": (C.c_size_t, [_i]),
     "gg_refine_plan": (C.c_int, [_i, _p, _p, _p, _p, _p, _p, _p, _sz, _p, _p]),
-    "gg_refine_apply": (C.c_int, [_i, _i, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "gg_refine_apply": (C.c_int, [_i, _i, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, C.c_ulonglong, C.c_uint, _p, _sz, _p]),
+    "gg_philox_normals": (C.c_int, [_ll, _p, _i, C.c_ulonglong, C.c_uint, _p, _p]),
+    "gg_philox4x32_10_host": (None, [_p, _p, _p]),
     "gg_pixel_loss_workspace_bytes": (C.c_size_t, []),
     "gg_pixel_loss": (C.c_int, [_ll, _i, _p, _p, _p, _p, _i, _f, _p, _p, _p, _sz, _p]),
+    "gg_loss_workspace_bytes": (C.c_size_t, []),
+    "gg_geom_loss": (C.c_int, [_ll, _i, _p, _p, _p, _p, _p, _f, _f, _p, _i, _i, _p, _p, _sz, _p]),
+    "gg_cosine_rows_loss": (C.c_int, [_ll, _i, _p, _ll, _p, _p, _ll, _p, _p, _p, _ll, _p, _ll, _p, _i, _p, _sz, _p]),
+    "gg_param_regs": (C.c_int, [_ll, _i, _p, _p, _f, _f, _f, _p, _p, _p, _p, _sz, _p]),
     "gg_ssim_workspace_bytes": (C.c_size_t, [_i, _i, _i, _i]),
     "gg_ssim_loss": (C.c_int, [_i, _i, _i, _i, _p, _i, _p, _i, _f, _p, _i, _i, _p, _p, _sz, _p]),
     "gg_densify_stats": (C.c_int, [_ll, _i, _p, _p, _i, _i, _i, _p, _p, _p, _p]),
     "gg_prepare_views": (C.c_int, [_i] * 6 + [_p] * 10 + [_i] * 4 + [_f] + [_p] * 7 + [_i, _p]),
     "gg_prepare_views_bwd": (C.c_int, [_i] * 6 + [_p] * 9 + [_i] * 2 + [_p] * 13),
     "gg_sh_grad_from_views": (C.c_int, [_i] * 4 + [_p] * 5),
+    "gg_nvls_exchange": (C.c_int, [_i, _i, _p, _p, _ll, _p, _p, _ll, _p]),
 }
 
 # optional symbols of later translation units (bound when present)

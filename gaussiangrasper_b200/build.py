@@ -26,6 +26,8 @@ UNITS = [
     ("blend.cu", []),
     ("fused.cu", ["-fmad=false"]),
     ("train.cu", ["-fmad=false"]),
+    ("exchange.cu", []),
+    ("loss.cu", ["-fmad=false"]),
 ]
 
 

@@ -11,10 +11,12 @@
 // Channel rows are gathered from colors[g * stride + 0..C).  One CTA per tile; entries are staged
 // into double-buffered shared memory with cp.async (LDGSTS) while the previous batch is blended.
 //
-// Backward: per-pixel back-to-front replay; the C+6 partial gradients of one Gaussian are
-// reduced across the warp with a transposed butterfly (31 shuffles for 32 values instead of
-// 32x5) after which lane l owns component l and issues a single red.global.add -- one atomic
-// per warp per component instead of one per pixel.
+// Backward (blend_bwd_warp_kernel, the default): every warp replays, back to front, only the entries the
+// forward recorded as contributing to its 8x4 pixel block (hit masks), gathers their rows itself and never
+// synchronises with another warp; per (pixel, entry) it stores two scalars in a warp-private shared-memory
+// matrix, and every 16 entries lane j turns entry j's column into the C+6 gradient components (transposed
+// accumulation) and issues one red.global.add per component -- one atomic per warp and entry instead of one
+// per pixel.  blend_bwd_kernel is the CTA-staged fallback for launches without hit masks (C > 64 column blocks).
 #include "gg_common.cuh"
 #include "gg_geo.cuh"
 #include "gg_b200.h"
@@ -965,6 +967,65 @@ extern "C" int gg_unpack_vgeo(long long n, int n_views, const float* v_geo, floa
                                                                          accumulate_opac);
     count_launch();
     return check_launch("unpack_vgeo_kernel");
+}
+
+// Workload counters of a binned batch (bench.py's roofline accounting, not part of a render): one thread per
+// pixel walks its tile list with the forward's tests and counts stats[0] += entries visited up to the stop
+// (K of SURVEY 8d, == gg_blend_fwd's pair_counter) and stats[1] += pairs that were blended.
+namespace gg {
+__global__ void __launch_bounds__(256)
+pair_stats_kernel(int n_views, long long n, int img_h, int img_w, int tiles_x, int tiles_y,
+                  const int32_t* __restrict__ ids_sorted, const int32_t* __restrict__ tile_ranges,
+                  const float* __restrict__ geo, unsigned long long* __restrict__ stats) {
+    const int n_tiles = tiles_x * tiles_y;
+    const int view = blockIdx.y, tile = blockIdx.x;
+    const int tile_y = tile / tiles_x, tile_x = tile - tile_y * tiles_x;
+    int tx, ty;
+    tile_pixel(tx, ty);
+    const int px = tile_x * GG_TILE + tx, py = tile_y * GG_TILE + ty;
+    unsigned long long visited = 0, blended = 0;
+    if (px < img_w && py < img_h) {
+        const int2 range = __ldg(reinterpret_cast<const int2*>(tile_ranges) + (long long)view * n_tiles + tile);
+        const float fpx = (float)px, fpy = (float)py;
+        float T = 1.0f;
+        for (int k = range.x; k < range.y; ++k) {
+            ++visited;
+            const long long g = (long long)view * n + __ldg(ids_sorted + k);
+            const float4 ga = __ldg(reinterpret_cast<const float4*>(geo) + 2 * g);
+            const float4 gb = __ldg(reinterpret_cast<const float4*>(geo) + 2 * g + 1);
+            const float s = eval_sigma(ga.x - fpx, ga.y - fpy, ga.z, ga.w, gb.x);
+            const float alpha = fminf(kAlphaMax, gb.y * __expf(-s));
+            if (s < 0.0f || s > gb.z || alpha < kAlphaMin) continue;
+            const float next_T = T * (1.0f - alpha);
+            if (next_T <= kTStop) break;
+            T = next_T;
+            ++blended;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        visited += __shfl_xor_sync(0xffffffffu, visited, o);
+        blended += __shfl_xor_sync(0xffffffffu, blended, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (visited) atomicAdd(stats, visited);
+        if (blended) atomicAdd(stats + 1, blended);
+    }
+}
+}  // namespace gg
+
+extern "C" int gg_blend_pair_stats(int n_views, long long n, int img_h, int img_w, int tiles_x, int tiles_y,
+                                   const int32_t* ids_sorted, const int32_t* tile_ranges, const float* geo,
+                                   unsigned long long* stats, void* stream) {
+    GG_REQUIRE(n_views >= 1 && n >= 1 && img_h > 0 && img_w > 0, "gg_blend_pair_stats: bad sizes");
+    GG_REQUIRE(tiles_x == (img_w + GG_TILE - 1) / GG_TILE && tiles_y == (img_h + GG_TILE - 1) / GG_TILE,
+               "gg_blend_pair_stats: tile bounds must be ceil(size/16)");
+    GG_REQUIRE(ids_sorted && tile_ranges && geo && stats, "gg_blend_pair_stats: null pointer");
+    dim3 grid((unsigned)(tiles_x * tiles_y), (unsigned)n_views);
+    gg::pair_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n_views, n, img_h, img_w, tiles_x, tiles_y, ids_sorted,
+                                                                tile_ranges, geo, stats);
+    count_launch();
+    return check_launch("pair_stats_kernel");
 }
 
 extern "C" int gg_blend_fwd(int n_views, long long n, int channels, int color_stride, int colors_per_view,

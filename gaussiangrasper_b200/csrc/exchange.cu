@@ -1,0 +1,128 @@
+// Gradient exchange of a view-sharded training step over NVLink 5 / NVSwitch, as ONE kernel over symmetric
+// (peer-mapped) memory instead of two NCCL collectives (BASELINE north_star "per-Gaussian gradients are
+// all-reduced over NVLink").
+//
+// Every rank holds, at the same offset of a symmetric allocation,
+//   bucket  : its own leaf gradients except the SH coefficients' (N x (11 + D) floats, GradientBucket layout)
+//   rgb_all : [world, V, N, 3] per-view colour gradients -- the factor the SH gradient is rebuilt from
+//             (distributed.FactoredExchange); a rank has written only its own slot.
+// gg_nvls_exchange then does, in one launch per rank,
+//   * all-gather of the rgb slots : the rank copies its slot into the same slot of every peer
+//                                   (multimem.st on the multicast address: one store, the switch replicates it);
+//   * all-reduce of the bucket    : two-shot through the switch -- the rank owns slice `rank` of the bucket, pulls
+//                                   the SUM of all ranks' copies of it with multimem.ld_reduce (the reduction happens
+//                                   in the NVSwitch), and multimem.st's the result back into every rank's copy.
+//     Per GPU and direction that moves (world-1)/world of the bucket once: the bandwidth-optimal schedule, with
+//     no intermediate buffer and no reduction arithmetic on the SMs.
+// Without a multicast mapping (no NVLS) the same schedule runs over the peers' mapped addresses with plain
+// ld.global / st.global.  The caller brackets the launch with cross-rank barriers (the symmetric-memory signal
+// pads): one before (every rank's backward has written its bucket and slot), one after (every slice is back).
+#include "gg_common.cuh"
+#include "gg_b200.h"
+
+namespace gg {
+
+constexpr int kMaxRanks = 16;
+
+struct ExchangeArgs {
+    int rank, world;
+    float* bucket_mc;              // multicast address of the bucket, or nullptr
+    float* bucket_peer[kMaxRanks]; // every rank's bucket as mapped here (own included)
+    long long bucket_vec4;         // float4 elements of the bucket
+    float* rgb_mc;
+    float* rgb_peer[kMaxRanks];
+    long long slot_vec4;           // float4 elements of one rank's rgb slot
+};
+
+__device__ __forceinline__ float4 multimem_ld_reduce_add(const float* mc) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(mc)
+                 : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void multimem_st(float* mc, const float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}
+
+template <bool kMulticast>
+__global__ void __launch_bounds__(512)
+nvls_exchange_kernel(const ExchangeArgs a) {
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    // ---- all-gather: my rgb slot -> the same slot on every rank -------------------------------------
+    {
+        const long long base = (long long)a.rank * a.slot_vec4;
+        const float4* src = reinterpret_cast<const float4*>(a.rgb_peer[a.rank]) + base;
+        for (long long i = tid; i < a.slot_vec4; i += stride) {
+            const float4 v = src[i];
+            if (kMulticast) {
+                multimem_st(a.rgb_mc + 4 * (base + i), v);
+            } else {
+                for (int p = 0; p < a.world; ++p)
+                    if (p != a.rank) reinterpret_cast<float4*>(a.rgb_peer[p])[base + i] = v;
+            }
+        }
+    }
+    // ---- all-reduce: slice `rank` of the bucket, summed over the ranks, written back to all of them ----
+    {
+        const long long per = (a.bucket_vec4 + a.world - 1) / a.world;
+        const long long lo = (long long)a.rank * per;
+        const long long hi = lo + per < a.bucket_vec4 ? lo + per : a.bucket_vec4;
+        for (long long i = lo + tid; i < hi; i += stride) {
+            if (kMulticast) {
+                const float4 v = multimem_ld_reduce_add(a.bucket_mc + 4 * i);
+                multimem_st(a.bucket_mc + 4 * i, v);
+            } else {
+                // fixed summation order (rank 0, 1, ...) so that every run gives the same bits
+                float4 s = reinterpret_cast<const float4*>(a.bucket_peer[0])[i];
+                for (int p = 1; p < a.world; ++p) {
+                    const float4 v = reinterpret_cast<const float4*>(a.bucket_peer[p])[i];
+                    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+                }
+                for (int p = 0; p < a.world; ++p) reinterpret_cast<float4*>(a.bucket_peer[p])[i] = s;
+            }
+        }
+    }
+}
+
+}  // namespace gg
+
+using namespace gg;
+
+extern "C" int gg_nvls_exchange(int rank, int world, float* bucket_multicast, float* const* bucket_peers,
+                                long long bucket_floats, float* rgb_multicast, float* const* rgb_peers,
+                                long long rgb_slot_floats, void* stream) {
+    GG_REQUIRE(world >= 2 && world <= kMaxRanks && rank >= 0 && rank < world, "gg_nvls_exchange: 2..16 ranks");
+    GG_REQUIRE(bucket_peers && rgb_peers, "gg_nvls_exchange: null peer table");
+    GG_REQUIRE(bucket_floats >= 0 && rgb_slot_floats >= 0 && bucket_floats % 4 == 0 && rgb_slot_floats % 4 == 0,
+               "gg_nvls_exchange: sizes must be multiples of 4 floats");
+    GG_REQUIRE((bucket_multicast == nullptr) == (rgb_multicast == nullptr),
+               "gg_nvls_exchange: both buffers or neither must have a multicast mapping");
+    ExchangeArgs a{};
+    a.rank = rank; a.world = world;
+    a.bucket_mc = bucket_multicast; a.rgb_mc = rgb_multicast;
+    a.bucket_vec4 = bucket_floats / 4; a.slot_vec4 = rgb_slot_floats / 4;
+    for (int p = 0; p < world; ++p) {
+        GG_REQUIRE(bucket_peers[p] && rgb_peers[p], "gg_nvls_exchange: null peer address");
+        GG_REQUIRE(((uintptr_t)bucket_peers[p] & 15) == 0 && ((uintptr_t)rgb_peers[p] & 15) == 0,
+                   "gg_nvls_exchange: peer buffers must be 16-byte aligned");
+        a.bucket_peer[p] = bucket_peers[p];
+        a.rgb_peer[p] = rgb_peers[p];
+    }
+    GG_REQUIRE(((uintptr_t)bucket_multicast & 15) == 0 && ((uintptr_t)rgb_multicast & 15) == 0,
+               "gg_nvls_exchange: multicast addresses must be 16-byte aligned");
+    if (a.bucket_vec4 == 0 && a.slot_vec4 == 0) return GG_OK;
+    // a copy-shaped kernel: enough CTAs to keep every NVLink port busy, not more (148 SMs x 2)
+    const int blocks = 148 * 2;
+    if (bucket_multicast)
+        nvls_exchange_kernel<true><<<blocks, 512, 0, (cudaStream_t)stream>>>(a);
+    else
+        nvls_exchange_kernel<false><<<blocks, 512, 0, (cudaStream_t)stream>>>(a);
+    count_launch();
+    return check_launch("nvls_exchange_kernel");
+}

@@ -18,14 +18,18 @@ struct AdamArgs {
     float* param[kMaxSegments];
     long long offset[kMaxSegments + 1];  // offsets into the flat buffers; offset[n_segments] = total
     long long count[kMaxSegments];       // elements of each segment (segments may be padded apart)
-    float step_size[kMaxSegments];       // lr / (1 - beta1^t)
-    float beta1, beta2, eps, inv_sqrt_bc2;
+    float step_size[kMaxSegments];       // lr / (1 - beta1^t), t = that segment's own update count
+    float inv_sqrt_bc2[kMaxSegments];    // 1 / sqrt(1 - beta2^t)
+    int mode[kMaxSegments];              // GG_ADAM_*
+    float beta1, beta2, eps;
 };
 
 // torch.optim.Adam (no amsgrad, no weight decay): m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
 // p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+// Gradient accumulation (trainer.py:466-481: a group's gradients are zeroed at step % k == 0 and its optimizer
+// steps at step % k == k-1 on the SUM of the k gradients): the modes keep that sum in `accum`.
 __global__ void __launch_bounds__(256)
-adam_kernel(const AdamArgs a, const float* __restrict__ grad, float* __restrict__ exp_avg,
+adam_kernel(const AdamArgs a, const float* __restrict__ grad, float* __restrict__ accum, float* __restrict__ exp_avg,
             float* __restrict__ exp_avg_sq) {
     const long long total = a.offset[a.n_segments];
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -35,13 +39,18 @@ adam_kernel(const AdamArgs a, const float* __restrict__ grad, float* __restrict_
         for (int s = 1; s < kMaxSegments; ++s)
             if (s < a.n_segments && i >= a.offset[s]) seg = s;
         if (i - a.offset[seg] >= a.count[seg]) continue;  // alignment padding between two segments
-        const float g = grad[i];
+        const int mode = a.mode[seg];
+        if (mode == GG_ADAM_SKIP) continue;
+        float g = grad[i];
+        if (mode == GG_ADAM_ACC_FIRST) { accum[i] = g; continue; }
+        if (mode == GG_ADAM_ACC) { accum[i] += g; continue; }
+        if (mode == GG_ADAM_ACC_STEP) g += accum[i];
         const float m = a.beta1 * exp_avg[i] + (1.0f - a.beta1) * g;
         const float v = a.beta2 * exp_avg_sq[i] + (1.0f - a.beta2) * g * g;
         exp_avg[i] = m;
         exp_avg_sq[i] = v;
         float* p = a.param[seg] + (i - a.offset[seg]);
-        *p = *p - a.step_size[seg] * (m / (sqrtf(v) * a.inv_sqrt_bc2 + a.eps));
+        *p = *p - a.step_size[seg] * (m / (sqrtf(v) * a.inv_sqrt_bc2[seg] + a.eps));
     }
 }
 
@@ -77,34 +86,43 @@ densify_stats_kernel(long long n, int n_views, const float* __restrict__ v_geo, 
 using namespace gg;
 
 extern "C" int gg_adam_step(int n_segments, float* const* params, const long long* offsets, const long long* counts,
-                            const float* lrs, const float* grad_flat, float* exp_avg_flat, float* exp_avg_sq_flat,
-                            float beta1, float beta2, float eps, int step, void* stream) {
+                            const float* lrs, const int* steps, const int* modes, const float* grad_flat,
+                            float* accum_flat, float* exp_avg_flat, float* exp_avg_sq_flat, float beta1, float beta2,
+                            float eps, void* stream) {
     GG_REQUIRE(n_segments >= 1 && n_segments <= kMaxSegments, "gg_adam_step: 1..8 segments");
-    GG_REQUIRE(params && offsets && counts && lrs && grad_flat && exp_avg_flat && exp_avg_sq_flat,
+    GG_REQUIRE(params && offsets && counts && lrs && steps && grad_flat && exp_avg_flat && exp_avg_sq_flat,
                "gg_adam_step: null pointer");
-    GG_REQUIRE(step >= 1 && beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f, "gg_adam_step: bad hyper-parameters");
+    GG_REQUIRE(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f, "gg_adam_step: bad hyper-parameters");
     AdamArgs a;
     a.n_segments = n_segments;
     long long end = 0;
-    const double bc1 = 1.0 - pow((double)beta1, (double)step);
-    const double bc2 = 1.0 - pow((double)beta2, (double)step);
     for (int s = 0; s < n_segments; ++s) {
         GG_REQUIRE(params[s] && counts[s] >= 0 && offsets[s] >= end, "gg_adam_step: segments must be ordered, disjoint");
+        const int mode = modes ? modes[s] : GG_ADAM_STEP;
+        GG_REQUIRE(mode >= GG_ADAM_STEP && mode <= GG_ADAM_SKIP, "gg_adam_step: unknown segment mode");
+        GG_REQUIRE((mode != GG_ADAM_ACC_FIRST && mode != GG_ADAM_ACC && mode != GG_ADAM_ACC_STEP) || accum_flat,
+                   "gg_adam_step: an accumulating segment needs accum_flat");
+        const bool stepping = mode == GG_ADAM_STEP || mode == GG_ADAM_ACC_STEP;
+        GG_REQUIRE(!stepping || steps[s] >= 1, "gg_adam_step: the update count of a stepping segment starts at 1");
         a.param[s] = params[s];
         a.offset[s] = offsets[s];
         a.count[s] = counts[s];
+        a.mode[s] = mode;
+        const int t = steps[s] >= 1 ? steps[s] : 1;
+        const double bc1 = 1.0 - pow((double)beta1, (double)t);
+        const double bc2 = 1.0 - pow((double)beta2, (double)t);
         a.step_size[s] = (float)((double)lrs[s] / bc1);
+        a.inv_sqrt_bc2[s] = (float)(1.0 / sqrt(bc2));
         end = offsets[s] + counts[s];
     }
-    for (int s = n_segments; s < kMaxSegments; ++s) a.count[s] = 0;
+    for (int s = n_segments; s < kMaxSegments; ++s) { a.count[s] = 0; a.mode[s] = GG_ADAM_SKIP; a.step_size[s] = 0.f; a.inv_sqrt_bc2[s] = 1.f; a.param[s] = nullptr; }
     a.offset[n_segments] = end;
     for (int s = n_segments + 1; s <= kMaxSegments; ++s) a.offset[s] = end;
     a.beta1 = beta1; a.beta2 = beta2; a.eps = eps;
-    a.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
     if (end == 0) return GG_OK;
     int blocks = div_up(end, 256 * 8);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a, grad_flat, exp_avg_flat, exp_avg_sq_flat);
+    adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a, grad_flat, accum_flat, exp_avg_flat, exp_avg_sq_flat);
     count_launch();
     return check_launch("adam_kernel");
 }
@@ -211,6 +229,47 @@ refine_map_kernel(int n, int samps, const uint8_t* __restrict__ flags, const int
     }
 }
 
+// Philox4x32-10 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC'11): a counter-based generator,
+// so the split samples are a pure function of (seed, refinement step, parent row, sample index).  Every rank of a
+// view-sharded run derives identical children without a broadcast (the reference draws torch.randn per process,
+// gaussian_splatting.py:491, which is what breaks its multi-GPU training).
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                                      uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// component e (0..2) of the standard-normal sample of (parent row, sample index): Box-Muller on the four words
+__device__ __forceinline__ float philox_normal(unsigned long long seed, uint32_t step, uint32_t parent, uint32_t sample, int e) {
+    uint32_t w[4];
+    philox4x32_10(parent, sample, step, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), w);
+    const float inv = 2.3283064365386963e-10f;  // 2^-32
+    const float u1 = ((float)(e < 2 ? w[0] : w[2]) + 0.5f) * inv, u2 = ((float)(e < 2 ? w[1] : w[3]) + 0.5f) * inv;
+    const float r = sqrtf(-2.0f * logf(fminf(fmaxf(u1, 1e-12f), 1.0f)));
+    const float th = 6.283185307179586f * u2;
+    return e == 1 ? r * sinf(th) : r * cosf(th);
+}
+
+__global__ void __launch_bounds__(256)
+philox_normals_kernel(long long count, const int32_t* __restrict__ parents, int n_samples, unsigned long long seed,
+                      uint32_t step, float* __restrict__ out) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)n_samples * count * 3) return;
+    const int e = (int)(idx % 3);
+    const long long row = idx / 3;
+    const long long r = row % count;
+    const uint32_t s = (uint32_t)(row / count);
+    const uint32_t parent = parents ? (uint32_t)parents[r] : (uint32_t)r;
+    out[idx] = philox_normal(seed, step, parent, s, e);
+}
+
 struct RefineArrays {
     int n_arrays;
     const float* src[GG_REFINE_MAX_ARRAYS];
@@ -223,7 +282,8 @@ __global__ void __launch_bounds__(256)
 refine_gather_kernel(long long n_out, const RefineArrays t, const int32_t* __restrict__ src_row,
                      const uint8_t* __restrict__ role, const int32_t* __restrict__ aux, const uint8_t* __restrict__ flags,
                      const float* __restrict__ means, const float* __restrict__ log_scales,
-                     const float* __restrict__ quats, const float* __restrict__ samples) {
+                     const float* __restrict__ quats, const float* __restrict__ samples, int n_split_all,
+                     unsigned long long seed, uint32_t step) {
     const int a = blockIdx.y;
     const int row = t.row[a], kind = t.kind[a];
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -242,10 +302,19 @@ refine_gather_kernel(long long n_out, const RefineArrays t, const int32_t* __res
         const float4 q = *reinterpret_cast<const float4*>(quats + 4 * (long long)i);
         const float inv = 1.0f / sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
         const float w = q.x * inv, x = q.y * inv, y = q.z * inv, z = q.w * inv;
-        const float* smp = samples + 3 * (long long)aux[j];
-        const float s0 = expf(log_scales[3 * (long long)i]) * smp[0];
-        const float s1 = expf(log_scales[3 * (long long)i + 1]) * smp[1];
-        const float s2 = expf(log_scales[3 * (long long)i + 2]) * smp[2];
+        float z0, z1, z2;
+        if (samples) {  // caller-provided normals, row s * n_split_all + (rank of the parent among the split parents)
+            const float* smp = samples + 3 * (long long)aux[j];
+            z0 = smp[0]; z1 = smp[1]; z2 = smp[2];
+        } else {        // counter-based: keyed on the parent's row and the sample index, not on any rank-local state
+            const uint32_t smp_i = (uint32_t)(aux[j] / n_split_all);
+            z0 = philox_normal(seed, step, (uint32_t)i, smp_i, 0);
+            z1 = philox_normal(seed, step, (uint32_t)i, smp_i, 1);
+            z2 = philox_normal(seed, step, (uint32_t)i, smp_i, 2);
+        }
+        const float s0 = expf(log_scales[3 * (long long)i]) * z0;
+        const float s1 = expf(log_scales[3 * (long long)i + 1]) * z1;
+        const float s2 = expf(log_scales[3 * (long long)i + 2]) * z2;
         float r0, r1, r2;  // row e of the rotation matrix (same convention as quat_to_rotmat)
         if (e == 0) { r0 = 1.f - 2.f * (y * y + z * z); r1 = 2.f * (x * y - w * z); r2 = 2.f * (x * z + w * y); }
         else if (e == 1) { r0 = 2.f * (x * y + w * z); r1 = 1.f - 2.f * (x * x + z * z); r2 = 2.f * (y * z - w * x); }
@@ -299,7 +368,8 @@ extern "C" int gg_refine_plan(int n, const float* xys_grad_norm, const float* vi
 extern "C" int gg_refine_apply(int n, int n_split_samples, const int32_t* totals, const void* plan_workspace,
                                int n_arrays, const float* const* src, float* const* dst, const int* row_floats,
                                const int* kinds, const float* means, const float* log_scales, const float* quats,
-                               const float* samples, void* scratch, size_t scratch_bytes, void* stream) {
+                               const float* samples, unsigned long long seed, unsigned int step, void* scratch,
+                               size_t scratch_bytes, void* stream) {
     GG_REQUIRE(n >= 1 && n_split_samples >= 1 && totals && plan_workspace, "gg_refine_apply: bad arguments");
     GG_REQUIRE(n_arrays >= 1 && n_arrays <= GG_REFINE_MAX_ARRAYS && src && dst && row_floats && kinds,
                "gg_refine_apply: 1..GG_REFINE_MAX_ARRAYS arrays");
@@ -308,7 +378,7 @@ extern "C" int gg_refine_apply(int n, int n_split_samples, const int32_t* totals
     GG_REQUIRE(n_keep >= 0 && n_sk >= 0 && n_dk >= 0 && n_sa >= n_sk && n_keep <= n, "gg_refine_apply: inconsistent totals");
     const long long n_out = n_keep + (long long)n_split_samples * n_sk + n_dk;
     GG_REQUIRE(n_out < (1ll << 31), "gg_refine_apply: too many Gaussians");
-    GG_REQUIRE(n_sk == 0 || samples, "gg_refine_apply: split children need normal samples");
+    // samples == NULL: the children's offsets come from Philox4x32-10 keyed on (seed, step, parent row, sample)
     if (n_out == 0) return GG_OK;
     GG_REQUIRE(scratch && scratch_bytes >= (size_t)n_out * 9 + 512, "gg_refine_apply: scratch too small (9 B per output row + 512)");
     cudaStream_t st = (cudaStream_t)stream;
@@ -337,9 +407,26 @@ extern "C" int gg_refine_apply(int n, int n_split_samples, const int32_t* totals
         if (row_floats[a] > max_row) max_row = row_floats[a];
     }
     dim3 grid((unsigned)div_up(n_out * max_row, 256), (unsigned)n_arrays);
-    refine_gather_kernel<<<grid, 256, 0, st>>>(n_out, tab, src_row, role, aux, flags, means, log_scales, quats, samples);
+    refine_gather_kernel<<<grid, 256, 0, st>>>(n_out, tab, src_row, role, aux, flags, means, log_scales, quats, samples,
+                                               (int)(n_sa > 0 ? n_sa : 1), seed, step);
     count_launch();
     return check_launch("refine_gather_kernel");
+}
+
+extern "C" int gg_philox_normals(long long count, const int32_t* parents, int n_samples, unsigned long long seed,
+                                 unsigned int step, float* out, void* stream) {
+    GG_REQUIRE(count >= 0 && n_samples >= 1 && count < (1ll << 31), "gg_philox_normals: bad sizes");
+    if (count == 0) return GG_OK;
+    GG_REQUIRE(out, "gg_philox_normals: null output");
+    const long long total = (long long)n_samples * count * 3;
+    philox_normals_kernel<<<(unsigned)div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(count, parents, n_samples, seed,
+                                                                                         step, out);
+    count_launch();
+    return check_launch("philox_normals_kernel");
+}
+
+extern "C" void gg_philox4x32_10_host(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4]) {
+    gg::philox4x32_10(counter[0], counter[1], counter[2], counter[3], key[0], key[1], out);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -40,7 +40,9 @@ class GradientBucket:
     N x (3+3+4+1+3K+D) floats of payload (408 MB at N = 1M, K = 25, D = 16) plus at most 3 padding
     floats per segment (they stay zero)."""
 
-    def __init__(self, params: Dict[str, torch.Tensor], group: Optional[dist.ProcessGroup] = None):
+    def __init__(self, params: Dict[str, torch.Tensor], group: Optional[dist.ProcessGroup] = None, allocator=None):
+        """allocator(numel) -> zero-filled fp32 CUDA tensor of at least numel elements (e.g. symmetric memory);
+        default torch.zeros."""
         self.names = [k for k in PARAM_ORDER if k in params]
         extra = [k for k in params if k not in PARAM_ORDER]
         if extra:
@@ -56,7 +58,12 @@ class GradientBucket:
         self.numel = off
         self.payload = sum(self.sizes.values())
         p0 = params[self.names[0]]
-        self.flat = torch.zeros(off, dtype=torch.float32, device=p0.device)
+        if allocator is None:
+            self.flat = torch.zeros(off, dtype=torch.float32, device=p0.device)
+        else:
+            self.flat = allocator(off)
+            if self.flat.numel() < off or self.flat.dtype != torch.float32 or not self.flat.is_contiguous():
+                raise ValueError("GradientBucket allocator must return a contiguous fp32 tensor of >= numel elements")
         self.group = group
 
     def view(self, name: str) -> torch.Tensor:
@@ -115,6 +122,11 @@ class FactoredExchange:
         self.rgb_send = torch.zeros((self.V, n, 3), dtype=torch.float32, device=dev) if self.on else self.rgb_all
         self._reconstruct = reconstruct
 
+    def rebuild(self, params: Dict[str, torch.Tensor]) -> "FactoredExchange":
+        """Adopt a refined parameter set (the Gaussian count changed): fresh bucket and factor tables."""
+        self.__init__(params, self.V, self.group, self._reconstruct)
+        return self
+
     def holder(self) -> dict:
         go = dict(self.bucket.unpack())
         go["v_rgb_views"] = self.rgb_send
@@ -155,6 +167,85 @@ class FactoredExchange:
         rec(int(degree), int(degrees_to_use), means.detach(), self.pos_all, self.rgb_all, out=self.sh_grad)
         if reduce_work is not None:
             reduce_work.wait()
+        grads = dict(self.bucket.unpack())
+        grads["sh_coeffs"] = self.sh_grad
+        return grads
+
+
+class NvlsExchange(FactoredExchange):
+    """FactoredExchange whose two collectives are ONE kernel of this library over symmetric memory
+    (csrc/exchange.cu, gg_nvls_exchange): the bucket and the gathered factor table live in
+    torch.distributed._symmetric_memory allocations (peer-mapped, with an NVLS multicast mapping on an NVSwitch
+    box); per step: barrier -> [multimem.st all-gather of the rgb slots + multimem.ld_reduce / multimem.st two-shot
+    all-reduce of the bucket] -> barrier -> SH rebuild.  No NCCL call on the data path, no staging copy, the
+    reduction arithmetic happens in the switch.  Same interface and same results (up to the order of the
+    world-term sums) as FactoredExchange; needs an initialised NCCL process group with more than one rank."""
+
+    def __init__(self, params: Dict[str, torch.Tensor], views_per_rank: int,
+                 group: Optional[dist.ProcessGroup] = None, reconstruct=None):
+        import torch.distributed._symmetric_memory as symm
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+            raise RuntimeError("NvlsExchange needs an initialised process group with more than one rank")
+        self._symm = symm
+        self.group = group
+        self.on = True
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.V = int(views_per_rank)
+        pg = group if group is not None else dist.group.WORLD
+        sh = params["sh_coeffs"]
+        n, dev = sh.shape[0], sh.device
+        self.n = n
+
+        def symmetric(numel):
+            numel = (int(numel) + 3) // 4 * 4
+            t = symm.empty(numel, dtype=torch.float32, device=dev)
+            t.zero_()
+            return t
+
+        self.bucket = GradientBucket({k: v for k, v in params.items() if k != "sh_coeffs"}, group, allocator=symmetric)
+        self.slot = (self.V * n * 3 + 3) // 4 * 4            # floats per rank slot, 16-byte multiple
+        self.rgb_sym = symmetric(self.world * self.slot)
+        self.h_bucket = symm.rendezvous(self.bucket.flat, pg)
+        self.h_rgb = symm.rendezvous(self.rgb_sym, pg)
+        self.multicast = bool(self.h_bucket.multicast_ptr) and bool(self.h_rgb.multicast_ptr)
+        self.sh_grad = torch.zeros(tuple(sh.shape), dtype=torch.float32, device=dev)
+        self.pos_all = torch.zeros((self.world * self.V, 3), dtype=torch.float32, device=dev)
+        self.rgb_send = self.rgb_sym[self.rank * self.slot:self.rank * self.slot + self.V * n * 3].view(self.V, n, 3)
+        # the reconstruction reads the views of all ranks: [world, V, n, 3] when the slots are unpadded
+        if self.slot != self.V * n * 3:
+            raise ValueError("NvlsExchange: views_per_rank * n * 3 must be a multiple of 4 floats")
+        self.rgb_all = self.rgb_sym.view(self.world * self.V, n, 3)
+        self._reconstruct = reconstruct
+        import ctypes as C
+        self._bucket_peers = (C.c_void_p * self.world)(*[int(p) for p in self.h_bucket.buffer_ptrs])
+        self._rgb_peers = (C.c_void_p * self.world)(*[int(p) for p in self.h_rgb.buffer_ptrs])
+
+    def rebuild(self, params: Dict[str, torch.Tensor]) -> "NvlsExchange":
+        self.__init__(params, self.V, self.group, self._reconstruct)
+        return self
+
+    def exchange(self, means: torch.Tensor, positions: torch.Tensor, degree: int, degrees_to_use: int,
+                 holder: Optional[dict] = None, all_positions: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        from . import _lib, ops
+        if holder is not None and holder.get("v_rgb_views") is not None and \
+                holder["v_rgb_views"].data_ptr() != self.rgb_send.data_ptr():
+            self.rgb_send.copy_(holder["v_rgb_views"].view_as(self.rgb_send))
+        if all_positions is not None:
+            self.pos_all.copy_(all_positions)
+        else:
+            dist.all_gather_into_tensor(self.pos_all, positions.detach().to(torch.float32).contiguous(), group=self.group)
+        dev = self.bucket.flat.device
+        self.h_bucket.barrier(channel=0)          # every rank's backward has written its bucket and its rgb slot
+        with _lib.device_guard(dev):
+            _lib.call("gg_nvls_exchange", self.rank, self.world,
+                      int(self.h_bucket.multicast_ptr) if self.multicast else None, self._bucket_peers,
+                      int(self.bucket.flat.numel()),
+                      int(self.h_rgb.multicast_ptr) if self.multicast else None, self._rgb_peers, int(self.slot),
+                      _lib.stream_ptr(dev))
+        self.h_bucket.barrier(channel=1)          # every rank's slice and slot have landed here
+        rec = self._reconstruct or ops.sh_grad_from_views
+        rec(int(degree), int(degrees_to_use), means.detach(), self.pos_all, self.rgb_all, out=self.sh_grad)
         grads = dict(self.bucket.unpack())
         grads["sh_coeffs"] = self.sh_grad
         return grads

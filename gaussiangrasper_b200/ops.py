@@ -557,6 +557,18 @@ def blend_bwd(binning: Binning, geo, colors, background, final_T, final_idx, v_o
     return v_geo, v_colors
 
 
+def blend_pair_stats(binning: Binning, geo, img_height, img_width):
+    """(pairs visited, pairs blended) of a binned batch -- the K of SURVEY 8d and its contributing subset."""
+    dev = require_cuda(geo)
+    stats = torch.zeros(2, dtype=torch.int64, device=dev)
+    tb = binning.tile_bounds
+    with _lib.device_guard(dev):
+        _lib.call("gg_blend_pair_stats", binning.n_views, binning.n, int(img_height), int(img_width), tb[0], tb[1],
+                  _ids_ptr(binning), ptr(binning.tile_ranges), ptr(geo), ptr(stats), stream_ptr(dev))
+    visited, blended = (int(x) for x in stats.tolist())
+    return visited, blended
+
+
 def unpack_vgeo(n, n_views, v_geo):
     dev = v_geo.device
     v_xys = torch.empty((n_views * n, 2), dtype=torch.float32, device=dev)

@@ -215,10 +215,13 @@ class _RenderViews(Function):
         nb = (degree + 1) ** 2
         go = (ctx.holder or {}).get("grad_out")  # optional caller-owned buffers (views of a flat bucket)
 
+        direct = set()   # leaves whose gradient goes straight into a caller-owned buffer
+
         def buf(name, shape):
             t = go.get(name) if go else None
             if t is None:
                 return torch.empty(shape, dtype=torch.float32, device=dev)
+            direct.add(name)
             # a caller-owned gradient buffer that does not fit (e.g. a bucket built before a densification
             # changed N) must not be bypassed silently: the optimizer would then consume stale contents
             if (t.numel() != int(torch.Size(shape).numel()) or not t.is_contiguous() or t.dtype != torch.float32
@@ -244,9 +247,17 @@ class _RenderViews(Function):
                       ops.ptr(v_q), ops.ptr(v_op), ops.ptr(v_sh), ops.ptr(v_f), ops.ptr(v_rgb), ops.stream_ptr(dev))
         if ctx.holder is not None:
             ctx.holder["v_geo"] = v_geo  # [V*n, 8]: columns 0..1 are d loss / d xys (densification statistic)
+            if ctx.holder.get("debug_activations"):
+                ctx.holder["v_chan"] = v_chan  # [V*n, CP]: gradient of the channel table (parity tests)
             if defer:
                 ctx.holder["v_rgb_views"] = v_rgb
-        return (v_means, v_ls, v_q, v_op.reshape(opacity_logit.shape), v_sh, v_f, None, None, None, None, None, None)
+        # A gradient written into a caller-owned buffer is NOT also handed to autograd: AccumulateGrad would either
+        # clone it (a wasted pass over the buffer) or adopt the buffer as `.grad` and add the next step's gradient
+        # into it in place -- on top of what this kernel has just written there.  Those leaves keep `.grad = None`.
+        ret = dict(means=v_means, log_scales=v_ls, quats=v_q, opacity_logit=v_op.reshape(opacity_logit.shape),
+                   sh_coeffs=v_sh, features=v_f)
+        return tuple(None if k in direct else ret[k] for k in
+                     ("means", "log_scales", "quats", "opacity_logit", "sh_coeffs", "features")) + (None,) * 6
 
 
 def smallest_axis_normals(quats: torch.Tensor, log_scales: torch.Tensor) -> torch.Tensor:
@@ -269,7 +280,8 @@ def render_views(means, log_scales, quats, opacity_logit, sh_coeffs, features, v
     backward, `v_geo` whose first two columns are d loss / d xys, the statistic the model's
     densification reads from `xys.grad` (gaussian_splatting.py:725,377).  If it carries
     `grad_out` (name -> preallocated fp32 tensor, e.g. `GradientBucket.unpack()`), the backward
-    writes the leaf gradients of a single-launch step straight into those buffers.  With
+    writes the leaf gradients of a single-launch step straight into those buffers (overwriting them) and the
+    leaves named there get NO `.grad` from autograd: the buffers are the gradients.  With
     `defer_sh_grad` set, the SH-coefficient gradient is not formed: `sh_coeffs.grad` stays None and
     `holder["v_rgb_views"]` [V,N,3] receives its per-view factor (see distributed.FactoredExchange).
     """

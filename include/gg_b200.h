@@ -170,6 +170,11 @@ int gg_blend_fwd(int n_views, long long n, int channels, int color_stride, int c
                  const float* colors, const float* bg,
                  float* out /*[V,H,W,out_stride]*/, float* final_T /*[V,H,W]*/, int32_t* final_idx /*[V,H,W]*/,
                  unsigned long long* pair_counter /*nullable*/, uint32_t* hit_words /*nullable*/, void* stream);
+/* Workload counters of a binned batch (bench.py's roofline accounting): stats[0] += pixel-Gaussian pairs visited
+ * up to each pixel's stop (K of SURVEY 8d), stats[1] += pairs blended.  stats: 2 device uint64, zeroed by the caller. */
+int gg_blend_pair_stats(int n_views, long long n, int img_h, int img_w, int tiles_x, int tiles_y,
+                        const int32_t* ids_sorted, const int32_t* tile_ranges, const float* geo /*[V*n,8]*/,
+                        unsigned long long* stats, void* stream);
 /* hit_words: table of gg_blend_hit_words(m, V*tiles, channels) uint32, ZERO-FILLED by the caller before
  * gg_blend_fwd, in which the forward records per (tile batch, 8x4-pixel warp) the entries that
  * contributed; handed to gg_blend_bwd (same channel count) it spares the backward the culling and
@@ -220,15 +225,38 @@ int gg_prepare_views_bwd(int n, int n_views, int feat_dim, int cp, int degree, i
 int gg_sh_grad_from_views(int n, int n_views, int degree, int degrees_to_use, const float* means,
                           const float* positions, const float* v_rgb_views, float* v_sh_coeffs, void* stream);
 
+/* Gradient exchange of a view-sharded training step as one kernel over symmetric memory: all-gather of
+ * the per-view colour-gradient slots (the SH gradient's factors, see gg_sh_grad_from_views) and a two-shot
+ * all-reduce of the other leaf gradients, through the NVSwitch with multimem.st / multimem.ld_reduce when the
+ * buffers have a multicast mapping (bucket_multicast / rgb_multicast non-NULL), else over the peers' mapped
+ * addresses.  bucket_peers / rgb_peers: HOST arrays of `world` device addresses (this rank's own included) of the
+ * same symmetric buffers; bucket_floats = size of the bucket; rgb_slot_floats = size of ONE rank's slot of the
+ * [world, slot] gather buffer (both multiples of 4).  The caller places a cross-rank barrier before the launch
+ * (every rank has written its bucket and its slot) and after it (every rank's slice has landed everywhere).
+ * Replaces ncclAllGather + ncclAllReduce of distributed.FactoredExchange. */
+int gg_nvls_exchange(int rank, int world, float* bucket_multicast /*nullable*/, float* const* bucket_peers,
+                     long long bucket_floats, float* rgb_multicast /*nullable*/, float* const* rgb_peers,
+                     long long rgb_slot_floats, void* stream);
+
 /* ---- next rows: the streaming steps directly behind the backward -----------------
  * gg_adam_step: fused torch.optim.Adam (no amsgrad / weight decay) over a flat gradient buffer that
  * holds up to 8 ordered, disjoint segments (padding between them is skipped), each with its own parameter
  * tensor and learning rate (replaces the
- * reference's per-group optimizers, method_configs.py:618-664).  params/offsets/counts/lrs are HOST
- * arrays of n_segments entries; `step` is the 1-based update count used for the bias corrections. */
+ * reference's per-group optimizers, method_configs.py:618-664).  params/offsets/counts/lrs/steps/modes are HOST
+ * arrays of n_segments entries; steps[s] is segment s's own 1-based update count (bias corrections), as every
+ * reference group has its own torch.optim.Adam.  modes (nullable = all GG_ADAM_STEP) implement the trainer's
+ * gradient accumulation (engine/trainer.py:466-481, method_configs.py:611: xyz / color / feature every 10 steps):
+ * ACC_FIRST accum = grad (the step after zero_grad), ACC accum += grad, ACC_STEP update with accum + grad,
+ * STEP update with grad, SKIP leave the segment alone.  accum_flat is laid out like grad_flat. */
+#define GG_ADAM_STEP 0
+#define GG_ADAM_ACC_FIRST 1
+#define GG_ADAM_ACC 2
+#define GG_ADAM_ACC_STEP 3
+#define GG_ADAM_SKIP 4
 int gg_adam_step(int n_segments, float* const* params, const long long* offsets, const long long* counts,
-                 const float* lrs, const float* grad_flat, float* exp_avg_flat, float* exp_avg_sq_flat, float beta1,
-                 float beta2, float eps, int step, void* stream);
+                 const float* lrs, const int* steps, const int* modes /*nullable*/, const float* grad_flat,
+                 float* accum_flat /*nullable unless a mode accumulates*/, float* exp_avg_flat, float* exp_avg_sq_flat,
+                 float beta1, float beta2, float eps, void* stream);
 /* gg_densify_stats: GaussianSplattingModel.after_train (gaussian_splatting.py:373-393) from the
  * blend gradient table: xys_grad_norm += |d loss / d xy|, vis_counts += 1, max_2dsize =
  * max(., radius / max(H, W)) for the Gaussians visible in each view; first_call != 0 initialises
@@ -247,7 +275,13 @@ int gg_densify_stats(long long n, int n_views, const float* v_geo /*[V*n,8]*/, c
  * array (parameters and Adam moments) into its new [n_out, row] array in one launch; `kinds` says how children
  * are formed: COPY (parent's row), MOMENT (zeros), MEANS (split children: mean + R(q/|q|)(exp(scale) * z), z =
  * samples[s * totals[3] + rank among all split parents]), LOG_SCALES (split parents and their children:
- * log(exp(s) / 1.6)).  means / log_scales / quats are the OLD parameter arrays. */
+ * log(exp(s) / 1.6)).  means / log_scales / quats are the OLD parameter arrays.
+ * samples == NULL: z comes from the counter-based generator Philox4x32-10 with counter (parent row, sample index,
+ * step, 0) and key (seed low, seed high), Box-Muller on the four output words -- a pure function of its arguments,
+ * so the ranks of a view-sharded run (identical parameters, all-reduced statistics) create identical children
+ * without exchanging anything (the reference draws torch.randn per process, :491).  gg_philox_normals writes the
+ * same numbers for given parent rows ([n_samples, count, 3]; parents == NULL means rows 0..count-1);
+ * gg_philox4x32_10_host is the raw block function on the host (known-answer tests). */
 typedef struct {
     float max_dim;              /* max(W, H) of the last rendered image (:415) */
     float densify_grad_thresh;  /* config.densify_grad_thresh */
@@ -273,8 +307,12 @@ int gg_refine_plan(int n, const float* xys_grad_norm, const float* vis_counts, c
                    size_t workspace_bytes, int32_t* totals_host /*[4]*/, void* stream);
 int gg_refine_apply(int n, int n_split_samples, const int32_t* totals /*[4] host*/, const void* plan_workspace,
                     int n_arrays, const float* const* src, float* const* dst, const int* row_floats, const int* kinds,
-                    const float* means, const float* log_scales, const float* quats, const float* samples,
-                    void* scratch /* 9 B per output row + 512 */, size_t scratch_bytes, void* stream);
+                    const float* means, const float* log_scales, const float* quats, const float* samples /*nullable*/,
+                    unsigned long long seed, unsigned int step, void* scratch /* 9 B per output row + 512 */,
+                    size_t scratch_bytes, void* stream);
+int gg_philox_normals(long long count, const int32_t* parents /*nullable*/, int n_samples, unsigned long long seed,
+                      unsigned int step, float* out, void* stream);
+void gg_philox4x32_10_host(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4]);
 
 /* ---- per-pixel loss with its gradient in one pass (the L1 term and its masked variant,
  * gaussian_splatting.py:853-866; kind 2 = mean squared error).  pred/target/grad are n contiguous floats
@@ -286,6 +324,34 @@ size_t gg_pixel_loss_workspace_bytes(void);
 int gg_pixel_loss(long long n, int channels, const float* pred, const float* target, const uint8_t* mask /*nullable*/,
                   const int32_t* valid_pixels /*nullable, device*/, int kind /*1 = L1, 2 = L2*/, float weight, float* grad,
                   float* loss, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- the other terms of get_loss_dict (gaussian_splatting.py:876-925), value and gradient in one pass each.
+ * workspace (all three): gg_loss_workspace_bytes() bytes, ZERO-FILLED when allocated.
+ * gg_geom_loss: loss[0] = w_depth * mean_mask |depth - gt_depth| (:880), loss[1] = w_normal * (1/2 MSE(normal, gt) +
+ *   1/2 (1 - mean cos(normal, gt))) over the masked pixels (:879, cosine_similarity_loss :113-118).  image is the
+ *   blended [n_pixels, stride] picture of render_views (depth = channel 3, normal = channels 4..6); gt_normal
+ *   [n_pixels, 3]; mask one byte per pixel; valid_pixels = device int32 count of set mask bytes.  grad
+ *   [n_pixels, grad_stride] receives channels 3..6 (written, or added when accumulate != 0).
+ * gg_cosine_rows_loss: loss = sum_k w_k (1 - cos(a_k, b_k)), rows a_k = a + (a_index ? a_index[k] : k) * a_stride
+ *   (dim floats), same for b; weight nullable (= 1).  The contrastive feature loss over sampled pixel pairs
+ *   (:905-912: a = b = the feature channels of the image, index lists = the pairs, w = 1 / (segments * pairs of the
+ *   segment)) and up_loss (:913-914: a = MLP outputs, b = sampled CLIP features).  grad_a / grad_b (nullable) are
+ *   ADDED to, with atomics when the operand is indexed (a pixel can be sampled twice).
+ * gg_param_regs: loss[0] = w_sh * mean ||sh[:, 1:, :]||_2 over (Gaussian, colour) (:920), loss[1] = w_scale * 0.1 *
+ *   mean(max(max_i s_i / min_i s_i, max_gauss_ratio) - max_gauss_ratio), s = exp(log_scales) (:921-923); the
+ *   gradients are ADDED to v_sh_coeffs / v_log_scales (nullable). */
+size_t gg_loss_workspace_bytes(void);
+int gg_geom_loss(long long n_pixels, int stride, const float* image, const float* gt_depth, const float* gt_normal,
+                 const uint8_t* mask, const int32_t* valid_pixels, float w_depth, float w_normal, float* grad,
+                 int grad_stride, int accumulate, float* loss /*[2]*/, void* workspace, size_t workspace_bytes, void* stream);
+int gg_cosine_rows_loss(long long n_rows, int dim, const float* a, long long a_stride, const int64_t* a_index /*nullable*/,
+                        const float* b, long long b_stride, const int64_t* b_index /*nullable*/,
+                        const float* weight /*nullable*/, float* grad_a /*nullable*/, long long grad_a_stride,
+                        float* grad_b /*nullable*/, long long grad_b_stride, float* loss /*[1]*/, int accumulate_loss,
+                        void* workspace, size_t workspace_bytes, void* stream);
+int gg_param_regs(long long n, int num_bases, const float* sh_coeffs, const float* log_scales, float max_gauss_ratio,
+                  float w_sh, float w_scale, float* v_sh_coeffs /*nullable*/, float* v_log_scales /*nullable*/,
+                  float* loss /*[2]*/, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- SSIM loss with its gradient: weight * (1 - SSIM) with pytorch_msssim's defaults as the
  * reference configures them (gaussian_splatting.py:284, :885: 11x11 Gaussian window, sigma 1.5, data_range 1, no

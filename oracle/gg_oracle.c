@@ -301,6 +301,9 @@ void gg_oracle_tile_ranges(int64_t m, const int64_t *keys_sorted, int num_tiles,
 /* flip it; parity tests compare those pixels at a looser bound.               */
 /* Returns the number of pixel-Gaussian pairs visited (K of SURVEY 8d).        */
 /* ------------------------------------------------------------------------- */
+/* T is a product of up to thousands of fp32 factors: two correct fp32 evaluations differ by sqrt(n) ulps in it,   */
+/* not by one, so the window around the T = 1e-4 stop is GG_T_WINDOW times wider than the one around alpha.        */
+#define GG_T_WINDOW 16.0f
 int64_t gg_oracle_blend_fwd(int channels, int img_h, int img_w, int tiles_x, int tiles_y,
                             const int32_t *ids_sorted, const int32_t *tile_ranges, const float *xys,
                             const float *conics, const float *opac, const float *colors,
@@ -333,7 +336,7 @@ int64_t gg_oracle_blend_fwd(int channels, int img_h, int img_w, int tiles_x, int
                 if (fabsf(alpha - (1.0f / 255.0f)) <= eps * (1.0f / 255.0f)) frag = 1;
                 if (alpha < 1.0f / 255.0f) continue;
                 const float next_T = T * (1.0f - alpha);
-                if (fabsf(next_T - 1e-4f) <= eps * 1e-4f) frag = 1;
+                if (fabsf(next_T - 1e-4f) <= GG_T_WINDOW * eps * 1e-4f) frag = 1;
                 if (next_T <= 1e-4f) break;
                 const float vis = alpha * T;
                 const float *col = colors + (size_t)g * channels;
@@ -356,13 +359,125 @@ int64_t gg_oracle_blend_fwd(int channels, int img_h, int img_w, int tiles_x, int
 /* 0.999 passes no gradient to sigma/opacity.                                  */
 /* v_xy[N,2], v_conic[N,3], v_colors[N,C], v_opac[N] are doubles.              */
 /* ------------------------------------------------------------------------- */
-/* Extended form.  Besides the gradients it can return, per gradient component,                                 */
-/*   abs_*  : the sum of the ABSOLUTE values of the per-pixel contributions (the scale fp32 accumulation error   */
-/*            is proportional to: a sum that cancels has |sum| << abs sum), and                                  */
-/*   taint_*: the same sum restricted to pixels the forward flags fragile (a pair within `eps` relative of a     */
-/*            branch threshold): a flip there changes that pixel's contributions by about alpha_min = 1/255.     */
-/* The parity tests bound |got - ref| <= rtol |ref| + k eps_fp32 abs + 0.01 taint element by element.            */
-/* abs / taint pointers may be NULL (all or none of each group).                                                 */
+/* Extended form.  Besides the gradients it can return, per gradient component, two error scales:              */
+/*   abs_*  : the sum of the magnitudes the component is accumulated from -- per pixel, the contribution with    */
+/*            every product of the alpha gradient taken in absolute value BEFORE it is summed over the channels  */
+/*            (col T - S/(1-a) cancels inside a pair as well as between pixels), times 1 + (|A dx^2|/2 +          */
+/*            |C dy^2|/2 + |B dx dy|): alpha = o exp(-sigma) inherits the ABSOLUTE fp32 error of sigma, which     */
+/*            grows with the three products sigma is summed from.  fp32 evaluation and accumulation errors are    */
+/*            proportional to this scale, not to |sum|.                                                           */
+/*   taint_*: what flipped branches change.  A pixel with a test within its window of a threshold (alpha = 1/255  */
+/*            and sigma = 0: `eps` relative / 1e-6 absolute; T = 1e-4: GG_T_WINDOW * eps, the forward's `fragile` */
+/*            flag) is evaluated a second time with every such test inverted; taint accumulates, per pair and     */
+/*            component, |contribution(flipped) - contribution(as decided)| -- the blended-or-not pair itself,    */
+/*            the rescaling of what lies behind it and the shift of the sums in front of it.                      */
+/* The parity tests bound |got - ref| <= rtol |ref| + k eps_fp32 abs + 2 taint, element by element.               */
+/* abs / taint pointers may be NULL (all or none of each group).  Rows of pixels run in parallel; the            */
+/* accumulations are atomic (fp64: the summation order does not matter at the tested tolerances).                */
+#define GG_ACC(dst, val) do { const double gg_v_ = (val); _Pragma("omp atomic") (dst) += gg_v_; } while (0)
+
+typedef struct {
+    int channels, n;
+    const int32_t *ids_sorted;
+    const float *xys, *conics, *opac, *colors, *bg;
+    float eps;
+} gg_bwd_ctx;
+
+/* One pixel: fp32 replay of A9 (with the near-threshold tests inverted when `flip`), then the fp64 backward over  */
+/* the pairs the replay blended.  Per pair k - start: six geometry terms, `channels` colour terms, and (base pass   */
+/* only) their magnitudes.  Returns 1 when some test sat inside its window.                                        */
+static int gg_pixel_bwd(const gg_bwd_ctx *c, int start, int end, float fx, float fy, const float *vo, int flip,
+                        unsigned char *inc, double *S, double *t_geo, double *t_col, double *a_geo, double *a_col) {
+    const int ch = c->channels;
+    float T = 1.0f;
+    int last = start, frag = 0;
+    for (int k = start; k < end; ++k) {
+        inc[k - start] = 0;
+        if (last < 0) continue; /* stopped: nothing behind is blended */
+        const int g = c->ids_sorted[k];
+        const float dx = c->xys[2 * g] - fx, dy = c->xys[2 * g + 1] - fy;
+        const float A = c->conics[3 * g], B = c->conics[3 * g + 1], C = c->conics[3 * g + 2];
+        const float sigma = 0.5f * (A * dx * dx + C * dy * dy) + B * dx * dy;
+        int neg = sigma < 0.0f;
+        if (fabsf(sigma) <= 1e-6f) { frag = 1; if (flip) neg = !neg; }
+        if (neg) continue;
+        const float alpha = fminf(0.999f, c->opac[g] * expf(-sigma));
+        int low = alpha < 1.0f / 255.0f;
+        if (fabsf(alpha - (1.0f / 255.0f)) <= c->eps * (1.0f / 255.0f)) { frag = 1; if (flip) low = !low; }
+        if (low) continue;
+        const float next_T = T * (1.0f - alpha);
+        int stop = next_T <= 1e-4f;
+        if (fabsf(next_T - 1e-4f) <= GG_T_WINDOW * c->eps * 1e-4f) { frag = 1; if (flip) stop = !stop; }
+        if (stop) { last = -(last + 1); continue; }
+        T = next_T;
+        last = k + 1;
+        inc[k - start] = 1;
+    }
+    if (last < 0) last = -last - 1;
+    /* transmittance behind the last blended pair, in double */
+    double Tfin = 1.0;
+    for (int k = start; k < last; ++k) {
+        if (!inc[k - start]) continue;
+        const int g = c->ids_sorted[k];
+        const double dx = (double)c->xys[2 * g] - fx, dy = (double)c->xys[2 * g + 1] - fy;
+        const double sg = 0.5 * ((double)c->conics[3 * g] * dx * dx + (double)c->conics[3 * g + 2] * dy * dy) +
+                          (double)c->conics[3 * g + 1] * dx * dy;
+        double al = (double)c->opac[g] * exp(-sg);
+        if (al > 0.999) al = 0.999;
+        Tfin *= (1.0 - al);
+    }
+    double bgdot = 0.0, bgabs = 0.0;
+    for (int q = 0; q < ch; ++q) {
+        S[q] = 0.0;
+        bgdot += (double)c->bg[q] * vo[q];
+        bgabs += fabs((double)c->bg[q] * vo[q]);
+    }
+    double Tcur = Tfin; /* transmittance after entry k */
+    for (int k = end - 1; k >= start; --k) {
+        double *tg = t_geo + 6 * (size_t)(k - start), *tc = t_col + (size_t)ch * (k - start);
+        for (int q = 0; q < 6; ++q) tg[q] = 0.0;
+        for (int q = 0; q < ch; ++q) tc[q] = 0.0;
+        if (a_geo) {
+            for (int q = 0; q < 6; ++q) a_geo[6 * (size_t)(k - start) + q] = 0.0;
+            for (int q = 0; q < ch; ++q) a_col[(size_t)ch * (k - start) + q] = 0.0;
+        }
+        if (!inc[k - start]) continue;
+        const int g = c->ids_sorted[k];
+        const double A = c->conics[3 * g], B = c->conics[3 * g + 1], C = c->conics[3 * g + 2];
+        const double dx = (double)c->xys[2 * g] - fx, dy = (double)c->xys[2 * g + 1] - fy;
+        const double sg = 0.5 * (A * dx * dx + C * dy * dy) + B * dx * dy;
+        const double amp = 1.0 + 0.5 * fabs(A) * dx * dx + 0.5 * fabs(C) * dy * dy + fabs(B * dx * dy);
+        const double vis = exp(-sg);
+        double al = (double)c->opac[g] * vis;
+        const int clamped = al > 0.999;
+        if (clamped) al = 0.999;
+        const double ra = 1.0 / (1.0 - al);
+        const double Tb = Tcur * ra; /* transmittance before entry k */
+        const double fac = al * Tb;
+        const float *col = c->colors + (size_t)g * ch;
+        double v_alpha = 0.0, v_alpha_abs = 0.0;
+        for (int q = 0; q < ch; ++q) {
+            tc[q] = fac * vo[q];
+            if (a_col) a_col[(size_t)ch * (k - start) + q] = fabs(tc[q]) * amp;
+            v_alpha += ((double)col[q] * Tb - S[q] * ra) * vo[q];
+            v_alpha_abs += (fabs((double)col[q] * Tb) + fabs(S[q] * ra)) * fabs((double)vo[q]);
+            S[q] += (double)col[q] * fac;
+        }
+        v_alpha += -Tfin * ra * bgdot;
+        v_alpha_abs += Tfin * ra * bgabs;
+        Tcur = Tb;
+        if (clamped) continue; /* App. B-6: a clamped alpha passes no gradient to sigma / opacity */
+        /* d alpha / d sigma = -o e^-s; the six factors multiply the alpha gradient */
+        const double f6[6] = {-al * (A * dx + B * dy), -al * (B * dx + C * dy), -al * 0.5 * dx * dx, -al * dx * dy,
+                              -al * 0.5 * dy * dy, vis};
+        for (int q = 0; q < 6; ++q) {
+            tg[q] = f6[q] * v_alpha;
+            if (a_geo) a_geo[6 * (size_t)(k - start) + q] = fabs(f6[q]) * v_alpha_abs * amp;
+        }
+    }
+    return frag;
+}
+
 void gg_oracle_blend_bwd_ex(int n, int channels, int img_h, int img_w, int tiles_x,
                             const int32_t *ids_sorted, const int32_t *tile_ranges, const float *xys,
                             const float *conics, const float *opac, const float *colors,
@@ -378,100 +493,63 @@ void gg_oracle_blend_bwd_ex(int n, int channels, int img_h, int img_w, int tiles
     if (abs_colors) memset(abs_colors, 0, sizeof(double) * (size_t)channels * (size_t)n);
     if (taint_geo) memset(taint_geo, 0, sizeof(double) * 6 * (size_t)n);
     if (taint_colors) memset(taint_colors, 0, sizeof(double) * (size_t)channels * (size_t)n);
+    const int n_tiles = tiles_x * ((img_h + GG_TILE - 1) / GG_TILE);
+    int longest = 1;
+    for (int t = 0; t < n_tiles; ++t)
+        if (tile_ranges[2 * t + 1] - tile_ranges[2 * t] > longest) longest = tile_ranges[2 * t + 1] - tile_ranges[2 * t];
+    const gg_bwd_ctx ctx = {channels, n, ids_sorted, xys, conics, opac, colors, bg, eps};
+    const int want_abs = abs_geo != NULL, want_taint = taint_geo != NULL;
+#pragma omp parallel
+    {
+    const size_t L = (size_t)longest;
     double *S = (double *)malloc(sizeof(double) * (size_t)channels);
+    unsigned char *inc = (unsigned char *)malloc(L);
+    double *t_geo = (double *)malloc(sizeof(double) * 6 * L), *t_col = (double *)malloc(sizeof(double) * channels * L);
+    double *a_geo = want_abs ? (double *)malloc(sizeof(double) * 6 * L) : NULL;
+    double *a_col = want_abs ? (double *)malloc(sizeof(double) * channels * L) : NULL;
+    double *f_geo = want_taint ? (double *)malloc(sizeof(double) * 6 * L) : NULL;
+    double *f_col = want_taint ? (double *)malloc(sizeof(double) * channels * L) : NULL;
+#pragma omp for schedule(dynamic, 4)
     for (int py = 0; py < img_h; ++py) {
         for (int pxi = 0; pxi < img_w; ++pxi) {
             const int tile = (py / GG_TILE) * tiles_x + (pxi / GG_TILE);
             const int start = tile_ranges[2 * tile], end = tile_ranges[2 * tile + 1];
-            const size_t pix = (size_t)py * img_w + pxi;
-            const float *vo = v_out + pix * channels;
-            const float fx = (float)pxi, fy = (float)py;
-            /* forward replay in fp32 to find the contributing set exactly as A9 does */
-            float T = 1.0f;
-            int last = start;
-            int frag = 0;
+            if (end <= start) continue;
+            const float *vo = v_out + ((size_t)py * img_w + pxi) * channels;
+            const int frag = gg_pixel_bwd(&ctx, start, end, (float)pxi, (float)py, vo, 0, inc, S, t_geo, t_col, a_geo, a_col);
             for (int k = start; k < end; ++k) {
-                const int g = ids_sorted[k];
-                const float dx = xys[2 * g] - fx, dy = xys[2 * g + 1] - fy;
-                const float A = conics[3 * g], B = conics[3 * g + 1], C = conics[3 * g + 2];
-                const float sigma = 0.5f * (A * dx * dx + C * dy * dy) + B * dx * dy;
-                if (fabsf(sigma) <= 1e-6f) frag = 1;
-                if (sigma < 0.0f) continue;
-                const float alpha = fminf(0.999f, opac[g] * expf(-sigma));
-                if (fabsf(alpha - (1.0f / 255.0f)) <= eps * (1.0f / 255.0f)) frag = 1;
-                if (alpha < 1.0f / 255.0f) continue;
-                const float next_T = T * (1.0f - alpha);
-                if (fabsf(next_T - 1e-4f) <= eps * 1e-4f) frag = 1;
-                if (next_T <= 1e-4f) break;
-                T = next_T;
-                last = k + 1;
-            }
-            /* back-to-front, double precision */
-            double Tfin = 1.0;
-            /* recompute T_final in double over the contributing set */
-            for (int k = start; k < last; ++k) {
-                const int g = ids_sorted[k];
-                const float dx = xys[2 * g] - fx, dy = xys[2 * g + 1] - fy;
-                const float A = conics[3 * g], B = conics[3 * g + 1], C = conics[3 * g + 2];
-                const float sigma = 0.5f * (A * dx * dx + C * dy * dy) + B * dx * dy;
-                if (sigma < 0.0f) continue;
-                const float alpha_f = fminf(0.999f, opac[g] * expf(-sigma));
-                if (alpha_f < 1.0f / 255.0f) continue;
-                const double ddx = (double)xys[2 * g] - fx, ddy = (double)xys[2 * g + 1] - fy;
-                const double sg = 0.5 * ((double)A * ddx * ddx + (double)C * ddy * ddy) + (double)B * ddx * ddy;
-                double al = (double)opac[g] * exp(-sg);
-                if (al > 0.999) al = 0.999;
-                Tfin *= (1.0 - al);
-            }
-            double bgdot = 0.0;
-            for (int c = 0; c < channels; ++c) { S[c] = 0.0; bgdot += (double)bg[c] * vo[c]; }
-            double Tcur = Tfin; /* transmittance after entry k */
-            for (int k = last - 1; k >= start; --k) {
-                const int g = ids_sorted[k];
-                const float dxf = xys[2 * g] - fx, dyf = xys[2 * g + 1] - fy;
-                const float A = conics[3 * g], B = conics[3 * g + 1], C = conics[3 * g + 2];
-                const float sigma_f = 0.5f * (A * dxf * dxf + C * dyf * dyf) + B * dxf * dyf;
-                if (sigma_f < 0.0f) continue;
-                const float alpha_f = fminf(0.999f, opac[g] * expf(-sigma_f));
-                if (alpha_f < 1.0f / 255.0f) continue;
-                const double dx = (double)xys[2 * g] - fx, dy = (double)xys[2 * g + 1] - fy;
-                const double sg = 0.5 * ((double)A * dx * dx + (double)C * dy * dy) + (double)B * dx * dy;
-                const double vis = exp(-sg);
-                double al = (double)opac[g] * vis;
-                const int clamped = al > 0.999;
-                if (clamped) al = 0.999;
-                const double ra = 1.0 / (1.0 - al);
-                const double Tb = Tcur * ra; /* transmittance before entry k */
-                const double fac = al * Tb;
-                const float *col = colors + (size_t)g * channels;
-                double v_alpha = 0.0;
-                for (int c = 0; c < channels; ++c) {
-                    const double t = fac * vo[c];
-                    v_colors[(size_t)g * channels + c] += t;
-                    if (abs_colors) abs_colors[(size_t)g * channels + c] += fabs(t);
-                    if (taint_colors && frag) taint_colors[(size_t)g * channels + c] += fabs(t);
-                    v_alpha += ((double)col[c] * Tb - S[c] * ra) * vo[c];
-                    S[c] += (double)col[c] * fac;
+                if (!inc[k - start]) continue;
+                const size_t g = (size_t)ids_sorted[k];
+                const double *tg = t_geo + 6 * (size_t)(k - start), *tc = t_col + (size_t)channels * (k - start);
+                GG_ACC(v_xy[2 * g], tg[0]); GG_ACC(v_xy[2 * g + 1], tg[1]);
+                GG_ACC(v_conic[3 * g], tg[2]); GG_ACC(v_conic[3 * g + 1], tg[3]); GG_ACC(v_conic[3 * g + 2], tg[4]);
+                GG_ACC(v_opac[g], tg[5]);
+                for (int q = 0; q < channels; ++q) GG_ACC(v_colors[g * channels + q], tc[q]);
+                if (want_abs) {
+                    for (int q = 0; q < 6; ++q) GG_ACC(abs_geo[6 * g + q], a_geo[6 * (size_t)(k - start) + q]);
+                    for (int q = 0; q < channels; ++q) GG_ACC(abs_colors[g * channels + q], a_col[(size_t)channels * (k - start) + q]);
                 }
-                v_alpha += -Tfin * ra * bgdot;
-                Tcur = Tb;
-                if (clamped) continue;
-                const double v_sigma = -al * v_alpha; /* d alpha / d sigma = -o e^-s */
-                const double t6[6] = {v_sigma * ((double)A * dx + (double)B * dy), v_sigma * ((double)B * dx + (double)C * dy),
-                                      0.5 * v_sigma * dx * dx, v_sigma * dx * dy, 0.5 * v_sigma * dy * dy, vis * v_alpha};
-                v_xy[2 * g] += t6[0];
-                v_xy[2 * g + 1] += t6[1];
-                v_conic[3 * g] += t6[2];
-                v_conic[3 * g + 1] += t6[3];
-                v_conic[3 * g + 2] += t6[4];
-                v_opac[g] += t6[5];
-                if (abs_geo) for (int q = 0; q < 6; ++q) abs_geo[6 * (size_t)g + q] += fabs(t6[q]);
-                if (taint_geo && frag) for (int q = 0; q < 6; ++q) taint_geo[6 * (size_t)g + q] += fabs(t6[q]);
+            }
+            if (want_taint && frag) {
+                gg_pixel_bwd(&ctx, start, end, (float)pxi, (float)py, vo, 1, inc, S, f_geo, f_col, NULL, NULL);
+                for (int k = start; k < end; ++k) {
+                    const size_t g = (size_t)ids_sorted[k], o6 = 6 * (size_t)(k - start), oc = (size_t)channels * (k - start);
+                    for (int q = 0; q < 6; ++q) {
+                        const double d = fabs(f_geo[o6 + q] - t_geo[o6 + q]);
+                        if (d > 0.0) GG_ACC(taint_geo[6 * g + q], d);
+                    }
+                    for (int q = 0; q < channels; ++q) {
+                        const double d = fabs(f_col[oc + q] - t_col[oc + q]);
+                        if (d > 0.0) GG_ACC(taint_colors[g * channels + q], d);
+                    }
+                }
             }
         }
     }
-    free(S);
+    free(S); free(inc); free(t_geo); free(t_col); free(a_geo); free(a_col); free(f_geo); free(f_col);
+    }
 }
+#undef GG_ACC
 
 void gg_oracle_blend_bwd(int n, int channels, int img_h, int img_w, int tiles_x,
                          const int32_t *ids_sorted, const int32_t *tile_ranges, const float *xys,

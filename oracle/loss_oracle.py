@@ -42,3 +42,68 @@ def main_loss(pred_rgb: torch.Tensor, gt_rgb: torch.Tensor, ssim_lambda: float =
     l1 = (gt_rgb - pred_rgb).abs().mean()
     s = 1 - ssim(gt_rgb.permute(2, 0, 1)[None], pred_rgb.permute(2, 0, 1)[None])
     return (1 - ssim_lambda) * l1 + ssim_lambda * s
+
+
+# ---------------------------------------------------------------------------------------------
+# the other terms of get_loss_dict, restated line by line (differentiable; gradients by autograd)
+# ---------------------------------------------------------------------------------------------
+def cosine_similarity_loss(e1: torch.Tensor, e2: torch.Tensor) -> torch.Tensor:
+    """gaussian_splatting.py:113-118: embeddings are [dim, K] (normalised and summed over dim 0)."""
+    e1 = F.normalize(e1, dim=0)
+    e2 = F.normalize(e2, dim=0)
+    return 1 - torch.sum(e1 * e2, dim=0).mean()
+
+
+def geom_losses(normal_hw3: torch.Tensor, depth_hw1: torch.Tensor, gt_normal_3hw: torch.Tensor,
+                gt_depth_1hw: torch.Tensor, depth_mask_1hw: torch.Tensor):
+    """:876-880 on outputs["normal"] [H,W,3], outputs["depth"] [H,W,1]; returns (depth_loss, normal_loss)."""
+    normal = normal_hw3.permute(2, 0, 1)
+    depth = depth_hw1.permute(2, 0, 1)
+    m = depth_mask_1hw
+    normal_loss = 0.5 * F.mse_loss(normal[:, m[0]], gt_normal_3hw[:, m[0]], reduction='mean') + \
+        0.5 * cosine_similarity_loss(normal[:, m[0]], gt_normal_3hw[:, m[0]])
+    depth_loss = F.l1_loss(depth[m], gt_depth_1hw[m], reduction='mean')
+    return depth_loss, normal_loss
+
+
+def feature_loss(feature_hwd: torch.Tensor, selected_pairs) -> torch.Tensor:
+    """:905-912."""
+    fea_loss = 0
+    for i in range(len(selected_pairs)):
+        f1 = feature_hwd[selected_pairs[i][0][:, 0], selected_pairs[i][0][:, 1]]
+        f2 = feature_hwd[selected_pairs[i][1][:, 0], selected_pairs[i][1][:, 1]]
+        fea_loss += cosine_similarity_loss(f1.permute(1, 0), f2.permute(1, 0))
+    return fea_loss / len(selected_pairs)
+
+
+def up_loss(feature_hwd: torch.Tensor, selected_points: torch.Tensor, gt_fea_fhw: torch.Tensor, mlp) -> torch.Tensor:
+    """:913-914."""
+    fea_up = mlp(feature_hwd[selected_points[:, 0], selected_points[:, 1], :]).permute(1, 0)
+    return cosine_similarity_loss(fea_up, gt_fea_fhw[:, selected_points[:, 0], selected_points[:, 1]])
+
+
+def regs(colors_all: torch.Tensor, scales: torch.Tensor, max_gauss_ratio: float = 10.0):
+    """:917-923; returns (sh_reg, scale_reg)."""
+    sh_reg = colors_all[:, 1:, :].norm(dim=1).mean()
+    scale_exp = torch.exp(scales)
+    scale_reg = torch.maximum(scale_exp.amax(dim=-1) / scale_exp.amin(dim=-1),
+                              torch.tensor(max_gauss_ratio, dtype=scales.dtype)) - max_gauss_ratio
+    return sh_reg, 0.1 * scale_reg.mean()
+
+
+class MLP(torch.nn.Module):
+    """:198-213 (in_dim -> hidden_list -> out_dim with ReLU between)."""
+
+    def __init__(self, in_dim=8, out_dim=512, hidden_list=(128,)):
+        super().__init__()
+        layers = []
+        lastv = in_dim
+        for hidden in hidden_list:
+            layers.append(torch.nn.Linear(lastv, hidden))
+            layers.append(torch.nn.ReLU())
+            lastv = hidden
+        layers.append(torch.nn.Linear(lastv, out_dim))
+        self.layers = torch.nn.Sequential(*layers)
+
+    def forward(self, x):
+        return self.layers(x)

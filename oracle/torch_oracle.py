@@ -248,6 +248,49 @@ def rasterize(xys, conics, opac, colors, ids_sorted, tile_ranges, H, W, bg, tile
     return out, fT, fidx
 
 
+def rasterize_literal(xys, conics, opac, colors, ids_sorted, tile_ranges, H, W, bg, crop):
+    """A9 as the literal per-pixel, per-entry loop (the shape of gsplat's `_torch_impl` rasterizer: Python loops
+    over pixels and intersections), on the pixel rectangle crop = (x0, y0, w, h).  Plain Python floats rounded to
+    fp32 after every operation would cost more than the loop itself, so the arithmetic is fp64; it is used to
+    validate the vectorised `rasterize` on small crops and as SURVEY 8d's CPU baseline (i).
+    Returns (out [h, w, C] float64 tensor, pairs visited)."""
+    x0, y0, w, h = crop
+    X, Cn, O = xys.double().tolist(), conics.double().tolist(), opac.reshape(-1).double().tolist()
+    Col, Bg = colors.double().tolist(), bg.double().tolist()
+    ids, ranges = ids_sorted.tolist(), tile_ranges.tolist()
+    ch = len(Bg)
+    tiles_x = (W + TILE - 1) // TILE
+    out = torch.zeros((h, w, ch), dtype=torch.float64)
+    pairs = 0
+    exp = math.exp
+    for py in range(y0, y0 + h):
+        for px in range(x0, x0 + w):
+            s, e = ranges[(py // TILE) * tiles_x + px // TILE]
+            acc = [0.0] * ch
+            T = 1.0
+            for k in range(s, e):
+                pairs += 1
+                g = ids[k]
+                dx, dy = X[g][0] - px, X[g][1] - py
+                A, B, C = Cn[g]
+                sigma = 0.5 * (A * dx * dx + C * dy * dy) + B * dx * dy
+                if sigma < 0.0:
+                    continue
+                alpha = min(0.999, O[g] * exp(-sigma))
+                if alpha < 1.0 / 255.0:
+                    continue
+                next_T = T * (1.0 - alpha)
+                if next_T <= 1e-4:
+                    break
+                vis = alpha * T
+                cg = Col[g]
+                for c in range(ch):
+                    acc[c] += vis * cg[c]
+                T = next_T
+            out[py - y0, px - x0] = torch.tensor([acc[c] + T * Bg[c] for c in range(ch)], dtype=torch.float64)
+    return out, pairs
+
+
 def rasterize_grads(xys, conics, opac, colors, ids_sorted, tile_ranges, H, W, bg, v_out, tiles=None):
     """Tile-by-tile autograd of A9 with bounded memory.
 

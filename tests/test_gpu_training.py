@@ -223,7 +223,7 @@ def test_training_loop_with_refinement():
     assert new_p["opacity_logit"].shape == (n2, 1) and new_p["sh_coeffs"].shape == (n2, 25, 3)
     P = {k: new_p[k].requires_grad_(True) for k in names}
     opt.rebuild(P, new_m)
-    assert opt.bucket.payload == sum(p.numel() for p in P.values()) <= opt.exp_avg.numel() and opt.t == 6
+    assert opt.bucket.payload == sum(p.numel() for p in P.values()) <= opt.exp_avg.numel() and opt.t == 6 and set(opt.steps.values()) == {6}
     # survivors kept their first moments, children start from zero
     ea = opt.moments()["means"][0]
     assert float(ea[:info["n_kept"]].abs().max()) > 0 and float(ea[info["n_kept"]:].abs().max()) == 0.0
@@ -301,3 +301,157 @@ def test_ssim_loss_and_main_loss_match_the_restatement():
     assert abs(float(lb) - float(loss)) < 2e-6
     with pytest.raises(ValueError):
         ssim_loss(torch.zeros((5, 70, 3), device=dev), torch.zeros((5, 70, 3), device=dev))
+
+
+def test_fused_adam_accumulation_and_schedules_match_the_trainer_loop():
+    """FusedAdam.train_step == the reference trainer's iteration (engine/trainer.py:466-497) driven with
+    torch.optim.Adam per group, its accumulation table (method_configs.py:611) and LambdaLR exponential decay
+    (engine/schedulers.py:116-141): zero_grad at it % k == 0, step at it % k == k-1, schedulers stepped every
+    iteration."""
+    import numpy as np
+    from gaussiangrasper_b200.distributed import GradientBucket
+    from gaussiangrasper_b200.training import (REFERENCE_ACCUMULATION, REFERENCE_LRS, REFERENCE_SCHEDULES, FusedAdam)
+    dev = torch.device("cuda:0")
+    n, D = 3001, 7
+    ours = _params(n, D, dev, seed=4)
+    ref = {k: v.clone().requires_grad_(True) for k, v in ours.items()}
+    short = {k: (lf, 25) for k, (lf, _) in REFERENCE_SCHEDULES.items()}   # decay visible within the test's 23 steps
+    opt = FusedAdam(ours, GradientBucket(ours), accumulation=REFERENCE_ACCUMULATION, schedules=short)
+    ref_opt = {k: torch.optim.Adam([ref[k]], lr=REFERENCE_LRS[k], eps=1e-15) for k in ref}
+    ref_sched = {}
+    for k, (lr_final, max_steps) in short.items():
+        lr0 = REFERENCE_LRS[k]
+
+        def func(step, lr0=lr0, lr_final=lr_final, max_steps=max_steps):
+            t = np.clip(step / max_steps, 0, 1)
+            return np.exp(np.log(lr0) * (1 - t) + np.log(lr_final) * t) / lr0
+        ref_sched[k] = torch.optim.lr_scheduler.LambdaLR(ref_opt[k], lr_lambda=func)
+    g = torch.Generator().manual_seed(9)
+    for it in range(23):
+        grads = {k: torch.randn(v.shape, generator=g).to(dev) for k, v in ours.items()}
+        # reference loop
+        for k in ref:
+            a = REFERENCE_ACCUMULATION.get(k, 1)
+            if it % a == 0:
+                ref_opt[k].zero_grad()
+            ref[k].grad = grads[k].clone() if ref[k].grad is None else ref[k].grad + grads[k]
+            if it % a == a - 1:
+                ref_opt[k].step()
+        for sch in ref_sched.values():
+            sch.step()
+        # ours
+        opt.bucket.pack(grads)
+        opt.train_step(it)
+        for k in ours:
+            assert torch.allclose(ours[k], ref[k].detach(), rtol=3e-6, atol=2e-7), (it, k)
+    assert opt.steps["means"] == 2 and opt.steps["quats"] == 23
+    # optimizer state round trip (what a checkpoint carries)
+    state = opt.state_dict()
+    opt2 = FusedAdam({k: v.clone() for k, v in ours.items()}, accumulation=REFERENCE_ACCUMULATION, schedules=short)
+    opt2.load_state_dict(state)
+    assert opt2.steps == opt.steps and torch.equal(opt2.exp_avg, opt.exp_avg) and torch.equal(opt2.exp_avg_sq, opt.exp_avg_sq)
+
+
+def test_refine_with_counter_based_samples():
+    """samples == NULL: the split children are drawn inside the kernel from Philox keyed on (seed, step, parent
+    row, sample index).  Same result as handing the kernel those numbers explicitly (gg_philox_normals for the
+    split parents in row order), the numbers are standard normal, and two calls agree bit for bit."""
+    from gaussiangrasper_b200.training import DensifyStats, philox_normals, refine_gaussians
+    from oracle import refine_oracle
+    dev = torch.device("cuda:0")
+    n, D = 20_003, 5
+    P, M, st = _refine_inputs(n, D, 12)
+    rules = dict(max_dim=640.0, densify_grad_thresh=0.0002, densify_size_thresh=0.01, split_screen_size=0.05,
+                 cull_alpha_thresh=0.1, cull_scale_thresh=0.5, cull_screen_size=0.15, do_densify=1, split_by_screen=1,
+                 do_cull=1, cull_by_scale=1, cull_by_screen=1)
+
+    def stats():
+        ds = DensifyStats(n, dev)
+        ds.xys_grad_norm, ds.vis_counts, ds.max_2Dsize = (st[k].to(dev) for k in ("xys_grad_norm", "vis_counts", "max_2dsize"))
+        return ds
+    Pd = {k: v.to(dev) for k, v in P.items()}
+    Md = {k: (a.to(dev), b.to(dev)) for k, (a, b) in M.items()}
+    seed, step = 0x1234_5678_9ABC_DEF0, 700
+    a_p, a_m, a_info = refine_gaussians(Pd, Md, stats(), rules, seed=seed, step=step)
+    b_p, b_m, b_info = refine_gaussians(Pd, Md, stats(), rules, seed=seed, step=step)
+    for k in a_p:
+        assert torch.equal(a_p[k], b_p[k]), k
+    # which rows split (the oracle's rule, :411-418)
+    avg = (st["xys_grad_norm"] / st["vis_counts"]) * 0.5 * rules["max_dim"]
+    smax = P["log_scales"].exp().max(dim=-1).values
+    splits = ((smax > rules["densify_size_thresh"]) | (st["max_2dsize"] > rules["split_screen_size"])) & \
+             (avg > rules["densify_grad_thresh"])
+    parents = torch.nonzero(splits).reshape(-1)
+    assert parents.numel() == a_info["n_split"] > 100
+    z = philox_normals(parents.numel(), 2, seed, step, dev, parents=parents.to(dev))     # [2, n_split, 3]
+    c_p, c_m, c_info = refine_gaussians(Pd, Md, stats(), rules, samples_fn=lambda k: z.reshape(-1, 3)[:k])
+    for k in a_p:
+        assert torch.equal(a_p[k], c_p[k]), k
+    # the oracle with the same numbers
+    want_p, _, info = refine_oracle.refine(P, M, st["xys_grad_norm"], st["vis_counts"], st["max_2dsize"], rules,
+                                           lambda k: z.reshape(-1, 3)[:k].cpu())
+    assert torch.allclose(a_p["means"].cpu(), want_p["means"], rtol=2e-6, atol=2e-6)
+    # another step or seed gives other children; the draws are standard normal
+    d_p, _, _ = refine_gaussians(Pd, Md, stats(), rules, seed=seed, step=step + 100)
+    assert not torch.equal(d_p["means"], a_p["means"])
+    big = philox_normals(200_000, 2, seed, 3, dev).reshape(-1)
+    assert abs(float(big.mean())) < 5e-3 and abs(float(big.std()) - 1.0) < 5e-3
+    assert abs(float((big ** 4).mean()) - 3.0) < 0.05 and float(big.abs().max()) < 7.0
+
+
+def _two_rank_refine_worker(rank, world, port, out_dir):
+    import os
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)   # gloo moves the CUDA tensors through the host
+    from gaussiangrasper_b200 import scenes
+    from gaussiangrasper_b200.render import ViewBatch, render_views
+    from gaussiangrasper_b200.training import DensifyStats, FusedAdam, refine_gaussians
+    dev = torch.device("cuda:0")
+    n, W, H, D = 6000, 96, 64, 4
+    sc = scenes.random_scene(n, feature_dim=D, seed=5)
+    sc["log_scales"] = sc["log_scales"] + 0.8
+    names = ("means", "log_scales", "quats", "opacity_logit", "sh_coeffs", "features")
+    P = {k: sc[k].to(dev).requires_grad_(True) for k in names}
+    opt = FusedAdam(P)
+    stats = DensifyStats(n, dev)
+    cams = scenes.orbit_cameras(2 * world, W, H, total=2 * world)
+    for it in range(2):   # two iterations, each rank renders its own view, gradients summed over the ranks
+        v = it * world + rank
+        holder = {"grad_out": opt.bucket.unpack()}
+        out = render_views(*(P[k] for k in names), ViewBatch.from_cameras([cams[v]], dev), holder=holder)
+        out["image"].backward(torch.randn((1, H, W, out["image"].shape[-1]), generator=torch.Generator().manual_seed(v)).to(dev) * 1e-3)
+        stats.update(holder["v_geo"], holder["radii"], H, W)
+        opt.bucket.all_reduce()
+        with torch.no_grad():
+            opt.step()
+    rules = dict(max_dim=float(max(W, H)), densify_grad_thresh=2e-7, densify_size_thresh=0.03, split_screen_size=0.05,
+                 cull_alpha_thresh=0.1, cull_scale_thresh=0.5, cull_screen_size=0.15, do_densify=1, split_by_screen=1,
+                 do_cull=1, cull_by_scale=0, cull_by_screen=0)
+    local_counts = stats.vis_counts.clone()
+    new_p, new_m, info = refine_gaussians({k: P[k].detach() for k in names}, opt.moments(), stats, rules, seed=77, step=2)
+    torch.save(dict(p={k: v.cpu() for k, v in new_p.items()}, m={k: (a.cpu(), b.cpu()) for k, (a, b) in new_m.items()},
+                    info=info, local_counts=local_counts.cpu(), counts=stats.vis_counts.cpu()),
+               os.path.join(out_dir, f"rank{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_refine_to_byte_identical_parameters(tmp_path):
+    """View-sharded refinement: two ranks (two processes on this GPU, gloo) render different
+    views, all-reduce gradients, accumulate their own densification statistics -- and after refine_gaussians hold
+    byte-identical parameters and Adam moments: statistics all-reduced, split samples counter-based."""
+    import torch.multiprocessing as mp
+    import socket
+    with socket.socket() as s_:
+        s_.bind(("127.0.0.1", 0))
+        port = s_.getsockname()[1]
+    mp.spawn(_two_rank_refine_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a, b = (torch.load(tmp_path / f"rank{r}.pt") for r in range(2))
+    assert a["info"] == b["info"] and a["info"]["n_split"] > 10 and a["info"]["n_out"] != a["info"]["n_in"]
+    assert not torch.equal(a["local_counts"], b["local_counts"])     # the ranks really saw different views
+    assert torch.equal(a["counts"], b["counts"])
+    for k in a["p"]:
+        assert a["p"][k].numpy().tobytes() == b["p"][k].numpy().tobytes(), k
+        for j in range(2):
+            assert a["m"][k][j].numpy().tobytes() == b["m"][k][j].numpy().tobytes(), (k, j)

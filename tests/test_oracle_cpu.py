@@ -230,3 +230,30 @@ def test_quat_to_rotmat_matches_reference_convention():
     # un-normalised input is normalised: 90 degrees about z
     assert torch.allclose(R[2], torch.tensor([[0.0, -1, 0], [1, 0, 0], [0, 0, 1]]), atol=1e-6)
     assert torch.allclose(R, torch_oracle.quat_to_rotmat(q), atol=1e-6)
+
+
+def test_literal_loop_equals_the_vectorised_blend_and_the_c_oracle():
+    """the literal per-pixel loop on a small crop validates the vectorised torch blend (and the
+    C oracle's loop) -- three restatements of A9, one result."""
+    n, W, H = 1500, 64, 48
+    sc = scenes.random_scene(n, feature_dim=2, seed=3)
+    sc["log_scales"] = sc["log_scales"] + 0.8
+    cam = scenes.look_at_camera((4.5, 0.3, 0.2), W, H)
+    q = sc["quats"] / sc["quats"].norm(dim=-1, keepdim=True)
+    xys, depths, radii, conics, nth, _ = torch_oracle.project_gaussians(
+        sc["means"], sc["log_scales"].exp(), 1.0, q, cam.viewmat, cam.fullmat, cam.fx, cam.fy, cam.cx, cam.cy, H, W,
+        cam.tile_bounds)
+    _, _, ids_s, ranges = torch_oracle.bin_and_sort(xys, depths, radii, nth, cam.tile_bounds)
+    g = torch.Generator().manual_seed(0)
+    cols = torch.rand((n, 4), generator=g)
+    bg = torch.tensor([0.0, 0.0, 0.0, 10.0])
+    op = torch.sigmoid(sc["opacity_logit"]).reshape(-1)
+    crop = (16, 8, 32, 24)
+    lit, pairs = torch_oracle.rasterize_literal(xys, conics, op, cols, ids_s, ranges, H, W, bg, crop)
+    vec, _, _ = torch_oracle.rasterize(xys.double(), conics.double(), op.double(), cols.double(), ids_s, ranges, H, W, bg)
+    assert pairs > 10_000
+    assert torch.allclose(lit, vec[8:32, 16:48], rtol=0, atol=1e-9)
+    cout, _, _, frag, _ = c_oracle.blend_fwd(H, W, cam.tile_bounds, ids_s.numpy(), ranges.numpy(), xys.numpy(), conics.numpy(),
+                                              op.numpy(), cols.numpy(), bg.numpy(), eps=2e-5)
+    ok = ~torch.from_numpy(frag[8:32, 16:48])
+    assert float((lit.float() - torch.from_numpy(cout[8:32, 16:48]))[ok].abs().max()) < 2e-5

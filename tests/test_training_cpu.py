@@ -6,6 +6,7 @@ import os
 import subprocess
 import sys
 
+import pytest
 import torch
 
 from gaussiangrasper_b200 import training
@@ -122,3 +123,73 @@ def test_ssim_restatement_properties():
     ca, cb = torch.full((1, 1, 20, 20), 0.3, dtype=torch.float64), torch.full((1, 1, 20, 20), 0.6, dtype=torch.float64)
     want = (2 * 0.3 * 0.6 + 1e-4) / (0.09 + 0.36 + 1e-4)
     assert abs(float(loss_oracle.ssim(ca, cb)) - want) < 1e-5   # the fp32 window sums to 1 only to ~1e-7
+
+
+def _philox_np(counter, key):
+    """Philox4x32-10 as published (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11;
+    Random123's reference implementation): plain integer arithmetic, written independently of csrc/train.cu."""
+    c = [int(x) & 0xFFFFFFFF for x in counter]
+    k = [int(x) & 0xFFFFFFFF for x in key]
+    for _ in range(10):
+        p0, p1 = 0xD2511F53 * c[0], 0xCD9E8D57 * c[2]
+        c = [((p1 >> 32) ^ c[1] ^ k[0]) & 0xFFFFFFFF, p1 & 0xFFFFFFFF, ((p0 >> 32) ^ c[3] ^ k[1]) & 0xFFFFFFFF,
+             p0 & 0xFFFFFFFF]
+        k = [(k[0] + 0x9E3779B9) & 0xFFFFFFFF, (k[1] + 0xBB67AE85) & 0xFFFFFFFF]
+    return c
+
+
+def test_philox_block_function_known_answers():
+    """The generator behind the rank-consistent split samples (gg_refine_apply with samples == NULL) against the
+    known-answer vectors of Random123 (kat_vectors, philox4x32 10 rounds) and the independent Python
+    restatement above -- host build of the same __host__ __device__ function the kernel calls."""
+    import ctypes as C
+    from gaussiangrasper_b200 import _lib
+    lib = _lib.load()
+    kats = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+            ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+            ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+             (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kats:
+        out = (C.c_uint32 * 4)()
+        lib.gg_philox4x32_10_host((C.c_uint32 * 4)(*ctr), (C.c_uint32 * 2)(*key), out)
+        assert tuple(out) == want, (ctr, [hex(x) for x in out])
+        assert tuple(_philox_np(ctr, key)) == want
+    import random
+    rnd = random.Random(3)
+    for _ in range(200):
+        ctr = [rnd.getrandbits(32) for _ in range(4)]
+        key = [rnd.getrandbits(32) for _ in range(2)]
+        out = (C.c_uint32 * 4)()
+        lib.gg_philox4x32_10_host((C.c_uint32 * 4)(*ctr), (C.c_uint32 * 2)(*key), out)
+        assert list(out) == _philox_np(ctr, key)
+
+
+def test_adam_plan_follows_the_trainer_loop():
+    """FusedAdam.plan == engine/trainer.py:466-481 for the reference's accumulation table (method_configs.py:611),
+    and the learning-rate schedule == ExponentialDecayScheduler's lambda (engine/schedulers.py:122-138)."""
+    import math
+    from gaussiangrasper_b200.training import (REFERENCE_ACCUMULATION, REFERENCE_LRS, REFERENCE_SCHEDULES,
+                                               exponential_decay_lr)
+    acc = dict(REFERENCE_ACCUMULATION)
+    assert acc == dict(means=10, sh_coeffs=10, features=10)
+    # the trainer: zero at step % k == 0, optimizer step at step % k == k - 1
+    from gaussiangrasper_b200.training import FusedAdam
+
+    class _B:   # plan() only looks at the names
+        names = ["means", "log_scales", "quats", "opacity_logit", "sh_coeffs", "features"]
+    opt = FusedAdam.__new__(FusedAdam)
+    opt.bucket, opt.accumulation = _B(), acc
+    for it in range(40):
+        plan = opt.plan(it)
+        for name in _B.names:
+            k = acc.get(name, 1)
+            zero, step = it % k == 0, it % k == k - 1
+            want = "step" if k == 1 else ("acc_step" if step else ("acc_first" if zero else "acc"))
+            assert plan[name] == want, (it, name)
+    for name, (lr_final, max_steps) in REFERENCE_SCHEDULES.items():
+        lr0 = REFERENCE_LRS[name]
+        assert exponential_decay_lr(lr0, lr_final, max_steps, 0) == pytest.approx(lr0, rel=1e-12)
+        assert exponential_decay_lr(lr0, lr_final, max_steps, max_steps) == pytest.approx(lr_final, rel=1e-12)
+        assert exponential_decay_lr(lr0, lr_final, max_steps, 10 * max_steps) == pytest.approx(lr_final, rel=1e-12)
+        mid = exponential_decay_lr(lr0, lr_final, max_steps, max_steps // 2)
+        assert mid == pytest.approx(math.sqrt(lr0 * lr_final), rel=1e-9)
