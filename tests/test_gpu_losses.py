@@ -41,7 +41,9 @@ def test_geom_loss_matches_the_restatement(dev, H, W, CP, accumulate):
     assert loss[1].item() == pytest.approx(1.3 * n_ref.item(), rel=2e-5)
     want = x.grad.float()
     got = grad.cpu() - (base.cpu() if accumulate else 0)
-    assert float((got[..., 3:7] - want[..., 3:7]).abs().max()) <= 2e-5 * float(want.abs().max()) + 1e-9
+    # (base + g) - base carries the rounding of the sum: eps_fp32 of |base| (up to ~5) on top of the kernel's own error
+    slack = 6e-7 if accumulate else 1e-9
+    assert float((got[..., 3:7] - want[..., 3:7]).abs().max()) <= 2e-5 * float(want.abs().max()) + slack
     other = got.clone()
     other[..., 3:7] = 0
     assert float(other.abs().max()) <= (1e-6 if accumulate else 0.0)   # nothing else is touched
@@ -80,7 +82,8 @@ def test_contrastive_feature_loss_and_up_loss(dev):
     assert float(grad[..., :7].abs().max()) == 0.0 and float(grad[..., 7 + D:].abs().max()) == 0.0
     for (k, p), (k2, p2) in zip(mlp.named_parameters(), mlp_ref.named_parameters()):
         assert k == k2
-        assert float((p.grad.cpu() - 0.5 * p2.grad.float()).abs().max()) <= 3e-5 * float(p2.grad.abs().max()) + 1e-9, k
+        # (the reference side was back-propagated from f + 0.5 u: its parameter gradients carry the 0.5 already)
+        assert float((p.grad.cpu() - p2.grad.float()).abs().max()) <= 3e-5 * float(p2.grad.abs().max()) + 1e-9, k
 
 
 @pytest.mark.parametrize("n", [1, 1000, 100_003])

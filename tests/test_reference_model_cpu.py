@@ -1,0 +1,26 @@
+"""The reference's own model file (nerfstudio/models/gaussian_splatting.py) driven through this repository's gsplat
+shim: get_outputs, get_loss_dict, backward and after_train run unmodified.  Needs the reference tree, which exists
+in the build container only (the GPU box has no /root/reference: the test skips there).  See
+tests/reference_model_driver.py for what is and is not exercised (no GPU here: the C-ABI calls under the autograd
+Functions are replaced by the CPU oracle for this test; the boundary -- import paths, argument orders, autograd
+obligations, error behaviour -- is the product's)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/nerfstudio/models/gaussian_splatting.py"),
+                    reason="the reference tree is not mounted on this machine")
+def test_reference_model_runs_through_the_shim(tmp_path):
+    r = subprocess.run([sys.executable, os.path.join(HERE, "reference_model_driver.py")], capture_output=True, text=True,
+                       timeout=900, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    rep = json.loads(r.stdout.strip().splitlines()[-1])
+    assert rep["ok"] and rep["visible"] > 500
+    assert set(rep["losses"]) == {"main_loss", "feature_loss", "up_loss", "depth_loss", "normal_loss", "sh_reg", "scale_reg"}
+    assert all(v > 0 for v in rep["grads"].values())
