@@ -342,12 +342,12 @@ def run_ours(args):
                 loss.backward()
         return o["rgb"]
 
-    def step():
-        if args.path == "dropin":
-            return step_dropin()
+    def render_part():
+        """Forward (and backward) of every launch group of the step; returns (outputs of the last group, holder).
+        Reads only tensors that live across steps (parameters, camera batches, cotangents): capturable."""
         for p in P.values():
             p.grad = None
-        out = None
+        out = holder = None
         # one launch group per step: the backward writes the leaf gradients straight into the flat
         # all-reduce buffer; several chunks accumulate in .grad and are packed afterwards
         direct = bucket is not None and len(chunks) == 1
@@ -358,22 +358,50 @@ def run_ours(args):
                                    P["features"], vb, holder=holder)
             if cfg["backward"]:
                 out["image"].backward(v_img[:vb.n_views])  # leaf gradients accumulate over the chunks
+        return out, holder
+
+    def comm_part(out, holder):
+        """The gradient exchange of a multi-GPU training step (never captured: NCCL / barriers of their own)."""
         if ex is not None:
             return ex.exchange(P["means"], chunks[0].positions, sh_degree, 4, holder, all_pos)["sh_coeffs"]
         if bucket is not None:
-            if not direct:
+            if not (bucket is not None and len(chunks) == 1):
                 bucket.pack({k: P[k].grad for k in names})
             bucket.all_reduce()
             return bucket.flat
         return out["image"]
+
+    def step_plain():
+        if args.path == "dropin":
+            return step_dropin()
+        return comm_part(*render_part())
 
     # SETUP_STEPS of initialisation (first-call capacity measurement, allocator growth, communicator set-up), then
     # exactly --warmup untimed warm-up steps
     if args.warmup < 3:
         raise SystemExit("bench.py: --warmup must be >= 3")
     for _ in range(SETUP_STEPS):
-        step()
+        step_plain()
     torch.cuda.synchronize()
+    # The render part of the step is captured into a CUDA graph once (the binning never reads the host, all
+    # buffers are capacity-sized): a step is then ONE graph launch + the exchange, not ~15 launches from Python.
+    cap = None
+    blend_names = ("gg_blend_fwd", "gg_blend_bwd")
+    if args.graph and args.path == "fused":
+        from gaussiangrasper_b200.graph import CapturedStep
+        try:
+            cap = CapturedStep(render_part, dev, warmup=2,
+                               capture_context=lambda: _lib.profile(only=blend_names, external=True))
+        except Exception as e:   # capture refused: plain launches
+            print(f"[bench] CUDA-graph capture failed ({type(e).__name__}: {str(e)[:200]}); plain launches", file=sys.stderr)
+            cap = None
+            torch.cuda.synchronize()
+
+    def step():
+        if cap is None:
+            return step_plain()
+        return comm_part(*cap.replay())
+
     n_warm = args.warmup
     for _ in range(n_warm):
         step()
@@ -389,8 +417,9 @@ def run_ours(args):
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     # inside the timed region only the two blend entry points carry an event pair (the roofline's
-    # launch duration is measured live, here); the full per-entry-point breakdown is a separate pass
-    with _lib.profile(only=("gg_blend_fwd", "gg_blend_bwd")) as prof_timed:
+    # launch duration is measured live, here); the full per-entry-point breakdown is a separate pass.
+    # With a captured step the pairs are external events recorded inside the graph (see below).
+    with _lib.profile(only=blend_names) as prof_timed:
         e0.record()
         for _ in range(args.steps):
             step()
@@ -400,18 +429,37 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    launches = _lib.launch_count() - l0
+    launches = _lib.launch_count() - l0 + (cap.launches * args.steps if cap is not None else 0)
     clocks = sampler.stop() if sampler else None
     ms = e0.elapsed_time(e1)
-    # per-entry-point breakdown: a separate, instrumented pass (an event pair around every C-ABI call
-    # perturbs the stream, so it stays out of the timed region above)
+    blend_source = "CUDA events around the C-ABI call, every step of the timed region"
+    if cap is not None:
+        cap.check()   # the intersection lists of the timed steps fitted the capacity frozen into the graph
+        # duration of the blend launches INSIDE the captured step: the event pairs recorded in the graph hold the
+        # times of the latest replay; 10 more replays of the same graph right behind the timed region, read one by one
+        try:
+            acc = {}
+            for _ in range(10):
+                cap.replay()
+                torch.cuda.synchronize()
+                for k, v in cap.context.ms().items():
+                    acc.setdefault(k, []).extend(v)
+            blend_calls = acc
+            blend_source = ("external CUDA events recorded inside the captured graph, read over 10 replays directly behind "
+                            "the timed region")
+        except Exception as e:
+            blend_calls = {}
+            blend_source = f"un-captured instrumented pass (events inside the graph unavailable: {type(e).__name__})"
+    # per-entry-point breakdown: a separate, instrumented pass of plain launches (an event pair around every
+    # C-ABI call perturbs the stream, so it stays out of the timed region above)
     prof_steps = min(args.steps, 10)
     with _lib.profile() as prof:
         for _ in range(prof_steps):
-            step()
+            step_plain()
         torch.cuda.synchronize()
         per_call = prof.ms()
-    per_call.update(blend_calls)   # the dominant kernels: from the timed region itself
+    blend_steps = {k: (10 if cap is not None else args.steps) for k in blend_calls if blend_calls[k]}
+    per_call.update({k: v for k, v in blend_calls.items() if v})   # the dominant kernels: from the timed path itself
     t_ms = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
@@ -498,6 +546,99 @@ def run_ours(args):
         rgb_done.synchronize()
         return float(loss_host[0])
 
+    # --- e2e through captured graphs (single launch group): forward + loss in one graph, backward in a second one
+    # that shares its memory pool, two such pairs ping-ponging on the two target buffers.  Per step the host does:
+    # camera H2D (in place), replay F, enqueue the D2H of rgb + loss behind F, replay B, prefetch the next target.
+    e2e_mode = "plain launches"
+    if cap is not None and len(chunks) == 1:
+        try:
+            from gaussiangrasper_b200.graph import CapturedStep
+            vb_e2e = ViewBatch.from_cameras(cams[:chunk], dev)
+            pairs_fb = []
+            for b_i in range(2):
+                state = {}
+
+                def fwd(b_i=b_i, state=state):
+                    for p in P.values():
+                        p.grad = None
+                    holder = ex.holder() if ex is not None else None
+                    with torch.set_grad_enabled(cfg["backward"]):
+                        out = render_views(P["means"], P["log_scales"], P["quats"], P["opacity_logit"], P["sh_coeffs"],
+                                           P["features"], vb_e2e, holder=holder)
+                    if cfg["backward"]:
+                        l, grad = pixel_loss(out["image"], target_dev[b_i], "l2")
+                    else:
+                        l, grad = out["alpha"].mean(), None
+                    state.update(out=out, grad=grad, holder=holder)
+                    return out["rgb"].detach(), l.detach().reshape(1)
+
+                def bwd(state=state):
+                    state["out"]["image"].backward(state["grad"])
+                    return state["holder"]
+
+                def both(fwd=fwd, bwd=bwd):        # warm-up of the pair outside any capture
+                    r = fwd()
+                    if cfg["backward"]:
+                        bwd()
+                    return r
+                for _ in range(2):
+                    both()
+                torch.cuda.synchronize()
+                F = CapturedStep(fwd, dev, warmup=0)
+                B = CapturedStep(bwd, dev, warmup=0, pool=F.pool()) if cfg["backward"] else None
+                pairs_fb.append((F, B))
+            e2e_mode = "captured graphs (forward+loss | backward), double-buffered targets"
+        except Exception as e:
+            print(f"[bench] e2e graph capture failed ({type(e).__name__}: {str(e)[:300]}); plain launches", file=sys.stderr)
+            pairs_fb = None
+            torch.cuda.synchronize()
+    else:
+        pairs_fb = None
+
+    def e2e_step_graph():
+        main = torch.cuda.current_stream(dev)
+        q = pf["q"]
+        b_i = q & 1
+        F, B = pairs_fb[b_i]
+        if cfg["backward"]:
+            if pf["ready"][b_i] is None:
+                prefetch_target(q, chunk)                                # very first step only
+            main.wait_event(pf["ready"][b_i])
+            pf["ready"][b_i] = None
+        if not pf.get("cams_staged"):
+            vb_e2e.update_(cams[:chunk])                                 # H2D: cameras (pinned), in place; first step only
+        rgb, l = F.replay()
+        fwd_done = main.record_event()
+        with torch.cuda.stream(d2h_stream):                              # D2H of the results runs under the backward
+            d2h_stream.wait_event(fwd_done)
+            rgb_host[:chunk].copy_(rgb, non_blocking=True)
+            loss_host.copy_(l, non_blocking=True)
+            results_done = d2h_stream.record_event()
+        holder = None
+        if B is not None:
+            holder = B.replay()
+            pf["consumed"][b_i] = main.record_event()                    # this target buffer may be refilled
+            prefetch_target(q + 1, chunk)                                # H2D: the next step's supervision images
+        pf["q"] = q + 1
+        if ex is not None:
+            ex.exchange(P["means"], vb_e2e.positions, sh_degree, 4, holder, all_pos)
+        elif bucket is not None:
+            bucket.pack({k: P[k].grad for k in names})
+            bucket.all_reduce()
+        # H2D: the NEXT step's cameras, staged behind this step's kernels like its images (stream order keeps them
+        # from overwriting the batch this step's backward still reads)
+        vb_e2e.update_(cams[:chunk])
+        pf["cams_staged"] = True
+        main.synchronize()
+        results_done.synchronize()
+        return float(loss_host[0])
+
+    if pairs_fb is not None:
+        plain_e2e_step = e2e_step
+        pf.update(q=0, ready=[None, None], consumed=[None, None])
+        pf.pop("vb", None)
+        e2e_step = e2e_step_graph
+
     for _ in range(2):
         e2e_step()
     if world > 1:
@@ -511,7 +652,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_val = mpix_per_step * args.steps / float(t_e2e.item())
-    if args.trace and rank == 0:
+    if args.trace and rank == 0 and world == 1:   # (single process only: the traced steps would leave the other ranks behind)
         _trace_timeline(e2e_step, step, args.trace)
     h2d = (chunk * H * W * CP * 4 if cfg["backward"] else 0) * (V // chunk) + V * 35 * 4
     d2h = V * H * W * 3 * 4 + 4
@@ -525,7 +666,7 @@ def run_ours(args):
     hbm_peak, peak_src = load_peaks()
     hbm_nominal = 8000.0   # B200 HBM3e nominal GB/s (the north star's "~8 TB/s"); the measured copy peak is the bar
     avg = {k: sum(v) / len(v) for k, v in per_call.items() if v}
-    share = {k: sum(v) / (args.steps if k in blend_calls else prof_steps) for k, v in per_call.items()}
+    share = {k: sum(v) / blend_steps.get(k, prof_steps) for k, v in per_call.items()}
     # workload counters of the first chunk: pairs visited (K of SURVEY 8d) and pairs blended, intersections M
     hold = {}
     with torch.no_grad():
@@ -627,7 +768,7 @@ def run_ours(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": config,
-        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "mode": e2e_mode},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roof,
@@ -636,6 +777,9 @@ def run_ours(args):
         "hbm_peak_GBs": {"measured": hbm_peak, "source": peak_src, "nominal": hbm_nominal},
         "stage_ms_per_step": share,
         "exchange_transport": transport,
+        "cuda_graph": (f"render part of the step captured once ({cap.launches} kernel launches of this library per replay)"
+                       if cap is not None else "off"),
+        "blend_launch_timing": blend_source,
         "fma_probe_tflops": fma_tflops,
         "cpu_baseline": cpu,
     }
@@ -688,6 +832,8 @@ def main():
                          "every leaf gradient")
     ap.add_argument("--transport", default="auto", choices=["auto", "nvls", "nccl"],
                     help="factored exchange: this library's symmetric-memory kernel (nvls; auto = when available) or NCCL")
+    ap.add_argument("--no-graph", dest="graph", action="store_false",
+                    help="enqueue every launch from Python instead of replaying the captured step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--trace", default="", help="diagnostic: write a GPU timeline (kernels + idle gaps) of one e2e and one "
                                                 "device-timed step to this file (torch.profiler; not part of the measurement)")

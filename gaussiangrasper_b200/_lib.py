@@ -76,7 +76,7 @@ _SIGNATURES = {
     "gg_prepare_views": (C.c_int, [_i] * 6 + [_p] * 10 + [_i] * 4 + [_f] + [_p] * 7 + [_i, _p]),
     "gg_prepare_views_bwd": (C.c_int, [_i] * 6 + [_p] * 9 + [_i] * 2 + [_p] * 13),
     "gg_sh_grad_from_views": (C.c_int, [_i] * 4 + [_p] * 5),
-    "gg_nvls_exchange": (C.c_int, [_i, _i, _p, _p, _ll, _p, _p, _ll, _p]),
+    "gg_nvls_exchange": (C.c_int, [_i, _i, _p, _p, _ll, _p, _p, _ll, _i, _p]),
 }
 
 # optional symbols of later translation units (bound when present)
@@ -141,24 +141,29 @@ def check(rc: int, what: str = "") -> None:
 # optional per-call CUDA-event timing (bench.py: "measured live inside the timed region")
 _profile = None
 _profile_only = None
+_profile_external = False
 
 
 class profile:
     """with _lib.profile() as prof: ...  ->  prof.ms() = {entry point: [ms per call]}
     only: restrict the event pairs to these entry points (every pair perturbs the stream a little)."""
 
-    def __init__(self, only=None):
+    def __init__(self, only=None, external=False):
+        """external: events that may be recorded inside a CUDA-graph capture (cudaEventRecordExternal); after a
+        replay they hold the times of that replay."""
         self.only = frozenset(only) if only else None
+        self.external = bool(external)
 
     def __enter__(self):
-        global _profile, _profile_only
+        global _profile, _profile_only, _profile_external
         self.records = {}
-        _profile, _profile_only = self.records, self.only
+        _profile, _profile_only, _profile_external = self.records, self.only, self.external
         return self
 
     def __exit__(self, *exc):
-        global _profile, _profile_only
+        global _profile, _profile_only, _profile_external
         _profile = _profile_only = None
+        _profile_external = False
         return False
 
     def ms(self):
@@ -172,8 +177,8 @@ def call(name: str, *args) -> None:
     if _profile is None or (_profile_only is not None and name not in _profile_only):
         rc = fn(*args)
     else:
-        a = torch.cuda.Event(enable_timing=True)
-        b = torch.cuda.Event(enable_timing=True)
+        a = torch.cuda.Event(enable_timing=True, external=_profile_external)
+        b = torch.cuda.Event(enable_timing=True, external=_profile_external)
         a.record()
         rc = fn(*args)
         b.record()

@@ -9,7 +9,7 @@ versa.  Pure host code (the reference's is Python too); no GPU involved.
 """
 from __future__ import annotations
 
-from typing import Dict, Mapping
+from typing import Dict, Mapping, Optional
 
 import torch
 
@@ -45,15 +45,88 @@ def params_from_reference(ckpt: Mapping) -> Dict[str, torch.Tensor]:
     return out
 
 
-def reference_state_dict(params: Mapping[str, torch.Tensor], prefix: str = "_model.") -> Dict[str, torch.Tensor]:
-    """The inverse: entries a reference `GaussianSplattingModel.load_state_dict` accepts (:300-312)."""
+def reference_state_dict(params: Mapping[str, torch.Tensor], prefix: str = "_model.",
+                         up_projection: Optional[torch.nn.Module] = None,
+                         extra: Optional[Mapping[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+    """The inverse: the Gaussian entries of a reference pipeline state dict.
+
+    `GaussianSplattingModel.load_state_dict` (:300-312) resizes its six Gaussian parameters to the checkpoint and
+    then forwards to `Module.load_state_dict(dict, **kwargs)`: a STRICT load also wants the model's other entries
+    -- the CLIP up-projection `fea_up.layers.{0,2}.{weight,bias}` and whatever the camera optimizer holds.  Pass
+    `up_projection` (losses.UpProjection: same parameter names) and / or `extra` (entries taken over verbatim, e.g.
+    the non-Gaussian entries of the checkpoint the scene came from, see split_reference_state) to produce them;
+    without them the result loads with `strict=False` only."""
     out = {}
     for ref_name, ours in NAME_MAP.items():
         t = params[ours].detach().to(torch.float32)
         if ref_name == "opacities":
             t = t.reshape(-1, 1)
         out[prefix + ref_name] = t.contiguous()
+    if up_projection is not None:
+        for k, v in up_projection.state_dict().items():
+            out[f"{prefix}fea_up.{k}"] = v.detach().to(torch.float32).cpu().contiguous()
+    for k, v in (extra or {}).items():
+        out.setdefault(k, v)
     return out
+
+
+def split_reference_state(state: Mapping[str, torch.Tensor]):
+    """(Gaussian entries, everything else) of a reference pipeline state dict."""
+    leaves = set(NAME_MAP)
+    gauss = {k: v for k, v in state.items() if k.rsplit(".", 1)[-1] in leaves}
+    return gauss, {k: v for k, v in state.items() if k not in gauss}
+
+
+# optimizer group names of the reference (get_gaussian_param_groups :577-586, method_configs.py:618-650) -> ours
+GROUP_MAP = dict(xyz="means", scaling="log_scales", rotation="quats", opacity="opacity_logit", color="sh_coeffs",
+                 feature="features")
+
+
+def trainer_checkpoint(step: int, params: Mapping[str, torch.Tensor], optimizer=None, up_projection=None,
+                       extra_pipeline: Optional[Mapping[str, torch.Tensor]] = None) -> dict:
+    """The dict the reference trainer saves (engine/trainer.py:437-449): {"step", "pipeline", "optimizers",
+    "schedulers", "scalers"}.  `optimizer` is a training.FusedAdam: every group becomes a torch.optim.Adam state dict
+    ({"state": {0: {step, exp_avg, exp_avg_sq}}, "param_groups": [...]}) and a LambdaLR-style scheduler entry, under
+    the reference's group names, so `Optimizers.load_optimizers` / `load_schedulers` accept them."""
+    ck = {"step": int(step), "pipeline": reference_state_dict(params, up_projection=up_projection, extra=extra_pipeline),
+          "optimizers": {}, "schedulers": {}, "scalers": {}}
+    if optimizer is not None:
+        st = optimizer.state_dict()
+        for group, ours in GROUP_MAP.items():
+            if ours not in st:
+                continue
+            e = st[ours]
+            shape = (params[ours].shape[0], 1) if ours == "opacity_logit" else tuple(params[ours].shape)
+            ck["optimizers"][group] = {
+                "state": {0: {"step": torch.tensor(float(e["step"])), "exp_avg": e["exp_avg"].reshape(shape).cpu(),
+                              "exp_avg_sq": e["exp_avg_sq"].reshape(shape).cpu()}} if e["step"] > 0 else {},
+                "param_groups": [{"lr": e["lr"], "betas": tuple(optimizer.betas), "eps": optimizer.eps, "weight_decay": 0,
+                                  "amsgrad": False, "maximize": False, "foreach": None, "capturable": False,
+                                  "differentiable": False, "fused": None, "initial_lr": e["lr_init"], "params": [0]}]}
+            if ours in optimizer.schedules:
+                ck["schedulers"][group] = {"base_lrs": [e["lr_init"]], "last_epoch": int(step), "_step_count": int(step) + 1,
+                                           "_get_lr_called_within_step": False, "_last_lr": [e["lr"]], "lr_lambdas": [None]}
+    return ck
+
+
+def optimizer_state_from_reference(ckpt: Mapping) -> Dict[str, dict]:
+    """The "optimizers" entry of a reference checkpoint as training.FusedAdam.load_state_dict takes it."""
+    out = {}
+    for group, ours in GROUP_MAP.items():
+        sd = ckpt.get("optimizers", {}).get(group)
+        if sd is None:
+            continue
+        pg = sd["param_groups"][0]
+        st = sd["state"].get(0) or next(iter(sd["state"].values()), None)
+        if st is None:
+            continue
+        out[ours] = dict(step=int(float(st["step"])), lr=float(pg["lr"]), lr_init=float(pg.get("initial_lr", pg["lr"])),
+                         exp_avg=st["exp_avg"], exp_avg_sq=st["exp_avg_sq"])
+    return out
+
+
+def save_training_checkpoint(path: str, step: int, params, optimizer=None, up_projection=None, extra_pipeline=None) -> None:
+    torch.save(trainer_checkpoint(step, params, optimizer, up_projection, extra_pipeline), path)
 
 
 def load_reference_checkpoint(path: str, map_location="cpu") -> Dict[str, torch.Tensor]:

@@ -25,7 +25,7 @@ namespace gg {
 constexpr int kMaxRanks = 16;
 
 struct ExchangeArgs {
-    int rank, world;
+    int rank, world, parts;        // parts: bit 0 = gather the rgb slots, bit 1 = reduce the bucket
     float* bucket_mc;              // multicast address of the bucket, or nullptr
     float* bucket_peer[kMaxRanks]; // every rank's bucket as mapped here (own included)
     long long bucket_vec4;         // float4 elements of the bucket
@@ -55,7 +55,7 @@ nvls_exchange_kernel(const ExchangeArgs a) {
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
     // ---- all-gather: my rgb slot -> the same slot on every rank -------------------------------------
-    {
+    if (a.parts & 1) {
         const long long base = (long long)a.rank * a.slot_vec4;
         const float4* src = reinterpret_cast<const float4*>(a.rgb_peer[a.rank]) + base;
         for (long long i = tid; i < a.slot_vec4; i += stride) {
@@ -69,15 +69,24 @@ nvls_exchange_kernel(const ExchangeArgs a) {
         }
     }
     // ---- all-reduce: slice `rank` of the bucket, summed over the ranks, written back to all of them ----
-    {
+    if (a.parts & 2) {
         const long long per = (a.bucket_vec4 + a.world - 1) / a.world;
         const long long lo = (long long)a.rank * per;
         const long long hi = lo + per < a.bucket_vec4 ? lo + per : a.bucket_vec4;
-        for (long long i = lo + tid; i < hi; i += stride) {
-            if (kMulticast) {
-                const float4 v = multimem_ld_reduce_add(a.bucket_mc + 4 * i);
-                multimem_st(a.bucket_mc + 4 * i, v);
-            } else {
+        if (kMulticast) {
+            // a round trip through the switch per load: keep kUnroll of them in flight per thread
+            constexpr int kUnroll = 4;
+            long long i = lo + tid;
+            for (; i + (kUnroll - 1) * stride < hi; i += kUnroll * stride) {
+                float4 v[kUnroll];
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u) v[u] = multimem_ld_reduce_add(a.bucket_mc + 4 * (i + u * stride));
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u) multimem_st(a.bucket_mc + 4 * (i + u * stride), v[u]);
+            }
+            for (; i < hi; i += stride) multimem_st(a.bucket_mc + 4 * i, multimem_ld_reduce_add(a.bucket_mc + 4 * i));
+        } else {
+            for (long long i = lo + tid; i < hi; i += stride) {
                 // fixed summation order (rank 0, 1, ...) so that every run gives the same bits
                 float4 s = reinterpret_cast<const float4*>(a.bucket_peer[0])[i];
                 for (int p = 1; p < a.world; ++p) {
@@ -96,15 +105,16 @@ using namespace gg;
 
 extern "C" int gg_nvls_exchange(int rank, int world, float* bucket_multicast, float* const* bucket_peers,
                                 long long bucket_floats, float* rgb_multicast, float* const* rgb_peers,
-                                long long rgb_slot_floats, void* stream) {
+                                long long rgb_slot_floats, int parts, void* stream) {
     GG_REQUIRE(world >= 2 && world <= kMaxRanks && rank >= 0 && rank < world, "gg_nvls_exchange: 2..16 ranks");
     GG_REQUIRE(bucket_peers && rgb_peers, "gg_nvls_exchange: null peer table");
+    GG_REQUIRE(parts >= 1 && parts <= 3, "gg_nvls_exchange: parts is 1 (gather), 2 (reduce) or 3 (both)");
     GG_REQUIRE(bucket_floats >= 0 && rgb_slot_floats >= 0 && bucket_floats % 4 == 0 && rgb_slot_floats % 4 == 0,
                "gg_nvls_exchange: sizes must be multiples of 4 floats");
     GG_REQUIRE((bucket_multicast == nullptr) == (rgb_multicast == nullptr),
                "gg_nvls_exchange: both buffers or neither must have a multicast mapping");
     ExchangeArgs a{};
-    a.rank = rank; a.world = world;
+    a.rank = rank; a.world = world; a.parts = parts;
     a.bucket_mc = bucket_multicast; a.rgb_mc = rgb_multicast;
     a.bucket_vec4 = bucket_floats / 4; a.slot_vec4 = rgb_slot_floats / 4;
     for (int p = 0; p < world; ++p) {
@@ -117,8 +127,9 @@ extern "C" int gg_nvls_exchange(int rank, int world, float* bucket_multicast, fl
     GG_REQUIRE(((uintptr_t)bucket_multicast & 15) == 0 && ((uintptr_t)rgb_multicast & 15) == 0,
                "gg_nvls_exchange: multicast addresses must be 16-byte aligned");
     if (a.bucket_vec4 == 0 && a.slot_vec4 == 0) return GG_OK;
-    // a copy-shaped kernel: enough CTAs to keep every NVLink port busy, not more (148 SMs x 2)
-    const int blocks = 148 * 2;
+    // a copy-shaped kernel: enough CTAs to keep every NVLink port busy; one CTA per SM when the two halves run as
+    // two concurrent launches, two when one launch does both
+    const int blocks = parts == 3 ? 148 * 2 : 148;
     if (bucket_multicast)
         nvls_exchange_kernel<true><<<blocks, 512, 0, (cudaStream_t)stream>>>(a);
     else

@@ -128,8 +128,11 @@ class FactoredExchange:
         return self
 
     def holder(self) -> dict:
-        go = dict(self.bucket.unpack())
-        go["v_rgb_views"] = self.rgb_send
+        go = getattr(self, "_go", None)
+        if go is None or go["v_rgb_views"].data_ptr() != self.rgb_send.data_ptr():
+            go = dict(self.bucket.unpack())      # views of the flat buffer: built once, they do not change
+            go["v_rgb_views"] = self.rgb_send
+            self._go = go
         return {"grad_out": go, "defer_sh_grad": True}
 
     def exchange(self, means: torch.Tensor, positions: torch.Tensor, degree: int, degrees_to_use: int,
@@ -232,20 +235,40 @@ class NvlsExchange(FactoredExchange):
                 holder["v_rgb_views"].data_ptr() != self.rgb_send.data_ptr():
             self.rgb_send.copy_(holder["v_rgb_views"].view_as(self.rgb_send))
         if all_positions is not None:
-            self.pos_all.copy_(all_positions)
+            key = (all_positions.data_ptr(), all_positions._version)
+            if getattr(self, "_pos_key", None) != key:     # the same table step after step: copied once
+                self.pos_all.copy_(all_positions)
+                self._pos_key = key
         else:
             dist.all_gather_into_tensor(self.pos_all, positions.detach().to(torch.float32).contiguous(), group=self.group)
         dev = self.bucket.flat.device
-        self.h_bucket.barrier(channel=0)          # every rank's backward has written its bucket and its rgb slot
-        with _lib.device_guard(dev):
+        main = torch.cuda.current_stream(dev)
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=dev)
+        side = self._side
+        rec = self._reconstruct or ops.sh_grad_from_views
+
+        def launch(parts):
             _lib.call("gg_nvls_exchange", self.rank, self.world,
                       int(self.h_bucket.multicast_ptr) if self.multicast else None, self._bucket_peers,
                       int(self.bucket.flat.numel()),
                       int(self.h_rgb.multicast_ptr) if self.multicast else None, self._rgb_peers, int(self.slot),
-                      _lib.stream_ptr(dev))
-        self.h_bucket.barrier(channel=1)          # every rank's slice and slot have landed here
-        rec = self._reconstruct or ops.sh_grad_from_views
-        rec(int(degree), int(degrees_to_use), means.detach(), self.pos_all, self.rgb_all, out=self.sh_grad)
+                      parts, _lib.stream_ptr(dev))
+
+        with _lib.device_guard(dev):
+            self.h_bucket.barrier(channel=0)      # every rank's backward has written its bucket and its rgb slot
+            ready = main.record_event()
+            # the reduction of the bucket on a side stream ...
+            side.wait_event(ready)
+            with torch.cuda.stream(side):
+                launch(2)
+                self.h_bucket.barrier(channel=1)  # every rank's slice of the bucket has landed everywhere
+                reduced = side.record_event()
+            # ... while the main stream gathers the factors and rebuilds the SH gradient from them
+            launch(1)
+            self.h_rgb.barrier(channel=0)         # every rank's rgb slot has landed here
+            rec(int(degree), int(degrees_to_use), means.detach(), self.pos_all, self.rgb_all, out=self.sh_grad)
+            main.wait_event(reduced)
         grads = dict(self.bucket.unpack())
         grads["sh_coeffs"] = self.sh_grad
         return grads

@@ -49,7 +49,7 @@ class ViewBatch:
         return self.viewmats.shape[0]
 
     @staticmethod
-    def from_cameras(cams: Sequence, device) -> "ViewBatch":
+    def from_cameras(cams: Sequence, device, out_packed: Optional[torch.Tensor] = None) -> "ViewBatch":
         # one packed row of 35 floats per camera, built once and kept on the camera object
         # The row is cached on the camera together with the identity and version counters of the tensors it
         # was built from: a camera optimiser that updates the pose in place, or assigns a new one, invalidates it.
@@ -70,35 +70,74 @@ class ViewBatch:
                     pass
             rows.append(r)
         V = len(rows)
+        H, W = cams[0].H, cams[0].W
         if device.type == "cuda":
-            # a small ring of reusable pinned staging buffers per (device, batch size): pinning memory per call
-            # costs more than the render's whole prepare stage.  Every slot carries the event recorded behind
-            # the asynchronous copy that last read it; a slot is rewritten only after that event has completed
-            # (normally long ago -- the wait is free unless a caller stages many batches without rendering).
-            dev_index = device.index if device.index is not None else torch.cuda.current_device()
-            key = (dev_index, V)
-            ring = _pinned_ring.get(key)
-            if ring is None:
-                ring = _pinned_ring[key] = [0, [torch.empty((V, 35)).pin_memory() for _ in range(8)], [None] * 8]
-            ring[0] = (ring[0] + 1) % len(ring[1])
-            stage = ring[1][ring[0]]
-            pending = ring[2][ring[0]]
-            if pending is not None:
-                pending.synchronize()
-            if V == 1:
-                stage[0].copy_(rows[0])
-            else:
-                torch.stack(rows, out=stage)
-            packed = stage.to(device, non_blocking=True)
+            stage, ring, slot = _stage_cameras(rows, device)
+            packed = out_packed if out_packed is not None else torch.empty(35 * V, dtype=torch.float32, device=device)
+            packed.copy_(stage, non_blocking=True)                  # ONE host->device copy per batch, any V
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(device))
-            ring[2][ring[0]] = ev
+            ring[2][slot] = ev
         else:
-            packed = torch.stack(rows)
-        if V == 1:  # slices of a single row are contiguous already
-            return ViewBatch(packed[:, :12], packed[:, 12:28], packed[:, 28:32], packed[:, 32:35], cams[0].H, cams[0].W)
-        return ViewBatch(packed[:, :12].contiguous(), packed[:, 12:28].contiguous(), packed[:, 28:32].contiguous(),
-                         packed[:, 32:35].contiguous(), cams[0].H, cams[0].W)
+            packed = _field_major(rows, torch.empty(35 * V, dtype=torch.float32))
+        return _views_of(packed, V, H, W)
+
+
+def _field_major(rows, out: torch.Tensor) -> torch.Tensor:
+    """[V x 12 viewmat | V x 16 fullmat | V x 4 intrinsics | V x 3 centre]: every field contiguous over the views,
+    so one flat buffer serves the kernels' four pointers."""
+    V = len(rows)
+    if V == 1:
+        out.copy_(rows[0])      # a single row is field-major already
+        return out
+    stacked = torch.stack(rows)                                   # [V, 35]
+    o = 0
+    for lo, hi in ((0, 12), (12, 28), (28, 32), (32, 35)):
+        w = hi - lo
+        out[o:o + V * w].view(V, w).copy_(stacked[:, lo:hi])
+        o += V * w
+    return out
+
+
+def _views_of(packed: torch.Tensor, V: int, H: int, W: int) -> "ViewBatch":
+    vb = ViewBatch(packed[:12 * V].view(V, 12), packed[12 * V:28 * V].view(V, 16), packed[28 * V:32 * V].view(V, 4),
+                   packed[32 * V:35 * V].view(V, 3), H, W)
+    vb._packed = packed
+    return vb
+
+
+def _stage_cameras(rows, device):
+    """Field-major rows in a pinned staging buffer from a small ring per (device, batch size): pinning memory per
+    call costs more than the render's whole prepare stage.  Every slot carries the event recorded behind the
+    asynchronous copy that last read it; a slot is rewritten only after that event has completed (normally long
+    ago -- the wait is free unless a caller stages many batches without rendering)."""
+    V = len(rows)
+    dev_index = device.index if device.index is not None else torch.cuda.current_device()
+    key = (dev_index, V)
+    ring = _pinned_ring.get(key)
+    if ring is None:
+        ring = _pinned_ring[key] = [0, [torch.empty(35 * V).pin_memory() for _ in range(8)], [None] * 8]
+    ring[0] = (ring[0] + 1) % len(ring[1])
+    slot = ring[0]
+    pending = ring[2][slot]
+    if pending is not None:
+        pending.synchronize()
+    return _field_major(rows, ring[1][slot]), ring, slot
+
+
+def _update_views(self: ViewBatch, cams: Sequence) -> ViewBatch:
+    """Refresh the cameras of this batch IN PLACE (same device tensors: what a captured CUDA graph reads) from a
+    new list of the same length and image size: one pinned staging row set, asynchronous copies."""
+    if len(cams) != self.n_views or cams[0].H != self.H or cams[0].W != self.W:
+        raise ValueError("update_ needs the same number of views and the same image size")
+    packed = getattr(self, "_packed", None)
+    if packed is None:
+        raise ValueError("update_ needs a batch made by ViewBatch.from_cameras")
+    ViewBatch.from_cameras(cams, packed.device, out_packed=packed)     # one copy into the same storage
+    return self
+
+
+ViewBatch.update_ = _update_views
 
 
 class _ProjectViews(Function):

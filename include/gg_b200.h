@@ -233,10 +233,12 @@ int gg_sh_grad_from_views(int n, int n_views, int degree, int degrees_to_use, co
  * same symmetric buffers; bucket_floats = size of the bucket; rgb_slot_floats = size of ONE rank's slot of the
  * [world, slot] gather buffer (both multiples of 4).  The caller places a cross-rank barrier before the launch
  * (every rank has written its bucket and its slot) and after it (every rank's slice has landed everywhere).
+ * parts: 1 = the gather only, 2 = the reduction only, 3 = both (the two halves can run as two concurrent launches
+ * so that the SH rebuild, which needs only the gathered factors, overlaps the reduction).
  * Replaces ncclAllGather + ncclAllReduce of distributed.FactoredExchange. */
 int gg_nvls_exchange(int rank, int world, float* bucket_multicast /*nullable*/, float* const* bucket_peers,
                      long long bucket_floats, float* rgb_multicast /*nullable*/, float* const* rgb_peers,
-                     long long rgb_slot_floats, void* stream);
+                     long long rgb_slot_floats, int parts, void* stream);
 
 /* ---- next rows: the streaming steps directly behind the backward -----------------
  * gg_adam_step: fused torch.optim.Adam (no amsgrad / weight decay) over a flat gradient buffer that

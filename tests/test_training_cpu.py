@@ -193,3 +193,80 @@ def test_adam_plan_follows_the_trainer_loop():
         assert exponential_decay_lr(lr0, lr_final, max_steps, 10 * max_steps) == pytest.approx(lr_final, rel=1e-12)
         mid = exponential_decay_lr(lr0, lr_final, max_steps, max_steps // 2)
         assert mid == pytest.approx(math.sqrt(lr0 * lr_final), rel=1e-9)
+
+
+def test_ply_export_has_the_reference_exporters_properties(tmp_path):
+    """scripts/exporter.py:482-530: x y z, zero normals, uint8 colours = SH2RGB(dc) * 255, f_dc_*, f_rest_0 (the
+    reference's loop over the last axis of a (N, -1, 1) reshape writes exactly one), opacity, scale_*, rot_*."""
+    import numpy as np
+    from gaussiangrasper_b200 import ply, scenes
+    n = 321
+    sc = scenes.random_scene(n, feature_dim=4, seed=2)
+    path = str(tmp_path / "point_cloud.ply")
+    assert ply.write_ply(path, sc) == n
+    got = ply.read_ply(path)
+    want = ["x", "y", "z", "nx", "ny", "nz", "red", "green", "blue", "f_dc_0", "f_dc_1", "f_dc_2", "f_rest_0", "opacity",
+            "scale_0", "scale_1", "scale_2", "rot_0", "rot_1", "rot_2", "rot_3"]
+    assert list(got) == want
+    assert np.array_equal(got["x"], sc["means"][:, 0].numpy()) and not got["nx"].any()
+    colors = sc["sh_coeffs"][:, 0, :].numpy() * 0.28209479177387814 + 0.5
+    assert np.allclose(got["f_dc_1"], colors[:, 1]) and got["red"].dtype == np.uint8
+    assert np.array_equal(got["red"], (colors.astype(np.float32) * 255).astype(np.uint8)[:, 0])
+    assert np.array_equal(got["f_rest_0"], sc["sh_coeffs"][:, 1, 0].numpy())
+    assert np.array_equal(got["opacity"], sc["opacity_logit"].reshape(-1).numpy())
+    assert np.array_equal(got["scale_2"], sc["log_scales"][:, 2].numpy()) and np.array_equal(got["rot_0"], sc["quats"][:, 0].numpy())
+    ply.write_ply(path, sc, full_sh=True)
+    full = ply.read_ply(path)
+    assert sum(k.startswith("f_rest_") for k in full) == 72
+    assert np.array_equal(full["f_rest_24"], sc["sh_coeffs"][:, 1, 1].numpy())     # channel-major: 24 coefficients per colour
+    header = open(path, "rb").read(200).decode("ascii", "replace")
+    assert header.startswith("ply\nformat binary_little_endian 1.0\nelement vertex 321\nproperty float x\n")
+
+
+def test_trainer_checkpoint_loads_into_torch_adam(tmp_path):
+    """engine/trainer.py:437-449: the saved dict has step / pipeline / optimizers / schedulers / scalers, and every
+    optimizer entry is a torch.optim.Adam state dict under the reference's group name."""
+    from gaussiangrasper_b200 import checkpoint, scenes
+    from gaussiangrasper_b200.losses import UpProjection
+    from gaussiangrasper_b200.training import REFERENCE_LRS, REFERENCE_SCHEDULES
+    n = 50
+    sc = scenes.random_scene(n, feature_dim=32, seed=3)
+    g = torch.Generator().manual_seed(1)
+
+    class FakeAdam:      # the parts of training.FusedAdam the writer reads (FusedAdam itself needs CUDA tensors)
+        betas, eps, schedules = (0.9, 0.999), 1e-15, REFERENCE_SCHEDULES
+
+        def state_dict(self):
+            return {k: dict(step=7 if k != "means" else 0, lr=REFERENCE_LRS[k] * 0.9, lr_init=REFERENCE_LRS[k],
+                            exp_avg=torch.randn(sc[k].shape, generator=g), exp_avg_sq=torch.rand(sc[k].shape, generator=g))
+                    for k in sc}
+    up = UpProjection(32)
+    ck = checkpoint.trainer_checkpoint(1234, sc, FakeAdam(), up_projection=up)
+    assert set(ck) == {"step", "pipeline", "optimizers", "schedulers", "scalers"} and ck["step"] == 1234
+    assert set(ck["optimizers"]) == {"xyz", "scaling", "rotation", "opacity", "color", "feature"}
+    assert set(ck["schedulers"]) == {"xyz", "scaling", "color", "feature"}          # opacity / rotation have none
+    assert {"_model.fea_up.layers.0.weight", "_model.fea_up.layers.2.bias"} <= set(ck["pipeline"])
+    ref_names = dict(xyz="means", scaling="scales", rotation="quats", opacity="opacities", color="colors_all", feature="feature")
+    for group, leaf in ref_names.items():
+        p = torch.nn.Parameter(ck["pipeline"]["_model." + leaf].clone())
+        opt = torch.optim.Adam([p], lr=1.0, eps=1e-15)
+        import copy
+        opt.load_state_dict(copy.deepcopy(ck["optimizers"][group]))   # the reference's Optimizers.load_optimizers does this
+        if group == "xyz":
+            assert len(opt.state) == 0                        # never stepped: torch keeps no state either
+        else:
+            st = opt.state[p]
+            assert st["exp_avg"].shape == p.shape and float(st["step"]) == 7.0
+        assert opt.param_groups[0]["lr"] == pytest.approx(REFERENCE_LRS[checkpoint.GROUP_MAP[group]] * 0.9)
+        p.grad = torch.ones_like(p)
+        opt.step()                                            # and it keeps training
+    path = str(tmp_path / "step-000001234.ckpt")
+    torch.save(ck, path)
+    loaded = torch.load(path, weights_only=False)
+    back = checkpoint.optimizer_state_from_reference(loaded)
+    assert set(back) == set(sc) - {"means"} and back["quats"]["step"] == 7
+    assert torch.equal(back["opacity_logit"]["exp_avg"], ck["optimizers"]["opacity"]["state"][0]["exp_avg"])
+    P = checkpoint.params_from_reference(loaded)
+    assert torch.equal(P["features"], sc["features"])
+    gauss, rest = checkpoint.split_reference_state(loaded["pipeline"])
+    assert len(gauss) == 6 and all("fea_up" in k for k in rest)
