@@ -268,7 +268,9 @@ def cpu_baseline_leg(sc, cam, D, n, W, H, backward):
 
 
 # ---------------------------------------------------------------------------------------------
-def run_ours(args):
+def run_ours(args, sub=False):
+    """One measurement; returns the JSON line as a dict on rank 0 (None elsewhere).  sub: a second workload inside
+    the same process group (BASELINE configs[3] reported next to configs[1] at N > 1)."""
     import torch.distributed as dist
 
     from gaussiangrasper_b200 import _lib, scenes
@@ -280,7 +282,7 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py (our arm) needs a CUDA device; there is no CPU fallback"
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
-    if world > 1:
+    if world > 1 and not sub:
         dist.init_process_group("nccl", device_id=dev)
     _lib.check(_lib.load().gg_check_device(), "gg_check_device")
 
@@ -327,7 +329,20 @@ def run_ours(args):
     all_pos = torch.stack([c.position for r in range(world) for c in
                            scenes.orbit_cameras(V, W, H, first=r * V, total=max(total_views, 8))]).float().to(dev) \
         if factored else None
-    bucket = GradientBucket(P) if (world > 1 and cfg["backward"] and not factored) else None
+    bucket = None
+    if world > 1 and cfg["backward"] and not factored:
+        if args.transport in ("auto", "nvls"):
+            try:   # plain all-reduce of every leaf gradient, as this library's two-shot NVLS kernel
+                from gaussiangrasper_b200.distributed import SymmetricBucket
+                bucket = SymmetricBucket(P)
+                transport = "gg_nvls_exchange kernel over symmetric memory, reduction only (%s)" % (
+                    "NVLS multimem.ld_reduce / multimem.st" if bucket.multicast else "peer ld/st, no multicast mapping")
+            except Exception as e:
+                if args.transport == "nvls":
+                    raise
+                bucket, transport = None, f"nccl (symmetric memory unavailable: {type(e).__name__}: {str(e)[:120]})"
+        if bucket is None:
+            bucket = GradientBucket(P)
 
     def step_dropin():
         from gaussiangrasper_b200.reference_flow import get_outputs
@@ -408,12 +423,14 @@ def run_ours(args):
     torch.cuda.synchronize()
 
     # --- timed region: exactly K steps, device-timed, max over ranks -------------------------
+    # the clock sampler starts BEFORE the ranks line up (NVML initialisation takes tens of ms on rank 0 only: started
+    # behind the barrier it would leave every other rank waiting inside its first timed step)
     sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    if sampler:
-        sampler.start()
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     # inside the timed region only the two blend entry points carry an event pair (the roofline's
@@ -460,6 +477,26 @@ def run_ours(args):
         per_call = prof.ms()
     blend_steps = {k: (10 if cap is not None else args.steps) for k in blend_calls if blend_calls[k]}
     per_call.update({k: v for k, v in blend_calls.items() if v})   # the dominant kernels: from the timed path itself
+    if args.diag and cap is not None:
+        # diagnostic: device time and host enqueue time of the two halves of a step, alone and together
+        def timed(fn, n=10):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            h0 = time.perf_counter()
+            a_.record()
+            for _ in range(n):
+                fn()
+            b_.record()
+            h1 = time.perf_counter()
+            torch.cuda.synchronize()
+            return a_.elapsed_time(b_) / n, (h1 - h0) * 1e3 / n
+        outs = cap.outputs
+        print(f"[diag rank {rank}] replay only      : device %.3f ms, host enqueue %.3f ms" % timed(lambda: cap.replay()), file=sys.stderr)
+        print(f"[diag rank {rank}] exchange only    : device %.3f ms, host enqueue %.3f ms" % timed(lambda: comm_part(*outs)), file=sys.stderr)
+        print(f"[diag rank {rank}] replay + exchange: device %.3f ms, host enqueue %.3f ms" % timed(step), file=sys.stderr)
+        print(f"[diag rank {rank}] plain launches   : device %.3f ms, host enqueue %.3f ms" % timed(step_plain), file=sys.stderr)
     t_ms = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
@@ -658,9 +695,7 @@ def run_ours(args):
     d2h = V * H * W * 3 * 4 + 4
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
 
     # --- roofline of the dominant kernel ------------------------------------------------------
     hbm_peak, peak_src = load_peaks()
@@ -783,9 +818,7 @@ def run_ours(args):
         "fma_probe_tflops": fma_tflops,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    return line
 
 
 def _trace_timeline(e2e_step, step, path):
@@ -834,14 +867,35 @@ def main():
                     help="factored exchange: this library's symmetric-memory kernel (nvls; auto = when available) or NCCL")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="enqueue every launch from Python instead of replaying the captured step")
+    ap.add_argument("--diag", action="store_true", help="diagnostic timings of the step's halves on stderr")
+    ap.add_argument("--no-config3", action="store_true", help="N > 1: do not add the configs[3] measurement to the line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--trace", default="", help="diagnostic: write a GPU timeline (kernels + idle gaps) of one e2e and one "
                                                 "device-timed step to this file (torch.profiler; not part of the measurement)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
-    else:
-        run_ours(args)
+        return
+    import copy
+    import torch.distributed as dist
+    line = run_ours(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 and args.config == 1 and not args.no_config3:
+        # BASELINE configs[3] (1 M Gaussians, 8 views per GPU, fwd+bwd + all-reduce) measured in the same run
+        a3 = copy.copy(args)
+        a3.config, a3.steps, a3.warmup, a3.no_cpu_baseline, a3.trace, a3.diag, a3.views, a3.feat = 3, 10, 3, True, "", False, 0, -1
+        try:
+            l3 = run_ours(a3, sub=True)
+            if line is not None and l3 is not None:
+                line["baseline_config3"] = {k: l3[k] for k in ("value", "unit", "ms_per_step", "steps", "warmup", "config", "e2e",
+                                                               "exchange_transport", "cuda_graph", "stage_ms_per_step", "scaling")}
+        except Exception as e:
+            if line is not None:
+                line["baseline_config3"] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    if world > 1 and dist.is_initialized():
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -70,6 +70,9 @@ _SIGNATURES = {
     "gg_geom_loss": (C.c_int, [_ll, _i, _p, _p, _p, _p, _p, _f, _f, _p, _i, _i, _p, _p, _sz, _p]),
     "gg_cosine_rows_loss": (C.c_int, [_ll, _i, _p, _ll, _p, _p, _ll, _p, _p, _p, _ll, _p, _ll, _p, _i, _p, _sz, _p]),
     "gg_param_regs": (C.c_int, [_ll, _i, _p, _p, _f, _f, _f, _p, _p, _p, _p, _sz, _p]),
+    "gg_mlp_packed_floats": (C.c_size_t, []),
+    "gg_mlp_pack_weights": (C.c_int, [_p, _p, _p, _p]),
+    "gg_mlp_up": (C.c_int, [_ll, _p, _ll, _p, _p, _p, _p, _p]),
     "gg_ssim_workspace_bytes": (C.c_size_t, [_i, _i, _i, _i]),
     "gg_ssim_loss": (C.c_int, [_i, _i, _i, _i, _p, _i, _p, _i, _f, _p, _i, _i, _p, _p, _sz, _p]),
     "gg_densify_stats": (C.c_int, [_ll, _i, _p, _p, _i, _i, _i, _p, _p, _p, _p]),

@@ -28,6 +28,7 @@ UNITS = [
     ("train.cu", ["-fmad=false"]),
     ("exchange.cu", []),
     ("loss.cu", ["-fmad=false"]),
+    ("mlp.cu", []),
 ]
 
 

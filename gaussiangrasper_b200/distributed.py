@@ -274,6 +274,41 @@ class NvlsExchange(FactoredExchange):
         return grads
 
 
+class SymmetricBucket(GradientBucket):
+    """GradientBucket in symmetric memory whose all_reduce() is this library's two-shot NVLS kernel
+    (gg_nvls_exchange, reduction only: multimem.ld_reduce of the rank's slice, multimem.st back to every rank)
+    between two cross-rank barriers, instead of ncclAllReduce.  For steps whose SH gradient is not factored (many
+    views per rank: BASELINE configs[3]).  Needs an initialised process group with more than one rank."""
+
+    def __init__(self, params: Dict[str, torch.Tensor], group: Optional[dist.ProcessGroup] = None):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+            raise RuntimeError("SymmetricBucket needs an initialised process group with more than one rank")
+        dev = next(iter(params.values())).device
+
+        def symmetric(numel):
+            t = symm.empty((int(numel) + 3) // 4 * 4, dtype=torch.float32, device=dev)
+            t.zero_()
+            return t
+        super().__init__(params, group, allocator=symmetric)
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.handle = symm.rendezvous(self.flat, group if group is not None else dist.group.WORLD)
+        self.multicast = bool(self.handle.multicast_ptr)
+        self._peers = (C.c_void_p * self.world)(*[int(p) for p in self.handle.buffer_ptrs])
+
+    def all_reduce(self, async_op: bool = False):
+        from . import _lib
+        dev = self.flat.device
+        mc = int(self.handle.multicast_ptr) if self.multicast else None
+        with _lib.device_guard(dev):
+            self.handle.barrier(channel=0)        # every rank's backward has written its bucket
+            _lib.call("gg_nvls_exchange", self.rank, self.world, mc, self._peers, int(self.flat.numel()), mc, self._peers,
+                      0, 2, _lib.stream_ptr(dev))
+            self.handle.barrier(channel=1)        # every slice has landed everywhere
+        return None
+
+
 def all_reduce_gradients(params: Dict[str, torch.Tensor], bucket: Optional[GradientBucket] = None,
                          group: Optional[dist.ProcessGroup] = None) -> GradientBucket:
     """Sum `.grad` of every parameter over the ranks and write the result back into `.grad`."""

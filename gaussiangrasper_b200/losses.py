@@ -215,3 +215,53 @@ def param_regs(sh_coeffs: torch.Tensor, log_scales: torch.Tensor, max_gauss_rati
                   _lib.ptr(v_sh_coeffs), _lib.ptr(v_log_scales), loss.data_ptr(), ws.data_ptr(), ws.numel(),
                   _lib.stream_ptr(dev))
     return loss
+
+
+_packed_cache = {}
+
+
+@torch.no_grad()
+def up_project(features: torch.Tensor, mlp: torch.nn.Module, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """`model.fea_up(outputs["feature"])` for a whole feature map (base_pipeline.py:408): [..., 32] -> [..., 512]
+    through the fused tcgen05 / TMEM kernel (csrc/mlp.cu: 3xTF32 split, fp32 accumulation, fp32-equivalent results).
+
+    features: fp32 CUDA tensor whose last dimension (32) has unit stride and whose rows are equally spaced -- e.g.
+    `render_views(...)["feature"]`, a channel slice of the blended image: no copy is made.  mlp: UpProjection (or
+    any module with `layers.0` = Linear(32,128), `layers.2` = Linear(128,512)).  Inference only (no autograd)."""
+    l0, l2 = mlp.layers[0], mlp.layers[2]
+    if tuple(l0.weight.shape) != (128, 32) or tuple(l2.weight.shape) != (512, 128):
+        raise ValueError("up_project implements the reference's MLP(32 -> 128 -> 512)")
+    dev = _lib.require_cuda(features, l0.weight, l2.weight, out)
+    if features.dtype != torch.float32 or features.shape[-1] != 32 or features.stride(-1) != 1:
+        raise ValueError("features must be fp32 [..., 32] with unit stride in the last dimension")
+    lead = features.shape[:-1]
+    n_rows = 1
+    for d in lead:
+        n_rows *= int(d)
+    # equally spaced rows: every leading stride must be the flattened multiple of the innermost leading stride
+    row_stride = int(features.stride(-2)) if features.dim() >= 2 else 32
+    expect = row_stride
+    for d in range(features.dim() - 2, -1, -1):
+        if features.shape[d] != 1 and features.stride(d) != expect:
+            features = features.contiguous()
+            row_stride = 32
+            break
+        expect *= int(features.shape[d])
+    key = (dev.index, l0.weight.data_ptr(), l0.weight._version, l2.weight.data_ptr(), l2.weight._version)
+    packed = _packed_cache.get(key)
+    lib = _lib.load()
+    with _lib.device_guard(dev):
+        if packed is None:
+            _packed_cache.clear()
+            packed = torch.empty(int(lib.gg_mlp_packed_floats()), dtype=torch.float32, device=dev)
+            _lib.call("gg_mlp_pack_weights", _lib.f32c(l0.weight.detach()).data_ptr(), _lib.f32c(l2.weight.detach()).data_ptr(),
+                      packed.data_ptr(), _lib.stream_ptr(dev))
+            _packed_cache[key] = packed
+        if out is None:
+            out = torch.empty(tuple(lead) + (512,), dtype=torch.float32, device=dev)
+        elif out.numel() != n_rows * 512 or not out.is_contiguous() or out.dtype != torch.float32:
+            raise ValueError("out must be a contiguous fp32 tensor of [..., 512]")
+        b1, b2 = _lib.f32c(l0.bias.detach()), _lib.f32c(l2.bias.detach())
+        _lib.call("gg_mlp_up", n_rows, features.data_ptr(), row_stride, packed.data_ptr(), b1.data_ptr(), b2.data_ptr(),
+                  out.data_ptr(), _lib.stream_ptr(dev))
+    return out

@@ -355,6 +355,17 @@ int gg_param_regs(long long n, int num_bases, const float* sh_coeffs, const floa
                   float w_sh, float w_scale, float* v_sh_coeffs /*nullable*/, float* v_log_scales /*nullable*/,
                   float* loss /*[2]*/, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- the CLIP up-projection MLP(32 -> 128 -> 512) of the reference model applied to a whole feature map
+ * (gaussian_splatting.py:198-213, :294; base_pipeline.py:408 in render.sh's flow): one fused tcgen05 / TMEM kernel,
+ * 3xTF32 split with fp32 accumulation (fp32-equivalent results), hidden activations kept on the SM, output written
+ * once.  gg_mlp_pack_weights splits W1 [128,32] and W2 [512,128] (torch.nn.Linear layout) into their TF32 halves in
+ * the kernel's shared-memory layout (gg_mlp_packed_floats() floats; once per weight set).  gg_mlp_up: x rows of 32
+ * floats, x_stride floats apart (e.g. the feature channels of render_views' image) -> y [n_rows, 512]. */
+size_t gg_mlp_packed_floats(void);
+int gg_mlp_pack_weights(const float* w1, const float* w2, float* packed, void* stream);
+int gg_mlp_up(long long n_rows, const float* x, long long x_stride, const float* packed, const float* b1, const float* b2,
+              float* y, void* stream);
+
 /* ---- SSIM loss with its gradient: weight * (1 - SSIM) with pytorch_msssim's defaults as the
  * reference configures them (gaussian_splatting.py:284, :885: 11x11 Gaussian window, sigma 1.5, data_range 1, no
  * padding, mean over batch, channels and positions).  pred / target / grad are channel-last [n_img, H, W, stride]

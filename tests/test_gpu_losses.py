@@ -129,3 +129,40 @@ def test_grad_out_leaves_get_no_autograd_grad(dev):
         for k in names:
             ref = want[k].reshape(bucket.view(k).shape)
             assert torch.allclose(bucket.view(k), ref, rtol=1e-4, atol=1e-6 * float(ref.abs().max())), (rep, k)
+
+
+@pytest.mark.parametrize("shape,strided", [((1, 32), False), ((127, 32), False), ((480, 640, 32), True), ((3, 50, 70, 32), True)])
+def test_up_projection_kernel_matches_fp64(dev, shape, strided):
+    """The tcgen05 / TMEM up-projection (3xTF32 split) against the same MLP in fp64: fp32-equivalent accuracy --
+    the error of a plain fp32 evaluation of the two layers, not TF32's 1e-3."""
+    from gaussiangrasper_b200.losses import UpProjection, up_project
+    torch.manual_seed(5)
+    mlp = UpProjection(32).to(dev)
+    with torch.no_grad():
+        for p in mlp.parameters():
+            p.mul_(3.0)                       # larger activations than the default initialisation gives
+    g = torch.Generator().manual_seed(sum(shape))
+    if strided:                               # the feature channels of a blended image: rows 40 floats apart
+        img = torch.randn(shape[:-1] + (40,), generator=g).to(dev)
+        x = img[..., 7:39]
+    else:
+        x = torch.randn(shape, generator=g).to(dev)
+    y = up_project(x, mlp)
+    assert y.shape == shape[:-1] + (512,)
+    ref64 = mlp.double()(x.double())
+    mlp.float()
+    scale = float(ref64.abs().max())
+    err = float((y.double() - ref64).abs().max()) / scale
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ref32 = mlp(x.contiguous())
+    err32 = float((ref32.double() - ref64).abs().max()) / scale
+    assert err <= 2e-6 + 4 * err32, (err, err32)
+    assert err < 1e-5
+    # repeated calls reuse the packed weights; changed weights are repacked
+    with torch.no_grad():
+        mlp.layers[2].bias.add_(1.0)
+        mlp.layers[0].weight.mul_(0.5)
+    y2 = up_project(x, mlp)
+    ref2 = mlp.double()(x.double())
+    mlp.float()
+    assert float((y2.double() - ref2).abs().max()) / float(ref2.abs().max()) < 1e-5
