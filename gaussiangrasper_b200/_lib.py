@@ -64,6 +64,7 @@ _SIGNATURES = {
     "gg_refine_apply": (C.c_int, [_i, _i, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, C.c_ulonglong, C.c_uint, _p, _sz, _p]),
     "gg_philox_normals": (C.c_int, [_ll, _p, _i, C.c_ulonglong, C.c_uint, _p, _p]),
     "gg_philox4x32_10_host": (None, [_p, _p, _p]),
+    "gg_knn3_scales": (C.c_int, [_i, _p, _p, _p, _p]),
     "gg_pixel_loss_workspace_bytes": (C.c_size_t, []),
     "gg_pixel_loss": (C.c_int, [_ll, _i, _p, _p, _p, _p, _i, _f, _p, _p, _p, _sz, _p]),
     "gg_loss_workspace_bytes": (C.c_size_t, []),

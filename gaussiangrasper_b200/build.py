@@ -12,7 +12,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libgg_b200.so")
+# GG_LIB_PATH: load this prebuilt library instead (kernel experiments: variants built with extra -D flags, see
+# tools/build_variant.py); it is never rebuilt implicitly
+LIB = os.environ.get("GG_LIB_PATH") or os.path.join(HERE, "libgg_b200.so")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
@@ -48,6 +50,10 @@ def _host_cxx_flags():
 
 
 def needs_build() -> bool:
+    if os.environ.get("GG_LIB_PATH"):
+        if not os.path.exists(LIB):
+            raise RuntimeError(f"GG_LIB_PATH={LIB} does not exist")
+        return False
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)

@@ -21,8 +21,24 @@
 #include "gg_geo.cuh"
 #include "gg_b200.h"
 
+#ifndef GG_BWD_DOT4
+#define GG_BWD_DOT4 0
+#endif
+#ifndef GG_BWD_B_UNROLL
+#define GG_BWD_B_UNROLL 16
+#endif
+// phase B of the warp backward (v_colour = fac . v_out) on mma.sync m16n8k8 TF32 with the 3xTF32 split: measured
+// 0.396 -> 0.340 ms at config 1 with unchanged parity (profiles/r02_blend_bwd_variants.txt).  0 = FP32-pipe version.
+#ifndef GG_BWD_MMA
+#define GG_BWD_MMA 1
+#endif
+#ifndef GG_BWD_MIN_BLOCKS
+#define GG_BWD_MIN_BLOCKS 5
+#endif
+
 namespace gg {
 
+constexpr int kBwdBUnroll = GG_BWD_B_UNROLL;
 constexpr int kBlendThreads = 256;
 constexpr float kAlphaMin = 1.0f / 255.0f;
 constexpr float kAlphaMax = 0.999f;
@@ -411,7 +427,7 @@ blend_bwd_kernel(const BlendArgs a) {
         const float* fr = facm + j * kHitRow + 16 * h;
         const float* wr = wm + j * kHitRow + 16 * h;
         const float bx = ga.x - rx0, by = ga.y - ry0 - (float)(2 * h);
-#pragma unroll 4
+#pragma unroll kBwdBUnroll
         for (int p = 0; p < 16; ++p) {
             const float f = live ? fr[p] : 0.0f;
             const float wv = live ? wr[p] : 0.0f;
@@ -585,7 +601,7 @@ constexpr size_t blend_bwd_warp_smem() {
 }
 
 template <int CP, bool kVec>
-__global__ void __launch_bounds__(kBwdWarps * 32, (CP <= 24) ? 5 : 1)
+__global__ void __launch_bounds__(kBwdWarps * 32, (CP <= 24) ? GG_BWD_MIN_BLOCKS : 1)
 blend_bwd_warp_kernel(const BlendArgs a) {
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -664,14 +680,98 @@ blend_bwd_warp_kernel(const BlendArgs a) {
             ga = __ldg(reinterpret_cast<const float4*>(a.geo) + 2 * (geo_base + g));
             gb = __ldg(reinterpret_cast<const float4*>(a.geo) + 2 * (geo_base + g) + 1);
         }
-        float acc[CP];
-#pragma unroll
-        for (int c = 0; c < CP; ++c) acc[c] = 0.0f;
         float m0 = 0.f, mx = 0.f, my = 0.f, mxx = 0.f, mxy = 0.f, myy = 0.f;
         const float* fr = facm + j * kHitRow + 16 * h;
         const float* wr = wm + j * kHitRow + 16 * h;
         const float bx = ga.x - rx0, by = ga.y - ry0 - (float)(2 * h);
-#pragma unroll 4
+        constexpr bool kMma = GG_BWD_MMA && (CP % 8 == 0);
+        if constexpr (kMma) {
+            // v_colour[16 entries x CP] = fac[16 x 32 pixels] . v_out[32 pixels x CP] on the tensor cores:
+            // mma.sync m16n8k8 TF32 with the 3xTF32 split (hi.hi + lo.hi + hi.lo, fp32 accumulation): fp32-equivalent.
+            const int g4 = lane >> 2, t4 = lane & 3;
+            float d[CP / 8][4];
+#pragma unroll
+            for (int nt = 0; nt < CP / 8; ++nt) d[nt][0] = d[nt][1] = d[nt][2] = d[nt][3] = 0.0f;
+            const bool row_lo = g4 < count, row_hi = g4 + 8 < count;   // rows beyond `count` hold stale values
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const int k0 = 8 * ks + t4;
+                float af[4];
+                af[0] = row_lo ? facm[g4 * kHitRow + k0] : 0.0f;
+                af[1] = row_hi ? facm[(g4 + 8) * kHitRow + k0] : 0.0f;
+                af[2] = row_lo ? facm[g4 * kHitRow + k0 + 4] : 0.0f;
+                af[3] = row_hi ? facm[(g4 + 8) * kHitRow + k0 + 4] : 0.0f;
+                uint32_t ah[4], al[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(ah[q]) : "f"(af[q]));
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(al[q]) : "f"(af[q] - __uint_as_float(ah[q])));
+                }
+#pragma unroll
+                for (int nt = 0; nt < CP / 8; ++nt) {
+                    const float b0f = vo_warp[k0 * CP + 8 * nt + g4], b1f = vo_warp[(k0 + 4) * CP + 8 * nt + g4];
+                    uint32_t bh0, bh1, bl0, bl1;
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(bh0) : "f"(b0f));
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(bh1) : "f"(b1f));
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(bl0) : "f"(b0f - __uint_as_float(bh0)));
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(bl1) : "f"(b1f - __uint_as_float(bh1)));
+#define GG_MMA_TF32(A, B0, B1)                                                                                        \
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, " \
+                 "{%0, %1, %2, %3};"                                                                                  \
+                 : "+f"(d[nt][0]), "+f"(d[nt][1]), "+f"(d[nt][2]), "+f"(d[nt][3])                                     \
+                 : "r"(A[0]), "r"(A[1]), "r"(A[2]), "r"(A[3]), "r"(B0), "r"(B1))
+                    GG_MMA_TF32(al, bh0, bh1);
+                    GG_MMA_TF32(ah, bl0, bl1);
+                    GG_MMA_TF32(ah, bh0, bh1);
+#undef GG_MMA_TF32
+                }
+            }
+            // lane holds entries g4 / g4 + 8, channels 8 nt + 2 t4 (+1)
+            const int gid_lo = __shfl_sync(0xffffffffu, fg, g4), gid_hi = __shfl_sync(0xffffffffu, fg, g4 + 8);
+            float* vc_lo = a.v_colors + (color_base + gid_lo) * (long long)a.color_stride;
+            float* vc_hi = a.v_colors + (color_base + gid_hi) * (long long)a.color_stride;
+#pragma unroll
+            for (int nt = 0; nt < CP / 8; ++nt) {
+                const int c0 = 8 * nt + 2 * t4;
+                if (row_lo) {
+                    if (c0 < a.channels) atomicAdd(vc_lo + c0, d[nt][0]);
+                    if (c0 + 1 < a.channels) atomicAdd(vc_lo + c0 + 1, d[nt][1]);
+                }
+                if (row_hi) {
+                    if (c0 < a.channels) atomicAdd(vc_hi + c0, d[nt][2]);
+                    if (c0 + 1 < a.channels) atomicAdd(vc_hi + c0 + 1, d[nt][3]);
+                }
+            }
+            // the six moments stay on the FP32 pipe (lane = entry j, pixel half h)
+#pragma unroll
+            for (int p = 0; p < 16; ++p) {
+                const float wv = live ? wr[p] : 0.0f;
+                const float dx = bx - (float)(p & 7), dy = by - (float)(p >> 3);
+                const float wdx = wv * dx, wdy = wv * dy;
+                m0 += wv; mx += wdx; my += wdy;
+                mxx = fmaf(wdx, dx, mxx); mxy = fmaf(wdx, dy, mxy); myy = fmaf(wdy, dy, myy);
+            }
+            m0 += __shfl_xor_sync(0xffffffffu, m0, 16);
+            mx += __shfl_xor_sync(0xffffffffu, mx, 16);
+            my += __shfl_xor_sync(0xffffffffu, my, 16);
+            mxx += __shfl_xor_sync(0xffffffffu, mxx, 16);
+            mxy += __shfl_xor_sync(0xffffffffu, mxy, 16);
+            myy += __shfl_xor_sync(0xffffffffu, myy, 16);
+            if (live && h == 0) {
+                const float o = gb.y, A = 2.0f * ga.z, B = ga.w, C = 2.0f * gb.x;
+                float* vg = a.v_geo + (geo_base + g) * 8;
+                atomicAdd(vg + 0, -o * fmaf(A, mx, B * my));
+                atomicAdd(vg + 1, -o * fmaf(B, mx, C * my));
+                atomicAdd(vg + 2, -0.5f * o * mxx);
+                atomicAdd(vg + 3, -o * mxy);
+                atomicAdd(vg + 4, -0.5f * o * myy);
+                atomicAdd(vg + 5, m0);
+            }
+        } else {
+        float acc[CP];
+#pragma unroll
+        for (int c = 0; c < CP; ++c) acc[c] = 0.0f;
+#pragma unroll kBwdBUnroll
         for (int p = 0; p < 16; ++p) {
             const float f = live ? fr[p] : 0.0f;
             const float wv = live ? wr[p] : 0.0f;
@@ -713,6 +813,7 @@ blend_bwd_warp_kernel(const BlendArgs a) {
 #pragma unroll
             for (int c = 0; c < CP; ++c)
                 if (c < a.channels && ((c < kSplit) == (h == 0))) atomicAdd(vc + c, acc[c]);
+        }
         }
         __syncwarp();
     };
@@ -799,6 +900,18 @@ blend_bwd_warp_kernel(const BlendArgs a) {
             float fac = 0.0f, w = 0.0f;
             if (valid) {
                 const float4* c4 = reinterpret_cast<const float4*>(rp + 8);
+#if GG_BWD_DOT4
+                float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;   // four independent chains
+#pragma unroll
+                for (int q = 0; q < CP / 4; ++q) {
+                    const float4 cc = c4[q];
+                    d0 = fmaf(cc.x, vo[4 * q], d0);
+                    d1 = fmaf(cc.y, vo[4 * q + 1], d1);
+                    d2 = fmaf(cc.z, vo[4 * q + 2], d2);
+                    d3 = fmaf(cc.w, vo[4 * q + 3], d3);
+                }
+                const float dot = (d0 + d1) + (d2 + d3);
+#else
                 float d0 = 0.0f, d1 = 0.0f;
 #pragma unroll
                 for (int q = 0; q < CP / 4; ++q) {
@@ -809,6 +922,7 @@ blend_bwd_warp_kernel(const BlendArgs a) {
                     d1 = fmaf(cc.w, vo[4 * q + 3], d1);
                 }
                 const float dot = d0 + d1;
+#endif
                 const float ra = 1.0f / (1.0f - alpha);
                 T *= ra;
                 fac = alpha * T;

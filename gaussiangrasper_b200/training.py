@@ -372,6 +372,21 @@ def refine_gaussians(params: Dict[str, torch.Tensor], moments: Optional[Dict[str
     return new_p, new_m, info
 
 
+@torch.no_grad()
+def knn_scale_init(means: torch.Tensor):
+    """The model's scale initialisation (gaussian_splatting.py:259-263): log of the mean distance to the three
+    nearest other points, on all three axes -- sklearn's NearestNeighbors on the host in the reference, one exact
+    brute-force kernel here.  Returns (log_scales [N,3], distances [N,3] ascending)."""
+    dev = _lib.require_cuda(means)
+    m = _lib.f32c(means.detach())
+    n = m.shape[0]
+    dist = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    ls = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    with _lib.device_guard(dev):
+        _lib.call("gg_knn3_scales", n, m.data_ptr(), dist.data_ptr(), ls.data_ptr(), _lib.stream_ptr(dev))
+    return ls, dist
+
+
 _loss_ws = {}
 
 

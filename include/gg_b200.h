@@ -316,6 +316,11 @@ int gg_philox_normals(long long count, const int32_t* parents /*nullable*/, int 
                       unsigned int step, float* out, void* stream);
 void gg_philox4x32_10_host(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4]);
 
+/* k-nearest-neighbour scale initialisation of the model (gaussian_splatting.py:259-263, :315-331): dist3 [n,3] =
+ * ascending distances to the three nearest OTHER points (exact, brute force), log_scales [n,3] = log of their mean on
+ * all three axes.  Either output may be NULL. */
+int gg_knn3_scales(int n, const float* means, float* dist3 /*nullable*/, float* log_scales /*nullable*/, void* stream);
+
 /* ---- per-pixel loss with its gradient in one pass (the L1 term and its masked variant,
  * gaussian_splatting.py:853-866; kind 2 = mean squared error).  pred/target/grad are n contiguous floats
  * ([..., channels]); mask (nullable) has one byte per pixel (n / channels), 0 = pixel ignored (zero loss and

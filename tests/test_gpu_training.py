@@ -503,3 +503,34 @@ def test_captured_step_replays_the_same_render_and_gradients():
         for k in names:
             ref = want_grad[k].reshape(bucket.view(k).shape)
             assert torch.allclose(bucket.view(k), ref, rtol=2e-4, atol=2e-6 * float(ref.abs().max())), (rep, k)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 3000, 20_011])
+def test_knn_scale_init_matches_the_reference_recipe(n):
+    """populate_modules' scale initialisation (:259-263): sklearn k-NN there, exact brute force here -- compared with
+    sklearn itself when the set is large enough for its k + 1 query, and with torch.cdist otherwise."""
+    import numpy as np
+    from gaussiangrasper_b200.training import knn_scale_init
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(n)
+    means = (torch.rand((n, 3), generator=g) - 0.5) * 10
+    if n >= 3000:
+        means[7] = means[11]          # an exact duplicate: its nearest "other" point sits at distance zero
+    ls, dist = knn_scale_init(means.to(dev))
+    d = torch.cdist(means.double(), means.double())
+    d.fill_diagonal_(float("inf"))
+    k = min(3, n - 1)
+    want = torch.sort(d, dim=1)[0][:, :k] if k > 0 else torch.zeros((n, 0), dtype=torch.float64)
+    got = dist.cpu().double()
+    if k > 0:
+        assert torch.allclose(got[:, :k], want, rtol=1e-5, atol=1e-6)
+    if k < 3:
+        fill = want[:, -1:] if k > 0 else torch.zeros((n, 1), dtype=torch.float64)
+        assert torch.allclose(got[:, k:], fill.expand(n, 3 - k), rtol=1e-5, atol=1e-6)
+    if n >= 4:
+        from sklearn.neighbors import NearestNeighbors
+        dist_sk, _ = NearestNeighbors(n_neighbors=4, algorithm="auto", metric="euclidean").fit(means.numpy()).kneighbors(means.numpy())
+        avg = torch.from_numpy(dist_sk[:, 1:].astype(np.float32)).mean(dim=-1, keepdim=True)
+        ref = torch.log(avg.repeat(1, 3))
+        ok = torch.isfinite(ref)
+        assert torch.allclose(ls.cpu()[ok], ref[ok], rtol=0, atol=2e-5)
