@@ -32,6 +32,10 @@
 #ifndef GG_BWD_MMA
 #define GG_BWD_MMA 1
 #endif
+// colour accumulation of the forward on mma.sync TF32 (3xTF32 split), see blend_fwd_kernel
+#ifndef GG_FWD_MMA
+#define GG_FWD_MMA 0
+#endif
 #ifndef GG_BWD_MIN_BLOCKS
 #define GG_BWD_MIN_BLOCKS 5
 #endif
@@ -178,6 +182,12 @@ blend_fwd_kernel(const BlendArgs a) {
     extern __shared__ __align__(16) float smem[];
     float* geo_sm = smem;                            // [kStages][BATCH][8]
     float* col_sm = smem + kStages * BATCH * 8;      // [kStages][BATCH][CP]
+    // tensor-core accumulation (GG_FWD_MMA): out[32 pixels x CP] += vis[32 x 8 entries] . colour[8 x CP]
+    constexpr bool kMma = GG_FWD_MMA && (CP % 8 == 0);
+    // per warp [8 entry slots][32 pixels], pixel index XOR-swizzled by 8 * (slot & 3): the A-fragment loads (4 slots
+    // x 8 pixels per instruction) then hit 32 different banks without padding
+    constexpr int kVisStride = 32;
+    float* vis_sm = smem + kStages * BATCH * (8 + CP) + (threadIdx.x >> 5) * 8 * kVisStride;
     const int n_tiles = a.tiles_x * a.tiles_y;
     const int lin = blockIdx.y * n_tiles + blockIdx.x;
     const int gtile = a.tile_order ? __ldg(a.tile_order + lin) : lin;  // longest lists first
@@ -196,9 +206,13 @@ blend_fwd_kernel(const BlendArgs a) {
     const long long geo_base = (long long)view * a.geo_view_stride;
     const long long color_base = (long long)view * a.color_view_stride;
 
+    // FP32 path: acc[c] of this thread's pixel.  MMA path: the same CP registers hold the warp's D fragments
+    // d[mt][nt][4]: pixels 16 mt + lane/4 (+8), channels 8 nt + 2 (lane%4) (+1).
     float acc[CP];
 #pragma unroll
     for (int c = 0; c < CP; ++c) acc[c] = 0.0f;
+    int n_slots = 0;   // MMA path: entries waiting in vis_sm (warp-uniform)
+    int slot_e = 0;    // ... lane l keeps the batch-local index of the entry in slot l & 7
     float T = 1.0f;
     int last = range.x;
     int stop = range.y;  // one past the last entry this pixel looked at
@@ -234,21 +248,84 @@ blend_fwd_kernel(const BlendArgs a) {
             unsigned hits[BATCH / 32];
 #pragma unroll
             for (int k = 0; k < BATCH / 32; ++k) hits[k] = 0u;
-            auto blend = [&](int e, float alpha) -> bool {
+            const float* cbuf = col_sm + buf * BATCH * CP;
+            const int lane_f = threadIdx.x & 31;
+            // MMA path: the waiting slots' [32 x n] weights times their colour rows, 3xTF32 split, fp32 accumulate
+            auto mma_flush = [&]() {
+                if constexpr (kMma) {
+                    __syncwarp();
+                    const int g4 = lane_f >> 2, t4 = lane_f & 3;
+                    const int e_lo = __shfl_sync(0xffffffffu, slot_e, t4), e_hi = __shfl_sync(0xffffffffu, slot_e, t4 + 4);
+                    const bool k_lo = t4 < n_slots, k_hi = t4 + 4 < n_slots;     // empty slots hold stale weights
+                    uint32_t ah[2][4], al[2][4];
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) {
+                        float af[4];
+                        const int sw = 8 * t4;   // == 8 * ((t4 + 4) & 3)
+                        af[0] = k_lo ? vis_sm[t4 * kVisStride + ((16 * mt + g4) ^ sw)] : 0.0f;
+                        af[1] = k_lo ? vis_sm[t4 * kVisStride + ((16 * mt + g4 + 8) ^ sw)] : 0.0f;
+                        af[2] = k_hi ? vis_sm[(t4 + 4) * kVisStride + ((16 * mt + g4) ^ sw)] : 0.0f;
+                        af[3] = k_hi ? vis_sm[(t4 + 4) * kVisStride + ((16 * mt + g4 + 8) ^ sw)] : 0.0f;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(ah[mt][q]) : "f"(af[q]));
+                            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(al[mt][q]) : "f"(af[q] - __uint_as_float(ah[mt][q])));
+                        }
+                    }
+#pragma unroll
+                    for (int nt = 0; nt < CP / 8; ++nt) {
+                        const float b0f = k_lo ? cbuf[e_lo * CP + 8 * nt + g4] : 0.0f;
+                        const float b1f = k_hi ? cbuf[e_hi * CP + 8 * nt + g4] : 0.0f;
+                        uint32_t bh0, bh1, bl0, bl1;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(bh0) : "f"(b0f));
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(bh1) : "f"(b1f));
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(bl0) : "f"(b0f - __uint_as_float(bh0)));
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(bl1) : "f"(b1f - __uint_as_float(bh1)));
+#pragma unroll
+                        for (int mt = 0; mt < 2; ++mt) {
+                            float* d = acc + (mt * (CP / 8) + nt) * 4;
+#define GG_MMA_TF32(A, B0, B1)                                                                                        \
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, " \
+                 "{%0, %1, %2, %3};"                                                                                  \
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])                                                     \
+                 : "r"(A[0]), "r"(A[1]), "r"(A[2]), "r"(A[3]), "r"(B0), "r"(B1))
+                            GG_MMA_TF32(al[mt], bh0, bh1);
+                            GG_MMA_TF32(ah[mt], bl0, bl1);
+                            GG_MMA_TF32(ah[mt], bh0, bh1);
+#undef GG_MMA_TF32
+                        }
+                    }
+                    n_slots = 0;
+                    __syncwarp();
+                }
+            };
+            auto blend = [&](int e, float alpha, float& vis_out) -> bool {
                 const float next_T = T * (1.0f - alpha);
                 if (next_T <= kTStop) { done = true; stop = first + e + 1; return false; }
                 const float vis = alpha * T;
+                if constexpr (kMma) {
+                    vis_out = vis;
+                } else {
 #pragma unroll
-                for (int q = 0; q < CP / 4; ++q) {
-                    const float4 cc = c4[e * (CP / 4) + q];
-                    acc[4 * q] = fmaf(vis, cc.x, acc[4 * q]);
-                    acc[4 * q + 1] = fmaf(vis, cc.y, acc[4 * q + 1]);
-                    acc[4 * q + 2] = fmaf(vis, cc.z, acc[4 * q + 2]);
-                    acc[4 * q + 3] = fmaf(vis, cc.w, acc[4 * q + 3]);
+                    for (int q = 0; q < CP / 4; ++q) {
+                        const float4 cc = c4[e * (CP / 4) + q];
+                        acc[4 * q] = fmaf(vis, cc.x, acc[4 * q]);
+                        acc[4 * q + 1] = fmaf(vis, cc.y, acc[4 * q + 1]);
+                        acc[4 * q + 2] = fmaf(vis, cc.z, acc[4 * q + 2]);
+                        acc[4 * q + 3] = fmaf(vis, cc.w, acc[4 * q + 3]);
+                    }
                 }
                 T = next_T;
                 last = first + e + 1;
                 return true;
+            };
+            // MMA path: an entry somebody contributed to takes the next slot
+            auto enqueue = [&](int e, float vis) {
+                if constexpr (kMma) {
+                    vis_sm[n_slots * kVisStride + (lane_f ^ (8 * (n_slots & 3)))] = vis;
+                    if ((lane_f & 7) == n_slots) slot_e = e;
+                    if (++n_slots == 8) mma_flush();
+                }
             };
 #pragma unroll
             for (int k = 0; k < BATCH / 32; ++k) {
@@ -271,13 +348,15 @@ blend_fwd_kernel(const BlendArgs a) {
                     const float a1 = fminf(kAlphaMax, gb1.y * __expf(-s1));
                     const bool ok0 = !(s0 < 0.0f || s0 > gb0.z) && a0 >= kAlphaMin;
                     const bool ok1 = two && !(s1 < 0.0f || s1 > gb1.z) && a1 >= kAlphaMin;
-                    const bool c0 = (ok0 && !done) ? blend(e0, a0) : false;
-                    const bool c1 = (ok1 && !done) ? blend(e1, a1) : false;
-                    if (__any_sync(0xffffffffu, c0)) hits[k] |= 1u << b0;
-                    if (__any_sync(0xffffffffu, c1)) hits[k] |= 1u << b1;
+                    float v0 = 0.0f, v1 = 0.0f;
+                    const bool c0 = (ok0 && !done) ? blend(e0, a0, v0) : false;
+                    const bool c1 = (ok1 && !done) ? blend(e1, a1, v1) : false;
+                    if (__any_sync(0xffffffffu, c0)) { hits[k] |= 1u << b0; enqueue(e0, v0); }
+                    if (__any_sync(0xffffffffu, c1)) { hits[k] |= 1u << b1; enqueue(e1, v1); }
                 }
                 if (__all_sync(0xffffffffu, done)) { warp_done = true; break; }
             }
+            if (n_slots) mma_flush();   // the staged colour rows of this batch are recycled two batches from now
             if (a.hit_words) {
                 // record index: see BlendArgs::hit_words (a.fwd_batch == BATCH in the forward)
                 const long long rec = (long long)(range.x / BATCH) + gtile + b;
@@ -290,7 +369,35 @@ blend_fwd_kernel(const BlendArgs a) {
         }
     }
     cp_async_wait<0>();
-    if (inside) {
+    if constexpr (kMma) {
+        // D fragments -> image: this lane holds pixels (16 mt + lane/4, +8) of the warp's 8x4 block, whose
+        // transmittance sits in the lanes of those pixels
+        const int lane_f = threadIdx.x & 31, g4 = lane_f >> 2, t4 = lane_f & 3;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int p = 16 * mt + g4 + 8 * hh;                         // pixel = lane index of its owner
+                const float Tp = __shfl_sync(0xffffffffu, T, p);
+                const int ppx = tile_x * GG_TILE + ((p & 7) | ((warp & 1) << 3));
+                const int ppy = tile_y * GG_TILE + ((p >> 3) | ((warp >> 1) << 2));
+                if (ppx < a.img_w && ppy < a.img_h) {
+                    float* o = a.out + (((long long)view * a.img_h + ppy) * a.img_w + ppx) * a.out_stride;
+#pragma unroll
+                    for (int nt = 0; nt < CP / 8; ++nt) {
+                        const int c0 = 8 * nt + 2 * t4;
+                        const float* d = acc + (mt * (CP / 8) + nt) * 4 + 2 * hh;
+                        if (c0 < a.channels) o[c0] = fmaf(Tp, __ldg(a.bg + c0), d[0]);
+                        if (c0 + 1 < a.channels) o[c0 + 1] = fmaf(Tp, __ldg(a.bg + c0 + 1), d[1]);
+                    }
+                }
+            }
+        if (inside) {
+            const long long pix = ((long long)view * a.img_h + py) * a.img_w + px;
+            a.final_T[pix] = T;
+            a.final_idx[pix] = last;
+        }
+    } else if (inside) {
         const long long pix = ((long long)view * a.img_h + py) * a.img_w + px;
         float* o = a.out + pix * a.out_stride;
 #pragma unroll
@@ -985,7 +1092,7 @@ unpack_vgeo_kernel(long long n, int n_views, const float* __restrict__ v_geo, fl
 template <int CP, int BATCH>
 static int launch_blend_impl(bool backward, const BlendArgs& a, int n_views, bool vec, cudaStream_t st) {
     dim3 grid(a.tiles_x * a.tiles_y, n_views);
-    size_t smem = sizeof(float) * kStages * BATCH * (8 + CP);
+    size_t smem = sizeof(float) * (kStages * BATCH * (8 + CP) + (GG_FWD_MMA && CP % 8 == 0 ? (kBlendThreads / 32) * 8 * 32 : 0));
     if (backward && a.hit_words) {
         const size_t wsmem = blend_bwd_warp_smem<CP>();
         dim3 wgrid(2 * a.tiles_x * a.tiles_y, n_views);
