@@ -94,6 +94,19 @@ prepare_views_kernel(const PrepArgs a, float* __restrict__ geo, float* __restric
     const bool active = i < a.n;
     const int rows_here = (int)min((long long)32, a.n - first);
     const long long vrow = (long long)view * a.n + i;
+    // ---- SH coefficients of the warp's 32 Gaussians: one contiguous span.  A full warp moves it with a single
+    // bulk copy (TMA engine), issued BEFORE the projection arithmetic so that the biggest transfer of the kernel
+    // (9.6 KB per warp) is in flight while the warp computes; the feature rows are prefetched into registers ----
+    const int row = a.nb * 3;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + (size_t)kPrepWarps * 32 * slab_row) + warp;
+    const bool bulk = rows_here == 32 && phase != 1;
+    if (bulk) {
+        if (lane == 0) {
+            mbar_init(bar, 1);
+            bulk_load(slab, a.sh + first * row, (uint32_t)(32 * row * sizeof(float)), bar);
+        }
+        __syncwarp();
+    }
     const Camera cam = load_camera_regs(a, view);
 
     Activated g;
@@ -123,20 +136,12 @@ prepare_views_kernel(const PrepArgs a, float* __restrict__ geo, float* __restric
             reinterpret_cast<float4*>(quats_out)[i] = make_float4(g.qh[0], g.qh[1], g.qh[2], g.qh[3]);
     }
     const bool vis = active && o.tiles > 0;
-    if (phase == 1 || !__any_sync(0xffffffffu, vis)) return;  // nothing of this warp reaches a tile list
-
-    // ---- SH coefficients of the warp's 32 Gaussians: one contiguous span.  A full warp moves it
-    // with a single bulk copy (TMA engine) and evaluates the SH basis while it lands ----
-    const int row = a.nb * 3;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + (size_t)kPrepWarps * 32 * slab_row) + warp;
-    const bool bulk = rows_here == 32;
-    if (bulk) {
-        if (lane == 0) {
-            mbar_init(bar, 1);
-            bulk_load(slab, a.sh + first * row, (uint32_t)(32 * row * sizeof(float)), bar);
-        }
-        __syncwarp();
-    } else {
+    if (phase == 1) return;
+    if (!__any_sync(0xffffffffu, vis)) {   // nothing of this warp reaches a tile list
+        if (bulk) mbar_wait(bar, 0);       // the copy must have landed before this shared memory can be handed on
+        return;
+    }
+    if (!bulk) {
         const float* gspan = a.sh + first * row;
         const int span = rows_here * row;
         for (int k = lane; k < span; k += 32) slab[k] = __ldg(gspan + k);

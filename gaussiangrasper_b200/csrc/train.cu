@@ -455,9 +455,16 @@ pixel_loss_kernel(long long n, int channels, const float* __restrict__ pred, con
                   float* __restrict__ loss, int vec4) {
     __shared__ float warp_sum[8];
     __shared__ bool last;
-    // mean over every element, or over the elements of the valid pixels only (gaussian_splatting.py:882)
-    const double denom = valid_pixels ? (double)max(*valid_pixels, 1) * (double)channels : (double)n;
-    const float scale = (float)((double)weight / denom);
+    __shared__ float s_scale;
+    // mean over every element, or over the elements of the valid pixels only (gaussian_splatting.py:882).
+    // ONE thread per block does the double-precision division: fp64 throughput on this part is ~1/64 of fp32, and
+    // half a million threads each dividing in double cost more than the whole memory traffic of the kernel.
+    if (threadIdx.x == 0) {
+        const double denom = valid_pixels ? (double)max(*valid_pixels, 1) * (double)channels : (double)n;
+        s_scale = (float)((double)weight / denom);
+    }
+    __syncthreads();
+    const float scale = s_scale;
     float acc = 0.0f;
     const long long stride = (long long)gridDim.x * blockDim.x;
     if (vec4) {
