@@ -500,6 +500,20 @@ def max_channels() -> int:
     return int(_lib.load().gg_blend_max_channels())
 
 
+def _channel_blocks(C: int, step: int):
+    """Column blocks of a C-channel blend: one launch for C <= step, else near-equal blocks of a multiple of 4
+    channels (16-byte aligned row pieces).  Returns ([(c0, c1), ...], same_batch): same_batch says that every block
+    stages the same number of entries per batch (<= 32 channels: 128, more: 64) -- then the contributor masks the
+    forward records for the first block are valid for all of them (they depend on the geometry only)."""
+    if C <= step:
+        return [(0, C)], True
+    nblk = (C + step - 1) // step
+    per = min(step, ((C + nblk - 1) // nblk + 3) // 4 * 4)
+    blocks = [(c0, min(C, c0 + per)) for c0 in range(0, C, per)]
+    wide = [(c1 - c0) > 32 for c0, c1 in blocks]
+    return blocks, all(wide) or not any(wide)
+
+
 def blend_fwd(binning: Binning, geo, colors, background, img_height, img_width, colors_per_view=False,
               pair_counter: Optional[torch.Tensor] = None, single_image: bool = False, record_hits: bool = True):
     """colors [rows, C] (C arbitrary; split into launches of <= 64 channels).  Returns
@@ -515,19 +529,19 @@ def blend_fwd(binning: Binning, geo, colors, background, img_height, img_width, 
     final_T = torch.empty((V, img_height, img_width), dtype=torch.float32, device=dev)
     final_idx = torch.empty((V, img_height, img_width), dtype=torch.int32, device=dev)
     tb = binning.tile_bounds
-    step = max_channels()
+    blocks, same_batch = _channel_blocks(C, max_channels())
     hit_words = None
-    if record_hits and C <= step and binning.capacity > 0:
-        nwords = int(_lib.load().gg_blend_hit_words(binning.capacity, binning.tile_ranges.shape[0], C))
+    if record_hits and same_batch and binning.capacity > 0:
+        nwords = int(_lib.load().gg_blend_hit_words(binning.capacity, binning.tile_ranges.shape[0], blocks[0][1] - blocks[0][0]))
         hit_words = torch.zeros(nwords, dtype=torch.int32, device=dev)
     with _lib.device_guard(dev):
-        for c0 in range(0, C, step):
-            c1 = min(C, c0 + step)
+        for c0, c1 in blocks:
             _lib.call("gg_blend_fwd",
                 V, n, c1 - c0, C, 1 if colors_per_view else 0, C, int(img_height), int(img_width), tb[0], tb[1],
                 _ids_ptr(binning), ptr(binning.tile_ranges), ptr(binning.tile_order), ptr(geo),
                 colors.data_ptr() + 4 * c0, background.data_ptr() + 4 * c0, out.data_ptr() + 4 * c0, ptr(final_T),
-                ptr(final_idx), ptr(pair_counter) if c0 == 0 else None, ptr(hit_words), stream_ptr(dev))
+                ptr(final_idx), ptr(pair_counter) if c0 == 0 else None, ptr(hit_words) if c0 == 0 else None,
+                stream_ptr(dev))
     return out, final_T, final_idx, hit_words
 
 
@@ -543,12 +557,11 @@ def blend_bwd(binning: Binning, geo, colors, background, final_T, final_idx, v_o
     v_geo = acc[:rows_g].view(V * n, 8)
     v_colors = acc[rows_g:].view(colors.shape)
     tb = binning.tile_bounds
-    step = max_channels()
-    if C > step:
+    blocks, same_batch = _channel_blocks(C, max_channels())
+    if not same_batch:
         hit_words = None
     with _lib.device_guard(dev):
-        for c0 in range(0, C, step):
-            c1 = min(C, c0 + step)
+        for c0, c1 in blocks:
             _lib.call("gg_blend_bwd",
                 V, n, c1 - c0, C, 1 if colors_per_view else 0, C, int(img_height), int(img_width), tb[0], tb[1],
                 _ids_ptr(binning), ptr(binning.tile_ranges), ptr(binning.tile_order), ptr(geo),
