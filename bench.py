@@ -102,6 +102,15 @@ SETUP_STEPS = 3   # untimed initialisation before the warm-up: first-call capaci
                   # allocator growth, NCCL communicator set-up.  Not counted as warm-up, never timed.
 
 
+def _exchange_mode(multicast: bool) -> str:
+    mode = os.environ.get("GG_NVLS_MODE", "1")
+    if mode == "0" and multicast:
+        return "NVLS multimem.ld_reduce / multimem.st"
+    if mode == "2" and multicast:
+        return "peer loads + multimem.st"
+    return "peer loads / stores over NVLink, fixed summation order" + ("; multicast mapping available" if multicast else "")
+
+
 def bench_config(args, world):
     from gaussiangrasper_b200 import scenes
     cfg = scenes.CONFIGS[args.config]
@@ -317,8 +326,7 @@ def run_ours(args, sub=False):
             try:   # one kernel of this library over symmetric memory (multimem through the NVSwitch)
                 from gaussiangrasper_b200.distributed import NvlsExchange
                 ex = NvlsExchange(P, chunks[0].n_views)
-                transport = "gg_nvls_exchange kernel over symmetric memory (%s)" % (
-                    "NVLS multimem.ld_reduce / multimem.st" if ex.multicast else "peer ld/st, no multicast mapping")
+                transport = "gg_nvls_exchange kernel over symmetric memory (%s)" % _exchange_mode(ex.multicast)
             except Exception as e:   # no symmetric memory on this box: NCCL collectives
                 if args.transport == "nvls":
                     raise
@@ -335,8 +343,7 @@ def run_ours(args, sub=False):
             try:   # plain all-reduce of every leaf gradient, as this library's two-shot NVLS kernel
                 from gaussiangrasper_b200.distributed import SymmetricBucket
                 bucket = SymmetricBucket(P)
-                transport = "gg_nvls_exchange kernel over symmetric memory, reduction only (%s)" % (
-                    "NVLS multimem.ld_reduce / multimem.st" if bucket.multicast else "peer ld/st, no multicast mapping")
+                transport = "gg_nvls_exchange kernel over symmetric memory, reduction only (%s)" % _exchange_mode(bucket.multicast)
             except Exception as e:
                 if args.transport == "nvls":
                     raise

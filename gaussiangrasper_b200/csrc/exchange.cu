@@ -14,11 +14,14 @@
 //                                   in the NVSwitch), and multimem.st's the result back into every rank's copy.
 //     Per GPU and direction that moves (world-1)/world of the bucket once: the bandwidth-optimal schedule, with
 //     no intermediate buffer and no reduction arithmetic on the SMs.
-// Without a multicast mapping (no NVLS) the same schedule runs over the peers' mapped addresses with plain
-// ld.global / st.global.  The caller brackets the launch with cross-rank barriers (the symmetric-memory signal
+// The same schedule also runs over the peers' mapped addresses with plain ld.global / st.global (W loads in flight
+// per element, fixed summation order: every rank computes the same bits) -- and that is the DEFAULT: on this pool's
+// NVSwitch boxes it measured faster than the multimem form at 2 and at 8 ranks (profiles/r02_exchange_tuning.txt);
+// GG_NVLS_MODE=0 / 2 select multimem everywhere / peer loads + multimem stores.  The caller brackets the launch with cross-rank barriers (the symmetric-memory signal
 // pads): one before (every rank's backward has written its bucket and slot), one after (every slice is back).
 #include "gg_common.cuh"
 #include "gg_b200.h"
+#include <cstdlib>
 
 namespace gg {
 
@@ -49,9 +52,12 @@ __device__ __forceinline__ void multimem_st(float* mc, const float4 v) {
                  : "memory");
 }
 
-template <bool kMulticast>
+// kMode 0: multimem.ld_reduce + multimem.st; 1: peer loads + peer stores (no multicast mapping needed);
+//       2: peer loads (the W slices arrive over W-1 independent NVLink paths) + multimem.st (one store, replicated)
+template <int kMode>
 __global__ void __launch_bounds__(512)
 nvls_exchange_kernel(const ExchangeArgs a) {
+    constexpr bool kMulticast = kMode != 1;
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
     // ---- all-gather: my rgb slot -> the same slot on every rank -------------------------------------
@@ -73,7 +79,7 @@ nvls_exchange_kernel(const ExchangeArgs a) {
         const long long per = (a.bucket_vec4 + a.world - 1) / a.world;
         const long long lo = (long long)a.rank * per;
         const long long hi = lo + per < a.bucket_vec4 ? lo + per : a.bucket_vec4;
-        if (kMulticast) {
+        if (kMode == 0) {
             // a round trip through the switch per load: keep kUnroll of them in flight per thread
             constexpr int kUnroll = 4;
             long long i = lo + tid;
@@ -87,13 +93,20 @@ nvls_exchange_kernel(const ExchangeArgs a) {
             for (; i < hi; i += stride) multimem_st(a.bucket_mc + 4 * i, multimem_ld_reduce_add(a.bucket_mc + 4 * i));
         } else {
             for (long long i = lo + tid; i < hi; i += stride) {
-                // fixed summation order (rank 0, 1, ...) so that every run gives the same bits
-                float4 s = reinterpret_cast<const float4*>(a.bucket_peer[0])[i];
-                for (int p = 1; p < a.world; ++p) {
-                    const float4 v = reinterpret_cast<const float4*>(a.bucket_peer[p])[i];
-                    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+                // fixed summation order (rank 0, 1, ...) so that every run and every rank gives the same bits
+                float4 v[kMaxRanks];
+#pragma unroll
+                for (int p = 0; p < kMaxRanks; ++p)
+                    if (p < a.world) v[p] = reinterpret_cast<const float4*>(a.bucket_peer[p])[i];   // W loads in flight
+                float4 s = v[0];
+#pragma unroll
+                for (int p = 1; p < kMaxRanks; ++p)
+                    if (p < a.world) { s.x += v[p].x; s.y += v[p].y; s.z += v[p].z; s.w += v[p].w; }
+                if (kMode == 2) {
+                    multimem_st(a.bucket_mc + 4 * i, s);
+                } else {
+                    for (int p = 0; p < a.world; ++p) reinterpret_cast<float4*>(a.bucket_peer[p])[i] = s;
                 }
-                for (int p = 0; p < a.world; ++p) reinterpret_cast<float4*>(a.bucket_peer[p])[i] = s;
             }
         }
     }
@@ -129,11 +142,26 @@ extern "C" int gg_nvls_exchange(int rank, int world, float* bucket_multicast, fl
     if (a.bucket_vec4 == 0 && a.slot_vec4 == 0) return GG_OK;
     // a copy-shaped kernel: enough CTAs to keep every NVLink port busy; one CTA per SM when the two halves run as
     // two concurrent launches, two when one launch does both
-    const int blocks = parts == 3 ? 148 * 2 : 148;
-    if (bucket_multicast)
-        nvls_exchange_kernel<true><<<blocks, 512, 0, (cudaStream_t)stream>>>(a);
+    int blocks = parts == 3 ? 148 * 2 : 148;
+    if (const char* e = getenv("GG_NVLS_BLOCKS")) {   // tuning knob (profiles/r02_exchange_tuning.txt)
+        const int v = atoi(e);
+        if (v >= 1 && v <= 148 * 16) blocks = v;
+    }
+    // mode 0: multimem.ld_reduce + multimem.st, 1: peer loads and stores, 2: peer loads + multimem.st.
+    // Default 1: measured fastest on this pool's boxes at 2 ranks (0.150 vs 0.229 ms) and at 8 ranks (0.294 vs 0.312
+    // / 0.323 ms), profiles/r02_exchange_tuning.txt; GG_NVLS_MODE selects the multimem variants where a multicast
+    // mapping exists.
+    int mode = 1;
+    if (const char* e = getenv("GG_NVLS_MODE")) {
+        const int v = atoi(e);
+        if (v == 1 || (bucket_multicast && (v == 0 || v == 2))) mode = v;
+    }
+    if (mode == 0)
+        nvls_exchange_kernel<0><<<blocks, 512, 0, (cudaStream_t)stream>>>(a);
+    else if (mode == 2)
+        nvls_exchange_kernel<2><<<blocks, 512, 0, (cudaStream_t)stream>>>(a);
     else
-        nvls_exchange_kernel<false><<<blocks, 512, 0, (cudaStream_t)stream>>>(a);
+        nvls_exchange_kernel<1><<<blocks, 512, 0, (cudaStream_t)stream>>>(a);
     count_launch();
     return check_launch("nvls_exchange_kernel");
 }
