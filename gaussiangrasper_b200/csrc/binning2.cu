@@ -189,7 +189,7 @@ __device__ __forceinline__ int warp_incl_scan_i(int v, int lane) {
 // base), tile_order (tiles by descending length bucket), info = {M, overflow, longest, 0}, redo[t] <- 0.
 __device__ __forceinline__ void scan_order_body(int num_tiles, long long capacity, int* counts, int32_t* tile_ranges,
                                                 int32_t* tile_order, int32_t* info, int32_t* lists,
-                                                int32_t* list_counts, int class_limit) {
+                                                int32_t* list_counts, int class_limit, int32_t* info_mapped) {
     __shared__ long long s_sum[32];
     __shared__ int s_max[32];
     __shared__ int s_wsum[32];
@@ -221,6 +221,11 @@ __device__ __forceinline__ void scan_order_body(int num_tiles, long long capacit
         info[1] = overflow ? 1 : 0;
         info[2] = mx;
         info[3] = 0;
+        if (info_mapped) {
+            // the host's copy, stored straight into its pinned (device-mapped) record: no copy-engine hop on the
+            // stream between the sort and the blend
+            *reinterpret_cast<int4*>(info_mapped) = make_int4((int)min(tot, (long long)INT32_MAX), overflow ? 1 : 0, mx, 0);
+        }
     }
     if (overflow) {
         for (int t = tid; t < num_tiles; t += 1024) {
@@ -280,8 +285,8 @@ __device__ __forceinline__ void scan_order_body(int num_tiles, long long capacit
 
 __global__ void __launch_bounds__(1024)
 tile_scan_order_kernel(int num_tiles, long long capacity, int* counts, int32_t* tile_ranges, int32_t* tile_order,
-                       int32_t* info, int32_t* lists, int32_t* list_counts, int class_limit) {
-    scan_order_body(num_tiles, capacity, counts, tile_ranges, tile_order, info, lists, list_counts, class_limit);
+                       int32_t* info, int32_t* lists, int32_t* list_counts, int class_limit, int32_t* info_mapped) {
+    scan_order_body(num_tiles, capacity, counts, tile_ranges, tile_order, info, lists, list_counts, class_limit, info_mapped);
 }
 
 // Exclusive prefix over the rows of a view's counting CTAs, per tile: CTA = 32 tiles x 32 row groups (thread
@@ -291,7 +296,7 @@ tile_scan_order_kernel(int num_tiles, long long capacity, int* counts, int32_t* 
 __global__ void __launch_bounds__(1024)
 tile_prefix_scan_kernel(int num_tiles, int tiles_per_view, int blocks_per_view, long long capacity, int* blockhist,
                         int* counts, int32_t* tile_ranges, int32_t* tile_order, int32_t* info, int32_t* lists,
-                        int32_t* list_counts, int class_limit, unsigned* done) {
+                        int32_t* list_counts, int class_limit, unsigned* done, int32_t* info_mapped) {
     __shared__ bool s_last;
     __shared__ int s_grp[32][33];
     constexpr int kMaxRows = 10;                      // rows per thread: 32 * 10 >= kHistBlocksTotal
@@ -330,7 +335,7 @@ tile_prefix_scan_kernel(int num_tiles, int tiles_per_view, int blocks_per_view, 
     if (!s_last) return;
     if (threadIdx.x == 0) *done = 0u;  // armed for the next call
     __threadfence();
-    scan_order_body(num_tiles, capacity, counts, tile_ranges, tile_order, info, lists, list_counts, class_limit);
+    scan_order_body(num_tiles, capacity, counts, tile_ranges, tile_order, info, lists, list_counts, class_limit, info_mapped);
 }
 
 __global__ void __launch_bounds__(256)
@@ -778,6 +783,16 @@ extern "C" int gg_bin_tiles(int n, int n_views, const float* xys, int xy_stride,
     unsigned long long* pairs = reinterpret_cast<unsigned long long*>(s + L.pairs);
     cudaStream_t st = (cudaStream_t)stream;
     const bool smem_path = T <= kHistMaxTiles;
+    // pinned host memory is mapped into the device's address space (UVA): the scan kernel stores the record there
+    // itself.  Anything else (pageable memory) gets the stream-ordered copy at the end.
+    int32_t* info_mapped = nullptr;
+    if (info_host && ((uintptr_t)info_host & 15) == 0) {
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, info_host) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+            info_mapped = reinterpret_cast<int32_t*>(at.devicePointer);
+        else
+            (void)cudaGetLastError();
+    }
     int blocks = 1, per = n;
     hist_blocks(n, n_views, blocks, per);
     const size_t hist_smem = sizeof(int) * (size_t)T;
@@ -792,13 +807,13 @@ extern "C" int gg_bin_tiles(int n, int n_views, const float* xys, int xy_stride,
                                                                                  tiles_y, blockhist, done);
         tile_prefix_scan_kernel<<<div_up(num_tiles, 32), 1024, 0, st>>>(num_tiles, T, blocks, capacity, blockhist,
                                                                           counts, tile_ranges, tile_order, info, lists,
-                                                                          list_counts, class_limit, done);
+                                                                          list_counts, class_limit, done, info_mapped);
         launches += 2;
     } else {
         GG_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)num_tiles, st));
         tile_count_kernel<<<div_up(total, 256), 256, 0, st>>>(total, n, xys, xy_stride, radii, tiles_x, tiles_y, counts);
         tile_scan_order_kernel<<<1, 1024, 0, st>>>(num_tiles, capacity, counts, tile_ranges, tile_order, info, lists,
-                                                   list_counts, class_limit);
+                                                   list_counts, class_limit, info_mapped);
         launches += 2;
     }
     if (capacity > 0) {
@@ -840,6 +855,7 @@ extern "C" int gg_bin_tiles(int n, int n_views, const float* xys, int xy_stride,
         launches += 4;
     }
     count_launch(launches);
-    if (info_host) GG_CUDA(cudaMemcpyAsync(info_host, info, sizeof(int32_t) * 4, cudaMemcpyDeviceToHost, st));
+    if (info_host && !info_mapped)
+        GG_CUDA(cudaMemcpyAsync(info_host, info, sizeof(int32_t) * 4, cudaMemcpyDeviceToHost, st));
     return check_launch("gg_bin_tiles");
 }

@@ -44,16 +44,27 @@ __device__ __forceinline__ void finish_sums(float (&acc)[kK], float* partial, un
         last = atomicAdd(counter, 1u) == gridDim.x - 1;
     }
     __syncthreads();
-    if (last && threadIdx.x == 0) {
+    if (last) {
+        // fixed-order sum of the partials by the whole last block (deterministic)
+        __shared__ double tree[256];
         __threadfence();
 #pragma unroll
         for (int k = 0; k < kK; ++k) {
             double s = 0.0;
-            for (unsigned b = 0; b < gridDim.x; ++b) s += (double)((volatile float*)partial)[k * kLossBlocks + b];
-            const float v = (float)(s * (double)scale[k]);
-            out[k] = accumulate ? out[k] + v : v;
+            for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) s += (double)__ldcg(partial + k * kLossBlocks + b);
+            tree[threadIdx.x] = s;
+            __syncthreads();
+            for (int o = 128; o > 0; o >>= 1) {
+                if ((int)threadIdx.x < o && threadIdx.x + o < blockDim.x) tree[threadIdx.x] += tree[threadIdx.x + o];
+                __syncthreads();
+            }
+            if (threadIdx.x == 0) {
+                const float v = (float)(tree[0] * (double)scale[k]);
+                out[k] = accumulate ? out[k] + v : v;
+            }
+            __syncthreads();
         }
-        *counter = 0u;  // ready for the next call
+        if (threadIdx.x == 0) *counter = 0u;  // ready for the next call
     }
 }
 

@@ -502,12 +502,23 @@ pixel_loss_kernel(long long n, int channels, const float* __restrict__ pred, con
         last = atomicAdd(counter, 1u) == gridDim.x - 1;
     }
     __syncthreads();
-    if (last && threadIdx.x == 0) {
+    if (last) {
+        // the last block to finish adds the partials in a fixed order (deterministic): strided per thread, then a
+        // shared-memory tree -- one thread walking 2048 partials alone was most of this kernel's time
+        __shared__ double tree[256];
         __threadfence();
         double s = 0.0;
-        for (unsigned b = 0; b < gridDim.x; ++b) s += (double)((volatile float*)partial)[b];
-        *loss = (float)(s * (double)scale);
-        *counter = 0u;  // ready for the next call
+        for (unsigned b = threadIdx.x; b < gridDim.x; b += 256) s += (double)__ldcg(partial + b);
+        tree[threadIdx.x] = s;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if ((int)threadIdx.x < o) tree[threadIdx.x] += tree[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            *loss = (float)(tree[0] * (double)scale);
+            *counter = 0u;  // ready for the next call
+        }
     }
 }
 
