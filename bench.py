@@ -102,11 +102,14 @@ SETUP_STEPS = 3   # untimed initialisation before the warm-up: first-call capaci
                   # allocator growth, NCCL communicator set-up.  Not counted as warm-up, never timed.
 
 
-def _exchange_mode(multicast: bool) -> str:
-    mode = os.environ.get("GG_NVLS_MODE", "1")
-    if mode == "0" and multicast:
+def _exchange_mode(multicast: bool, world: int, bucket_bytes: int) -> str:
+    """Which form of the exchange kernel csrc/exchange.cu picks for the bucket reduction (same rule as there)."""
+    mode = os.environ.get("GG_NVLS_MODE", "")
+    if mode not in ("0", "1", "2") or (mode in ("0", "2") and not multicast):
+        mode = "0" if (multicast and world >= 4 and bucket_bytes >= (80 << 20)) else "1"
+    if mode == "0":
         return "NVLS multimem.ld_reduce / multimem.st"
-    if mode == "2" and multicast:
+    if mode == "2":
         return "peer loads + multimem.st"
     return "peer loads / stores over NVLink, fixed summation order" + ("; multicast mapping available" if multicast else "")
 
@@ -326,7 +329,7 @@ def run_ours(args, sub=False):
             try:   # one kernel of this library over symmetric memory (multimem through the NVSwitch)
                 from gaussiangrasper_b200.distributed import NvlsExchange
                 ex = NvlsExchange(P, chunks[0].n_views)
-                transport = "gg_nvls_exchange kernel over symmetric memory (%s)" % _exchange_mode(ex.multicast)
+                transport = "gg_nvls_exchange kernel over symmetric memory (%s)" % _exchange_mode(ex.multicast, world, ex.bucket.flat.numel() * 4)
             except Exception as e:   # no symmetric memory on this box: NCCL collectives
                 if args.transport == "nvls":
                     raise
@@ -343,7 +346,7 @@ def run_ours(args, sub=False):
             try:   # plain all-reduce of every leaf gradient, as this library's two-shot NVLS kernel
                 from gaussiangrasper_b200.distributed import SymmetricBucket
                 bucket = SymmetricBucket(P)
-                transport = "gg_nvls_exchange kernel over symmetric memory, reduction only (%s)" % _exchange_mode(bucket.multicast)
+                transport = "gg_nvls_exchange kernel over symmetric memory, reduction only (%s)" % _exchange_mode(bucket.multicast, world, bucket.flat.numel() * 4)
             except Exception as e:
                 if args.transport == "nvls":
                     raise

@@ -67,6 +67,35 @@ __device__ __forceinline__ BoxOf load_box(long long i, long long total, int n, c
     return b;
 }
 
+// The three loads of a row, none depending on another (load_box reads the centre only when the radius is positive:
+// two dependent DRAM latencies).  The shared-memory kernels below issue them one iteration ahead of their use.
+struct RawRow {
+    int r;
+    float2 c;
+    float d;
+};
+template <bool kDepth>
+__device__ __forceinline__ RawRow load_raw(long long i, bool in_range, const float* __restrict__ xys, int xy_stride,
+                                           const float* __restrict__ depths, const int32_t* __restrict__ radii) {
+    RawRow w{0, make_float2(0.0f, 0.0f), 0.0f};
+    if (in_range) {
+        w.r = __ldg(radii + i);
+        w.c = __ldg(reinterpret_cast<const float2*>(xys + i * xy_stride));
+        if (kDepth) w.d = __ldg(depths + i);
+    }
+    return w;
+}
+// the box of a loaded row, tile ids local to the view
+__device__ __forceinline__ BoxOf box_of(const RawRow& w, int tiles_x, int tiles_y) {
+    BoxOf b{0, 0, 1, 0, 0};
+    if (w.r > 0) {
+        const TileBox tb = tile_box(w.c.x, w.c.y, (float)w.r, tiles_x, tiles_y);
+        b.x0 = tb.x0; b.y0 = tb.y0; b.w = max(tb.x1 - tb.x0, 1);
+        b.cnt = max(tb.area(), 0);
+    }
+    return b;
+}
+
 __global__ void __launch_bounds__(256)
 tile_count_kernel(long long total, int n, const float* __restrict__ xys, int xy_stride,
                   const int32_t* __restrict__ radii, int tiles_x, int tiles_y, int* __restrict__ counts) {
@@ -138,10 +167,12 @@ tile_hist_kernel(int n, int per, const float* __restrict__ xys, int xy_stride, c
     __syncthreads();
     const int lo = min(n, (int)blockIdx.x * per), hi = min(n, lo + per);
     const long long vbase = (long long)view * n;
+    RawRow next = load_raw<false>(vbase + lo + threadIdx.x, lo + (int)threadIdx.x < hi, xys, xy_stride, nullptr, radii);
     for (int i0 = lo; i0 < hi; i0 += kHistThreads) {
-        const int g = i0 + threadIdx.x;
-        BoxOf b = load_box(g < hi ? vbase + g : -1, vbase + hi, n, xys, xy_stride, radii, tiles_x, tiles_y);
-        b.tile0 = 0;  // tile ids local to the view
+        const RawRow cur = next;
+        const int gn = i0 + kHistThreads + threadIdx.x;
+        next = load_raw<false>(vbase + gn, gn < hi, xys, xy_stride, nullptr, radii);
+        const BoxOf b = box_of(cur, tiles_x, tiles_y);
         GG_SMALL_BOX_LOOP(b, atomicAdd(&sh_hist[tile], 1);)
         GG_BIG_BOX_LOOP(b, 0ull, atomicAdd(&sh_hist[tile], 1);)
     }
@@ -165,12 +196,15 @@ tile_place_kernel(int n, int per, const float* __restrict__ xys, int xy_stride, 
     __syncthreads();
     const int lo = min(n, (int)blockIdx.x * per), hi = min(n, lo + per);
     const long long vbase = (long long)view * n;
+    RawRow next = load_raw<true>(vbase + lo + threadIdx.x, lo + (int)threadIdx.x < hi, xys, xy_stride, depths, radii);
     for (int i0 = lo; i0 < hi; i0 += kHistThreads) {
         const int g = i0 + threadIdx.x;
-        BoxOf b = load_box(g < hi ? vbase + g : -1, vbase + hi, n, xys, xy_stride, radii, tiles_x, tiles_y);
-        b.tile0 = 0;
+        const RawRow cur = next;
+        const int gn = g + kHistThreads;
+        next = load_raw<true>(vbase + gn, gn < hi, xys, xy_stride, depths, radii);
+        const BoxOf b = box_of(cur, tiles_x, tiles_y);
         unsigned long long rec = 0ull;
-        if (b.cnt > 0) rec = ((unsigned long long)__float_as_uint(depths[vbase + g]) << 32) | (unsigned)g;
+        if (b.cnt > 0) rec = ((unsigned long long)__float_as_uint(cur.d) << 32) | (unsigned)g;
         GG_SMALL_BOX_LOOP(b, { const int pos = atomicAdd(&sh_cur[tile], 1); if (pos >= 0 && pos < capacity) pairs[pos] = rec; })
         GG_BIG_BOX_LOOP(b, rec, { const int pos = atomicAdd(&sh_cur[tile], 1); if (pos >= 0 && pos < capacity) pairs[pos] = r; })
     }

@@ -16,8 +16,9 @@
 //     no intermediate buffer and no reduction arithmetic on the SMs.
 // The same schedule also runs over the peers' mapped addresses with plain ld.global / st.global (W loads in flight
 // per element, fixed summation order: every rank computes the same bits) -- and that is the DEFAULT: on this pool's
-// NVSwitch boxes it measured faster than the multimem form at 2 and at 8 ranks (profiles/r02_exchange_tuning.txt);
-// GG_NVLS_MODE=0 / 2 select multimem everywhere / peer loads + multimem stores.  The caller brackets the launch with cross-rank barriers (the symmetric-memory signal
+// NVSwitch boxes it measured faster than the multimem form at 2 ranks and, for buckets of config 1's size, at 8
+// (profiles/r02_exchange_tuning.txt); reductions of >= 80 MB over >= 4 ranks take the multimem form (fewer bytes per
+// link).  GG_NVLS_MODE=0 / 1 / 2 force multimem / peer / peer loads + multimem stores.  The caller brackets the launch with cross-rank barriers (the symmetric-memory signal
 // pads): one before (every rank's backward has written its bucket and slot), one after (every slice is back).
 #include "gg_common.cuh"
 #include "gg_b200.h"
@@ -148,10 +149,14 @@ extern "C" int gg_nvls_exchange(int rank, int world, float* bucket_multicast, fl
         if (v >= 1 && v <= 148 * 16) blocks = v;
     }
     // mode 0: multimem.ld_reduce + multimem.st, 1: peer loads and stores, 2: peer loads + multimem.st.
-    // Default 1: measured fastest on this pool's boxes at 2 ranks (0.150 vs 0.229 ms) and at 8 ranks (0.294 vs 0.312
-    // / 0.323 ms), profiles/r02_exchange_tuning.txt; GG_NVLS_MODE selects the multimem variants where a multicast
-    // mapping exists.
+    // Default: peer loads and stores -- measured fastest at 2 ranks (0.150 vs 0.229 ms) and, for config 1's 54 MB
+    // bucket, at 8 ranks (0.294 vs 0.312 / 0.323 ms), profiles/r02_exchange_tuning.txt.  The peer form moves
+    // 2 (W-1)/W of the bucket per GPU and direction, the multimem form 1x (the switch adds and replicates): with
+    // many ranks and a large bucket the bytes decide -- configs[3]'s 108 MB bucket at 8 ranks took 0.84 ms through
+    // multimem and 1.09 ms through peer loads -- so reductions of >= 80 MB over >= 4 ranks go through the switch.
+    // GG_NVLS_MODE overrides (the multimem forms need a multicast mapping).
     int mode = 1;
+    if (bucket_multicast && (parts & 2) && world >= 4 && bucket_floats * 4ll >= (80ll << 20)) mode = 0;
     if (const char* e = getenv("GG_NVLS_MODE")) {
         const int v = atoi(e);
         if (v == 1 || (bucket_multicast && (v == 0 || v == 2))) mode = v;

@@ -202,18 +202,30 @@ prepare_views_kernel(const PrepArgs a, float* __restrict__ geo, float* __restric
 
 // Channel rows for ALL views of a batch in one pass over the Gaussians (phase 2 of the fused
 // path): the 300-byte SH row, the feature row and the quaternion are read once per Gaussian and
-// reused for every view, instead of once per (view, Gaussian).  Per view only radii/depths are read
-// and the CP-float row is written (coalesced through shared memory).
+// reused for every view, instead of once per (view, Gaussian).  Per view only the depth is read and the
+// CP-float row is written (coalesced through shared memory).
+//
+// Shared memory per warp: slab [32][row | 1] SH coefficients -- the ODD row stride puts coefficient k of the 32
+// lanes' rows in 32 different banks (with the dense stride of 48 floats every read was a 16-way conflict, and the
+// V x 48 reads per Gaussian were the whole kernel) -- and rbuf [32][cp], the channel rows: features, normal and
+// padding are written once, each view only rewrites rgb + depth of its visible rows; rows culled in a view are
+// stored as zeros straight from the copy-out loop.
+__device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+
+__host__ __device__ __forceinline__ int chan_slab_stride(int row) { return row | 1; }
+
 __global__ void __launch_bounds__(kPrepThreads)
 prepare_chan_kernel(const PrepArgs a, float* __restrict__ chan, const float* __restrict__ depths,
                     const int32_t* __restrict__ radii) {
     extern __shared__ __align__(16) float sm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = a.nb * 3, D = a.feat_dim, cp = a.cp;
-    const int per_warp = 32 * (row + D + cp);
-    float* slab = sm + (size_t)warp * per_warp;   // [32][row]  SH coefficients
-    float* fslab = slab + 32 * row;               // [32][D]    features
-    float* rbuf = fslab + 32 * D;                 // [32][cp]   channel rows of the current view
+    const int srow = chan_slab_stride(row);
+    float* slab = sm + (size_t)warp * 32 * (srow + cp);   // [32][srow]  SH coefficients
+    float* rbuf = slab + 32 * srow;                       // [32][cp]    channel rows
     const long long first = ((long long)blockIdx.x * kPrepWarps + warp) * 32;
     if (first >= a.n) return;
     const long long i = first + lane;
@@ -226,61 +238,78 @@ prepare_chan_kernel(const PrepArgs a, float* __restrict__ chan, const float* __r
             if (radii[(long long)v * a.n + i] > 0) vismask |= 1u << (v & 31);
     const bool many_views = a.n_views > 32;  // the bit mask is only a hint then
     if (!many_views && !__any_sync(0xffffffffu, vismask != 0)) return;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + (size_t)kPrepWarps * per_warp) + warp;
-    const bool bulk = rows_here == 32;
-    if (bulk) {
-        if (lane == 0) {
-            mbar_init(bar, 1);
-            bulk_load(slab, a.sh + first * row, (uint32_t)(32 * row * sizeof(float)), bar);
-        }
-    } else {
+    {   // SH coefficients: coalesced 4-byte async copies into the odd-stride rows
         const float* gspan = a.sh + first * row;
-        for (int k = lane; k < rows_here * row; k += 32) slab[k] = __ldg(gspan + k);
+        int l = 0, j = lane;
+        while (j >= row) { j -= row; ++l; }
+        for (int k = lane; k < rows_here * row; k += 32) {
+            cp_async_f32(slab + l * srow + j, gspan + k);
+            j += 32;
+            while (j >= row) { j -= row; ++l; }
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
     }
-    {
+    {   // feature rows (one coalesced span) and the zero padding
         const float* fspan = a.features + first * D;
-        for (int k = lane; k < rows_here * D; k += 32) fslab[k] = __ldg(fspan + k);
+        for (int k = lane; k < rows_here * D; k += 32) {
+            const int l = k / D, d = k - l * D;
+            rbuf[l * cp + 7 + d] = __ldg(fspan + k);
+        }
+        for (int d = 7 + D; d < cp; ++d) rbuf[lane * cp + d] = 0.0f;
     }
-    float p[3] = {0.f, 0.f, 0.f}, nrm[3] = {0.f, 0.f, 0.f};
+    float p[3] = {0.f, 0.f, 0.f};
+    float* r = rbuf + lane * cp;
     if (active) {
         const Activated g = load_activated(a, i);
         p[0] = g.p[0]; p[1] = g.p[1]; p[2] = g.p[2];
         const Rot3 R = quat_to_rot(g.qh[0], g.qh[1], g.qh[2], g.qh[3]);
-        nrm[0] = R.m[g.kmin]; nrm[1] = R.m[3 + g.kmin]; nrm[2] = R.m[6 + g.kmin];
+        r[4] = R.m[g.kmin]; r[5] = R.m[3 + g.kmin]; r[6] = R.m[6 + g.kmin];
     }
+    auto visible = [&](int v) -> bool {
+        if (!many_views) return (vismask >> v) & 1u;
+        return active && radii[(long long)v * a.n + i] > 0;
+    };
+    // depth of the next view is requested before this view's rows are built
+    bool vis_next = visible(0);
+    float dep_next = vis_next ? __ldg(depths + i) : 0.0f;
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     __syncwarp();
-    if (bulk) mbar_wait(bar, 0);
     const int nuse = sh_num_bases(a.deg_use);
-    const float* cf = slab + lane * row;
-    const float* fr = fslab + lane * D;
-    float* r = rbuf + lane * cp;
+    const float* cf = slab + lane * srow;
+    const int vec_per_row = cp >> 2;                 // cp is a multiple of 4
+    const int nvec = rows_here * vec_per_row;
     for (int v = 0; v < a.n_views; ++v) {
-        const long long vrow = (long long)v * a.n + i;
-        const bool vis = active && radii[vrow] > 0;
-        if (!__any_sync(0xffffffffu, vis)) continue;
+        const bool vis = vis_next;
+        const float dep = dep_next;
+        if (v + 1 < a.n_views) {
+            vis_next = visible(v + 1);
+            dep_next = vis_next ? __ldg(depths + (long long)(v + 1) * a.n + i) : 0.0f;
+        }
+        const unsigned vm = __ballot_sync(0xffffffffu, vis);
+        if (!vm) continue;
         if (vis) {
             float Y[25];
             sh_basis(a.deg_use, p[0] - __ldg(a.positions + 3 * v), p[1] - __ldg(a.positions + 3 * v + 1),
                      p[2] - __ldg(a.positions + 3 * v + 2), Y);
             float rgb[3] = {0.f, 0.f, 0.f};
-            for (int b = 0; b < nuse; ++b) {
 #pragma unroll
-                for (int c = 0; c < 3; ++c) rgb[c] = rgb[c] + Y[b] * cf[3 * b + c];
+            for (int b = 0; b < 25; ++b) {  // fully unrolled: Y stays in registers
+                if (b < nuse) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) rgb[c] = rgb[c] + Y[b] * cf[3 * b + c];
+                }
             }
 #pragma unroll
             for (int c = 0; c < 3; ++c) r[c] = fminf(1.0f, fmaxf(0.0f, rgb[c] + 0.5f));
-            r[3] = depths[vrow];
-            r[4] = nrm[0]; r[5] = nrm[1]; r[6] = nrm[2];
-            for (int d = 0; d < D; ++d) r[7 + d] = fr[d];
-            for (int d = 7 + D; d < cp; ++d) r[d] = 0.0f;
-        } else {
-            for (int d = 0; d < cp; ++d) r[d] = 0.0f;
+            r[3] = dep;
         }
         __syncwarp();
         float4* g4 = reinterpret_cast<float4*>(chan + ((long long)v * a.n + first) * cp);
         const float4* s4 = reinterpret_cast<const float4*>(rbuf);
-        const int nvec = (rows_here * cp) >> 2;
-        for (int k = lane; k < nvec; k += 32) g4[k] = s4[k];
+        for (int k = lane; k < nvec; k += 32) {
+            const int l = k / vec_per_row;
+            g4[k] = ((vm >> l) & 1u) ? s4[k] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
         __syncwarp();
     }
 }
@@ -525,7 +554,7 @@ extern "C" int gg_prepare_views(int n, int n_views, int feat_dim, int cp, int de
     GG_REQUIRE(geo && chan && depths && radii && num_tiles_hit, "gg_prepare_views: null output pointer");
     GG_REQUIRE(((uintptr_t)geo & 15) == 0 && ((uintptr_t)chan & 15) == 0, "gg_prepare_views: geo/chan misaligned");
     if (phase == 2 && n_views > 1) {  // one view: the per-view kernel below has the better occupancy
-        const size_t smem2 = sizeof(float) * kPrepWarps * 32 * (size_t)(a.nb * 3 + feat_dim + cp) + sizeof(uint64_t) * kPrepWarps;
+        const size_t smem2 = sizeof(float) * kPrepWarps * 32 * (size_t)(chan_slab_stride(a.nb * 3) + cp);
         GG_CUDA(cudaFuncSetAttribute(prepare_chan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         prepare_chan_kernel<<<div_up(n, kPrepThreads), kPrepThreads, smem2, (cudaStream_t)stream>>>(a, chan, depths,
                                                                                                    radii);

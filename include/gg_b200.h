@@ -136,8 +136,10 @@ int gg_bin_finish(int n, int n_views, long long m, const float* xys, int xy_stri
  * formulation above, bit for bit): per-tile counts -> scan (tile_ranges, the intersection count M and the
  * capacity check stay on the device) -> entries scattered into their tile's segment -> every tile sorted by
  * (depth bits, id) in shared memory.  `capacity` = entries ids_sorted (and the scratch) can hold; info
- * (device, nullable: kept in the scratch) / info_host (pinned host, nullable; valid once the stream has
- * passed this call) receive {M, overflow, longest tile list, 0}.  If M > capacity nothing is binned: overflow = 1,
+ * (device, nullable: kept in the scratch) / info_host (host, nullable; valid once the stream has
+ * passed this call) receive {M, overflow, longest tile list, 0}.  A 16-byte aligned pinned info_host is written by
+ * the scan kernel itself through its device mapping (no copy on the stream); any other host pointer gets a
+ * stream-ordered cudaMemcpyAsync.  If M > capacity nothing is binned: overflow = 1,
  * every tile range is (0,0) (the blend kernels then render the background only) and the caller repeats the call
  * with capacity >= M.  capacity = 0 only counts.  The scratch needs no initialisation.
  * longest_hint: the longest tile list an earlier call reported (info[2]) or 0 if unknown; it only decides
