@@ -755,8 +755,13 @@ struct Bin2Layout {
 };
 
 // CTAs per view and Gaussians per CTA of the shared-memory counting / placement kernels
-static void hist_blocks(int n, int n_views, int& blocks, int& per) {
-    int b = kHistBlocksTotal / n_views;
+static void hist_blocks(int n, int n_views, long long tiles_per_view, int& blocks, int& per) {
+    // every placing CTA keeps one partially written 128-byte line open per tile: beyond ~half the L2 of open lines
+    // the records are evicted half-filled and fetched again (config 2: 2.2 GB written for 1.1 GB of records), so
+    // large tile grids run one CTA per SM instead of two (measured 33.9 -> 32.4 ms of binning per step there)
+    const int total_blocks = (long long)kHistBlocksTotal * tiles_per_view * 128 > (64ll << 20) ? kHistBlocksTotal / 2
+                                                                                                : kHistBlocksTotal;
+    int b = total_blocks / n_views;
     if (b < 1) b = 1;
     const int by_work = (n + kHistThreads - 1) / kHistThreads;
     if (b > by_work) b = by_work;
@@ -828,7 +833,7 @@ extern "C" int gg_bin_tiles(int n, int n_views, const float* xys, int xy_stride,
             (void)cudaGetLastError();
     }
     int blocks = 1, per = n;
-    hist_blocks(n, n_views, blocks, per);
+    hist_blocks(n, n_views, T, blocks, per);
     const size_t hist_smem = sizeof(int) * (size_t)T;
     int launches = 0;
     // the 1024-thread bucket class (8193 .. 24576 entries) is launched only when such tiles are expected; a tile

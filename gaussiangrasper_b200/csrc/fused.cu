@@ -468,7 +468,7 @@ sh_grad_views_kernel(int n, int n_views, int deg_use, const float* __restrict__ 
     if (active) {
         const float px = __ldg(means + 3 * i), py = __ldg(means + 3 * i + 1), pz = __ldg(means + 3 * i + 2);
         const int nuse = sh_num_bases(deg_use);
-        constexpr int kPre = 4;  // factors of kPre views are in flight before the first is used
+        constexpr int kPre = NB > 16 ? 4 : 8;  // factors of kPre views are in flight before the first is used
         for (int v0 = 0; v0 < n_views; v0 += kPre) {
             float f[kPre][3];
 #pragma unroll

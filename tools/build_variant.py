@@ -14,7 +14,7 @@ nvcc = B._nvcc()
 objs, procs = [], []
 for src, extra in B.UNITS:
     path = os.path.join(B.CSRC, src)
-    touched = src == "blend.cu"          # the experiments so far only touch the blend kernels
+    touched = src in os.environ.get("GG_VARIANT_UNITS", "blend.cu").split(",")   # units the -D flags apply to
     obj = os.path.join(out_dir if touched else obj_dir, (f"{name}_" if touched else "") + src.replace(".cu", ".o"))
     objs.append(obj)
     if touched or not os.path.exists(obj) or os.path.getmtime(obj) < os.path.getmtime(path):
