@@ -77,17 +77,21 @@ __device__ __forceinline__ Activated load_activated(const PrepArgs& a, long long
     return g;
 }
 
+// (forcing 6 / 7 resident CTAs -- 80 / 72 registers, spills -- measured slower: 0.079 / 0.080 vs 0.073 ms at config 1)
 __global__ void __launch_bounds__(kPrepThreads)
 prepare_views_kernel(const PrepArgs a, float* __restrict__ geo, float* __restrict__ chan,
                      float* __restrict__ depths, int32_t* __restrict__ radii, int32_t* __restrict__ num_tiles_hit,
-                     float* __restrict__ scales_out, float* __restrict__ quats_out, int slab_row, int phase) {
+                     float* __restrict__ scales_out, float* __restrict__ quats_out, int slab_row, int phase,
+                     int feat_bulk) {
     // phase 0: everything; 1: geometry only (geo, depths, radii, num_tiles_hit); 2: channel rows
     // only, from the radii / depths phase 1 left behind.  The split lets the host read the number
     // of intersections (needed to size the sort) while phase 2 keeps the GPU busy.
     extern __shared__ __align__(16) float sm[];
     const int view = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* slab = sm + (size_t)warp * 32 * slab_row;
+    const int fcols = feat_bulk ? a.feat_dim : 0;          // feature rows staged next to the SH slab
+    float* slab = sm + (size_t)warp * 32 * (slab_row + fcols);
+    float* fbuf = slab + 32 * slab_row;                    // [32][D]
     const long long first = ((long long)blockIdx.x * kPrepWarps + warp) * 32;
     if (first >= a.n) return;  // whole warp; no block-level barrier is used in this kernel
     const long long i = first + lane;
@@ -96,14 +100,17 @@ prepare_views_kernel(const PrepArgs a, float* __restrict__ geo, float* __restric
     const long long vrow = (long long)view * a.n + i;
     // ---- SH coefficients of the warp's 32 Gaussians: one contiguous span.  A full warp moves it with a single
     // bulk copy (TMA engine), issued BEFORE the projection arithmetic so that the biggest transfer of the kernel
-    // (9.6 KB per warp) is in flight while the warp computes; the feature rows are prefetched into registers ----
+    // (9.6 KB per warp) is in flight while the warp computes; the warp's feature rows (one contiguous span too)
+    // ride on the same barrier, so that the row assembly below does not pay a second DRAM latency ----
     const int row = a.nb * 3;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + (size_t)kPrepWarps * 32 * slab_row) + warp;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + (size_t)kPrepWarps * 32 * (slab_row + fcols)) + warp;
     const bool bulk = rows_here == 32 && phase != 1;
+    const bool fbulk = bulk && fcols > 0;
     if (bulk) {
         if (lane == 0) {
-            mbar_init(bar, 1);
+            mbar_init(bar, fbulk ? 2 : 1);
             bulk_load(slab, a.sh + first * row, (uint32_t)(32 * row * sizeof(float)), bar);
+            if (fbulk) bulk_load(fbuf, a.features + first * fcols, (uint32_t)(32 * fcols * sizeof(float)), bar);
         }
         __syncwarp();
     }
@@ -187,7 +194,7 @@ prepare_views_kernel(const PrepArgs a, float* __restrict__ geo, float* __restric
         const float* fspan = a.features + first * D;
         for (int k = lane; k < rows_here * D; k += 32) {
             const int l = k / D, d = k - l * D;
-            slab[l * a.cp + 7 + d] = ((vismask >> l) & 1u) ? __ldg(fspan + k) : 0.0f;
+            slab[l * a.cp + 7 + d] = ((vismask >> l) & 1u) ? (fbulk ? fbuf[k] : __ldg(fspan + k)) : 0.0f;
         }
     }
     __syncwarp();
@@ -562,12 +569,15 @@ extern "C" int gg_prepare_views(int n, int n_views, int feat_dim, int cp, int de
         return check_launch("prepare_chan_kernel");
     }
     const int slab_row = a.nb * 3 > cp ? a.nb * 3 : cp;
-    const size_t smem = sizeof(float) * kPrepWarps * 32 * (size_t)slab_row + sizeof(uint64_t) * kPrepWarps;
+    // the feature rows travel as a bulk copy too when their spans are 16-byte aligned (32 rows = 128 D bytes)
+    const int feat_bulk = (feat_dim > 0 && phase != 1 && ((uintptr_t)features & 15) == 0) ? 1 : 0;
+    const size_t smem = sizeof(float) * kPrepWarps * 32 * (size_t)(slab_row + (feat_bulk ? feat_dim : 0)) +
+                        sizeof(uint64_t) * kPrepWarps;
     GG_CUDA(cudaFuncSetAttribute(prepare_views_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(div_up(n, kPrepThreads), n_views);
     prepare_views_kernel<<<grid, kPrepThreads, smem, (cudaStream_t)stream>>>(a, geo, chan, depths, radii,
                                                                              num_tiles_hit, scales_out, quats_out,
-                                                                             slab_row, phase);
+                                                                             slab_row, phase, feat_bulk);
     count_launch();
     return check_launch("prepare_views_kernel");
 }
