@@ -19,6 +19,7 @@
 // per pixel.  blend_bwd_kernel is the CTA-staged fallback for launches without hit masks (C > 64 column blocks).
 #include "gg_common.cuh"
 #include "gg_geo.cuh"
+#include "gg_tma.cuh"
 #include "gg_b200.h"
 
 #ifndef GG_BWD_DOT4
@@ -35,6 +36,11 @@
 // colour accumulation of the forward on mma.sync TF32 (3xTF32 split), see blend_fwd_kernel
 #ifndef GG_FWD_MMA
 #define GG_FWD_MMA 0
+#endif
+// forward staging ring synchronised by mbarriers (data-ready / buffer-free) instead of one CTA barrier per batch:
+// a warp only waits for the copies and for the buffer it refills, so it may run one batch ahead of the slowest
+#ifndef GG_FWD_RING
+#define GG_FWD_RING 0
 #endif
 #ifndef GG_BWD_MIN_BLOCKS
 #define GG_BWD_MIN_BLOCKS 5
@@ -89,6 +95,15 @@ __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+// this thread's earlier cp.async copies arrive on the mbarrier when they have landed
+__device__ __forceinline__ void cp_async_arrive_on(uint64_t* bar) {
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(b) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(b) : "memory");
+}
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
@@ -223,20 +238,45 @@ blend_fwd_kernel(const BlendArgs a) {
     const int nb = (total + BATCH - 1) / BATCH;
     // kStages-deep ring of staging buffers: batch b+2 is issued while batch b is blended, and one
     // barrier per batch both publishes batch b and retires the buffer batch b+2 will overwrite
+#if GG_FWD_RING
+    __shared__ uint64_t full_bar[kStages], empty_bar[kStages];
+    __shared__ int done_warps;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s_ = 0; s_ < kStages; ++s_) { mbar_init(&full_bar[s_], kBlendThreads); mbar_init(&empty_bar[s_], kBlendThreads / 32); }
+        done_warps = 0;
+    }
+    __syncthreads();
+    bool counted = false;
+#endif
     auto stage = [&](int b) {
         const int first = range.x + b * BATCH;
         const int buf = b % kStages;
         stage_batch<CP, BATCH, kVec>(a, geo_base, color_base, first, min(BATCH, range.y - first),
                                      geo_sm + buf * BATCH * 8, col_sm + buf * BATCH * CP);
+#if GG_FWD_RING
+        cp_async_arrive_on(&full_bar[buf]);
+#else
         cp_async_commit();
+#endif
     };
     if (nb > 0) stage(0);
     if (nb > 1) stage(1);
     for (int b = 0; b < nb; ++b) {
         const int buf = b % kStages;
+#if GG_FWD_RING
+        mbar_wait(&full_bar[buf], (unsigned)((b / kStages) & 1));            // every thread's copies of batch b landed
+        if (*reinterpret_cast<volatile int*>(&done_warps) == kBlendThreads / 32) break;
+        if (b + 2 < nb) {
+            // the buffer batch b+2 goes into was batch b-1's: every warp must have left it
+            if (b >= 1) mbar_wait(&empty_bar[(b - 1) % kStages], (unsigned)(((b - 1) / kStages) & 1));
+            stage(b + 2);
+        }
+#else
         if (b + 1 < nb) cp_async_wait<1>(); else cp_async_wait<0>();
         if (__syncthreads_count(warp_done) == kBlendThreads) break;
         if (b + 2 < nb) stage(b + 2);
+#endif
         const int first = range.x + b * BATCH;
         const int cnt = min(BATCH, range.y - first);
         if (!warp_done) {
@@ -367,8 +407,20 @@ blend_fwd_kernel(const BlendArgs a) {
                     if (lane_id == k) dst[k] = hits[k];
             }
         }
+#if GG_FWD_RING
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) {
+            if (warp_done && !counted) atomicAdd(&done_warps, 1);
+            mbar_arrive_cta(&empty_bar[buf]);                                   // this warp is out of batch b's buffer
+        }
+        counted = counted || warp_done;
+#endif
     }
+#if GG_FWD_RING
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+#else
     cp_async_wait<0>();
+#endif
     if constexpr (kMma) {
         // D fragments -> image: this lane holds pixels (16 mt + lane/4, +8) of the warp's 8x4 block, whose
         // transmittance sits in the lanes of those pixels
