@@ -370,6 +370,40 @@ def test_tile_binning_overflow_is_reported_and_recovered(dev):
     run(small)
 
 
+def test_bin_tiles_info_record_pinned_and_pageable(dev):
+    """gg_bin_tiles through the C ABI: the {M, overflow, longest, 0} record must reach a pinned host buffer (stored by
+    the scan kernel through its device mapping) and a pageable one (stream-ordered copy) alike."""
+    import ctypes
+    from gaussiangrasper_b200 import _lib, ops
+    xys, depths, radii, nth, tb = _synthetic_projection(20_000, 320, 240, 21, radius_hi=20)
+    n = len(radii)
+    _, _, _, _, ids_s, ranges = c_oracle.bin_and_sort(xys, depths, radii, nth, tb)
+    m = len(ids_s)
+    t = lambda a: torch.from_numpy(a).to(dev)
+    d_xys, d_depths, d_radii = t(xys), t(depths), t(radii)
+    T = tb[0] * tb[1]
+    cap = m + 1000
+    lib = _lib.load()
+    nbytes = int(lib.gg_bin_tiles_scratch_bytes(1, T, cap))
+    stream = ops.stream_ptr(torch.device(dev))
+    pinned = torch.full((4,), -1, dtype=torch.int32).pin_memory()
+    pageable = np.full(8, -1, dtype=np.int32)[1:5]     # neither pinned nor 16-byte aligned
+    for host_ptr, read in ((pinned.data_ptr(), lambda: pinned.numpy().copy()),
+                           (pageable.ctypes.data, lambda: pageable.copy())):
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        ids = torch.empty(cap, dtype=torch.int32, device=dev)
+        rng_t = torch.empty((T, 2), dtype=torch.int32, device=dev)
+        order = torch.empty(T, dtype=torch.int32, device=dev)
+        with _lib.device_guard(torch.device(dev)):
+            _lib.call("gg_bin_tiles", n, 1, ops.ptr(d_xys), 2, ops.ptr(d_depths), ops.ptr(d_radii), tb[0], tb[1], cap,
+                      ops.ptr(scratch), nbytes, ops.ptr(ids), ops.ptr(rng_t), ops.ptr(order), None, host_ptr, 0, stream)
+        torch.cuda.synchronize()
+        rec = read()
+        lens = ranges[:, 1] - ranges[:, 0]
+        assert rec.tolist() == [m, 0, int(lens.max()), 0], rec
+        assert np.array_equal(ids[:m].cpu().numpy(), ids_s)
+
+
 # ---------------------------------------------------------------------------------------------
 def compare_image(got, ref, frag, what):
     ok = ~frag
