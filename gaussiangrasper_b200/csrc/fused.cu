@@ -224,6 +224,17 @@ __device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gmem_
 
 __host__ __device__ __forceinline__ int chan_slab_stride(int row) { return row | 1; }
 
+// rgb += sum_b Y[b] * coefficient row b, in the order of the per-view kernel (b ascending, channel inner); the
+// basis count is a template parameter so that the unrolled loop carries no per-term predicate
+template <int NUSE>
+__device__ __forceinline__ void sh_dot(const float* __restrict__ Y, const float* __restrict__ cf, float (&rgb)[3]) {
+#pragma unroll
+    for (int b = 0; b < NUSE; ++b) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) rgb[c] = rgb[c] + Y[b] * cf[3 * b + c];
+    }
+}
+
 __global__ void __launch_bounds__(kPrepThreads)
 prepare_chan_kernel(const PrepArgs a, float* __restrict__ chan, const float* __restrict__ depths,
                     const int32_t* __restrict__ radii) {
@@ -285,6 +296,8 @@ prepare_chan_kernel(const PrepArgs a, float* __restrict__ chan, const float* __r
     const float* cf = slab + lane * srow;
     const int vec_per_row = cp >> 2;                 // cp is a multiple of 4
     const int nvec = rows_here * vec_per_row;
+    const int row0 = lane / vec_per_row, piece0 = lane - row0 * vec_per_row;      // row / piece of float4 number `lane`
+    const int row_step = 32 / vec_per_row, piece_step = 32 - row_step * vec_per_row;   // ... and of 32 pieces further
     for (int v = 0; v < a.n_views; ++v) {
         const bool vis = vis_next;
         const float dep = dep_next;
@@ -299,12 +312,12 @@ prepare_chan_kernel(const PrepArgs a, float* __restrict__ chan, const float* __r
             sh_basis(a.deg_use, p[0] - __ldg(a.positions + 3 * v), p[1] - __ldg(a.positions + 3 * v + 1),
                      p[2] - __ldg(a.positions + 3 * v + 2), Y);
             float rgb[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-            for (int b = 0; b < 25; ++b) {  // fully unrolled: Y stays in registers
-                if (b < nuse) {
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) rgb[c] = rgb[c] + Y[b] * cf[3 * b + c];
-                }
+            switch (nuse) {   // warp-uniform
+                case 1: sh_dot<1>(Y, cf, rgb); break;
+                case 4: sh_dot<4>(Y, cf, rgb); break;
+                case 9: sh_dot<9>(Y, cf, rgb); break;
+                case 16: sh_dot<16>(Y, cf, rgb); break;
+                default: sh_dot<25>(Y, cf, rgb); break;
             }
 #pragma unroll
             for (int c = 0; c < 3; ++c) r[c] = fminf(1.0f, fmaxf(0.0f, rgb[c] + 0.5f));
@@ -313,9 +326,12 @@ prepare_chan_kernel(const PrepArgs a, float* __restrict__ chan, const float* __r
         __syncwarp();
         float4* g4 = reinterpret_cast<float4*>(chan + ((long long)v * a.n + first) * cp);
         const float4* s4 = reinterpret_cast<const float4*>(rbuf);
+        // piece k of the span belongs to row k / vec_per_row: tracked incrementally (no division per piece)
+        int l = row0, q = piece0;
         for (int k = lane; k < nvec; k += 32) {
-            const int l = k / vec_per_row;
             g4[k] = ((vm >> l) & 1u) ? s4[k] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            l += row_step; q += piece_step;
+            if (q >= vec_per_row) { q -= vec_per_row; ++l; }
         }
         __syncwarp();
     }
