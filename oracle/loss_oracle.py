@@ -1,6 +1,9 @@
 """CPU restatement (torch) of the image losses of GaussianSplattingModel.get_loss_dict.
 
-TEST INFRASTRUCTURE ONLY.  PARITY UNPINNED: `pytorch_msssim` (requirements.txt of the reference) is not
+TEST INFRASTRUCTURE ONLY.  Every term but SSIM is PINNED TO THE REFERENCE: tests/golden/ref_losses_small.npz holds the
+values and gradients of the reference's own get_loss_dict (tests/golden/make_reference_golden.py) and
+tests/test_reference_golden_cpu.py checks this file against them (values to 2e-6, gradients to 2e-5 of the largest
+entry).  SSIM: PARITY UNPINNED -- `pytorch_msssim` (requirements.txt of the reference) is not
 installed here and the reference pins no vectors; `ssim` restates its published algorithm
 (pytorch_msssim/ssim.py: _fspecial_gauss_1d, gaussian_filter, _ssim, ssim with size_average=True,
 nonnegative_ssim=False, K=(0.01, 0.03), win_size 11, win_sigma 1.5) as the reference configures it

@@ -1,8 +1,10 @@
 """CPU restatement (torch, fp32) of the reference's densify / cull step and its Adam-state surgery.
 
 TEST INFRASTRUCTURE ONLY -- imported by tests/ (and nothing else); the product path never touches it.
-PARITY UNPINNED: the reference holds no golden vectors for this step; this file follows the reference
-source line by line instead (nerfstudio/models/gaussian_splatting.py):
+PINNED TO THE REFERENCE: tests/golden/refine_small.npz is the output of the reference's own
+GaussianSplattingModel.refinement_after on real torch.optim.Adam objects (tests/golden/make_reference_golden.py, run
+where /root/reference is mounted); this file reproduces it bit for bit (tests/test_golden.py).  It follows the
+reference source line by line (nerfstudio/models/gaussian_splatting.py):
   refinement_after  :396-464     split_gaussians :485-518     dup_gaussians :520-533
   cull_gaussians    :466-483     dup_in_optim    :352-371     remove_from_optim :333-350
 Parameters use this repository's names (log_scales = model.scales, opacity_logit = model.opacities,

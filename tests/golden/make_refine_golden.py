@@ -1,8 +1,10 @@
 #!/usr/bin/env python
-"""Generates tests/golden/refine_small.npz with the refinement oracle (oracle/refine_oracle.py).
+"""Seeded inputs of the refinement fixture tests/golden/refine_small.npz, and the oracle's version of it.
 
-PARITY UNPINNED (see make_golden.py): these vectors pin the ORACLE's restatement of refinement_after
-(nerfstudio/models/gaussian_splatting.py:396-546) and, through it, the CUDA path; they are not reference outputs.
+The committed refine_small.npz is written by tests/golden/make_reference_golden.py: the REFERENCE's own
+GaussianSplattingModel.refinement_after (nerfstudio/models/gaussian_splatting.py:402-464) run on `inputs(SEED)`.  This
+script runs oracle/refine_oracle.py on the same inputs and reports whether it reproduces the committed file (it does,
+array by array, bit for bit -- tests/test_golden.py::test_refine_oracle_reproduces_golden keeps checking that).
 
     python tests/golden/make_refine_golden.py
 """
@@ -61,5 +63,7 @@ def build():
 
 if __name__ == "__main__":
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "refine_small.npz")
-    np.savez_compressed(path, **build())
-    print(path, os.path.getsize(path), "bytes")
+    ref, mine = np.load(path), build()
+    same = all(np.array_equal(ref[k], v) for k, v in mine.items())
+    print("oracle/refine_oracle.py", "reproduces" if same else "DIFFERS FROM", path)
+    raise SystemExit(0 if same else 1)

@@ -1,0 +1,210 @@
+"""Checks against the fixtures the REFERENCE ITSELF produced (tests/golden/make_reference_golden.py: the unmodified
+nerfstudio/models/gaussian_splatting.py run on seeded inputs): get_loss_dict with its gradients, the k-NN scale
+initialisation and the up-projection MLP.  Each check is written once, against the signatures of the product's loss
+functions (gaussiangrasper_b200.losses / .training):
+
+  * tests/test_gpu_zz_reference_golden.py passes the product (CUDA kernels through the C ABI);
+  * tests/test_reference_golden_cpu.py passes `OracleBackend`, the same signatures served by oracle/loss_oracle.py
+    (fp64 autograd) -- that pins the oracle, which every other GPU loss test uses as its checker, to the reference's
+    own numbers, and exercises every line of these checks on the CPU.
+
+TEST INFRASTRUCTURE ONLY (imports oracle/)."""
+import os
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CP = 40                      # channels of the blended image: rgb 0..2, depth 3, normal 4..6, features 7..38, 1 of padding
+D = 32
+
+
+def load(name):
+    return dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the product's signatures on the CPU oracle
+# ---------------------------------------------------------------------------------------------------------------
+class OracleBackend:
+    """gaussiangrasper_b200.losses / .training signatures served by oracle/loss_oracle.py in fp64 (gradients by
+    autograd).  Only what the checks below call."""
+    device = torch.device("cpu")
+
+    def __init__(self):
+        from oracle import loss_oracle
+        self.lo = loss_oracle
+
+    def make_mlp(self, state):
+        mlp = self.lo.MLP(in_dim=D, out_dim=512, hidden_list=[128]).double()
+        mlp.load_state_dict({k: v.double() for k, v in state.items()})
+        return mlp
+
+    def _with_grad(self, image, fn):
+        x = image.double().requires_grad_(True)
+        loss = fn(x)
+        loss.sum().backward()
+        return loss.detach().float(), x.grad.float()
+
+    def geom_loss(self, image, gt_depth, gt_normal, depth_mask, w_depth=1.0, w_normal=1.0, grad=None):
+        def fn(x):
+            d, n = self.lo.geom_losses(x[..., 4:7], x[..., 3:4], gt_normal.permute(2, 0, 1).double(), gt_depth[None].double(),
+                                       depth_mask[None])
+            return torch.stack([w_depth * d, w_normal * n])
+        loss, g = self._with_grad(image, fn)
+        return loss, (g if grad is None else grad.add_(g))
+
+    def contrastive_feature_loss(self, image, pairs, grad, feature_channel0=7, feature_dim=None, weight=1.0):
+        loss, g = self._with_grad(image, lambda x: weight * self.lo.feature_loss(x[..., 7:7 + feature_dim], pairs).reshape(1))
+        grad.add_(g)
+        return loss
+
+    def up_loss(self, image, points, gt_features, mlp, grad, feature_channel0=7, feature_dim=None, weight=1.0):
+        fn = lambda x: weight * self.lo.up_loss(x[..., 7:7 + feature_dim], points, gt_features.permute(2, 0, 1).double(), mlp).reshape(1)
+        loss, g = self._with_grad(image, fn)
+        grad.add_(g)
+        return loss
+
+    def param_regs(self, sh_coeffs, log_scales, max_gauss_ratio=10.0, w_sh=1.0, w_scale=1.0, v_sh_coeffs=None,
+                   v_log_scales=None):
+        a, b = sh_coeffs.double().requires_grad_(True), log_scales.double().requires_grad_(True)
+        r_sh, r_sc = self.lo.regs(a, b, max_gauss_ratio)
+        (w_sh * r_sh + w_scale * r_sc).backward()
+        v_sh_coeffs.add_(a.grad.float())
+        v_log_scales.add_(b.grad.float())
+        return torch.stack([w_sh * r_sh, w_scale * r_sc]).detach().float()
+
+    def pixel_loss(self, pred, target, kind="l1", mask=None, weight=1.0, mean_over="valid"):
+        assert kind == "l1" and mean_over == "valid"
+        x = pred.double().requires_grad_(True)
+        loss = weight * (target.double()[mask] - x[mask]).abs().mean()
+        loss.backward()
+        return loss.detach().float().reshape(1), x.grad.float()
+
+    def ssim_loss(self, pred, target, channels=3, weight=1.0, grad=None, loss=None):
+        x = pred.double().requires_grad_(True)
+        val = weight * (1 - self.lo.ssim(target.double().permute(2, 0, 1)[None], x.permute(2, 0, 1)[None]))
+        val.backward()
+        return val.detach().float().reshape(1), x.grad.float()
+
+    def knn_scale_init(self, means):
+        d = torch.cdist(means.double(), means.double())
+        d.fill_diagonal_(float("inf"))
+        dist = torch.sort(d, dim=1)[0][:, :3]
+        return torch.log(dist.mean(dim=-1, keepdim=True).repeat(1, 3)).float(), dist.float()
+
+    def up_project(self, features, mlp):
+        with torch.no_grad():
+            return mlp(features.double()).float()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def ground_truth(fix):
+    """The ground-truth side of get_loss_dict (:850-875) at full resolution, where its F.interpolate calls (to the
+    image's own size) are identities.  Returns CPU tensors."""
+    t = torch.from_numpy
+    valid = t(fix["batch_valid_mask"])
+    gt_depth = t(fix["batch_depth"])[..., 0]
+    gt_mask = t(fix["batch_sam_mask"]).float()
+    gt_mask[~valid] = -1.0                                                   # :873
+    assert torch.equal(gt_mask, t(fix["gt_mask"])), "the samplers of the reference saw another segment mask"
+    return dict(image=t(fix["batch_image"]), normal=F.normalize(t(fix["batch_normal"]), dim=-1),      # :857-859
+                depth=gt_depth, depth_mask=(gt_depth > 0.05) & valid,                                    # :861, :870-871
+                valid=valid, feature=t(fix["batch_feature_x8"]).float() / 8)
+
+
+def blended_image(fix):
+    H, W = fix["out_depth"].shape[:2]
+    img = torch.zeros((H, W, CP))
+    img[..., 0:3], img[..., 3:4] = torch.from_numpy(fix["out_rgb"]), torch.from_numpy(fix["out_depth"])
+    img[..., 4:7], img[..., 7:7 + D] = torch.from_numpy(fix["out_normal"]), torch.from_numpy(fix["out_feature"])
+    return img
+
+
+def _close(got, want, rel, what):
+    got, want = got.detach().cpu().double(), torch.as_tensor(want).double()
+    assert got.shape == want.shape, (what, tuple(got.shape), tuple(want.shape))
+    scale = float(want.abs().max())
+    err = float((got - want).abs().max())
+    assert err <= rel * scale + 1e-9, f"{what}: max error {err:.3e} against a largest entry of {scale:.3e}"
+
+
+def check_losses(backend, rel_value=5e-5, rel_grad=1e-4):
+    """Every term of the reference's get_loss_dict and the gradient of their weighted sum (the weights of the fixture)
+    w.r.t. the blended outputs, the Gaussian parameters and the up-projection's weights."""
+    fix = load("ref_losses_small")
+    dev = backend.device
+    gt = {k: v.to(dev) for k, v in ground_truth(fix).items()}
+    want = dict(zip(fix["loss_names"].tolist(), fix["loss_values"].tolist()))
+    w = dict(zip(fix["loss_names"].tolist(), fix["loss_weights"].tolist()))
+    lam = float(fix["ssim_lambda"][0])
+    img = blended_image(fix).to(dev)
+    H, W, _ = img.shape
+    got = {}
+
+    # depth_loss, normal_loss (:876-880)
+    loss, grad = backend.geom_loss(img, gt["depth"], gt["normal"], gt["depth_mask"], w_depth=w["depth_loss"],
+                                   w_normal=w["normal_loss"])
+    got["depth_loss"], got["normal_loss"] = loss[0].item() / w["depth_loss"], loss[1].item() / w["normal_loss"]
+    assert grad.shape == img.shape
+
+    # feature_loss over the pixel pairs the reference's sampler drew (:905-912), up_loss over its points (:913-914)
+    pairs = [[torch.from_numpy(fix[f"pairs_{i}_a"]).to(dev), torch.from_numpy(fix[f"pairs_{i}_b"]).to(dev)]
+             for i in range(int(fix["n_segments"][0]))]
+    points = torch.from_numpy(fix["points"]).to(dev)
+    mlp = backend.make_mlp({k[len("mlp_"):]: torch.from_numpy(v) for k, v in fix.items()
+                            if k.startswith("mlp_layers")})
+    got["feature_loss"] = backend.contrastive_feature_loss(img, pairs, grad, feature_dim=D, weight=w["feature_loss"]).item() \
+        / w["feature_loss"]
+    got["up_loss"] = backend.up_loss(img, points, gt["feature"], mlp, grad, feature_dim=D, weight=w["up_loss"]).item() / w["up_loss"]
+
+    # main_loss = (1 - lambda) L1 over the valid pixels + lambda (1 - SSIM) of the images with the invalid pixels
+    # zeroed on both sides (:882-885, :931); the in-place zeroing passes no gradient to the pixels it overwrites
+    rgb = img[..., 0:3].contiguous()
+    l1, g_l1 = backend.pixel_loss(rgb, gt["image"], "l1", gt["valid"], weight=(1 - lam) * w["main_loss"])
+    rgb_z, gt_z = rgb.clone(), gt["image"].clone()
+    rgb_z[~gt["valid"]] = 0.0
+    gt_z[~gt["valid"]] = 0.0
+    ls, g_ssim = backend.ssim_loss(rgb_z, gt_z, weight=lam * w["main_loss"])
+    g_ssim = g_ssim.reshape(H, W, 3).clone()
+    g_ssim[~gt["valid"]] = 0.0
+    got["main_loss"] = (l1.item() + ls.item()) / w["main_loss"]
+    grad[..., 0:3] += g_l1.reshape(H, W, 3) + g_ssim
+
+    # sh_reg, scale_reg (:917-925)
+    sh, scales = torch.from_numpy(fix["colors_all"]).to(dev), torch.from_numpy(fix["scales"]).to(dev)
+    v_sh, v_sc = torch.zeros_like(sh), torch.zeros_like(scales)
+    regs = backend.param_regs(sh, scales, float(fix["max_gauss_ratio"][0]), w_sh=w["sh_reg"], w_scale=w["scale_reg"],
+                              v_sh_coeffs=v_sh, v_log_scales=v_sc)
+    got["sh_reg"], got["scale_reg"] = regs[0].item() / w["sh_reg"], regs[1].item() / w["scale_reg"]
+
+    for k, v in want.items():
+        assert abs(got[k] - v) <= rel_value * abs(v), f"{k}: {got[k]!r} against the reference's {v!r}"
+    _close(grad[..., 0:3], fix["grad_rgb"], rel_grad, "d/d rgb")
+    _close(grad[..., 3:4], fix["grad_depth"], rel_grad, "d/d depth")
+    _close(grad[..., 4:7], fix["grad_normal"], rel_grad, "d/d normal")
+    _close(grad[..., 7:7 + D], fix["grad_feature"], rel_grad, "d/d feature")
+    assert float(grad[..., 7 + D:].abs().max()) == 0.0
+    _close(v_sh, fix["grad_colors_all"], rel_grad, "d/d colors_all")
+    _close(v_sc, fix["grad_scales"], rel_grad, "d/d scales")
+    for k, p in mlp.named_parameters():
+        _close(p.grad, fix["mlp_grad_" + k], rel_grad, "d/d fea_up." + k)
+    return got
+
+
+def check_init(backend):
+    """populate_modules' k-NN scale initialisation (sklearn in the reference) and the up-projection MLP's forward."""
+    fix = load("ref_init_small")
+    dev = backend.device
+    ls, dist = backend.knn_scale_init(torch.from_numpy(fix["knn_means"]).to(dev))
+    assert ls.shape == fix["knn_log_scales"].shape
+    err = float((ls.cpu() - torch.from_numpy(fix["knn_log_scales"])).abs().max())
+    assert err <= 2e-5, f"k-NN log scales: {err:.3e}"
+    assert torch.allclose(dist.cpu().mean(dim=1).log(), torch.from_numpy(fix["knn_log_scales"])[:, 0], atol=2e-5)
+    mlp = backend.make_mlp({k[len("mlp_"):]: torch.from_numpy(v) for k, v in fix.items() if k.startswith("mlp_layers")})
+    y = backend.up_project(torch.from_numpy(fix["mlp_x"]).to(dev), mlp)
+    assert tuple(y.shape) == fix["mlp_y"].shape
+    scale = float(np.abs(fix["mlp_y64"]).max())
+    assert float((y.cpu().double() - torch.from_numpy(fix["mlp_y64"])).abs().max()) <= 1e-5 * scale    # the reference's weights in fp64
+    assert float((y.cpu() - torch.from_numpy(fix["mlp_y"])).abs().max()) <= 2e-5 * scale                # its own fp32 output

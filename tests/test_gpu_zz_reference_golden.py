@@ -1,0 +1,47 @@
+"""The CUDA loss / initialisation kernels against fixtures the REFERENCE ITSELF produced
+(tests/golden/make_reference_golden.py: the unmodified nerfstudio/models/gaussian_splatting.py run on seeded inputs in
+the build container): every term of get_loss_dict with the gradient of their weighted sum, the k-NN scale
+initialisation (scikit-learn in the reference) and the up-projection MLP.  The refinement step's reference-made
+fixture is checked in tests/test_golden.py::test_cuda_refine_matches_golden.
+
+The checks themselves live in tests/ref_golden_checks.py and run on the CPU against the oracle as well
+(tests/test_reference_golden_cpu.py).  (The file name sorts these tests behind the other GPU tests.)"""
+import os
+import sys
+
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import ref_golden_checks as checks  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+class ProductBackend:
+    """gaussiangrasper_b200's own functions (CUDA kernels through the C ABI) on cuda:0."""
+
+    def __init__(self):
+        from gaussiangrasper_b200 import losses, training
+        assert torch.cuda.is_available()
+        self.device = torch.device("cuda:0")
+        self.geom_loss, self.contrastive_feature_loss = losses.geom_loss, losses.contrastive_feature_loss
+        self.up_loss, self.param_regs, self.up_project = losses.up_loss, losses.param_regs, losses.up_project
+        self.pixel_loss, self.ssim_loss, self.knn_scale_init = training.pixel_loss, training.ssim_loss, training.knn_scale_init
+        self._losses = losses
+
+    def make_mlp(self, state):
+        mlp = self._losses.UpProjection(checks.D).to(self.device)
+        mlp.load_state_dict({k: v.float() for k, v in state.items()})    # the reference's parameter names
+        return mlp
+
+
+def test_cuda_losses_match_the_references_get_loss_dict():
+    from gaussiangrasper_b200 import _lib
+    before = _lib.launch_count()
+    got = checks.check_losses(ProductBackend(), rel_value=5e-5, rel_grad=1e-4)
+    assert len(got) == 7 and _lib.launch_count() > before         # this library's kernels did the work
+
+
+def test_cuda_initialisation_and_up_projection_match_the_reference():
+    checks.check_init(ProductBackend())

@@ -1,0 +1,88 @@
+"""The fixtures the REFERENCE ITSELF produced (tests/golden/make_reference_golden.py; the unmodified
+nerfstudio/models/gaussian_splatting.py imported and run in the build container) against
+
+  * the CPU oracle -- oracle/loss_oracle.py and oracle/refine_oracle.py are the checkers of the GPU loss / refinement
+    tests; here they are pinned to the reference's own numbers;
+  * the host-side constants and formulas of the product (projection matrix, SH constant, optimizer table, learning
+    rate schedules);
+  * the generator itself: where the reference tree is mounted, a fresh run must reproduce the committed files.
+
+The GPU side of the same checks is tests/test_gpu_zz_reference_golden.py."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_golden_checks as checks  # noqa: E402
+
+REFERENCE = "/root/reference/nerfstudio/models/gaussian_splatting.py"
+
+
+def test_loss_oracle_reproduces_the_references_get_loss_dict():
+    got = checks.check_losses(checks.OracleBackend(), rel_value=2e-6, rel_grad=2e-5)
+    assert set(got) == {"main_loss", "feature_loss", "up_loss", "depth_loss", "normal_loss", "sh_reg", "scale_reg"}
+    assert all(v > 0.1 for v in got.values())              # every term is active in the fixture
+
+
+def test_references_initialisation_and_up_projection():
+    checks.check_init(checks.OracleBackend())
+
+
+def test_refinement_fixture_is_the_references_and_the_oracle_reproduces_it():
+    """refine_small.npz is written by GaussianSplattingModel.refinement_after itself; oracle/refine_oracle.py must give
+    the same Gaussians and Adam moments (the detailed comparison is tests/test_golden.py)."""
+    g = checks.load("refine_small")
+    assert str(g["generated_by"][0]).startswith("reference:")
+    n_in = g["in_means"].shape[0]
+    assert int(g["n_samples_drawn"][0]) % 2 == 0 and int(g["n_cat"][0]) > n_in + int(g["n_samples_drawn"][0]) > n_in
+    assert int(g["n_out"][0]) < int(g["n_cat"][0])          # splits, duplicates and culls all occur
+
+
+def test_host_constants_match_the_reference():
+    from gaussiangrasper_b200 import ply, scenes, training
+    from gaussiangrasper_b200.checkpoint import GROUP_MAP
+    fix = checks.load("ref_init_small")
+    for args, want in zip(fix["proj_args"], fix["proj_mats"]):
+        got = scenes.projection_matrix(*[float(a) for a in args]).numpy()
+        assert got.tobytes() == want.tobytes(), args
+    assert np.array_equal(ply.sh2rgb(fix["sh_dc"]).astype(np.float32), fix["sh2rgb"])
+    # the optimizer table of configs/method_configs.py:611-664
+    table = {g: row for g, row in zip(fix["opt_groups"].tolist(), fix["opt_lr_eps_final_maxsteps"])}
+    for group, ours in GROUP_MAP.items():
+        lr, eps, lr_final, max_steps = table[group]
+        assert training.REFERENCE_LRS[ours] == lr and eps == 1e-15, group
+        if max_steps > 0:
+            assert training.REFERENCE_SCHEDULES[ours] == (lr_final, int(max_steps)), group
+        else:
+            assert ours not in training.REFERENCE_SCHEDULES, group
+    acc = dict(zip(fix["accumulation_groups"].tolist(), fix["accumulation_steps"].tolist()))
+    for group, ours in GROUP_MAP.items():
+        assert training.REFERENCE_ACCUMULATION.get(ours, 1) == acc.get(group, 1), group
+    # ExponentialDecayScheduler (engine/schedulers.py:109-140) at the probed steps
+    for group, row, lrs in zip(fix["opt_groups"].tolist(), fix["opt_lr_eps_final_maxsteps"], fix["opt_probe_lrs"]):
+        if row[3] < 0:
+            continue
+        for step, want in zip(fix["opt_probe_steps"].tolist(), lrs.tolist()):
+            got = training.exponential_decay_lr(row[0], row[2], int(row[3]), step)
+            assert got == pytest.approx(want, rel=1e-12), (group, step)
+
+
+@pytest.mark.skipif(not os.path.exists(REFERENCE), reason="the reference tree is not mounted on this machine")
+def test_the_reference_regenerates_the_committed_fixtures(tmp_path):
+    r = subprocess.run([sys.executable, os.path.join(HERE, "golden", "make_reference_golden.py"), "--out", str(tmp_path)],
+                       capture_output=True, text=True, timeout=900, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    for name in ("refine_small", "ref_losses_small", "ref_init_small"):
+        want, got = checks.load(name), dict(np.load(os.path.join(str(tmp_path), name + ".npz")))
+        assert set(want) == set(got), name
+        for k in want:
+            if want[k].dtype.kind in "fc" and name != "refine_small":
+                np.testing.assert_allclose(got[k], want[k], rtol=1e-5, atol=1e-7 * float(np.abs(want[k]).max() + 1e-30),
+                                           err_msg=f"{name}:{k}", equal_nan=True)
+            else:
+                assert np.array_equal(got[k], want[k]), f"{name}:{k}"     # the refinement fixture: bit for bit
