@@ -87,6 +87,40 @@ def look_at_camera(position, W: int, H: int, target=(0.0, 0.0, 0.0)) -> Camera:
     return Camera(viewmat, projmat @ viewmat, fx, fy, cx, cy, H, W, pos.float())
 
 
+def camera_from_c2w(camera_to_world, fx: float, fy: float, cx: float, cy: float, W: int, H: int) -> Camera:
+    """The camera set-up of GaussianSplattingModel.get_outputs (gaussian_splatting.py:657-678) for one nerfstudio
+    camera: `camera_to_world` [3,4] (or [4,4]) in nerfstudio's convention (+x right, +y up, -z forward).  The y and z
+    axes are flipped (the reference multiplies by SO3.from_x_radians(pi): diag(1,-1,-1) up to 1e-16), the pose is
+    inverted analytically, the fields of view come from the focal lengths and the projection is
+    projection_matrix(0.001, 1000, fovx, fovy)."""
+    c2w = torch.as_tensor(camera_to_world, dtype=torch.float32).detach().cpu()
+    R = c2w[:3, :3] * torch.tensor([1.0, -1.0, -1.0])        # R @ diag(1,-1,-1): columns y, z negated       (:662-663)
+    T = c2w[:3, 3:4]
+    viewmat = torch.eye(4, dtype=torch.float32)               # analytic inverse                              (:665-669)
+    viewmat[:3, :3] = R.T
+    viewmat[:3, 3:4] = -R.T @ T
+    # nerfstudio keeps the intrinsics as fp32 tensors: `.item()` hands gsplat the rounded values, and the quotient
+    # under the atan is an fp32 tensor operation (:671-674)
+    f32 = lambda v: torch.tensor(float(v), dtype=torch.float32)
+    fx, fy, cx, cy = (f32(v).item() for v in (fx, fy, cx, cy))
+    fovx = 2 * math.atan((torch.tensor(int(W)) / (2 * f32(fx))).item())
+    fovy = 2 * math.atan((torch.tensor(int(H)) / (2 * f32(fy))).item())
+    projmat = projection_matrix(0.001, 1000, fovx, fovy)      #                                               (:677)
+    return Camera(viewmat, projmat @ viewmat, float(fx), float(fy), float(cx), float(cy), int(H), int(W),
+                  c2w[:3, 3].clone())                         # SH view directions start at the camera centre (:727)
+
+
+def cameras_from_nerfstudio(cameras) -> List[Camera]:
+    """One Camera per entry of a nerfstudio `Cameras` object (anything with `camera_to_worlds` [V,3,4] and per-camera
+    `fx, fy, cx, cy, width, height` tensors of shape [V,1]) -- what get_outputs reads from its `camera` argument."""
+    c2w = cameras.camera_to_worlds
+    if c2w.dim() == 2:
+        c2w = c2w[None]
+    pick = lambda t, i: float(torch.as_tensor(t).reshape(-1)[i if torch.as_tensor(t).numel() > 1 else 0])
+    return [camera_from_c2w(c2w[i], pick(cameras.fx, i), pick(cameras.fy, i), pick(cameras.cx, i), pick(cameras.cy, i),
+                            int(pick(cameras.width, i)), int(pick(cameras.height, i))) for i in range(c2w.shape[0])]
+
+
 def orbit_cameras(n_views: int, W: int, H: int, radius: float = 4.5, first: int = 0, total: int = None) -> List[Camera]:
     """View k of `total` on a circle of radius 4.5 in the xz-plane at height 0.5*sin(2*pi*k/total)."""
     total = total or n_views

@@ -17,7 +17,8 @@ inputs.  Needs /root/reference (build container only); the resulting fixtures tr
                          and is stored as such
   ref_init_small.npz     populate_modules' k-nearest-neighbour scale initialisation (:259-263, k_nearest_sklearn
                          :315-331 with the real scikit-learn), the up-projection MLP (:198-213) forward on seeded
-                         weights, projection_matrix (:87-105), SH2RGB (:80-85), the optimizer table of the method
+                         weights, projection_matrix (:87-105), SH2RGB (:80-85), the arguments get_outputs (:624-713) hands to
+                         ProjectGaussians.apply for a few nerfstudio cameras, the optimizer table of the method
                          (configs/method_configs.py:611-664, read from the source's syntax tree) and the trainer's
                          ExponentialDecayScheduler (nerfstudio/engine/schedulers.py:109-140, imported and run) learning
                          rates for it
@@ -237,7 +238,50 @@ def init_fixture(gs):
     # its syntax tree (importing that module needs open3d, tyro and the whole model zoo), and the learning rates the
     # trainer's ExponentialDecayScheduler (engine/schedulers.py:109-140, imported and run) produces from it
     out.update(optimizer_table())
+    out.update(camera_table(gs, model))
     return out
+
+
+def camera_table(gs, model):
+    """What get_outputs (:624-713) hands to ProjectGaussians.apply for a few nerfstudio cameras: the call is
+    intercepted at the gsplat boundary (arguments recorded, get_outputs abandoned there)."""
+    from nerfstudio.cameras.cameras import Cameras, CameraType
+
+    class Recorded(Exception):
+        pass
+
+    class Recorder:
+        @staticmethod
+        def apply(means, scales, glob_scale, quats, viewmat, fullmat, fx, fy, cx, cy, H, W, tile_bounds):
+            raise Recorded(dict(viewmat=viewmat.detach().clone(), fullmat=fullmat.detach().clone(),
+                                intr=[fx, fy, cx, cy], size=[H, W], tile_bounds=list(tile_bounds), glob_scale=glob_scale))
+    g = torch.Generator().manual_seed(31)
+    model.train()
+    model.step = 600
+    rows = dict(c2w=[], intr_in=[], size_in=[], viewmat=[], fullmat=[], intr=[], size=[], tile_bounds=[])
+    orig = gs.ProjectGaussians
+    gs.ProjectGaussians = Recorder
+    try:
+        for (W, H) in ((640, 480), (1280, 720), (333, 217), (1920, 1080)):
+            q = torch.nn.functional.normalize(torch.randn(4, generator=g), dim=0)
+            R = gs.quat_to_rotmat(q[None])[0]
+            t = torch.randn(3, 1, generator=g) * 3
+            c2w = torch.cat([R, t], dim=1)[None]
+            fx, fy = 0.6 * W * (1 + 0.1 * float(torch.rand(1, generator=g))), 0.6 * W * (1 + 0.1 * float(torch.rand(1, generator=g)))
+            cx, cy = W / 2 + float(torch.randn(1, generator=g)) * 5, H / 2 + float(torch.randn(1, generator=g)) * 5
+            cam = Cameras(camera_to_worlds=c2w, fx=fx, fy=fy, cx=cx, cy=cy, width=W, height=H, camera_type=CameraType.PERSPECTIVE)
+            try:
+                model.get_outputs(cam)
+                raise AssertionError("ProjectGaussians.apply was not reached")
+            except Recorded as r:
+                rec = r.args[0]
+            assert rec["glob_scale"] == 1 and model.last_size == (H, W)
+            rows["c2w"].append(c2w[0].numpy()); rows["intr_in"].append([fx, fy, cx, cy]); rows["size_in"].append([W, H])
+            rows["viewmat"].append(rec["viewmat"].numpy()); rows["fullmat"].append(rec["fullmat"].numpy())
+            rows["intr"].append(rec["intr"]); rows["size"].append(rec["size"]); rows["tile_bounds"].append(rec["tile_bounds"])
+    finally:
+        gs.ProjectGaussians = orig
+    return {"cam_" + k: np.array(v) for k, v in rows.items()}
 
 
 def optimizer_table():

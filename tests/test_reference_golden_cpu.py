@@ -72,6 +72,44 @@ def test_host_constants_match_the_reference():
             assert got == pytest.approx(want, rel=1e-12), (group, step)
 
 
+def test_camera_setup_equals_what_get_outputs_hands_to_the_projection():
+    """scenes.camera_from_c2w / cameras_from_nerfstudio against the arguments the reference's get_outputs (:624-713)
+    passed to ProjectGaussians.apply for the same nerfstudio cameras: bit for bit."""
+    import types
+    from gaussiangrasper_b200 import scenes
+    from gaussiangrasper_b200.render import ViewBatch
+    fix = checks.load("ref_init_small")
+    V = len(fix["cam_c2w"])
+    assert V >= 4
+    cams = []
+    for i in range(V):
+        fx, fy, cx, cy = fix["cam_intr_in"][i]
+        W, H = (int(v) for v in fix["cam_size_in"][i])
+        c = scenes.camera_from_c2w(fix["cam_c2w"][i], fx, fy, cx, cy, W, H)
+        assert c.viewmat[:3].numpy().tobytes() == fix["cam_viewmat"][i].tobytes(), i
+        assert c.fullmat.numpy().tobytes() == fix["cam_fullmat"][i].tobytes(), i
+        assert [c.fx, c.fy, c.cx, c.cy] == fix["cam_intr"][i].tolist() and [c.H, c.W] == fix["cam_size"][i].tolist()
+        assert list(c.tile_bounds) == fix["cam_tile_bounds"][i].tolist()
+        assert torch.equal(c.position, torch.from_numpy(fix["cam_c2w"][i][:, 3]))
+        cams.append(c)
+    # a nerfstudio-shaped batch ([V,3,4] poses, [V,1] intrinsics) of equal-sized views -> the same cameras, and the
+    # packed ViewBatch the fused path consumes
+    same = [i for i in range(V) if fix["cam_size_in"][i].tolist() == fix["cam_size_in"][0].tolist()] + [0]
+    col = lambda j: torch.tensor([[fix["cam_intr_in"][i][j]] for i in same], dtype=torch.float32)
+    W, H = (int(v) for v in fix["cam_size_in"][0])
+    batch = types.SimpleNamespace(camera_to_worlds=torch.from_numpy(fix["cam_c2w"][same]), fx=col(0), fy=col(1), cx=col(2),
+                                  cy=col(3), width=torch.full((len(same), 1), W), height=torch.full((len(same), 1), H))
+    got = scenes.cameras_from_nerfstudio(batch)
+    assert len(got) == len(same)
+    for c, i in zip(got, same):
+        assert torch.equal(c.viewmat, cams[i].viewmat) and torch.equal(c.fullmat, cams[i].fullmat) and c.fx == cams[i].fx
+    vb = ViewBatch.from_cameras(got, torch.device("cpu"))
+    assert vb.n_views == len(same) and (vb.H, vb.W) == (H, W)
+    assert vb.viewmats[0].numpy().tobytes() == fix["cam_viewmat"][same[0]].tobytes()
+    assert vb.fullmats[-1].numpy().tobytes() == fix["cam_fullmat"][0].tobytes()
+    assert torch.equal(vb.positions[0], cams[same[0]].position)
+
+
 @pytest.mark.skipif(not os.path.exists(REFERENCE), reason="the reference tree is not mounted on this machine")
 def test_the_reference_regenerates_the_committed_fixtures(tmp_path):
     r = subprocess.run([sys.executable, os.path.join(HERE, "golden", "make_reference_golden.py"), "--out", str(tmp_path)],
@@ -82,7 +120,7 @@ def test_the_reference_regenerates_the_committed_fixtures(tmp_path):
         assert set(want) == set(got), name
         for k in want:
             if want[k].dtype.kind in "fc" and name != "refine_small":
-                np.testing.assert_allclose(got[k], want[k], rtol=1e-5, atol=1e-7 * float(np.abs(want[k]).max() + 1e-30),
+                np.testing.assert_allclose(got[k], want[k], rtol=1e-5, atol=1e-7 * float(np.nanmax(np.abs(want[k])) + 1e-30),
                                            err_msg=f"{name}:{k}", equal_nan=True)
             else:
                 assert np.array_equal(got[k], want[k]), f"{name}:{k}"     # the refinement fixture: bit for bit
