@@ -83,11 +83,16 @@ GROUP_MAP = dict(xyz="means", scaling="log_scales", rotation="quats", opacity="o
 
 
 def trainer_checkpoint(step: int, params: Mapping[str, torch.Tensor], optimizer=None, up_projection=None,
-                       extra_pipeline: Optional[Mapping[str, torch.Tensor]] = None) -> dict:
+                       extra_pipeline: Optional[Mapping[str, torch.Tensor]] = None,
+                       extra_optimizers: Optional[Mapping[str, dict]] = None,
+                       extra_schedulers: Optional[Mapping[str, dict]] = None) -> dict:
     """The dict the reference trainer saves (engine/trainer.py:437-449): {"step", "pipeline", "optimizers",
     "schedulers", "scalers"}.  `optimizer` is a training.FusedAdam: every group becomes a torch.optim.Adam state dict
     ({"state": {0: {step, exp_avg, exp_avg_sq}}, "param_groups": [...]}) and a LambdaLR-style scheduler entry, under
-    the reference's group names, so `Optimizers.load_optimizers` / `load_schedulers` accept them."""
+    the reference's group names, so `Optimizers.load_optimizers` / `load_schedulers` accept them.
+    `extra_optimizers` / `extra_schedulers`: state dicts of the groups FusedAdam does not own -- "up_net" (the torch
+    optimizer of the up-projection MLP, whose parameters get their `.grad` from losses.up_loss) and "camera_opt" --
+    taken over verbatim; without them a resumed reference run restarts those groups' moments."""
     ck = {"step": int(step), "pipeline": reference_state_dict(params, up_projection=up_projection, extra=extra_pipeline),
           "optimizers": {}, "schedulers": {}, "scalers": {}}
     if optimizer is not None:
@@ -106,6 +111,10 @@ def trainer_checkpoint(step: int, params: Mapping[str, torch.Tensor], optimizer=
             if ours in optimizer.schedules:
                 ck["schedulers"][group] = {"base_lrs": [e["lr_init"]], "last_epoch": int(step), "_step_count": int(step) + 1,
                                            "_get_lr_called_within_step": False, "_last_lr": [e["lr"]], "lr_lambdas": [None]}
+    for k, v in (extra_optimizers or {}).items():
+        ck["optimizers"].setdefault(k, v)
+    for k, v in (extra_schedulers or {}).items():
+        ck["schedulers"].setdefault(k, v)
     return ck
 
 
@@ -125,8 +134,10 @@ def optimizer_state_from_reference(ckpt: Mapping) -> Dict[str, dict]:
     return out
 
 
-def save_training_checkpoint(path: str, step: int, params, optimizer=None, up_projection=None, extra_pipeline=None) -> None:
-    torch.save(trainer_checkpoint(step, params, optimizer, up_projection, extra_pipeline), path)
+def save_training_checkpoint(path: str, step: int, params, optimizer=None, up_projection=None, extra_pipeline=None,
+                             extra_optimizers=None, extra_schedulers=None) -> None:
+    torch.save(trainer_checkpoint(step, params, optimizer, up_projection, extra_pipeline, extra_optimizers,
+                                  extra_schedulers), path)
 
 
 def load_reference_checkpoint(path: str, map_location="cpu") -> Dict[str, torch.Tensor]:

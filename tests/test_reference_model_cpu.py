@@ -24,3 +24,18 @@ def test_reference_model_runs_through_the_shim(tmp_path):
     assert rep["ok"] and rep["visible"] > 500
     assert set(rep["losses"]) == {"main_loss", "feature_loss", "up_loss", "depth_loss", "normal_loss", "sh_reg", "scale_reg"}
     assert all(v > 0 for v in rep["grads"].values())
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/nerfstudio/models/gaussian_splatting.py"),
+                    reason="the reference tree is not mounted on this machine")
+def test_checkpoints_resume_in_both_directions_with_the_references_own_classes(tmp_path):
+    """tests/reference_checkpoint_driver.py: the reference's GaussianSplattingModel.load_state_dict (strict) and
+    Optimizers.load_optimizers / load_schedulers take this repository's trainer_checkpoint, and a step continued on the
+    resumed objects is bit-identical to the step of the run that was saved; the reverse direction reads the trainer's
+    dict into render_views parameters and FusedAdam state."""
+    r = subprocess.run([sys.executable, os.path.join(HERE, "reference_checkpoint_driver.py")], capture_output=True, text=True,
+                       timeout=900, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    rep = json.loads(r.stdout.strip().splitlines()[-1])
+    assert rep["ok"] and rep["groups"] == ["color", "feature", "opacity", "rotation", "scaling", "up_net", "xyz"]
+    assert rep["schedulers"] == ["color", "feature", "scaling", "up_net", "xyz"]
