@@ -18,7 +18,8 @@ inputs.  Needs /root/reference (build container only); the resulting fixtures tr
   ref_init_small.npz     populate_modules' k-nearest-neighbour scale initialisation (:259-263, k_nearest_sklearn
                          :315-331 with the real scikit-learn), the up-projection MLP (:198-213) forward on seeded
                          weights, projection_matrix (:87-105), SH2RGB (:80-85), the arguments get_outputs (:624-713) hands to
-                         ProjectGaussians.apply for a few nerfstudio cameras, the optimizer table of the method
+                         ProjectGaussians.apply for a few nerfstudio cameras, after_train's densification statistics (:373-393) over
+                         three steps, the optimizer table of the method
                          (configs/method_configs.py:611-664, read from the source's syntax tree) and the trainer's
                          ExponentialDecayScheduler (nerfstudio/engine/schedulers.py:109-140, imported and run) learning
                          rates for it
@@ -239,6 +240,31 @@ def init_fixture(gs):
     # trainer's ExponentialDecayScheduler (engine/schedulers.py:109-140, imported and run) produces from it
     out.update(optimizer_table())
     out.update(camera_table(gs, model))
+    out.update(after_train_table(gs))
+    return out
+
+
+def after_train_table(gs):
+    """GaussianSplattingModel.after_train (:373-393), three training steps: the densification statistics it keeps from
+    xys.grad and radii."""
+    n, H, W = 701, 480, 640
+    model = small_model(gs, n)
+    model.train()
+    model.last_size = (H, W)
+    g = torch.Generator().manual_seed(41)
+    out = dict(stats_size=np.array([H, W]))
+    for it in range(3):
+        radii = torch.randint(-1, 40, (n,), generator=g, dtype=torch.int32).clamp(min=0)
+        radii[it::3] = 0
+        v_xy = torch.randn((n, 2), generator=g) * 1e-4
+        v_xy[radii == 0] = 0                      # invisible Gaussians receive no gradient
+        model.radii = radii
+        model.xys = torch.zeros((n, 2), requires_grad=True)
+        model.xys.grad = v_xy.clone()
+        model.after_train(it)
+        out[f"stats_radii_{it}"], out[f"stats_vxy_{it}"] = radii.numpy(), v_xy.numpy()
+        out[f"stats_norm_{it}"], out[f"stats_count_{it}"] = model.xys_grad_norm.numpy().copy(), model.vis_counts.numpy().copy()
+        out[f"stats_max2d_{it}"] = model.max_2Dsize.numpy().copy()
     return out
 
 

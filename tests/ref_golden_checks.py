@@ -1,6 +1,6 @@
 """Checks against the fixtures the REFERENCE ITSELF produced (tests/golden/make_reference_golden.py: the unmodified
 nerfstudio/models/gaussian_splatting.py run on seeded inputs): get_loss_dict with its gradients, the k-NN scale
-initialisation and the up-projection MLP.  Each check is written once, against the signatures of the product's loss
+initialisation, the up-projection MLP and after_train's densification statistics.  Each check is written once, against the signatures of the product's loss
 functions (gaussiangrasper_b200.losses / .training):
 
   * tests/test_gpu_zz_reference_golden.py passes the product (CUDA kernels through the C ABI);
@@ -93,6 +93,22 @@ class OracleBackend:
         d.fill_diagonal_(float("inf"))
         dist = torch.sort(d, dim=1)[0][:, :3]
         return torch.log(dist.mean(dim=-1, keepdim=True).repeat(1, 3)).float(), dist.float()
+
+    def make_stats(self, n):
+        """training.DensifyStats' update / attributes: after_train (:373-393) restated."""
+        class Stats:
+            xys_grad_norm = vis_counts = max_2Dsize = None
+
+            def update(st, v_geo, radii, H, W):
+                visible = radii > 0
+                grads = v_geo[:, :2].norm(dim=-1)
+                if st.xys_grad_norm is None:
+                    st.xys_grad_norm, st.vis_counts, st.max_2Dsize = grads.clone(), torch.ones_like(grads), torch.zeros_like(grads)
+                else:
+                    st.vis_counts[visible] += 1
+                    st.xys_grad_norm[visible] += grads[visible]
+                st.max_2Dsize[visible] = torch.maximum(st.max_2Dsize[visible], radii[visible].float() / float(max(H, W)))
+        return Stats()
 
     def up_project(self, features, mlp):
         with torch.no_grad():
@@ -208,3 +224,21 @@ def check_init(backend):
     scale = float(np.abs(fix["mlp_y64"]).max())
     assert float((y.cpu().double() - torch.from_numpy(fix["mlp_y64"])).abs().max()) <= 1e-5 * scale    # the reference's weights in fp64
     assert float((y.cpu() - torch.from_numpy(fix["mlp_y"])).abs().max()) <= 2e-5 * scale                # its own fp32 output
+
+
+def check_after_train(backend):
+    """The densification statistics of the reference's after_train (:373-393) over three steps."""
+    fix = load("ref_init_small")
+    dev = backend.device
+    H, W = (int(v) for v in fix["stats_size"])
+    n = fix["stats_radii_0"].shape[0]
+    stats = backend.make_stats(n)
+    for it in range(3):
+        v_geo = torch.zeros((n, 8))
+        v_geo[:, :2] = torch.from_numpy(fix[f"stats_vxy_{it}"])
+        v_geo[:, 2:] = 7.0                                    # the other columns of the packed gradient are not read
+        stats.update(v_geo.to(dev), torch.from_numpy(fix[f"stats_radii_{it}"]).to(dev), H, W)
+        assert torch.allclose(stats.xys_grad_norm.cpu(), torch.from_numpy(fix[f"stats_norm_{it}"]), rtol=2e-6, atol=1e-10), it
+        assert torch.equal(stats.vis_counts.cpu(), torch.from_numpy(fix[f"stats_count_{it}"])), it
+        assert torch.allclose(stats.max_2Dsize.cpu(), torch.from_numpy(fix[f"stats_max2d_{it}"]), rtol=1e-6, atol=0), it
+    assert float(stats.vis_counts.max()) == 3.0 and float(stats.vis_counts.min()) == 1.0

@@ -30,6 +30,10 @@ class ProductBackend:
         self.pixel_loss, self.ssim_loss, self.knn_scale_init = training.pixel_loss, training.ssim_loss, training.knn_scale_init
         self._losses = losses
 
+    def make_stats(self, n):
+        from gaussiangrasper_b200.training import DensifyStats
+        return DensifyStats(n, self.device)
+
     def make_mlp(self, state):
         mlp = self._losses.UpProjection(checks.D).to(self.device)
         mlp.load_state_dict({k: v.float() for k, v in state.items()})    # the reference's parameter names
@@ -45,3 +49,7 @@ def test_cuda_losses_match_the_references_get_loss_dict():
 
 def test_cuda_initialisation_and_up_projection_match_the_reference():
     checks.check_init(ProductBackend())
+
+
+def test_cuda_densification_statistics_match_the_references_after_train():
+    checks.check_after_train(ProductBackend())

@@ -33,6 +33,10 @@ def test_references_initialisation_and_up_projection():
     checks.check_init(checks.OracleBackend())
 
 
+def test_references_after_train_statistics():
+    checks.check_after_train(checks.OracleBackend())
+
+
 def test_refinement_fixture_is_the_references_and_the_oracle_reproduces_it():
     """refine_small.npz is written by GaussianSplattingModel.refinement_after itself; oracle/refine_oracle.py must give
     the same Gaussians and Adam moments (the detailed comparison is tests/test_golden.py)."""
