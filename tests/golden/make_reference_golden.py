@@ -19,7 +19,7 @@ inputs.  Needs /root/reference (build container only); the resulting fixtures tr
                          :315-331 with the real scikit-learn), the up-projection MLP (:198-213) forward on seeded
                          weights, projection_matrix (:87-105), SH2RGB (:80-85), the arguments get_outputs (:624-713) hands to
                          ProjectGaussians.apply for a few nerfstudio cameras, after_train's densification statistics (:373-393) over
-                         three steps, the optimizer table of the method
+                         three steps, nerfstudio's own real-SH basis (utils/math.py:29-92), the optimizer table of the method
                          (configs/method_configs.py:611-664, read from the source's syntax tree) and the trainer's
                          ExponentialDecayScheduler (nerfstudio/engine/schedulers.py:109-140, imported and run) learning
                          rates for it
@@ -241,6 +241,12 @@ def init_fixture(gs):
     out.update(optimizer_table())
     out.update(camera_table(gs, model))
     out.update(after_train_table(gs))
+    # the reference's own real spherical-harmonics basis (nerfstudio/utils/math.py:29-92), 5 levels = degree 4: the
+    # same 25 functions in the same order as gsplat's, without the (-1)^|m| sign gsplat (like the 3DGS authors) carries
+    from nerfstudio.utils.math import components_from_spherical_harmonics
+    d = torch.nn.functional.normalize(torch.randn((96, 3), generator=torch.Generator().manual_seed(51)).double(), dim=-1)
+    out["sh_dirs"] = d.float().numpy()
+    out["sh_components"] = components_from_spherical_harmonics(5, d.float()).numpy()
     return out
 
 

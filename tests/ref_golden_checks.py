@@ -242,3 +242,29 @@ def check_after_train(backend):
         assert torch.equal(stats.vis_counts.cpu(), torch.from_numpy(fix[f"stats_count_{it}"])), it
         assert torch.allclose(stats.max_2Dsize.cpu(), torch.from_numpy(fix[f"stats_max2d_{it}"]), rtol=1e-6, atol=0), it
     assert float(stats.vis_counts.max()) == 3.0 and float(stats.vis_counts.min()) == 1.0
+
+
+def check_sh_basis(sh_forward, device=torch.device("cpu")):
+    """The 25 basis functions of the SH evaluation (gsplat's A10 table) against the reference's OWN real-SH basis
+    (nerfstudio/utils/math.py:29-92): identical functions in identical order up to the sign (-1)^|m| that gsplat's
+    convention carries.  `sh_forward(degrees_to_use, dirs [N,3], coeffs [N,K,3]) -> [N,3]`; the basis is read off with
+    one-hot coefficients."""
+    fix = load("ref_init_small")
+    dirs = torch.from_numpy(fix["sh_dirs"]).to(device)
+    want = torch.from_numpy(fix["sh_components"]).double()
+    n = dirs.shape[0]
+    sign = torch.tensor([(-1.0) ** abs(m) for l in range(5) for m in range(-l, l + 1)], dtype=torch.float64)
+    assert sign.numel() == 25
+    for b in range(25):
+        coeffs = torch.zeros((n, 25, 3), device=device)
+        coeffs[:, b, 0], coeffs[:, b, 1], coeffs[:, b, 2] = 1.0, 2.0, -0.5
+        got = torch.as_tensor(sh_forward(4, dirs, coeffs)).detach().cpu().double()
+        for c, w in enumerate((1.0, 2.0, -0.5)):
+            err = float((got[:, c] - w * sign[b] * want[:, b]).abs().max())
+            assert err <= 2e-6, f"basis {b}, colour {c}: {err:.3e}"
+    # fewer degrees in use: the higher bands are ignored
+    coeffs = torch.ones((n, 25, 3), device=device)
+    for deg, nb in ((0, 1), (1, 4), (2, 9), (3, 16)):
+        got = torch.as_tensor(sh_forward(deg, dirs, coeffs)).detach().cpu().double()
+        ref = (sign[:nb] * want[:, :nb]).sum(dim=1)
+        assert float((got - ref[:, None]).abs().max()) <= 5e-6, deg

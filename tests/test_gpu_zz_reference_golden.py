@@ -53,3 +53,8 @@ def test_cuda_initialisation_and_up_projection_match_the_reference():
 
 def test_cuda_densification_statistics_match_the_references_after_train():
     checks.check_after_train(ProductBackend())
+
+
+def test_cuda_sh_basis_equals_the_references_own_real_sh_basis():
+    from gaussiangrasper_b200 import SphericalHarmonics
+    checks.check_sh_basis(lambda deg, d, c: SphericalHarmonics.apply(deg, d, c), torch.device("cuda:0"))

@@ -33,6 +33,13 @@ def test_references_initialisation_and_up_projection():
     checks.check_init(checks.OracleBackend())
 
 
+def test_oracle_sh_basis_equals_the_references_own_real_sh_basis():
+    """Row a2: both restatements of gsplat's SH table against nerfstudio/utils/math.py's basis."""
+    from oracle import c_oracle, torch_oracle
+    checks.check_sh_basis(lambda deg, d, c: c_oracle.sh_fwd(deg, d.numpy(), c.numpy()))
+    checks.check_sh_basis(lambda deg, d, c: torch_oracle.spherical_harmonics(deg, d.double(), c.double()))
+
+
 def test_references_after_train_statistics():
     checks.check_after_train(checks.OracleBackend())
 
