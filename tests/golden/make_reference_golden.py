@@ -19,7 +19,8 @@ inputs.  Needs /root/reference (build container only); the resulting fixtures tr
                          :315-331 with the real scikit-learn), the up-projection MLP (:198-213) forward on seeded
                          weights, projection_matrix (:87-105), SH2RGB (:80-85), the arguments get_outputs (:624-713) hands to
                          ProjectGaussians.apply for a few nerfstudio cameras, after_train's densification statistics (:373-393) over
-                         three steps, nerfstudio's own real-SH basis (utils/math.py:29-92), the optimizer table of the method
+                         three steps, nerfstudio's own real-SH basis (utils/math.py:29-92) and quaternion -> rotation
+                         matrix (cameras/camera_utils.py:142-161), the optimizer table of the method
                          (configs/method_configs.py:611-664, read from the source's syntax tree) and the trainer's
                          ExponentialDecayScheduler (nerfstudio/engine/schedulers.py:109-140, imported and run) learning
                          rates for it
@@ -247,6 +248,11 @@ def init_fixture(gs):
     d = torch.nn.functional.normalize(torch.randn((96, 3), generator=torch.Generator().manual_seed(51)).double(), dim=-1)
     out["sh_dirs"] = d.float().numpy()
     out["sh_components"] = components_from_spherical_harmonics(5, d.float()).numpy()
+    # the reference's own quaternion (w, x, y, z; any length) -> rotation matrix (nerfstudio/cameras/camera_utils.py:142-161)
+    from nerfstudio.cameras.camera_utils import quaternion_matrix
+    q = torch.randn((64, 4), generator=torch.Generator().manual_seed(52)) * 1.7
+    out["quat_wxyz"] = q.numpy()
+    out["quat_rotmat"] = np.stack([quaternion_matrix(row)[:3, :3] for row in q.numpy()])
     return out
 
 

@@ -268,3 +268,29 @@ def check_sh_basis(sh_forward, device=torch.device("cpu")):
         got = torch.as_tensor(sh_forward(deg, dirs, coeffs)).detach().cpu().double()
         ref = (sign[:nb] * want[:, :nb]).sum(dim=1)
         assert float((got - ref[:, None]).abs().max()) <= 5e-6, deg
+
+
+def check_quaternion_convention(quat_to_rotmat=None, project=None, device=torch.device("cpu")):
+    """The (w, x, y, z) quaternion convention against the reference's OWN quaternion_matrix
+    (nerfstudio/cameras/camera_utils.py:142-161): `quat_to_rotmat(q [N,4]) -> [N,3,3]` directly, and `project(means,
+    scales, quats, camera) -> cov3d [N,6]` (the upper triangle of R S S^T R^T the projection emits) through
+    the matrices it implies."""
+    from gaussiangrasper_b200 import scenes
+    fix = load("ref_init_small")
+    q = torch.from_numpy(fix["quat_wxyz"])
+    R = torch.from_numpy(fix["quat_rotmat"])                       # fp64, [N,3,3]
+    if quat_to_rotmat is not None:
+        got = torch.as_tensor(quat_to_rotmat(q.to(device))).detach().cpu().double()
+        assert float((got - R).abs().max()) <= 2e-6
+    if project is not None:
+        n = q.shape[0]
+        g = torch.Generator().manual_seed(5)
+        scales = torch.rand((n, 3), generator=g) * 0.2 + 0.01
+        means = (torch.rand((n, 3), generator=g) - 0.5) * 0.5      # all in front of a camera 4.5 away
+        cam = scenes.look_at_camera((4.5, 0.3, 0.2), 160, 120)
+        qn = q / q.norm(dim=-1, keepdim=True)                      # what the model passes (:703)
+        cov3d = torch.as_tensor(project(means.to(device), scales.to(device), qn.to(device), cam)).detach().cpu().double()
+        want = R @ torch.diag_embed(scales.double() ** 2) @ R.transpose(1, 2)
+        tri = torch.stack([want[:, 0, 0], want[:, 0, 1], want[:, 0, 2], want[:, 1, 1], want[:, 1, 2], want[:, 2, 2]], dim=1)
+        assert cov3d.shape == tri.shape
+        assert float((cov3d - tri).abs().max()) <= 2e-6 * float(tri.abs().max())

@@ -58,3 +58,14 @@ def test_cuda_densification_statistics_match_the_references_after_train():
 def test_cuda_sh_basis_equals_the_references_own_real_sh_basis():
     from gaussiangrasper_b200 import SphericalHarmonics
     checks.check_sh_basis(lambda deg, d, c: SphericalHarmonics.apply(deg, d, c), torch.device("cuda:0"))
+
+
+def test_cuda_projection_covariance_follows_the_references_quaternion_matrix():
+    from gaussiangrasper_b200 import ProjectGaussians
+    dev = torch.device("cuda:0")
+
+    def project(means, scales, quats, cam):
+        out = ProjectGaussians.apply(means, scales, 1.0, quats, cam.viewmat[:3].to(dev), cam.fullmat.to(dev), cam.fx, cam.fy,
+                                     cam.cx, cam.cy, cam.H, cam.W, cam.tile_bounds)
+        return out[5]
+    checks.check_quaternion_convention(None, project, dev)

@@ -40,6 +40,21 @@ def test_oracle_sh_basis_equals_the_references_own_real_sh_basis():
     checks.check_sh_basis(lambda deg, d, c: torch_oracle.spherical_harmonics(deg, d.double(), c.double()))
 
 
+def test_quaternion_convention_equals_the_references_own_quaternion_matrix():
+    """Rows a1 / a6: the product's quat_to_rotmat, the oracles' and the covariance the projection oracle emits."""
+    from gaussiangrasper_b200 import _torch_impl
+    from oracle import c_oracle, refine_oracle, torch_oracle
+    checks.check_quaternion_convention(_torch_impl.quat_to_rotmat)
+    checks.check_quaternion_convention(refine_oracle.quat_to_rotmat)
+    checks.check_quaternion_convention(torch_oracle.quat_to_rotmat)
+
+    def project(means, scales, quats, cam):
+        out = c_oracle.project_fwd(means.numpy(), scales.numpy(), 1.0, quats.numpy(), cam.viewmat[:3].numpy(),
+                                   cam.fullmat.numpy(), cam.fx, cam.fy, cam.cx, cam.cy, cam.H, cam.W, cam.tile_bounds)
+        return out[5]
+    checks.check_quaternion_convention(None, project)
+
+
 def test_references_after_train_statistics():
     checks.check_after_train(checks.OracleBackend())
 
