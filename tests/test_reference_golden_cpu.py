@@ -55,6 +55,21 @@ def test_quaternion_convention_equals_the_references_own_quaternion_matrix():
     checks.check_quaternion_convention(None, project)
 
 
+def test_samplers_draw_what_the_references_samplers_drew():
+    """losses.sampling_pairs_in_mask / sampling_in_mask (:120-148) on the segment mask of the fixture, from the seed the
+    reference's get_loss_dict ran under: the same pixel lists, in the same order."""
+    from gaussiangrasper_b200 import losses
+    fix = checks.load("ref_losses_small")
+    mask = torch.from_numpy(fix["gt_mask"])
+    torch.manual_seed(13)                                   # make_reference_golden.losses_fixture
+    pairs = losses.sampling_pairs_in_mask(mask, int(fix["pairs_num"][0]))
+    points = losses.sampling_in_mask(mask, int(fix["points_num"][0]))
+    assert len(pairs) == int(fix["n_segments"][0])
+    for i, (a, b) in enumerate(pairs):
+        assert torch.equal(a, torch.from_numpy(fix[f"pairs_{i}_a"])) and torch.equal(b, torch.from_numpy(fix[f"pairs_{i}_b"])), i
+    assert torch.equal(points, torch.from_numpy(fix["points"]))
+
+
 def test_references_after_train_statistics():
     checks.check_after_train(checks.OracleBackend())
 
