@@ -24,6 +24,8 @@ inputs.  Needs /root/reference (build container only); the resulting fixtures tr
                          (configs/method_configs.py:611-664, read from the source's syntax tree) and the trainer's
                          ExponentialDecayScheduler (nerfstudio/engine/schedulers.py:109-140, imported and run) learning
                          rates for it
+  ref_trainer_small.npz  Trainer.train_iteration (engine/trainer.py:458-499) itself, 25 iterations with the real Optimizers
+                         and the method's gradient-accumulation table: parameters after every iteration
 """
 import os
 import sys
@@ -369,11 +371,69 @@ def optimizer_table():
                 accumulation_groups=np.array(list(accumulation)), accumulation_steps=np.array(list(accumulation.values())))
 
 
+# ---------------------------------------------------------------------------------------------------------------
+def trainer_fixture(gs):
+    """Trainer.train_iteration (engine/trainer.py:458-499), the reference's own function, run for 25 iterations on a
+    stand-in `self` that holds the REAL Optimizers (built from the method's optimizer table), the method's gradient
+    accumulation table and a pipeline whose loss is linear in the parameters -- so that every iteration's gradients
+    are the stored arrays.  Stored: initial parameters, gradients per iteration, parameters after every iteration."""
+    from collections import defaultdict
+    from reference_model_driver import import_with_stubs
+    from nerfstudio.engine.optimizers import AdamOptimizerConfig, Optimizers
+    from nerfstudio.engine.schedulers import ExponentialDecaySchedulerConfig
+    tr, _ = import_with_stubs("nerfstudio.engine.trainer")
+    table = optimizer_table()
+    cfg = {}
+    for group, (lr, eps, lr_final, max_steps) in zip(table["opt_groups"].tolist(), table["opt_lr_eps_final_maxsteps"]):
+        cfg[group] = {"optimizer": AdamOptimizerConfig(lr=float(lr), eps=float(eps)),
+                      "scheduler": ExponentialDecaySchedulerConfig(lr_final=float(lr_final), max_steps=int(max_steps))
+                      if max_steps > 0 else None}
+    torch.manual_seed(61)
+    n, T = 24, 25
+    model = small_model(gs, n)
+    g = torch.Generator().manual_seed(62)
+    with torch.no_grad():
+        model.colors_all[:, 1:, :] = torch.randn(model.colors_all[:, 1:, :].shape, generator=g) * 0.1
+    groups = model.get_param_groups()
+    accumulation = defaultdict(lambda: 1)
+    accumulation.update(dict(zip(table["accumulation_groups"].tolist(), table["accumulation_steps"].tolist())))
+    grads = {k: torch.randn((T,) + tuple(getattr(model, attr).shape), generator=g) * 1e-2 for k, attr in PARAM_OF.items()}
+
+    class Pipeline:
+        model_ = model
+
+        def get_train_loss_dict(self, step):
+            loss = {k: (getattr(model, attr) * grads[k][step]).sum() for k, attr in PARAM_OF.items()}
+            return None, loss, {}
+    fake = types.SimpleNamespace(optimizers=Optimizers(cfg, groups), gradient_accumulation_steps=accumulation, device="cpu",
+                                 mixed_precision=False, pipeline=Pipeline(), config=types.SimpleNamespace(log_gradients=False),
+                                 grad_scaler=torch.cuda.amp.GradScaler(enabled=False))
+    out = dict(steps=np.array([T]))
+    for k, attr in PARAM_OF.items():
+        out["init_" + k] = getattr(model, attr).detach().numpy().copy()
+        out["grads_" + k] = grads[k].numpy()
+    traj = {k: [] for k in PARAM_OF}
+    lrs = {k: [] for k in GROUP_OF}
+    for step in range(T):
+        for k, grp in GROUP_OF.items():
+            lrs[k].append(float(fake.optimizers.optimizers[grp].param_groups[0]["lr"]))      # the rate this iteration uses
+        tr.Trainer.train_iteration(fake, step)
+        for k, attr in PARAM_OF.items():
+            traj[k].append(getattr(model, attr).detach().numpy().copy())
+    for k in PARAM_OF:
+        out["after_" + k] = np.stack(traj[k])
+        out["lr_" + k] = np.array(lrs[k], dtype=np.float64)
+        opt = fake.optimizers.optimizers[GROUP_OF[k]]
+        out["final_step_" + k] = np.array([float(opt.state[opt.param_groups[0]["params"][0]]["step"])])
+    return out
+
+
 def main():
     assert os.path.exists(os.path.join(REF, "nerfstudio/models/gaussian_splatting.py")), "needs /root/reference"
     out_dir = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else HERE
     gs = import_reference()
-    for name, fn in (("refine_small", refine_fixture), ("ref_losses_small", losses_fixture), ("ref_init_small", init_fixture)):
+    for name, fn in (("refine_small", refine_fixture), ("ref_losses_small", losses_fixture), ("ref_init_small", init_fixture),
+                     ("ref_trainer_small", trainer_fixture)):
         path = os.path.join(out_dir, name + ".npz")
         np.savez_compressed(path, **fn(gs))
         print(path, os.path.getsize(path), "bytes")

@@ -1,6 +1,7 @@
 """Checks against the fixtures the REFERENCE ITSELF produced (tests/golden/make_reference_golden.py: the unmodified
 nerfstudio/models/gaussian_splatting.py run on seeded inputs): get_loss_dict with its gradients, the k-NN scale
-initialisation, the up-projection MLP and after_train's densification statistics.  Each check is written once, against the signatures of the product's loss
+initialisation, the up-projection MLP, after_train's densification statistics, nerfstudio's own SH basis and
+quaternion convention, and the parameter trajectory of the reference's own Trainer.train_iteration.  Each check is written once, against the signatures of the product's loss
 functions (gaussiangrasper_b200.losses / .training):
 
   * tests/test_gpu_zz_reference_golden.py passes the product (CUDA kernels through the C ABI);
@@ -109,6 +110,48 @@ class OracleBackend:
                     st.xys_grad_norm[visible] += grads[visible]
                 st.max_2Dsize[visible] = torch.maximum(st.max_2Dsize[visible], radii[visible].float() / float(max(H, W)))
         return Stats()
+
+    def make_adam(self, params):
+        """training.FusedAdam.reference(params): the product's own host logic (FusedAdam.plan, REFERENCE_* tables,
+        exponential_decay_lr) around a plain-torch restatement of what gg_adam_step does per mode."""
+        from gaussiangrasper_b200 import training
+
+        class CpuAdam:
+            def __init__(self):
+                self.names = [k for k in params]
+                self.bucket = self                      # FusedAdam.plan reads self.bucket.names; pack() below
+                self.accumulation = dict(training.REFERENCE_ACCUMULATION)
+                self.schedules = dict(training.REFERENCE_SCHEDULES)
+                self.lr_init = dict(training.REFERENCE_LRS)
+                self.lrs = dict(self.lr_init)
+                self.steps = {k: 0 for k in params}
+                self.m = {k: torch.zeros_like(v, dtype=torch.float64) for k, v in params.items()}
+                self.v = {k: torch.zeros_like(v, dtype=torch.float64) for k, v in params.items()}
+                self.acc = {k: torch.zeros_like(v, dtype=torch.float64) for k, v in params.items()}
+
+            def pack(self, grads):
+                self.grads = grads
+
+            def train_step(self, it):
+                for k, (lr_final, max_steps) in self.schedules.items():
+                    self.lrs[k] = training.exponential_decay_lr(self.lr_init[k], lr_final, max_steps, it)
+                modes = training.FusedAdam.plan(self, it)
+                for k, mode in modes.items():
+                    g = self.grads[k].double()
+                    if mode == "acc_first":
+                        self.acc[k] = g.clone()
+                    elif mode in ("acc", "acc_step"):
+                        self.acc[k] += g
+                    if mode in ("step", "acc_step"):
+                        g = self.acc[k] if mode == "acc_step" else g
+                        self.steps[k] += 1
+                        t = self.steps[k]
+                        self.m[k] = 0.9 * self.m[k] + 0.1 * g
+                        self.v[k] = 0.999 * self.v[k] + 0.001 * g * g
+                        upd = self.lrs[k] * (self.m[k] / (1 - 0.9 ** t)) / ((self.v[k] / (1 - 0.999 ** t)).sqrt() + 1e-15)
+                        params[k].copy_((params[k].double() - upd).float())
+                return modes
+        return CpuAdam()
 
     def up_project(self, features, mlp):
         with torch.no_grad():
@@ -294,3 +337,32 @@ def check_quaternion_convention(quat_to_rotmat=None, project=None, device=torch.
         tri = torch.stack([want[:, 0, 0], want[:, 0, 1], want[:, 0, 2], want[:, 1, 1], want[:, 1, 2], want[:, 2, 2]], dim=1)
         assert cov3d.shape == tri.shape
         assert float((cov3d - tri).abs().max()) <= 2e-6 * float(tri.abs().max())
+
+
+def check_trainer(backend):
+    """FusedAdam.reference(...).train_step(it) against the parameters the reference's OWN Trainer.train_iteration
+    (engine/trainer.py:458-499) left after each of 25 iterations -- real Optimizers from the method's optimizer table,
+    its gradient-accumulation table, its schedulers."""
+    fix = load("ref_trainer_small")
+    dev = backend.device
+    names = ("means", "log_scales", "quats", "opacity_logit", "sh_coeffs", "features")
+    params = {k: torch.from_numpy(fix["init_" + k]).clone().to(dev) for k in names}
+    params["opacity_logit"] = params["opacity_logit"].reshape(-1)              # [N] here, [N,1] in the reference
+    opt = backend.make_adam(params)
+    T = int(fix["steps"][0])
+    for it in range(T):
+        grads = {k: torch.from_numpy(fix["grads_" + k][it]).to(dev).reshape(params[k].shape) for k in names}
+        opt.bucket.pack(grads)
+        opt.train_step(it)
+        for k in names:
+            assert opt.lrs[k] == pytest_approx(float(fix["lr_" + k][it])), (it, k, opt.lrs[k])
+            want = torch.from_numpy(fix["after_" + k][it]).reshape(params[k].shape)
+            assert torch.allclose(params[k].cpu(), want, rtol=3e-6, atol=2e-7), (it, k, float((params[k].cpu() - want).abs().max()))
+    for k in names:
+        assert opt.steps[k] == int(fix["final_step_" + k][0]), k
+    assert opt.steps["means"] == 2 and opt.steps["quats"] == T
+
+
+def pytest_approx(v, rel=1e-12):
+    import pytest
+    return pytest.approx(v, rel=rel)

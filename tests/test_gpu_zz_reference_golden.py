@@ -34,6 +34,10 @@ class ProductBackend:
         from gaussiangrasper_b200.training import DensifyStats
         return DensifyStats(n, self.device)
 
+    def make_adam(self, params):
+        from gaussiangrasper_b200.training import FusedAdam
+        return FusedAdam.reference(params)
+
     def make_mlp(self, state):
         mlp = self._losses.UpProjection(checks.D).to(self.device)
         mlp.load_state_dict({k: v.float() for k, v in state.items()})    # the reference's parameter names
@@ -69,3 +73,7 @@ def test_cuda_projection_covariance_follows_the_references_quaternion_matrix():
                                      cam.cx, cam.cy, cam.H, cam.W, cam.tile_bounds)
         return out[5]
     checks.check_quaternion_convention(None, project, dev)
+
+
+def test_cuda_fused_adam_follows_the_references_own_train_iteration():
+    checks.check_trainer(ProductBackend())

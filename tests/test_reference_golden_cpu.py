@@ -70,6 +70,12 @@ def test_samplers_draw_what_the_references_samplers_drew():
     assert torch.equal(points, torch.from_numpy(fix["points"]))
 
 
+def test_host_side_of_the_fused_adam_follows_the_references_own_train_iteration():
+    """FusedAdam.plan, the REFERENCE_* tables and exponential_decay_lr (the host logic around gg_adam_step) against
+    the trajectory of the reference's own Trainer.train_iteration."""
+    checks.check_trainer(checks.OracleBackend())
+
+
 def test_references_after_train_statistics():
     checks.check_after_train(checks.OracleBackend())
 
@@ -156,7 +162,7 @@ def test_the_reference_regenerates_the_committed_fixtures(tmp_path):
     r = subprocess.run([sys.executable, os.path.join(HERE, "golden", "make_reference_golden.py"), "--out", str(tmp_path)],
                        capture_output=True, text=True, timeout=900, cwd=str(tmp_path))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
-    for name in ("refine_small", "ref_losses_small", "ref_init_small"):
+    for name in ("refine_small", "ref_losses_small", "ref_init_small", "ref_trainer_small"):
         want, got = checks.load(name), dict(np.load(os.path.join(str(tmp_path), name + ".npz")))
         assert set(want) == set(got), name
         for k in want:
