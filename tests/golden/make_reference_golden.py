@@ -26,6 +26,8 @@ inputs.  Needs /root/reference (build container only); the resulting fixtures tr
                          rates for it
   ref_trainer_small.npz  Trainer.train_iteration (engine/trainer.py:458-499) itself, 25 iterations with the real Optimizers
                          and the method's gradient-accumulation table: parameters after every iteration
+  ref_ply_small.npz      ExportGaussianSplat.main (scripts/exporter.py:482-530) itself on a small model; open3d is absent,
+                         the attribute map it hands to o3d.t.geometry.PointCloud is recorded
 """
 import os
 import sys
@@ -428,12 +430,65 @@ def trainer_fixture(gs):
     return out
 
 
+def ply_fixture(gs):
+    """ExportGaussianSplat.main (nerfstudio/scripts/exporter.py:482-530), the reference's own exporter, run on a small
+    model: open3d is absent, so the attribute map the exporter builds and hands to o3d.t.geometry.PointCloud is
+    recorded instead of written (names in the order the exporter inserts them, arrays, dtypes).  The order in which
+    open3d then writes the properties into the file is open3d's and not visible here."""
+    from reference_model_driver import import_with_stubs
+    ex, _ = import_with_stubs("nerfstudio.scripts.exporter")
+    torch.manual_seed(71)
+    model = small_model(gs, 40)
+    g = torch.Generator().manual_seed(72)
+    with torch.no_grad():
+        model.colors_all.copy_(torch.randn(model.colors_all.shape, generator=g) * 3.0)   # colours beyond [0,1] too: the uint8 cast
+        model.opacities.copy_(torch.randn(model.opacities.shape, generator=g))
+    recorded = {}
+
+    class O3D:
+        class core:
+            float32 = "float32"
+
+            @staticmethod
+            def Tensor(a, dtype):
+                return np.asarray(a, dtype=np.float32)
+
+        class t:
+            class geometry:
+                @staticmethod
+                def PointCloud(m):
+                    recorded.update(m)
+                    return m
+
+            class io:
+                @staticmethod
+                def write_point_cloud(path, pcd):
+                    recorded["__path__"] = path
+    orig_o3d, orig_setup = ex.o3d, ex.eval_setup
+    ex.o3d = O3D
+    ex.eval_setup = lambda cfg: (None, types.SimpleNamespace(model=model), None, None)
+    try:
+        import pathlib
+        import tempfile
+        with tempfile.TemporaryDirectory() as d:
+            ex.ExportGaussianSplat.main(types.SimpleNamespace(output_dir=pathlib.Path(d), load_config=None))
+    finally:
+        ex.o3d, ex.eval_setup = orig_o3d, orig_setup
+    assert recorded.pop("__path__").endswith("point_cloud.ply")
+    out = dict(attribute_names=np.array(list(recorded)))
+    for k, v in recorded.items():
+        out["attr_" + k] = np.asarray(v)
+    for k, attr in PARAM_OF.items():
+        out["param_" + k] = getattr(model, attr).detach().numpy().copy()
+    return out
+
+
 def main():
     assert os.path.exists(os.path.join(REF, "nerfstudio/models/gaussian_splatting.py")), "needs /root/reference"
     out_dir = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else HERE
     gs = import_reference()
     for name, fn in (("refine_small", refine_fixture), ("ref_losses_small", losses_fixture), ("ref_init_small", init_fixture),
-                     ("ref_trainer_small", trainer_fixture)):
+                     ("ref_trainer_small", trainer_fixture), ("ref_ply_small", ply_fixture)):
         path = os.path.join(out_dir, name + ".npz")
         np.savez_compressed(path, **fn(gs))
         print(path, os.path.getsize(path), "bytes")

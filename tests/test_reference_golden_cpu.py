@@ -76,6 +76,34 @@ def test_host_side_of_the_fused_adam_follows_the_references_own_train_iteration(
     checks.check_trainer(checks.OracleBackend())
 
 
+def test_ply_writer_carries_what_the_references_exporter_hands_to_open3d(tmp_path):
+    """ply.write_ply against the attribute map the reference's own ExportGaussianSplat.main (scripts/exporter.py:482-530)
+    built for the same parameters (open3d's PointCloud call recorded): every attribute, value for value, with the
+    uint8 colours' wrap-around cast, the single f_rest_0 column, and the exporter's insertion order (positions,
+    normals, colors, f_dc_*, f_rest_0, opacity, scale_*, rot_*)."""
+    from gaussiangrasper_b200 import ply
+    fix = checks.load("ref_ply_small")
+    names = ("means", "log_scales", "quats", "opacity_logit", "sh_coeffs", "features")
+    params = {k: torch.from_numpy(fix["param_" + k]) for k in names}
+    path = str(tmp_path / "point_cloud.ply")
+    assert ply.write_ply(path, params) == params["means"].shape[0]
+    got = ply.read_ply(path)
+    expand = dict(positions=("x", "y", "z"), normals=("nx", "ny", "nz"), colors=("red", "green", "blue"))
+    order = []
+    for attr in fix["attribute_names"].tolist():
+        want = fix["attr_" + attr]
+        cols = expand.get(attr, (attr,))
+        assert want.shape[1] == len(cols), attr
+        for j, c in enumerate(cols):
+            assert got[c].dtype == want.dtype, (c, got[c].dtype, want.dtype)
+            assert np.array_equal(got[c], want[:, j]), c
+            order.append(c)
+    assert list(got) == order
+    assert (fix["attr_colors"] == 0).sum() + (fix["attr_colors"] == 255).sum() < fix["attr_colors"].size   # a real test of the cast
+    colors = fix["param_sh_coeffs"][:, 0, :] * 0.28209479177387814 + 0.5
+    assert (colors < 0).any() and (colors > 1).any()          # values outside [0, 1] went through the uint8 cast
+
+
 def test_references_after_train_statistics():
     checks.check_after_train(checks.OracleBackend())
 
@@ -162,7 +190,7 @@ def test_the_reference_regenerates_the_committed_fixtures(tmp_path):
     r = subprocess.run([sys.executable, os.path.join(HERE, "golden", "make_reference_golden.py"), "--out", str(tmp_path)],
                        capture_output=True, text=True, timeout=900, cwd=str(tmp_path))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
-    for name in ("refine_small", "ref_losses_small", "ref_init_small", "ref_trainer_small"):
+    for name in ("refine_small", "ref_losses_small", "ref_init_small", "ref_trainer_small", "ref_ply_small"):
         want, got = checks.load(name), dict(np.load(os.path.join(str(tmp_path), name + ".npz")))
         assert set(want) == set(got), name
         for k in want:
