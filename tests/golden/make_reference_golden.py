@@ -28,6 +28,9 @@ inputs.  Needs /root/reference (build container only); the resulting fixtures tr
                          and the method's gradient-accumulation table: parameters after every iteration
   ref_ply_small.npz      ExportGaussianSplat.main (scripts/exporter.py:482-530) itself on a small model; open3d is absent,
                          the attribute map it hands to o3d.t.geometry.PointCloud is recorded
+  ref_outputs_small.npz  GaussianSplattingModel.get_outputs (:624-802) + backward itself, SH degree 4; the operator classes it
+                         calls are this repository's with the CPU oracle underneath (gsplat is absent): pins the glue around
+                         the operators to the reference's code
 """
 import os
 import sys
@@ -483,12 +486,67 @@ def ply_fixture(gs):
     return out
 
 
+def outputs_fixture(gs):
+    """GaussianSplattingModel.get_outputs (:624-802) + backward, the reference's own model code, at SH degree 4 on a
+    48x64 view.  gsplat itself is absent: the four operator classes the model calls are this repository's autograd
+    Functions with the CPU oracle underneath (tests/reference_model_driver.install_oracle_backend), so the fixture pins
+    everything AROUND the operators -- activations, view directions, SH clamp, the smallest-axis normal, backgrounds,
+    channel order, which gradients flow where -- to the reference's code, and the operators to the oracle.  Also stored:
+    the pixels the oracle flags as decided within 2e-5 of a blending threshold."""
+    from nerfstudio.cameras.cameras import Cameras, CameraType
+    from reference_model_driver import install_oracle_backend
+    from oracle import c_oracle
+    from gaussiangrasper_b200 import scenes
+    install_oracle_backend()
+    torch.manual_seed(81)
+    n, H, W = 800, 48, 64
+    model = small_model(gs, n)
+    model.train()
+    g = torch.Generator().manual_seed(82)
+    with torch.no_grad():
+        model.means.mul_(0.3)
+        model.scales.add_(-2.3 + 0.4 * torch.randn(model.scales.shape, generator=g))
+        model.quats.mul_(1.0 + torch.rand((n, 1), generator=g))                  # un-normalised, as during training
+        model.opacities.copy_(torch.randn(model.opacities.shape, generator=g) * 1.5)
+        model.colors_all[:, 1:, :] = torch.randn(model.colors_all[:, 1:, :].shape, generator=g) * 0.15
+    model.step = 4600                        # full resolution (:599-603), SH degree min(4600 // 1000, 4) = 4 (:729)
+    c2w = torch.tensor([[[0.96, 0.0, 0.28, 1.1], [0.0, 1.0, 0.0, 0.1], [-0.28, 0.0, 0.96, 3.8]]])
+    fx, fy, cx, cy = 61.5, 60.25, 32.75, 23.5
+    cam = Cameras(camera_to_worlds=c2w, fx=fx, fy=fy, cx=cx, cy=cy, width=W, height=H, camera_type=CameraType.PERSPECTIVE)
+    out = model.get_outputs(cam)
+    v = dict(rgb=torch.randn((H, W, 3), generator=g), feature=torch.randn((H, W, 32), generator=g),
+             depth=torch.randn((H, W, 1), generator=g) * 0.1, normal=torch.randn((H, W, 3), generator=g))
+    sum((out[k] * v[k]).sum() for k in v).backward()
+    res = dict(c2w=c2w[0].numpy(), intrinsics=np.array([fx, fy, cx, cy]), size=np.array([H, W]), step=np.array([4600]),
+               radii=model.radii.numpy().copy(), xys=model.xys.detach().numpy().copy(), grad_xys=model.xys.grad.numpy().copy())
+    for k, attr in PARAM_OF.items():
+        res["param_" + k] = getattr(model, attr).detach().numpy().copy()
+        res["grad_" + k] = getattr(model, attr).grad.numpy().copy()
+    for k in v:
+        res["out_" + k], res["v_" + k] = out[k].detach().numpy().copy(), v[k].numpy()
+    # fragile pixels: the oracle's own flag on the same projection
+    c = scenes.camera_from_c2w(c2w[0], fx, fy, cx, cy, W, H)
+    q = model.quats.detach() / model.quats.detach().norm(dim=-1, keepdim=True)
+    xys, depths, radii, conics, nth, _ = c_oracle.project_fwd(model.means.detach().numpy(), model.scales.detach().exp().numpy(), 1.0,
+                                                              q.numpy(), c.viewmat[:3].numpy(), c.fullmat.numpy(), c.fx, c.fy,
+                                                              c.cx, c.cy, H, W, c.tile_bounds)
+    assert np.array_equal(radii, res["radii"]) and np.array_equal(xys, res["xys"])
+    _, _, _, _, ids_s, ranges = c_oracle.bin_and_sort(xys, depths, radii, nth, c.tile_bounds)
+    ref = c_oracle.blend_fwd(H, W, c.tile_bounds, ids_s, ranges, xys, conics, torch.sigmoid(model.opacities.detach()).reshape(-1).numpy(),
+                             np.zeros((n, 3), np.float32), np.zeros(3, np.float32), eps=2e-5)
+    res["fragile"] = ref[3]
+    res["visible"] = np.array([int((radii > 0).sum())])
+    res["intersections"] = np.array([len(ids_s)])
+    return res
+
+
 def main():
     assert os.path.exists(os.path.join(REF, "nerfstudio/models/gaussian_splatting.py")), "needs /root/reference"
     out_dir = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else HERE
     gs = import_reference()
     for name, fn in (("refine_small", refine_fixture), ("ref_losses_small", losses_fixture), ("ref_init_small", init_fixture),
-                     ("ref_trainer_small", trainer_fixture), ("ref_ply_small", ply_fixture)):
+                     ("ref_trainer_small", trainer_fixture), ("ref_ply_small", ply_fixture),
+                     ("ref_outputs_small", outputs_fixture)):      # (last: it swaps the oracle in underneath the operators)
         path = os.path.join(out_dir, name + ".npz")
         np.savez_compressed(path, **fn(gs))
         print(path, os.path.getsize(path), "bytes")

@@ -366,3 +366,36 @@ def check_trainer(backend):
 def pytest_approx(v, rel=1e-12):
     import pytest
     return pytest.approx(v, rel=rel)
+
+
+def check_outputs(render, rtol_grad=2e-3):
+    """One view through the whole model-side path against what the reference's OWN get_outputs + backward produced
+    (ref_outputs_small.npz; the operators underneath were this repository's classes on the CPU oracle): images to
+    1e-4 on every pixel the oracle does not flag as threshold-fragile, the six leaf gradients and xys.grad relative to
+    each array's largest entry (99.95 % of the entries within rtol_grad, every entry within 50 rtol_grad).
+    `render(params, camera, v) -> (outputs, gradients)`: params / v / outputs are dicts of CPU tensors, gradients has
+    the six parameter names and "xys"."""
+    from gaussiangrasper_b200 import scenes
+    fix = load("ref_outputs_small")
+    H, W = (int(x) for x in fix["size"])
+    fx, fy, cx, cy = (float(x) for x in fix["intrinsics"])
+    cam = scenes.camera_from_c2w(fix["c2w"], fx, fy, cx, cy, W, H)
+    names = ("means", "log_scales", "quats", "opacity_logit", "sh_coeffs", "features")
+    params = {k: torch.from_numpy(fix["param_" + k]) for k in names}
+    v = {k: torch.from_numpy(fix["v_" + k]) for k in ("rgb", "feature", "depth", "normal")}
+    outs, grads = render(params, cam, v)
+    frag = fix["fragile"].astype(bool)
+    assert frag.mean() < 0.02
+    for k in v:
+        got, want = np.asarray(outs[k], dtype=np.float64), fix["out_" + k].astype(np.float64)
+        assert got.shape == want.shape, (k, got.shape, want.shape)
+        err = np.abs(got - want)
+        assert err[~frag].max() <= 1e-4, f"{k}: {err[~frag].max():.3e} on stable pixels"
+        assert err.max() <= 5e-2, k
+    assert float((fix["out_depth"] > 9.9).mean()) > 0 and int(fix["visible"][0]) > 500       # background and splats both occur
+    for k in names + ("xys",):
+        got, want = np.asarray(grads[k], dtype=np.float64).reshape(-1), fix["grad_" + k].astype(np.float64).reshape(-1)
+        assert got.shape == want.shape, k
+        rel = np.abs(got - want) / (np.abs(want).max() + 1e-30)
+        assert np.quantile(rel, 0.9995) <= rtol_grad, f"{k}: q99.95 {np.quantile(rel, 0.9995):.3e}"
+        assert rel.max() <= 50 * rtol_grad, f"{k}: max {rel.max():.3e}"

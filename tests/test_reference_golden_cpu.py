@@ -104,6 +104,17 @@ def test_ply_writer_carries_what_the_references_exporter_hands_to_open3d(tmp_pat
     assert (colors < 0).any() and (colors > 1).any()          # values outside [0, 1] went through the uint8 cast
 
 
+def test_model_oracle_reproduces_the_references_get_outputs_and_backward():
+    """Row a7: `oracle_model` (tests/test_gpu_parity.py) -- the fp64 restatement of the model-side path that the GPU
+    tests of the fused render_views use as their checker -- against the reference's own get_outputs + backward."""
+    import test_gpu_parity as tgp
+
+    def render(params, cam, v):
+        outs, grads = tgp.oracle_model(params, cam, v)
+        return {k: o.detach().numpy() for k, o in outs.items()}, {k: g.numpy() for k, g in grads.items()}
+    checks.check_outputs(render, rtol_grad=2e-5)
+
+
 def test_references_after_train_statistics():
     checks.check_after_train(checks.OracleBackend())
 
@@ -190,7 +201,7 @@ def test_the_reference_regenerates_the_committed_fixtures(tmp_path):
     r = subprocess.run([sys.executable, os.path.join(HERE, "golden", "make_reference_golden.py"), "--out", str(tmp_path)],
                        capture_output=True, text=True, timeout=900, cwd=str(tmp_path))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
-    for name in ("refine_small", "ref_losses_small", "ref_init_small", "ref_trainer_small", "ref_ply_small"):
+    for name in ("refine_small", "ref_losses_small", "ref_init_small", "ref_trainer_small", "ref_ply_small", "ref_outputs_small"):
         want, got = checks.load(name), dict(np.load(os.path.join(str(tmp_path), name + ".npz")))
         assert set(want) == set(got), name
         for k in want:
