@@ -17,6 +17,11 @@
  *   SphericalHarmonics.apply    gaussian_splatting.py:730
  *   RasterizeGaussians.apply    gaussian_splatting.py:735,759,773
  *   NDRasterizeGaussians.apply  gaussian_splatting.py:747
+ * Two pieces of it ARE held by the reference and are checked against it
+ * (tests/test_reference_golden_cpu.py): the 25 spherical-harmonics basis functions
+ * (nerfstudio/utils/math.py:29-92, equal up to gsplat's (-1)^|m| sign) and the
+ * (w, x, y, z) quaternion -> rotation convention behind the 3D covariance
+ * (nerfstudio/cameras/camera_utils.py:142-161).
  *
  * Floating point discipline: every fp32 expression below is written with an
  * explicit left-to-right operation order and must be compiled with
