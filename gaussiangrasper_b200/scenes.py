@@ -87,12 +87,25 @@ def look_at_camera(position, W: int, H: int, target=(0.0, 0.0, 0.0)) -> Camera:
     return Camera(viewmat, projmat @ viewmat, fx, fy, cx, cy, H, W, pos.float())
 
 
-def camera_from_c2w(camera_to_world, fx: float, fy: float, cx: float, cy: float, W: int, H: int) -> Camera:
+def downscale_factor(step: int, num_downscales: int = 1, resolution_schedule: int = 250) -> int:
+    """The resolution warm-up of training (gaussian_splatting.py:599-603): renders are 2^d times smaller until
+    step reaches d * resolution_schedule."""
+    return 2 ** max(num_downscales - step // resolution_schedule, 0)
+
+
+def camera_from_c2w(camera_to_world, fx: float, fy: float, cx: float, cy: float, W: int, H: int,
+                    downscale: int = 1) -> Camera:
     """The camera set-up of GaussianSplattingModel.get_outputs (gaussian_splatting.py:657-678) for one nerfstudio
     camera: `camera_to_world` [3,4] (or [4,4]) in nerfstudio's convention (+x right, +y up, -z forward).  The y and z
     axes are flipped (the reference multiplies by SO3.from_x_radians(pi): diag(1,-1,-1) up to 1e-16), the pose is
     inverted analytically, the fields of view come from the focal lengths and the projection is
-    projection_matrix(0.001, 1000, fovx, fovy)."""
+    projection_matrix(0.001, 1000, fovx, fovy).  `downscale` > 1 is the training warm-up (downscale_factor): the
+    reference rescales the camera by 1 / downscale first (:656, Cameras.rescale_output_resolution -- fp32 products,
+    sizes truncated)."""
+    if downscale != 1:
+        sc = torch.tensor([1 / downscale])                    # fp32, like the reference's scaling tensor
+        fx, fy, cx, cy = ((torch.tensor(float(v), dtype=torch.float32) * sc).item() for v in (fx, fy, cx, cy))
+        W, H = int((torch.tensor(int(W)) * sc).to(torch.int64)), int((torch.tensor(int(H)) * sc).to(torch.int64))
     c2w = torch.as_tensor(camera_to_world, dtype=torch.float32).detach().cpu()
     R = c2w[:3, :3] * torch.tensor([1.0, -1.0, -1.0])        # R @ diag(1,-1,-1): columns y, z negated       (:662-663)
     T = c2w[:3, 3:4]
@@ -110,7 +123,7 @@ def camera_from_c2w(camera_to_world, fx: float, fy: float, cx: float, cy: float,
                   c2w[:3, 3].clone())                         # SH view directions start at the camera centre (:727)
 
 
-def cameras_from_nerfstudio(cameras) -> List[Camera]:
+def cameras_from_nerfstudio(cameras, downscale: int = 1) -> List[Camera]:
     """One Camera per entry of a nerfstudio `Cameras` object (anything with `camera_to_worlds` [V,3,4] and per-camera
     `fx, fy, cx, cy, width, height` tensors of shape [V,1]) -- what get_outputs reads from its `camera` argument."""
     c2w = cameras.camera_to_worlds
@@ -118,7 +131,8 @@ def cameras_from_nerfstudio(cameras) -> List[Camera]:
         c2w = c2w[None]
     pick = lambda t, i: float(torch.as_tensor(t).reshape(-1)[i if torch.as_tensor(t).numel() > 1 else 0])
     return [camera_from_c2w(c2w[i], pick(cameras.fx, i), pick(cameras.fy, i), pick(cameras.cx, i), pick(cameras.cy, i),
-                            int(pick(cameras.width, i)), int(pick(cameras.height, i))) for i in range(c2w.shape[0])]
+                            int(pick(cameras.width, i)), int(pick(cameras.height, i)), downscale)
+            for i in range(c2w.shape[0])]
 
 
 def orbit_cameras(n_views: int, W: int, H: int, radius: float = 4.5, first: int = 0, total: int = None) -> List[Camera]:

@@ -303,11 +303,14 @@ def camera_table(gs, model):
     g = torch.Generator().manual_seed(31)
     model.train()
     model.step = 600
-    rows = dict(c2w=[], intr_in=[], size_in=[], viewmat=[], fullmat=[], intr=[], size=[], tile_bounds=[])
+    rows = dict(c2w=[], intr_in=[], size_in=[], viewmat=[], fullmat=[], intr=[], size=[], tile_bounds=[], step=[], downscale=[])
     orig = gs.ProjectGaussians
     gs.ProjectGaussians = Recorder
     try:
-        for (W, H) in ((640, 480), (1280, 720), (333, 217), (1920, 1080)):
+        # (step 100 lies in the resolution warm-up: the model renders at half size, :599-603, :655-656)
+        for (W, H), step in (((640, 480), 600), ((1280, 720), 600), ((333, 217), 600), ((1920, 1080), 600), ((640, 480), 100),
+                             ((333, 217), 249), ((333, 217), 250)):
+            model.step = step
             q = torch.nn.functional.normalize(torch.randn(4, generator=g), dim=0)
             R = gs.quat_to_rotmat(q[None])[0]
             t = torch.randn(3, 1, generator=g) * 3
@@ -320,7 +323,9 @@ def camera_table(gs, model):
                 raise AssertionError("ProjectGaussians.apply was not reached")
             except Recorded as r:
                 rec = r.args[0]
-            assert rec["glob_scale"] == 1 and model.last_size == (H, W)
+            d = model._get_downscale_factor()
+            assert rec["glob_scale"] == 1 and model.last_size == tuple(rec["size"]) and d == (2 if step < 250 else 1)
+            rows["step"].append(step); rows["downscale"].append(d)
             rows["c2w"].append(c2w[0].numpy()); rows["intr_in"].append([fx, fy, cx, cy]); rows["size_in"].append([W, H])
             rows["viewmat"].append(rec["viewmat"].numpy()); rows["fullmat"].append(rec["fullmat"].numpy())
             rows["intr"].append(rec["intr"]); rows["size"].append(rec["size"]); rows["tile_bounds"].append(rec["tile_bounds"])

@@ -171,7 +171,9 @@ def test_camera_setup_equals_what_get_outputs_hands_to_the_projection():
     for i in range(V):
         fx, fy, cx, cy = fix["cam_intr_in"][i]
         W, H = (int(v) for v in fix["cam_size_in"][i])
-        c = scenes.camera_from_c2w(fix["cam_c2w"][i], fx, fy, cx, cy, W, H)
+        d = scenes.downscale_factor(int(fix["cam_step"][i]))
+        assert d == int(fix["cam_downscale"][i])
+        c = scenes.camera_from_c2w(fix["cam_c2w"][i], fx, fy, cx, cy, W, H, downscale=d)
         assert c.viewmat[:3].numpy().tobytes() == fix["cam_viewmat"][i].tobytes(), i
         assert c.fullmat.numpy().tobytes() == fix["cam_fullmat"][i].tobytes(), i
         assert [c.fx, c.fy, c.cx, c.cy] == fix["cam_intr"][i].tolist() and [c.H, c.W] == fix["cam_size"][i].tolist()
@@ -180,7 +182,9 @@ def test_camera_setup_equals_what_get_outputs_hands_to_the_projection():
         cams.append(c)
     # a nerfstudio-shaped batch ([V,3,4] poses, [V,1] intrinsics) of equal-sized views -> the same cameras, and the
     # packed ViewBatch the fused path consumes
-    same = [i for i in range(V) if fix["cam_size_in"][i].tolist() == fix["cam_size_in"][0].tolist()] + [0]
+    assert sorted(set(fix["cam_downscale"].tolist())) == [1, 2]
+    same = [i for i in range(V) if fix["cam_size_in"][i].tolist() == fix["cam_size_in"][0].tolist()
+            and int(fix["cam_downscale"][i]) == 1] + [0]
     col = lambda j: torch.tensor([[fix["cam_intr_in"][i][j]] for i in same], dtype=torch.float32)
     W, H = (int(v) for v in fix["cam_size_in"][0])
     batch = types.SimpleNamespace(camera_to_worlds=torch.from_numpy(fix["cam_c2w"][same]), fx=col(0), fy=col(1), cx=col(2),
