@@ -19,7 +19,8 @@ inputs.  Needs /root/reference (build container only); the resulting fixtures tr
                          :315-331 with the real scikit-learn), the up-projection MLP (:198-213) forward on seeded
                          weights, projection_matrix (:87-105), SH2RGB (:80-85), the arguments get_outputs (:624-713) hands to
                          ProjectGaussians.apply for a few nerfstudio cameras, after_train's densification statistics (:373-393) over
-                         three steps, nerfstudio's own real-SH basis (utils/math.py:29-92) and quaternion -> rotation
+                         three steps, the rules refinement_after applies at every refinement step of a run (observed on probe Gaussians),
+                         nerfstudio's own real-SH basis (utils/math.py:29-92) and quaternion -> rotation
                          matrix (cameras/camera_utils.py:142-161), the optimizer table of the method
                          (configs/method_configs.py:611-664, read from the source's syntax tree) and the trainer's
                          ExponentialDecayScheduler (nerfstudio/engine/schedulers.py:109-140, imported and run) learning
@@ -152,6 +153,68 @@ def refine_fixture(gs):
     return out
 
 
+def schedule_table(gs):
+    """Which rules refinement_after (:402-464) applies at which step, observed on the reference's own method: six probe
+    Gaussians, each built so that exactly one rule decides its fate (copies of it afterwards tell whether the rule
+    fired).  -1 = not observable at that step (the rule sits inside a branch that was not taken)."""
+    import contextlib
+    import io
+    model = small_model(gs, 16)
+    model.train()
+    cfg = model.config
+    n, K, D = 6, 25, 32
+    hi, lo = 1.0, 0.0                                  # avg_grad_norm far above / below densify_grad_thresh
+
+    def probe(step, num_train_data):
+        P = dict(means=torch.arange(n * 3, dtype=torch.float32).reshape(n, 3),
+                 log_scales=torch.log(torch.tensor([0.005, 0.7, 0.005, 0.005, 0.005, 0.005]))[:, None].repeat(1, 3),
+                 quats=torch.tensor([[1.0, 0, 0, 0]]).repeat(n, 1),
+                 opacity_logit=torch.tensor([3.0, 3.0, 3.0, -5.0, 3.0, 3.0])[:, None],
+                 sh_coeffs=torch.zeros(n, K, 3), features=torch.zeros(n, D))
+        P["features"][:, 0] = torch.arange(n)          # the identity each copy carries along
+        for k, attr in PARAM_OF.items():
+            setattr(model, attr, torch.nn.Parameter(P[k].clone()))
+        groups = model.get_gaussian_param_groups()
+        optimizers = types.SimpleNamespace(optimizers={})
+        for k, grp in GROUP_OF.items():
+            (param,) = groups[grp]
+            opt = torch.optim.Adam([param], lr=1e-3, eps=1e-15)
+            opt.state[param] = dict(step=torch.tensor(1.0), exp_avg=torch.ones_like(param), exp_avg_sq=torch.ones_like(param))
+            optimizers.optimizers[grp] = opt
+        model.step, model.num_train_data, model.last_size = step, num_train_data, (480, 640)
+        grad = torch.tensor([hi, lo, lo, lo, hi, lo]) / (0.5 * 640)
+        model.xys_grad_norm, model.vis_counts = grad.clone(), torch.ones(n)
+        model.max_2Dsize = torch.tensor([0.1, 0.0, 0.2, 0.0, 0.0, 0.0])
+        with contextlib.redirect_stdout(io.StringIO()):
+            model.refinement_after(optimizers, step)
+        if model.xys_grad_norm is not None:
+            return [0, -1, -1, -1, -1, -1, -1]           # before warmup_length: nothing happens
+        ids = model.feature.detach()[:, 0].round().long()
+        copies = torch.bincount(ids, minlength=n).tolist()
+        assert copies[5] == 1
+        densify = int(copies[4] == 2)
+        # probe 0 is small: split by its screen size it leaves two children AND, being small and high-gradient, a
+        # duplicate (:419-421 decide the duplicates after the split) -- 4 copies; without the screen rule 2 (a duplicate)
+        assert not densify or copies[0] in (2, 4)
+        split_by_screen = int(copies[0] == 4) if densify else -1
+        cull = int(copies[3] == 0)
+        by_scale = int(copies[1] == 0) if cull else -1
+        by_screen = int(copies[2] == 0) if by_scale == 1 else -1
+        reset_value = torch.logit(torch.tensor(cfg.cull_alpha_thresh * 0.8)).item()
+        reset = int(bool((model.opacities.detach() == reset_value).all()))
+        opt = optimizers.optimizers["opacity"]
+        moments_zeroed = bool((opt.state[opt.param_groups[0]["params"][0]]["exp_avg"] == 0).all())
+        assert moments_zeroed == bool(reset)
+        return [1, densify, split_by_screen, cull, by_scale, by_screen, reset]
+    rows = []
+    for num_train_data, last in ((4, 16000), (150, 7000), (350, 7000)):
+        for step in range(0, last + 1, cfg.refine_every):           # the callback fires every refine_every iterations (:566-571)
+            rows.append([step, num_train_data] + probe(step, num_train_data))
+    return dict(schedule_columns=np.array(["step", "num_train_data", "active", "do_densify", "split_by_screen", "do_cull",
+                                           "cull_by_scale", "cull_by_screen", "reset_opacity"]),
+                schedule_rows=np.array(rows, dtype=np.int64))
+
+
 # ---------------------------------------------------------------------------------------------------------------
 def losses_fixture(gs):
     H, W, D = 40, 48, 32
@@ -249,6 +312,7 @@ def init_fixture(gs):
     out.update(optimizer_table())
     out.update(camera_table(gs, model))
     out.update(after_train_table(gs))
+    out.update(schedule_table(gs))
     # the reference's own real spherical-harmonics basis (nerfstudio/utils/math.py:29-92), 5 levels = degree 4: the
     # same 25 functions in the same order as gsplat's, without the (-1)^|m| sign gsplat (like the 3DGS authors) carries
     from nerfstudio.utils.math import components_from_spherical_harmonics

@@ -115,6 +115,28 @@ def test_model_oracle_reproduces_the_references_get_outputs_and_backward():
     checks.check_outputs(render, rtol_grad=2e-5)
 
 
+def test_refine_schedule_equals_the_rules_the_references_refinement_after_applied():
+    """training.refine_schedule against what the reference's own refinement_after (:402-464) was OBSERVED to do at every
+    refinement step of a run (probe Gaussians whose fate depends on one rule each; -1 = not observable at that step),
+    for three training-set sizes."""
+    from gaussiangrasper_b200 import training
+    fix = checks.load("ref_init_small")
+    cols = fix["schedule_columns"].tolist()
+    assert cols[:3] == ["step", "num_train_data", "active"]
+    seen = {k: set() for k in cols[3:]}
+    for step, num_train_data, active, *flags in fix["schedule_rows"].tolist():
+        got = training.refine_schedule(step, num_train_data, 640)
+        if not active:
+            assert got is None, step
+            continue
+        assert got is not None, step
+        for k, v in zip(cols[3:], flags):
+            if v >= 0:
+                assert int(got[k]) == v, (step, num_train_data, k)
+                seen[k].add(v)
+    assert all(v == {0, 1} for v in seen.values()), seen          # every rule was seen both on and off
+
+
 def test_references_after_train_statistics():
     checks.check_after_train(checks.OracleBackend())
 
