@@ -131,6 +131,38 @@ def sampling_pairs_in_mask(mask: torch.Tensor, sample_num: int, generator: Optio
     return pairs
 
 
+def _resized(t_hwc: torch.Tensor, size: Tuple[int, int], mode: str) -> torch.Tensor:
+    """[H, W, C] -> [h, w, C] with F.interpolate's `mode` (half-pixel centres, no anti-aliasing)."""
+    return torch.nn.functional.interpolate(t_hwc.permute(2, 0, 1)[None], size=size, mode=mode)[0].permute(1, 2, 0)
+
+
+def prepare_targets(batch: Dict[str, torch.Tensor], downscale: int = 1) -> Dict[str, torch.Tensor]:
+    """The supervision of one view as the loss functions of this module take it, from the reference's batch
+    (get_loss_dict, gaussian_splatting.py:849-875): `image` [H,W,3], `normal` [H,W,3], `depth` [H,W,1], `sam_mask`
+    [H,W] segment ids, `valid_mask` [H,W], `feature` [H,W,F].  With downscale d > 1 (the resolution warm-up,
+    scenes.downscale_factor) everything is brought to [H // d, W // d]: image, normal and depth bilinearly, the masks,
+    the depth validity (depth > 0.05, decided BEFORE the resize) and the features by nearest neighbour.
+
+    Returns channel-last tensors: image [h,w,3]; normal [h,w,3] (unit length); depth [h,w]; depth_mask [h,w] bool
+    (valid depth and valid pixel); valid [h,w] bool; segments [h,w] float (-1 on invalid pixels: what the samplers
+    take); feature [h,w,F]."""
+    F = torch.nn.functional
+    image = batch["image"]
+    size = (image.shape[0] // downscale, image.shape[1] // downscale) if downscale > 1 else tuple(image.shape[:2])
+    if downscale > 1:
+        image = _resized(image, size, "bilinear")
+    normal = F.normalize(_resized(batch["normal"], size, "bilinear"), dim=-1)
+    depth_full = batch["depth"].reshape(batch["depth"].shape[0], batch["depth"].shape[1], 1)
+    depth_ok = _resized((depth_full > 0.05).to(depth_full.dtype), size, "nearest")[..., 0]
+    depth = _resized(depth_full, size, "bilinear")[..., 0]
+    valid = _resized(batch["valid_mask"].float()[..., None], size, "nearest")[..., 0] > 0
+    segments = _resized(batch["sam_mask"].float()[..., None], size, "nearest")[..., 0].clone()
+    segments[~valid] = -1.0
+    feature = _resized(batch["feature"].float(), size, "nearest")
+    return dict(image=image, normal=normal, depth=depth, depth_mask=(depth_ok > 0) & valid, valid=valid,
+                segments=segments, feature=feature)
+
+
 def _pixel_rows(image: torch.Tensor, c0: int, D: int) -> Tuple[torch.Tensor, int]:
     """[pixels, D] strided view of the feature channels of a [H, W, CP] image."""
     H, W, CP = image.shape

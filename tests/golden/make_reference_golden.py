@@ -29,6 +29,8 @@ inputs.  Needs /root/reference (build container only); the resulting fixtures tr
                          and the method's gradient-accumulation table: parameters after every iteration
   ref_ply_small.npz      ExportGaussianSplat.main (scripts/exporter.py:482-530) itself on a small model; open3d is absent,
                          the attribute map it hands to o3d.t.geometry.PointCloud is recorded
+  ref_targets_small.npz  the ground-truth side of get_loss_dict (:849-875) at half resolution (step 100): the method's own local
+                         tensors (gt_img, gt_normal, gt_depth, depth_mask, gt_mask, valid_mask, gt_fea), read from its frame
   ref_outputs_small.npz  GaussianSplattingModel.get_outputs (:624-802) + backward itself, SH degree 4; the operator classes it
                          calls are this repository's with the CPU oracle underneath (gsplat is absent): pins the glue around
                          the operators to the reference's code
@@ -281,6 +283,49 @@ def losses_fixture(gs):
     out["scales"], out["grad_scales"] = model.scales.detach().numpy(), model.scales.grad.numpy()
     for k, p in model.fea_up.named_parameters():
         out["mlp_" + k], out["mlp_grad_" + k] = p.detach().numpy(), p.grad.numpy()
+    return out
+
+
+def targets_fixture(gs):
+    """The ground-truth side of get_loss_dict (:849-875) during the resolution warm-up (step 100: half size): the
+    method's own local tensors, read from its frame when it returns."""
+    H, W, D = 40, 48, 32
+    torch.manual_seed(91)
+    model = small_model(gs, 100)
+    model.train()
+    model.step = 100
+    d = model._get_downscale_factor()
+    assert d == 2
+    g = torch.Generator().manual_seed(92)
+    outputs = dict(rgb=torch.rand((H // d, W // d, 3), generator=g) * 1.0, depth=torch.rand((H // d, W // d, 1), generator=g) + 0.5,
+                   normal=torch.randn((H // d, W // d, 3), generator=g), feature=torch.randn((H // d, W // d, D), generator=g))
+    seg = torch.randint(0, 3, (H, W), generator=g)
+    depth = torch.rand((H, W, 1), generator=g) * 5 + 0.1
+    depth[:7, :] = 0.01
+    depth[20:23, 10:30] = 0.04
+    batch = dict(image=torch.rand((H, W, 3), generator=g), normal=torch.randn((H, W, 3), generator=g), depth=depth,
+                 sam_mask=seg, valid_mask=torch.rand((H, W), generator=g) > 0.2,
+                 feature=torch.randint(-1, 2, (H, W, 512), generator=g).float())
+    saved = {k: v.clone() for k, v in batch.items()}
+    captured = {}
+    code = gs.GaussianSplattingModel.get_loss_dict.__code__
+
+    def profiler(frame, event, arg):
+        if event == "return" and frame.f_code is code:
+            for k in ("gt_img", "gt_normal", "gt_depth", "depth_mask", "gt_mask", "valid_mask", "gt_fea"):
+                captured[k] = frame.f_locals[k].detach().clone()
+    sys.setprofile(profiler)
+    try:
+        model.get_loss_dict(outputs, batch)
+    finally:
+        sys.setprofile(None)
+    assert captured["gt_img"].shape == (H // d, W // d, 3)
+    out = dict(downscale=np.array([d]), step=np.array([100]))
+    for k, v in saved.items():
+        out["batch_" + k] = v.numpy()
+    out["batch_feature"] = out["batch_feature"].astype(np.int8)              # values -1, 0, 1
+    for k, v in captured.items():
+        out["local_" + k] = v.numpy() if k != "gt_fea" else v.numpy().astype(np.int8)
     return out
 
 
@@ -614,7 +659,7 @@ def main():
     out_dir = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else HERE
     gs = import_reference()
     for name, fn in (("refine_small", refine_fixture), ("ref_losses_small", losses_fixture), ("ref_init_small", init_fixture),
-                     ("ref_trainer_small", trainer_fixture), ("ref_ply_small", ply_fixture),
+                     ("ref_trainer_small", trainer_fixture), ("ref_ply_small", ply_fixture), ("ref_targets_small", targets_fixture),
                      ("ref_outputs_small", outputs_fixture)):      # (last: it swaps the oracle in underneath the operators)
         path = os.path.join(out_dir, name + ".npz")
         np.savez_compressed(path, **fn(gs))

@@ -137,6 +137,35 @@ def test_refine_schedule_equals_the_rules_the_references_refinement_after_applie
     assert all(v == {0, 1} for v in seen.values()), seen          # every rule was seen both on and off
 
 
+def test_prepare_targets_equals_the_ground_truth_side_of_the_references_get_loss_dict():
+    """losses.prepare_targets against the local tensors of the reference's own get_loss_dict (:849-875), read from its
+    frame: at half resolution (training step 100: image / normal / depth resized bilinearly, masks and features by
+    nearest neighbour, depth validity decided before the resize) bit for bit, and at full resolution."""
+    from gaussiangrasper_b200 import losses, scenes
+    fix = checks.load("ref_targets_small")
+    d = int(fix["downscale"][0])
+    assert d == 2 == scenes.downscale_factor(int(fix["step"][0]))
+    batch = {k[len("batch_"):]: torch.from_numpy(v) for k, v in fix.items() if k.startswith("batch_")}
+    t = losses.prepare_targets(batch, d)
+    loc = {k[len("local_"):]: torch.from_numpy(v) for k, v in fix.items() if k.startswith("local_")}
+    valid = loc["valid_mask"]
+    assert torch.equal(t["valid"], valid) and 0.05 < float((~valid).float().mean()) < 0.5
+    assert torch.equal(t["image"][valid], loc["gt_img"][valid])        # (the reference zeroes its copy's invalid pixels later, :883)
+    assert torch.equal(t["normal"].permute(2, 0, 1), loc["gt_normal"])
+    assert torch.equal(t["depth"][None], loc["gt_depth"]) and torch.equal(t["depth_mask"][None], loc["depth_mask"])
+    assert torch.equal(t["segments"], loc["gt_mask"]) and torch.equal(t["feature"].permute(2, 0, 1), loc["gt_fea"].float())
+    assert bool((t["depth_mask"] != ((t["depth"] > 0.05) & valid)).any())   # validity was decided before the resize: it matters here
+    # full resolution: the fixture of the loss values
+    fix1 = checks.load("ref_losses_small")
+    batch1 = {k[len("batch_"):]: torch.from_numpy(v) for k, v in fix1.items() if k.startswith("batch_") and k != "batch_feature_x8"}
+    batch1["feature"] = torch.from_numpy(fix1["batch_feature_x8"]).float() / 8
+    t1, want = losses.prepare_targets(batch1, 1), checks.ground_truth(fix1)
+    assert torch.equal(t1["segments"], torch.from_numpy(fix1["gt_mask"]))
+    for k in ("image", "depth", "depth_mask", "valid", "feature"):
+        assert torch.equal(t1[k], want[k]), k
+    assert torch.allclose(t1["normal"], want["normal"], rtol=0, atol=2e-7)     # normalised in another memory layout there
+
+
 def test_references_after_train_statistics():
     checks.check_after_train(checks.OracleBackend())
 
@@ -227,7 +256,7 @@ def test_the_reference_regenerates_the_committed_fixtures(tmp_path):
     r = subprocess.run([sys.executable, os.path.join(HERE, "golden", "make_reference_golden.py"), "--out", str(tmp_path)],
                        capture_output=True, text=True, timeout=900, cwd=str(tmp_path))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
-    for name in ("refine_small", "ref_losses_small", "ref_init_small", "ref_trainer_small", "ref_ply_small", "ref_outputs_small"):
+    for name in ("refine_small", "ref_losses_small", "ref_init_small", "ref_trainer_small", "ref_ply_small", "ref_outputs_small", "ref_targets_small"):
         want, got = checks.load(name), dict(np.load(os.path.join(str(tmp_path), name + ".npz")))
         assert set(want) == set(got), name
         for k in want:
