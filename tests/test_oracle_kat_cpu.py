@@ -267,3 +267,39 @@ def test_blend_backward_vs_finite_differences(seed):
             assert abs(fd - ref) <= 2e-5 * max(1.0, abs(ref)), (name, int(k), fd, ref)
             checked += 1
     assert checked >= 30
+
+
+def test_offaxis_rotated_gaussians_ewa_from_a_numerical_jacobian():
+    """Projection (Appendix A1-A5) of rotated, anisotropic, off-axis Gaussians against a derivation that shares no
+    formula with the oracle: the rotation matrices are the reference's own (nerfstudio's quaternion_matrix, stored in
+    tests/golden/ref_init_small.npz), and the Jacobian of the pinhole projection is taken NUMERICALLY (central
+    differences of (fx x/z + cx, fy y/z + cy) in float64) instead of from the analytic EWA expression:
+    cov2d = J (W Sigma W^T) J^T + 0.3 I, conic = cov2d^-1, radius = ceil(3 sqrt(lambda_max)), xys = projection - 0.5."""
+    import os
+    fix = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_init_small.npz"))
+    q, R = fix["quat_wxyz"][:24].astype(np.float32), fix["quat_rotmat"][:24]
+    n = len(q)
+    g = np.random.default_rng(3)
+    means = np.stack([g.uniform(-1.2, 1.2, n), g.uniform(-0.9, 0.9, n), g.uniform(2.5, 6.0, n)], axis=1).astype(np.float32)
+    scales = g.uniform(0.05, 0.4, (n, 3)).astype(np.float32)
+    qn = (q / np.linalg.norm(q, axis=1, keepdims=True)).astype(np.float32)
+
+    def pinhole(p):
+        return np.array([FX * p[0] / p[2] + CX, FY * p[1] / p[2] + CY])
+    for got in project_both(means, scales, qn):
+        xys, depths, radii, conics, nth, cov3d = got
+        for i in range(n):
+            p = means[i].astype(np.float64)                      # identity view matrix: camera space = world space
+            h = 1e-6
+            J = np.stack([(pinhole(p + h * e) - pinhole(p - h * e)) / (2 * h) for e in np.eye(3)], axis=1)   # [2,3]
+            Sigma = R[i] @ np.diag(scales[i].astype(np.float64) ** 2) @ R[i].T
+            cov2d = J @ Sigma @ J.T + 0.3 * np.eye(2)
+            det = cov2d[0, 0] * cov2d[1, 1] - cov2d[0, 1] ** 2
+            conic = np.array([cov2d[1, 1], -cov2d[0, 1], cov2d[0, 0]]) / det
+            b = 0.5 * (cov2d[0, 0] + cov2d[1, 1])
+            lam = b + math.sqrt(max(0.1, b * b - det))
+            np.testing.assert_allclose(xys[i], pinhole(p) - 0.5, atol=5e-4)
+            np.testing.assert_allclose(depths[i], p[2], rtol=1e-6)
+            np.testing.assert_allclose(conics[i], conic, rtol=2e-4, atol=1e-7)
+            assert abs(int(radii[i]) - math.ceil(3 * math.sqrt(lam))) <= (1 if abs(3 * math.sqrt(lam) % 1) < 1e-3 else 0)
+            assert radii[i] > 0 and nth[i] > 0
