@@ -313,6 +313,23 @@ def check_sh_basis(sh_forward, device=torch.device("cpu")):
         assert float((got - ref[:, None]).abs().max()) <= 5e-6, deg
 
 
+def check_sh_gradient(sh_backward, device=torch.device("cpu")):
+    """d colour / d coefficients = the basis itself: `sh_backward(degrees_to_use, dirs [N,3], v_colors [N,3]) ->
+    v_coeffs [N,25,3]` must be (-1)^|m| x the reference's basis (nerfstudio/utils/math.py) times v_colors, and zero in
+    the bands above degrees_to_use."""
+    fix = load("ref_init_small")
+    dirs = torch.from_numpy(fix["sh_dirs"]).to(device)
+    Y = torch.from_numpy(fix["sh_components"]).double()
+    sign = torch.tensor([(-1.0) ** abs(m) for l in range(5) for m in range(-l, l + 1)], dtype=torch.float64)
+    v = torch.randn((dirs.shape[0], 3), generator=torch.Generator().manual_seed(7))
+    for deg, nb in ((4, 25), (2, 9), (0, 1)):
+        got = torch.as_tensor(sh_backward(deg, dirs, v.to(device))).detach().cpu().double()
+        want = (sign * Y)[:, :, None] * v.double()[:, None, :]
+        want[:, nb:, :] = 0.0
+        assert got.shape == want.shape
+        assert float((got - want).abs().max()) <= 5e-6, deg
+
+
 def check_quaternion_convention(quat_to_rotmat=None, project=None, device=torch.device("cpu")):
     """The (w, x, y, z) quaternion convention against the reference's OWN quaternion_matrix
     (nerfstudio/cameras/camera_utils.py:142-161): `quat_to_rotmat(q [N,4]) -> [N,3,3]` directly, and `project(means,

@@ -61,7 +61,14 @@ def test_cuda_densification_statistics_match_the_references_after_train():
 
 def test_cuda_sh_basis_equals_the_references_own_real_sh_basis():
     from gaussiangrasper_b200 import SphericalHarmonics
-    checks.check_sh_basis(lambda deg, d, c: SphericalHarmonics.apply(deg, d, c), torch.device("cuda:0"))
+    dev = torch.device("cuda:0")
+    checks.check_sh_basis(lambda deg, d, c: SphericalHarmonics.apply(deg, d, c), dev)
+
+    def backward(deg, d, v):
+        coeffs = torch.zeros((d.shape[0], 25, 3), device=dev, requires_grad=True)
+        SphericalHarmonics.apply(deg, d, coeffs).backward(v)
+        return coeffs.grad
+    checks.check_sh_gradient(backward, dev)
 
 
 def test_cuda_projection_covariance_follows_the_references_quaternion_matrix():

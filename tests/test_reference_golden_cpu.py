@@ -38,6 +38,7 @@ def test_oracle_sh_basis_equals_the_references_own_real_sh_basis():
     from oracle import c_oracle, torch_oracle
     checks.check_sh_basis(lambda deg, d, c: c_oracle.sh_fwd(deg, d.numpy(), c.numpy()))
     checks.check_sh_basis(lambda deg, d, c: torch_oracle.spherical_harmonics(deg, d.double(), c.double()))
+    checks.check_sh_gradient(lambda deg, d, v: c_oracle.sh_bwd(4, deg, d.numpy(), v.numpy()))
 
 
 def test_quaternion_convention_equals_the_references_own_quaternion_matrix():
