@@ -252,6 +252,15 @@ def test_camera_setup_equals_what_get_outputs_hands_to_the_projection():
     assert torch.equal(vb.positions[0], cams[same[0]].position)
 
 
+def test_gpu_reference_tests_dry_run_on_the_cpu(tmp_path):
+    """tests/dry_run_gpu_reference_tests.py: every test function of tests/test_gpu_zz_reference_golden.py executed with
+    the CUDA entry points replaced by oracle-backed stand-ins (a check of the GPU tests' own code)."""
+    r = subprocess.run([sys.executable, os.path.join(HERE, "dry_run_gpu_reference_tests.py")], capture_output=True, text=True,
+                       timeout=900, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "DRY RUN PASSED 7" in r.stdout, r.stdout[-2000:]
+
+
 @pytest.mark.skipif(not os.path.exists(REFERENCE), reason="the reference tree is not mounted on this machine")
 def test_the_reference_regenerates_the_committed_fixtures(tmp_path):
     r = subprocess.run([sys.executable, os.path.join(HERE, "golden", "make_reference_golden.py"), "--out", str(tmp_path)],
