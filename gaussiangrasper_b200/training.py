@@ -25,6 +25,12 @@ REFERENCE_SCHEDULES = dict(means=(1.6e-6, 30000), sh_coeffs=(1e-4, 30000), featu
 _MODE = dict(step=0, acc_first=1, acc=2, acc_step=3, skip=4)   # GG_ADAM_* of include/gg_b200.h
 
 
+def sh_degrees_to_use(step: int, sh_degree: int = 4, sh_degree_interval: int = 1000) -> int:
+    """How many SH bands the model evaluates at training step `step` (gaussian_splatting.py:729: one more band every
+    sh_degree_interval steps) -- the `degrees_to_use` argument of render_views / SphericalHarmonics."""
+    return min(step // sh_degree_interval, sh_degree)
+
+
 def exponential_decay_lr(lr_init: float, lr_final: float, max_steps: int, step: int) -> float:
     """engine/schedulers.py:122-138 without warm-up: log-linear interpolation lr_init -> lr_final over max_steps."""
     import math

@@ -356,6 +356,7 @@ def init_fixture(gs):
     # trainer's ExponentialDecayScheduler (engine/schedulers.py:109-140, imported and run) produces from it
     out.update(optimizer_table())
     out.update(camera_table(gs, model))
+    out.update(sh_degree_table(gs, model))
     out.update(after_train_table(gs))
     out.update(schedule_table(gs))
     # the reference's own real spherical-harmonics basis (nerfstudio/utils/math.py:29-92), 5 levels = degree 4: the
@@ -370,6 +371,46 @@ def init_fixture(gs):
     out["quat_wxyz"] = q.numpy()
     out["quat_rotmat"] = np.stack([quaternion_matrix(row)[:3, :3] for row in q.numpy()])
     return out
+
+
+def sh_degree_table(gs, model):
+    """The number of SH bands get_outputs (:726-731) asks SphericalHarmonics.apply for, per training step: both
+    operator classes intercepted (a stand-in projection, the SH call recorded and get_outputs abandoned there)."""
+    from nerfstudio.cameras.cameras import Cameras, CameraType
+
+    class Recorded(Exception):
+        pass
+
+    class Projection:
+        @staticmethod
+        def apply(means, *a):
+            n = means.shape[0]
+            return (means[:, :2] * 1.0, torch.ones(n), torch.ones(n, dtype=torch.int32), torch.ones(n, 3),
+                    torch.ones(n, dtype=torch.int32), torch.ones(n, 6))
+
+    class SH:
+        @staticmethod
+        def apply(n, viewdirs, coeffs):
+            raise Recorded(n, tuple(coeffs.shape))
+    steps = [0, 499, 500, 999, 1000, 1999, 2000, 2999, 3000, 3999, 4000, 4001, 9000, 29999]
+    got = []
+    orig = gs.ProjectGaussians, gs.SphericalHarmonics
+    gs.ProjectGaussians, gs.SphericalHarmonics = Projection, SH
+    model.train()
+    try:
+        for step in steps:
+            model.step = step
+            cam = Cameras(camera_to_worlds=torch.eye(4)[None, :3], fx=60.0, fy=60.0, cx=32.0, cy=24.0, width=64, height=48,
+                          camera_type=CameraType.PERSPECTIVE)
+            try:
+                model.get_outputs(cam)
+                raise AssertionError("SphericalHarmonics.apply was not reached")
+            except Recorded as r:
+                assert r.args[1][1:] == (25, 3)
+                got.append(int(r.args[0]))
+    finally:
+        gs.ProjectGaussians, gs.SphericalHarmonics = orig
+    return dict(sh_steps=np.array(steps), sh_degrees_to_use=np.array(got))
 
 
 def after_train_table(gs):

@@ -201,6 +201,10 @@ def test_host_constants_match_the_reference():
     acc = dict(zip(fix["accumulation_groups"].tolist(), fix["accumulation_steps"].tolist()))
     for group, ours in GROUP_MAP.items():
         assert training.REFERENCE_ACCUMULATION.get(ours, 1) == acc.get(group, 1), group
+    # the SH bands get_outputs asked SphericalHarmonics.apply for, per step (:729)
+    for step, want in zip(fix["sh_steps"].tolist(), fix["sh_degrees_to_use"].tolist()):
+        assert training.sh_degrees_to_use(step) == want, step
+    assert sorted(set(fix["sh_degrees_to_use"].tolist())) == [0, 1, 2, 3, 4]
     # ExponentialDecayScheduler (engine/schedulers.py:109-140) at the probed steps
     for group, row, lrs in zip(fix["opt_groups"].tolist(), fix["opt_lr_eps_final_maxsteps"], fix["opt_probe_lrs"]):
         if row[3] < 0:
