@@ -703,7 +703,15 @@ def main():
                      ("ref_trainer_small", trainer_fixture), ("ref_ply_small", ply_fixture), ("ref_targets_small", targets_fixture),
                      ("ref_outputs_small", outputs_fixture)):      # (last: it swaps the oracle in underneath the operators)
         path = os.path.join(out_dir, name + ".npz")
-        np.savez_compressed(path, **fn(gs))
+        new = {k: np.asarray(v) for k, v in fn(gs).items()}
+        if os.path.exists(path):            # an .npz differs byte-wise from run to run (zip time stamps): keep equal content
+            old = np.load(path)
+            if set(old.files) == set(new) and all(old[k].dtype == new[k].dtype and old[k].shape == new[k].shape and
+                                                  np.array_equal(old[k], new[k], equal_nan=new[k].dtype.kind in "fc")
+                                                  for k in new):
+                print(path, "unchanged")
+                continue
+        np.savez_compressed(path, **new)
         print(path, os.path.getsize(path), "bytes")
 
 
